@@ -1,0 +1,135 @@
+/*
+ * movfem_b200.h -- C ABI of the B200-native vector-FEM assembly for MoVFEM_3DMT.
+ *
+ * This is the drop-in boundary.  It replaces, in the reference,
+ *
+ *   MoVFEM_3DMT.f90:80-97   call global_vfem(irn,jcn,a,rhs) + find_zeros/rem_zeros
+ *   global_assembly.f90:38-39  ga_cgne / ga_nzindx  (DOF numbering + pattern, once per mesh)
+ *
+ * and nothing else: the Fortran driver, geometry, readers and the ZMUMPS solve stay.
+ * All entry points are extern "C", take plain pointers and sizes, return 0 on success or
+ * a negative MOVFEM_E_* code (the reference's `stop`s at global_assembly.f90:56-57,109-111,
+ * n_fem.f90:374-377, problem.f90:260-271 become return codes).  Arrays use the Fortran
+ * caller's conventions: column-major, 1-based index VALUES, caller-owned host memory.
+ *
+ * The Fortran-side binding (ISO_C_BINDING) is in movfem_b200/fortran/movfem_cuda.f90 and
+ * described in INTEGRATION.md.
+ */
+#ifndef MOVFEM_B200_H
+#define MOVFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* error codes */
+#define MOVFEM_OK                 0
+#define MOVFEM_E_BADARG         (-1)  /* inconsistent descriptor / null pointer            */
+#define MOVFEM_E_CUDA           (-2)  /* CUDA runtime error (see movfem_last_error)        */
+#define MOVFEM_E_SINGULAR_JAC   (-3)  /* n_fem.f90:374-377  'no transformation!! nf_det=0' */
+#define MOVFEM_E_SINGULAR_MODEL (-4)  /* problem.f90:260-271 'no sigma/mu inversion'       */
+#define MOVFEM_E_NOGPU          (-5)  /* no CUDA device: there is NO CPU fallback          */
+#define MOVFEM_E_CAPACITY       (-6)  /* caller array too small                            */
+#define MOVFEM_E_UNSUPPORTED    (-7)  /* e.g. Dirichlet boundary model 2/3   */
+
+/* assembly output modes */
+#define MOVFEM_MODE_T2  0  /* what ZMUMPS receives: upper triangle, row-major sorted, values
+                              rounded through float32 (global_assembly.f90:157,166,169),
+                              exact zeros stripped (global_assembly.f90:123-150)           */
+#define MOVFEM_MODE_T1  1  /* tap before ga_sort_sparse: same ordering and pattern
+                              (structural upper triangle, nothing stripped), double values */
+
+/*
+ * Mesh / problem descriptor.  Every field is the reference module variable of the same
+ * name (geometry.f90:17-26, boundary_conds.f90:15-25, problem.f90:18, v_fem.f90:16,
+ * n_fem.f90:14) so the Fortran shim fills it by plain assignment.
+ */
+typedef struct movfem_desc {
+    int32_t g_nx, g_ny, g_nz;   /* grid LINES per axis: elements are (g_nx-1)(g_ny-1)(g_nz-1) */
+    int32_t nord;               /* g_nordx=g_nordy=g_nordz: 2 (8-node) or 3 (20/27-node)      */
+    int32_t mn;                 /* nf_mn: 8, 20 or 27 nodes per element                       */
+    int32_t me;                 /* vf_me: 12, 36 or 54 edge DOFs per element                  */
+    int32_t nextd;              /* geometry.f90 nextd: extension / GPML layers per side       */
+    int32_t nzl_top;            /* g_nzl(g_nsf): element layers of the top extension          */
+    int32_t dirichlet;          /* boundary_conds.f90:15  1 = Dirichlet, 0 = GPML             */
+    int32_t bd_inimod;          /* boundary model (PARAM.INP line 7); only 1 (zero) supported */
+    int32_t gpml_sch;           /* 0 = Fang 1996, 1 = Zhou 2012 (boundary_conds.f90:100-108)  */
+    int32_t sym;                /* global_assembly.f90:18; the driver hard-codes 1            */
+    int32_t ndir;               /* problem.f90 ndir; the driver hard-codes 2                  */
+    int32_t pe_sch;             /* problem.f90 pe_sch; the driver hard-codes 1 (secondary E)  */
+    double  a0, b0, nn;         /* GPML constants (PARAM.INP last line)                       */
+    const double *g_xp;         /* (g_nnx)   x of node lines                                  */
+    const double *g_yp;         /* (g_nny)   y of node lines                                  */
+    const double *g_zp;         /* (g_npt)   z of every node, id=(ii-1)*g_nyz+(jj-1)*g_nnz+kk */
+    const double *g_mu;         /* (6,g_npt) real permeability tensor 11,12,13,22,23,33       */
+    /* element slab owned by this handle (multi-GPU slab sharding); 1-based,
+       inclusive, in the reference's ie index.  0,0 = whole mesh.                            */
+    int32_t ie_lo, ie_hi;
+} movfem_desc;
+
+typedef struct movfem_handle movfem_handle;
+
+/* phase timings of the last movfem_assemble call, milliseconds (CUDA events) */
+typedef struct movfem_stats {
+    double ms_h2d, ms_node, ms_element, ms_gather, ms_finalize, ms_d2h, ms_total;
+    int64_t nz;           /* entries delivered                                  */
+    int64_t launches;     /* kernels launched by the call                       */
+} movfem_stats;
+
+/* Create: uploads the mesh once, builds gne + pattern ON THE DEVICE
+   (replaces ga_init -> ga_cgne/ga_nzindx, global_assembly.f90:26-41).                        */
+int movfem_create(const movfem_desc *desc, int device, movfem_handle **out);
+void movfem_destroy(movfem_handle *h);
+
+/* nne, nnze (full structural pattern, what MoVFEM_3DMT.f90:72-78 allocates) and the
+   structural upper-triangle count (capacity the graft actually needs).                      */
+int movfem_sizes(const movfem_handle *h, int32_t *nne, int64_t *nnze_full, int64_t *nz_upper);
+
+/* gne(ne,me), column-major, Fortran values (1-based, -face for Dirichlet edges):
+   global_assembly.f90:183-195.  solution.f90:331-336 consumes it after the solve.           */
+int movfem_get_gne(const movfem_handle *h, int32_t *gne);
+
+/* Structural upper-triangle pattern in delivery order (row-major, 1-based). */
+int movfem_get_pattern(const movfem_handle *h, int32_t *irn, int32_t *jcn);
+
+/*
+ * One frequency: replaces MoVFEM_3DMT.f90:82-97.
+ *   freq_index  1-based position in the reference's sequential frequency loop (element
+ *               (1,1,1) sees stale GPML flags from the previous frequency)
+ *   omega       geometry.f90 omega = 2*pi*f
+ *   g_sigma     (6,g_npt) complex128, re-read every call
+ *   irn,jcn,a   capacity >= nz_upper entries;  rhs  ndir*nne entries
+ *   nz_out      number of triplets delivered (mumps_par%nz)
+ */
+int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega,
+                    const double *g_sigma /* complex128 as re,im pairs */,
+                    int32_t *irn, int32_t *jcn, double *a, double *rhs,
+                    int64_t *nz_out, int32_t mode);
+
+/*
+ * Device-resident variant used for kernel-only timing and for device consumers
+ * (SURVEY 8f-3): g_sigma_dev is a device pointer; results stay on the device and are
+ * reachable through movfem_device_result.  No host copies, asynchronous on the stream.
+ */
+int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega,
+                           const double *g_sigma_dev, int32_t mode);
+int movfem_device_result(const movfem_handle *h, const int32_t **irn, const int32_t **jcn,
+                         const double **a, const double **rhs, int64_t *nz /* syncs */);
+
+/* stream the handle launches on (cudaStream_t as void*); set before assembling. */
+int movfem_set_stream(movfem_handle *h, void *cuda_stream);
+int movfem_get_stats(const movfem_handle *h, movfem_stats *out);
+const char *movfem_last_error(const movfem_handle *h);
+const char *movfem_version(void);
+
+/* debug / parity tap: element matrices of one element as the kernels compute them
+   (K_e, M_e lower-by-local-index packed me*(me+1)/2, b_e me*ndir complex).                  */
+int movfem_debug_element(movfem_handle *h, int32_t ide /*1-based*/, double *Ke, double *Me,
+                         double *be);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOVFEM_B200_H */
