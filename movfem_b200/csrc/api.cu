@@ -1,0 +1,620 @@
+// movfem_b200/csrc/api.cu -- the C ABI (include/movfem_b200.h) over the CUDA kernels.
+//
+// One handle = one mesh on one GPU.  create() uploads the mesh and builds gne + pattern on the
+// device; assemble() runs one frequency: node fields -> element matrices -> deterministic
+// gather / A = K + i*w32*M / float32 round trip / zero strip -> RHS, and copies the triplets into
+// the caller's (Fortran-owned) arrays.  There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/movfem_b200.h"
+#include "common.cuh"
+#include "element.cuh"
+#include "finalize.cuh"
+#include "pattern.cuh"
+#include "ref_element.h"
+
+using namespace movfem;
+
+namespace {
+
+// ---- kernel configurations (tuned on B200) -------------------------------------
+//                    MN  ME NGP GCH EB THREADS PML
+using Cfg12  = ElemCfg<8, 12, 8, 4, 8, 96, false>;
+using Cfg12p = ElemCfg<8, 12, 8, 4, 8, 96, true>;
+using Cfg36  = ElemCfg<20, 36, 27, 3, 2, 96, false>;
+using Cfg36p = ElemCfg<20, 36, 27, 3, 2, 96, true>;
+using Cfg54  = ElemCfg<27, 54, 27, 3, 1, 128, false>;
+using Cfg54p = ElemCfg<27, 54, 27, 3, 1, 128, true>;
+
+enum { EV_START, EV_H2D, EV_NODE, EV_ELEM, EV_GATHER, EV_FINAL, EV_D2H, EV_COUNT };
+
+}  // namespace
+
+struct movfem_handle {
+    movfem_desc d;
+    int device;
+    MeshDims m;
+    PmlParams pml;
+    int NP, ngp;
+    int nne;
+    int64_t nzu, ncontrib, nnze_full;
+    cudaStream_t stream;
+    bool own_stream;
+    // device memory
+    double *d_xp, *d_yp, *d_zp, *d_mu;
+    double2 *d_sigma;
+    NodeRec *d_nodes;
+    ElemTables *d_tab;
+    ShareTables *d_share;
+    int *d_gne, *d_ownE;
+    uint8_t *d_ownL;
+    int *d_irn, *d_jcn, *d_irn_c, *d_jcn_c, *d_rown;
+    int64_t *d_cptr;
+    uint32_t *d_src;
+    double *d_Ke, *d_Me, *d_be;
+    double2 *d_a, *d_a_c, *d_rhs;
+    int *d_list_plain, *d_list_pml;
+    int n_plain, n_pml;
+    int *d_blkcnt;
+    int64_t *d_blkoff, *d_finbsum;
+    int nblk_fin;
+    int *d_status, *d_flags;
+    // pinned host scratch
+    int *h_status;      // [0] status [1..2] flags
+    int64_t *h_count;   // total non-zeros
+    // state
+    bool km_valid;      // Ke/Me of the unstretched elements are cached
+    bool compacted;     // last result lives in the *_c arrays
+    int64_t nz_last;
+    int32_t mode_last;
+    cudaEvent_t ev[EV_COUNT];
+    movfem_stats stats;
+    int64_t launches;
+    char err[512];
+};
+
+namespace {
+
+void set_err(movfem_handle *h, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            set_err(h, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return MOVFEM_E_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+template <class T>
+cudaError_t dmalloc(T **p, size_t n) { return cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+// exclusive scan helper (pattern.cuh kernels): out has n+1 entries
+int scan_counts(movfem_handle *h, const int *d_in, int64_t n, int64_t *d_out) {
+    const int nb = (int)((n + kScanTile - 1) / kScanTile);
+    int64_t *d_bsum = nullptr;
+    CK(dmalloc(&d_bsum, (size_t)nb + 1));
+    scan_block_sums<<<nb, kScanThreads, 0, h->stream>>>(d_in, n, d_bsum);
+    scan_block_offsets<<<1, 1024, 0, h->stream>>>(d_bsum, nb);
+    scan_finish<<<nb, kScanThreads, 0, h->stream>>>(d_in, n, d_bsum, d_out);
+    h->launches += 3;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaFree(d_bsum));
+    return 0;
+}
+
+void build_tables(const movfem_desc &d, const MeshDims &m, ElemTables &T, ShareTables &S) {
+    std::memset(&T, 0, sizeof(T));
+    std::memset(&S, 0, sizeof(S));
+    Shape shape(d.mn);
+    int i1[27], j1[27], k1[27], en[54], ed[54];
+    node_offsets(d.mn, d.nord, i1, j1, k1);
+    edge_dir_table(d.me, en, ed);
+    double pt[3], wt[3];
+    const int n1 = gauss_rule(d.me, pt, wt);
+    for (int a = 0; a < n1; ++a)
+        for (int b = 0; b < n1; ++b)
+            for (int c = 0; c < n1; ++c) {
+                const int g = a * n1 * n1 + b * n1 + c;   // integration.f90:273
+                T.rw[g][0] = pt[a]; T.rw[g][1] = pt[b]; T.rw[g][2] = pt[c];
+                T.rw[g][3] = wt[a] * wt[b] * wt[c];
+            }
+    for (int g = 0; g < m.ngp; ++g) {
+        const double *r = T.rw[g];
+        for (int l = 0; l < d.mn; ++l) {
+            T.N[g][l] = shape.nf_ln(l + 1, r[0], r[1], r[2]);
+            for (int k = 0; k < 3; ++k) T.dN[g][l][k] = shape.nf_dln_dxi(k + 1, l + 1, r[0], r[1], r[2]);
+        }
+        for (int e = 0; e < d.me; ++e) {
+            T.phi[g][e] = shape.mix_ln(en[e], ed[e], r[0], r[1], r[2]);
+            for (int k = 0; k < 3; ++k) T.dphi[g][e][k] = shape.mix_dln_dxi(ed[e], k + 1, en[e], r[0], r[1], r[2]);
+        }
+    }
+    for (int l = 0; l < d.mn; ++l) {
+        T.node_off[l] = (i1[l] - 1) * m.nyz + (j1[l] - 1) * m.nnz + (k1[l] - 1);   // n_fem.f90:81
+        T.node_i[l] = i1[l] - 1; T.node_j[l] = j1[l] - 1;
+    }
+    for (int e = 0; e < d.me; ++e) T.edir[e] = ed[e] - 1;
+
+    // sharing tables: global_assembly.f90:242-265 (me=12), 310-351 (me=36), 396-443 (me=54);
+    // the same lists are the Dirichlet face lists of boundary_conds.f90:276-388
+    struct L { int n; int mine[12], theirs[12]; };
+    L x, y, z;
+    if (d.me == 12) {
+        z = {4, {2, 5, 7, 10}, {3, 6, 8, 11}};
+        y = {4, {1, 5, 6, 9}, {4, 7, 8, 12}};
+        x = {4, {1, 2, 3, 4}, {9, 10, 11, 12}};
+    } else if (d.me == 36) {
+        z = {10, {3, 4, 9, 10, 13, 14, 19, 20, 27, 33}, {5, 6, 11, 12, 15, 16, 21, 22, 28, 34}};
+        y = {10, {1, 2, 9, 10, 11, 12, 17, 18, 25, 32}, {7, 8, 13, 14, 15, 16, 23, 24, 29, 35}};
+        x = {10, {1, 2, 3, 4, 5, 6, 7, 8, 26, 31}, {17, 18, 19, 20, 21, 22, 23, 24, 30, 36}};
+    } else {
+        z = {12, {3, 8, 13, 16, 18, 23, 24, 29, 32, 34, 39, 44}, {5, 10, 15, 17, 20, 25, 26, 31, 33, 36, 41, 46}};
+        y = {12, {1, 2, 13, 14, 15, 21, 22, 29, 30, 31, 37, 38}, {11, 12, 18, 19, 20, 27, 28, 34, 35, 36, 47, 48}};
+        x = {12, {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12}, {37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48}};
+    }
+    const L *ax[3] = {&x, &y, &z};
+    for (int a = 0; a < 3; ++a)
+        for (int t = 0; t < ax[a]->n; ++t) {
+            S.back[a][ax[a]->mine[t]] = (uint8_t)ax[a]->theirs[t];
+            S.fwd[a][ax[a]->theirs[t]] = (uint8_t)ax[a]->mine[t];
+            S.face[ax[a]->mine[t]] |= (uint8_t)(1u << a);          // faces 1,2,3: ie=1, je=1, ke=1
+            S.face[ax[a]->theirs[t]] |= (uint8_t)(1u << (a + 3));  // faces 4,5,6: ie=nx, je=ny, ke=nz
+        }
+}
+
+void init_pml(const movfem_desc &d, const MeshDims &m, PmlParams &p) {
+    std::memset(&p, 0, sizeof(p));
+    p.sch = d.gpml_sch; p.a0 = d.a0; p.b0 = d.b0; p.nn = d.nn;
+    if (d.dirichlet) return;
+    // init_gpml, boundary_conds.f90:51-70
+    const int nextd = d.nextd, g1 = d.nord - 1;
+    const int gl[3] = {d.g_nx, d.g_ny, d.g_nz};
+    for (int a = 0; a < 3; ++a) {
+        p.el_a[a][0] = nextd; p.el_a[a][1] = gl[a] - nextd;
+        p.el_b[a][0] = 1;     p.el_b[a][1] = gl[a] - 1;
+    }
+    p.a[0][0] = d.g_xp[nextd * g1]; p.a[0][1] = d.g_xp[m.nnx - nextd * g1 - 1];
+    p.b[0][0] = d.g_xp[0];          p.b[0][1] = d.g_xp[m.nnx - 1];
+    p.a[1][0] = d.g_yp[nextd * g1]; p.a[1][1] = d.g_yp[m.nny - nextd * g1 - 1];
+    p.b[1][0] = d.g_yp[0];          p.b[1][1] = d.g_yp[m.nny - 1];
+    const int64_t last = (int64_t)(m.nnx - 1) * m.nyz + (int64_t)(m.nny - 1) * m.nnz + m.nnz;   // 1-based id of the last node
+    p.a[2][0] = d.g_zp[nextd * g1]; p.a[2][1] = d.g_zp[last - d.nzl_top * g1 - 1];
+    p.b[2][0] = d.g_zp[0];          p.b[2][1] = d.g_zp[last - 1];
+    const double f1 = (double)1.e-5f, f2 = (double)1.e3f;   // boundary_conds.f90:40 default-real literals
+    p.omegar[0] = 2.0 * kPi * f1; p.omegar[1] = 2.0 * kPi * f2;
+}
+
+template <class CFG, bool DO_KM>
+int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist) {
+    if (nlist <= 0) return 0;
+    auto kern = element_kernel<CFG, DO_KM>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::SMEM));
+    A.list = d_list; A.nlist = nlist;
+    const int grid = (nlist + CFG::EB - 1) / CFG::EB;
+    kern<<<grid, CFG::THREADS, CFG::SMEM, h->stream>>>(A);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <class CP, class CQ>
+int run_elements(movfem_handle *h, ElemArgs &A, bool full) {
+    int rc;
+    // unstretched elements: K_e, M_e are frequency independent -> computed on the first
+    // frequency and whenever Re(sigma) changed; their RHS is rebuilt every frequency
+    if (full) {
+        A.skip_unless_changed = 0;
+        if ((rc = launch_elements<CP, true>(h, A, h->d_list_plain, h->n_plain))) return rc;
+    } else {
+        A.skip_unless_changed = 0;
+        if ((rc = launch_elements<CP, false>(h, A, h->d_list_plain, h->n_plain))) return rc;
+        A.skip_unless_changed = 1;   // refresh K/M only if the node kernel saw Re(sigma) change
+        if ((rc = launch_elements<CP, true>(h, A, h->d_list_plain, h->n_plain))) return rc;
+        A.skip_unless_changed = 0;
+    }
+    // stretched (GPML) elements depend on omega through h: always recomputed
+    if ((rc = launch_elements<CQ, true>(h, A, h->d_list_pml, h->n_pml))) return rc;
+    return 0;
+}
+
+void free_all(movfem_handle *h) {
+    cudaSetDevice(h->device);
+    void *ptrs[] = {h->d_xp, h->d_yp, h->d_zp, h->d_mu, h->d_sigma, h->d_nodes, h->d_tab, h->d_share, h->d_gne, h->d_ownE,
+                    h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_src, h->d_Ke, h->d_Me,
+                    h->d_be, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum,
+                    h->d_status, h->d_flags};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->h_count) cudaFreeHost(h->h_count);
+    for (int i = 0; i < EV_COUNT; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+}
+
+int build_pattern(movfem_handle *h) {
+    const MeshDims &m = h->m;
+    int *d_cnt = nullptr;
+    int64_t *d_base = nullptr;
+    CK(dmalloc(&d_cnt, (size_t)m.ne));
+    CK(dmalloc(&d_base, (size_t)m.ne + 1));
+    gne_count_kernel<<<(m.ne + 255) / 256, 256, 0, h->stream>>>(m, h->d_share, d_cnt);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    int rc = scan_counts(h, d_cnt, m.ne, d_base);
+    if (rc) return rc;
+    int64_t nne64 = 0;
+    CK(cudaMemcpy(&nne64, d_base + m.ne, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (nne64 <= 0 || nne64 > 0x1fffffff) { set_err(h, "nne=%lld out of range", (long long)nne64); return MOVFEM_E_CAPACITY; }
+    h->nne = (int)nne64;
+    CK(dmalloc(&h->d_gne, (size_t)m.ne * m.me));
+    CK(dmalloc(&h->d_ownE, (size_t)h->nne));
+    CK(dmalloc(&h->d_ownL, (size_t)h->nne));
+    const int64_t nt = (int64_t)m.ne * m.me;
+    gne_assign_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, h->stream>>>(m, h->d_share, d_base, h->d_gne, h->d_ownE, h->d_ownL);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaFree(d_cnt));
+    CK(cudaFree(d_base));
+
+    int *d_rowcnt = nullptr, *d_rowcand = nullptr;
+    int64_t *d_rowptr = nullptr, *d_cbase = nullptr;
+    CK(dmalloc(&d_rowcnt, (size_t)h->nne));
+    CK(dmalloc(&d_rowcand, (size_t)h->nne));
+    CK(dmalloc(&d_rowptr, (size_t)h->nne + 1));
+    CK(dmalloc(&d_cbase, (size_t)h->nne + 1));
+    const int rgrid = (h->nne + kRowWarps - 1) / kRowWarps;
+    if (m.me == 12)
+        row_kernel<64, false><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->nne, h->NP,
+                                                                     d_rowcnt, d_rowcand, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    else
+        row_kernel<256, false><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->nne, h->NP,
+                                                                      d_rowcnt, d_rowcand, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    if ((rc = scan_counts(h, d_rowcnt, h->nne, d_rowptr))) return rc;
+    if ((rc = scan_counts(h, d_rowcand, h->nne, d_cbase))) return rc;
+    CK(cudaMemcpy(&h->nzu, d_rowptr + h->nne, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&h->ncontrib, d_cbase + h->nne, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    h->nnze_full = 2 * h->nzu - h->nne;   // structurally symmetric pattern, every row has its diagonal
+    if (h->nzu > 0x7fffffffLL || h->ncontrib > 0xffffffffLL || (int64_t)m.ne * h->NP > 0xffffffffLL) {
+        set_err(h, "pattern too large for 32-bit slots: nz_upper=%lld contributions=%lld", (long long)h->nzu, (long long)h->ncontrib);
+        return MOVFEM_E_CAPACITY;
+    }
+    CK(dmalloc(&h->d_irn, (size_t)h->nzu));
+    CK(dmalloc(&h->d_jcn, (size_t)h->nzu));
+    CK(dmalloc(&h->d_cptr, (size_t)h->nzu + 1));
+    CK(dmalloc(&h->d_src, (size_t)h->ncontrib));
+    CK(dmalloc(&h->d_rown, (size_t)h->nne * 4));
+    if (m.me == 12)
+        row_kernel<64, true><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->nne, h->NP, nullptr,
+                                                                    nullptr, d_rowptr, d_cbase, h->d_irn, h->d_jcn, h->d_cptr, h->d_src, h->d_rown);
+    else
+        row_kernel<256, true><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->nne, h->NP, nullptr,
+                                                                     nullptr, d_rowptr, d_cbase, h->d_irn, h->d_jcn, h->d_cptr, h->d_src, h->d_rown);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->d_cptr + h->nzu, &h->ncontrib, sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaFree(d_rowcnt)); CK(cudaFree(d_rowcand)); CK(cudaFree(d_rowptr)); CK(cudaFree(d_cbase));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *movfem_version(void) { return "movfem_b200 0.1.0 (sm_100a)"; }
+
+const char *movfem_last_error(const movfem_handle *h) { return h ? h->err : "null handle"; }
+
+int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
+    if (!d || !out) return MOVFEM_E_BADARG;
+    *out = nullptr;
+    if (!((d->mn == 8 && d->me == 12 && d->nord == 2) || (d->mn == 20 && d->me == 36 && d->nord == 3) ||
+          (d->mn == 27 && d->me == 54 && d->nord == 3)))
+        return MOVFEM_E_BADARG;
+    if (d->g_nx < 2 || d->g_ny < 2 || d->g_nz < 2 || !d->g_xp || !d->g_yp || !d->g_zp || !d->g_mu) return MOVFEM_E_BADARG;
+    if (d->ndir != 2 || d->pe_sch != 1 || d->sym != 1) return MOVFEM_E_UNSUPPORTED;   // the driver hard-codes these
+    if (d->dirichlet && d->bd_inimod != 1) return MOVFEM_E_UNSUPPORTED;
+    if (d->ie_lo != 0 || d->ie_hi != 0) return MOVFEM_E_UNSUPPORTED;
+    if (!d->dirichlet && (d->nextd < 1 || 2 * d->nextd > std::min(d->g_nx, std::min(d->g_ny, d->g_nz)) - 1)) return MOVFEM_E_BADARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return MOVFEM_E_NOGPU;
+
+    movfem_handle *h = new (std::nothrow) movfem_handle();
+    if (!h) return MOVFEM_E_BADARG;
+    h->d = *d; h->device = device; h->err[0] = 0;
+    *out = h;   // returned even on failure so the caller can read movfem_last_error, then destroy
+    MeshDims &m = h->m;
+    m.nx = d->g_nx - 1; m.ny = d->g_ny - 1; m.nz = d->g_nz - 1;
+    m.nord = d->nord; m.mn = d->mn; m.me = d->me; m.ngp = d->me == 12 ? 8 : 27;
+    m.nnx = m.nx * (m.nord - 1) + 1; m.nny = m.ny * (m.nord - 1) + 1; m.nnz = m.nz * (m.nord - 1) + 1;
+    m.nyz = m.nny * m.nnz;
+    const int64_t ne64 = (int64_t)m.nx * m.ny * m.nz, npt64 = (int64_t)m.nnx * m.nyz;
+    if (ne64 > 0x7fffffffLL / 64 * 8 || npt64 > 0x7fffffffLL) { set_err(h, "mesh too large"); return MOVFEM_E_CAPACITY; }
+    m.ne = (int)ne64; m.npt = (int)npt64; m.dirichlet = d->dirichlet ? 1 : 0;
+    h->NP = m.me * (m.me + 1) / 2; h->ngp = m.ngp;
+
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    for (int i = 0; i < EV_COUNT; ++i) CK(cudaEventCreate(&h->ev[i]));
+    CK(cudaMallocHost((void **)&h->h_status, 4 * sizeof(int)));
+    CK(cudaMallocHost((void **)&h->h_count, sizeof(int64_t)));
+
+    // mesh upload (once per run)
+    CK(dmalloc(&h->d_xp, (size_t)m.nnx)); CK(dmalloc(&h->d_yp, (size_t)m.nny));
+    CK(dmalloc(&h->d_zp, (size_t)m.npt)); CK(dmalloc(&h->d_mu, (size_t)6 * m.npt));
+    CK(dmalloc(&h->d_sigma, (size_t)6 * m.npt)); CK(dmalloc(&h->d_nodes, (size_t)m.npt));
+    CK(cudaMemcpy(h->d_xp, d->g_xp, sizeof(double) * m.nnx, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_yp, d->g_yp, sizeof(double) * m.nny, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_zp, d->g_zp, sizeof(double) * m.npt, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_mu, d->g_mu, sizeof(double) * 6 * m.npt, cudaMemcpyHostToDevice));
+    CK(cudaMemset(h->d_nodes, 0, sizeof(NodeRec) * (size_t)m.npt));
+
+    // tables
+    {
+        std::vector<ElemTables> T(1);
+        ShareTables S;
+        build_tables(*d, m, T[0], S);
+        CK(dmalloc(&h->d_tab, 1)); CK(dmalloc(&h->d_share, 1));
+        CK(cudaMemcpy(h->d_tab, T.data(), sizeof(ElemTables), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_share, &S, sizeof(ShareTables), cudaMemcpyHostToDevice));
+    }
+    init_pml(*d, m, h->pml);
+
+    CK(dmalloc(&h->d_status, 1)); CK(dmalloc(&h->d_flags, 2));
+    CK(cudaMemset(h->d_status, 0, sizeof(int))); CK(cudaMemset(h->d_flags, 0, 2 * sizeof(int)));
+
+    int rc = build_pattern(h);
+    if (rc) return rc;
+
+    // element lists: stretched = predecessor in loop order carries a GPML flag (Q17); element (1,1,1)
+    // always goes through the stretched kernel (its flags are a per-call input)
+    {
+        std::vector<int> plain, pmlv;
+        plain.reserve(m.ne);
+        for (int e = 0; e < m.ne; ++e) {
+            bool st = false;
+            if (!m.dirichlet) {
+                if (e == 0) st = true;
+                else { int f[3]; effective_pml(m, h->pml, e, f); st = f[0] || f[1] || f[2]; }
+            }
+            (st ? pmlv : plain).push_back(e);
+        }
+        h->n_plain = (int)plain.size(); h->n_pml = (int)pmlv.size();
+        CK(dmalloc(&h->d_list_plain, plain.size())); CK(dmalloc(&h->d_list_pml, pmlv.size()));
+        if (!plain.empty()) CK(cudaMemcpy(h->d_list_plain, plain.data(), sizeof(int) * plain.size(), cudaMemcpyHostToDevice));
+        if (!pmlv.empty()) CK(cudaMemcpy(h->d_list_pml, pmlv.data(), sizeof(int) * pmlv.size(), cudaMemcpyHostToDevice));
+    }
+
+    // work / result arrays
+    CK(dmalloc(&h->d_Ke, (size_t)m.ne * h->NP)); CK(dmalloc(&h->d_Me, (size_t)m.ne * h->NP));
+    CK(dmalloc(&h->d_be, (size_t)m.ne * m.me * 4));
+    CK(dmalloc(&h->d_a, (size_t)h->nzu)); CK(dmalloc(&h->d_a_c, (size_t)h->nzu));
+    CK(dmalloc(&h->d_irn_c, (size_t)h->nzu)); CK(dmalloc(&h->d_jcn_c, (size_t)h->nzu));
+    CK(dmalloc(&h->d_rhs, (size_t)2 * h->nne));
+    h->nblk_fin = (int)((h->nzu + kFinThreads - 1) / kFinThreads);
+    CK(dmalloc(&h->d_blkcnt, (size_t)h->nblk_fin)); CK(dmalloc(&h->d_blkoff, (size_t)h->nblk_fin + 1));
+    CK(dmalloc(&h->d_finbsum, (size_t)(h->nblk_fin + kScanTile - 1) / kScanTile + 1));
+    h->km_valid = false;
+    return MOVFEM_OK;
+}
+
+void movfem_destroy(movfem_handle *h) {
+    if (!h) return;
+    free_all(h);
+    delete h;
+}
+
+int movfem_sizes(const movfem_handle *h, int32_t *nne, int64_t *nnze_full, int64_t *nz_upper) {
+    if (!h) return MOVFEM_E_BADARG;
+    if (nne) *nne = h->nne;
+    if (nnze_full) *nnze_full = h->nnze_full;
+    if (nz_upper) *nz_upper = h->nzu;
+    return MOVFEM_OK;
+}
+
+int movfem_get_gne(const movfem_handle *hc, int32_t *gne) {
+    movfem_handle *h = const_cast<movfem_handle *>(hc);
+    if (!h || !gne) return MOVFEM_E_BADARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(gne, h->d_gne, sizeof(int) * (size_t)h->m.ne * h->m.me, cudaMemcpyDeviceToHost));
+    return MOVFEM_OK;
+}
+
+int movfem_get_pattern(const movfem_handle *hc, int32_t *irn, int32_t *jcn) {
+    movfem_handle *h = const_cast<movfem_handle *>(hc);
+    if (!h || !irn || !jcn) return MOVFEM_E_BADARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(irn, h->d_irn, sizeof(int) * (size_t)h->nzu, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(jcn, h->d_jcn, sizeof(int) * (size_t)h->nzu, cudaMemcpyDeviceToHost));
+    return MOVFEM_OK;
+}
+
+int movfem_set_stream(movfem_handle *h, void *cuda_stream) {
+    if (!h) return MOVFEM_E_BADARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) { CK(cudaStreamDestroy(h->stream)); h->own_stream = false; }
+    h->stream = (cudaStream_t)cuda_stream;
+    return MOVFEM_OK;
+}
+
+int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, const double *g_sigma_dev, int32_t mode) {
+    if (!h || !g_sigma_dev || freq_index < 1 || (mode != MOVFEM_MODE_T1 && mode != MOVFEM_MODE_T2)) return MOVFEM_E_BADARG;
+    CK(cudaSetDevice(h->device));
+    const MeshDims &m = h->m;
+    cudaStream_t st = h->stream;
+    h->launches = 0;
+    // Q17: element (1,1,1) sees the SAVEd in_pml: zeros on the first assembled frequency, the flags
+    // of the last element afterwards
+    if (!m.dirichlet) {
+        if (freq_index == 1) h->pml.first[0] = h->pml.first[1] = h->pml.first[2] = 0;
+        else get_pml(h->pml, m.nx, m.ny, m.nz, h->pml.first);
+    }
+    CK(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), st));
+    CK(cudaEventRecord(h->ev[EV_H2D], st));
+    node_kernel<<<(m.npt + 127) / 128, 128, 0, st>>>(m.npt, omega, h->d_zp, h->d_mu, reinterpret_cast<const double2 *>(g_sigma_dev),
+                                                    h->d_nodes, h->d_status, h->d_flags, h->km_valid ? 1 : 0);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[EV_NODE], st));
+
+    ElemArgs A;
+    A.m = m; A.pml = h->pml; A.omega = omega; A.T = h->d_tab; A.nodes = h->d_nodes; A.xp = h->d_xp; A.yp = h->d_yp;
+    A.list = nullptr; A.nlist = 0; A.Ke = h->d_Ke; A.Me = h->d_Me; A.be = h->d_be; A.status = h->d_status; A.flags = h->d_flags;
+    A.skip_unless_changed = 0;
+    int rc;
+    const bool full = !h->km_valid;
+    if (m.me == 12) rc = run_elements<Cfg12, Cfg12p>(h, A, full);
+    else if (m.me == 36) rc = run_elements<Cfg36, Cfg36p>(h, A, full);
+    else rc = run_elements<Cfg54, Cfg54p>(h, A, full);
+    if (rc) return rc;
+    h->km_valid = true;
+    CK(cudaEventRecord(h->ev[EV_ELEM], st));
+
+    gather_finalize_kernel<<<h->nblk_fin, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cptr, h->d_src, h->d_Ke, h->d_Me, h->d_a,
+                                                              h->d_blkcnt, mode == MOVFEM_MODE_T1 ? 1 : 0);
+    rhs_kernel<<<(h->nne + 127) / 128, 128, 0, st>>>(h->nne, h->d_rown, reinterpret_cast<const double4 *>(h->d_be), h->d_rhs);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev[EV_GATHER], st));
+    h->compacted = false; h->nz_last = -1; h->mode_last = mode;
+    if (mode == MOVFEM_MODE_T2) {
+        // non-zero counts per block -> offsets; compaction itself runs only if something was stripped
+        const int nb = (h->nblk_fin + kScanTile - 1) / kScanTile;
+        int64_t *d_bsum = h->d_finbsum;
+        scan_block_sums<<<nb, kScanThreads, 0, st>>>(h->d_blkcnt, h->nblk_fin, d_bsum);
+        scan_block_offsets<<<1, 1024, 0, st>>>(d_bsum, nb);
+        scan_finish<<<nb, kScanThreads, 0, st>>>(h->d_blkcnt, h->nblk_fin, d_bsum, h->d_blkoff);
+        h->launches += 3;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->h_count, h->d_blkoff + h->nblk_fin, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(h->ev[EV_FINAL], st));
+    return MOVFEM_OK;
+}
+
+// completes the last assemble_device call: status check, zero strip if needed; returns device pointers
+int movfem_device_result(const movfem_handle *hc, const int32_t **irn, const int32_t **jcn, const double **a,
+                         const double **rhs, int64_t *nz) {
+    movfem_handle *h = const_cast<movfem_handle *>(hc);
+    if (!h) return MOVFEM_E_BADARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->h_status[0] != 0) {
+        const int s = h->h_status[0];
+        CK(cudaMemset(h->d_status, 0, sizeof(int)));
+        h->km_valid = false;
+        set_err(h, s == -3 ? "no transformation!! nf_det=0!! (n_fem.f90:374-377)" : "no sigma/mu inversion on a node (problem.f90:260-271)");
+        return s == -3 ? MOVFEM_E_SINGULAR_JAC : MOVFEM_E_SINGULAR_MODEL;
+    }
+    if (h->nz_last < 0) {
+        if (h->mode_last == MOVFEM_MODE_T1) h->nz_last = h->nzu;
+        else {
+            h->nz_last = *h->h_count;
+            if (h->nz_last != h->nzu) {   // find_zeros > 0: rem_zeros (global_assembly.f90:134-150)
+                compact_kernel<<<h->nblk_fin, kFinThreads, 0, h->stream>>>(h->nzu, h->d_blkoff, h->d_irn, h->d_jcn, h->d_a, h->d_irn_c,
+                                                                          h->d_jcn_c, h->d_a_c);
+                h->launches += 1;
+                CK(cudaGetLastError());
+                CK(cudaStreamSynchronize(h->stream));
+                h->compacted = true;
+            }
+        }
+    }
+    if (irn) *irn = h->compacted ? h->d_irn_c : h->d_irn;
+    if (jcn) *jcn = h->compacted ? h->d_jcn_c : h->d_jcn;
+    if (a) *a = reinterpret_cast<const double *>(h->compacted ? h->d_a_c : h->d_a);
+    if (rhs) *rhs = reinterpret_cast<const double *>(h->d_rhs);
+    if (nz) *nz = h->nz_last;
+    return MOVFEM_OK;
+}
+
+int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega, const double *g_sigma, int32_t *irn, int32_t *jcn,
+                    double *a, double *rhs, int64_t *nz_out, int32_t mode) {
+    if (!h || !g_sigma || !irn || !jcn || !a || !rhs || !nz_out) return MOVFEM_E_BADARG;
+    CK(cudaSetDevice(h->device));
+    const MeshDims &m = h->m;
+    cudaStream_t st = h->stream;
+    CK(cudaEventRecord(h->ev[EV_START], st));
+    CK(cudaMemcpyAsync(h->d_sigma, g_sigma, sizeof(double2) * (size_t)6 * m.npt, cudaMemcpyHostToDevice, st));
+    int rc = movfem_assemble_device(h, freq_index, omega, reinterpret_cast<const double *>(h->d_sigma), mode);
+    if (rc) return rc;
+    const int32_t *d_irn, *d_jcn;
+    const double *d_a, *d_rhs;
+    int64_t nz = 0;
+    rc = movfem_device_result(h, &d_irn, &d_jcn, &d_a, &d_rhs, &nz);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(irn, d_irn, sizeof(int) * (size_t)nz, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(jcn, d_jcn, sizeof(int) * (size_t)nz, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(a, d_a, sizeof(double2) * (size_t)nz, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(rhs, d_rhs, sizeof(double2) * (size_t)2 * h->nne, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(h->ev[EV_D2H], st));
+    CK(cudaStreamSynchronize(st));
+    *nz_out = nz;
+    auto ms = [&](int a_, int b_) { float t = 0; cudaEventElapsedTime(&t, h->ev[a_], h->ev[b_]); return (double)t; };
+    h->stats.ms_h2d = ms(EV_START, EV_H2D); h->stats.ms_node = ms(EV_H2D, EV_NODE); h->stats.ms_element = ms(EV_NODE, EV_ELEM);
+    h->stats.ms_gather = ms(EV_ELEM, EV_GATHER); h->stats.ms_finalize = ms(EV_GATHER, EV_FINAL); h->stats.ms_d2h = ms(EV_FINAL, EV_D2H);
+    h->stats.ms_total = ms(EV_START, EV_D2H); h->stats.nz = nz; h->stats.launches = h->launches;
+    return MOVFEM_OK;
+}
+
+int movfem_get_stats(const movfem_handle *h, movfem_stats *out) {
+    if (!h || !out) return MOVFEM_E_BADARG;
+    *out = h->stats;
+    return MOVFEM_OK;
+}
+
+// parity tap: K_e, M_e (packed lower by local index) and b_e of one element after the last assemble
+int movfem_debug_element(movfem_handle *h, int32_t ide, double *Ke, double *Me, double *be) {
+    if (!h || ide < 1 || ide > h->m.ne) return MOVFEM_E_BADARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    const size_t e = (size_t)ide - 1;
+    if (Ke) CK(cudaMemcpy(Ke, h->d_Ke + e * h->NP, sizeof(double) * h->NP, cudaMemcpyDeviceToHost));
+    if (Me) CK(cudaMemcpy(Me, h->d_Me + e * h->NP, sizeof(double) * h->NP, cudaMemcpyDeviceToHost));
+    if (be) CK(cudaMemcpy(be, h->d_be + e * h->m.me * 4, sizeof(double) * h->m.me * 4, cudaMemcpyDeviceToHost));
+    return MOVFEM_OK;
+}
+
+// parity tap: the reference-element tables as uploaded (N[g][l], dN[g][l][3], phi[g][e], dphi[g][e][3], rw[g][4])
+int movfem_debug_tables(movfem_handle *h, double *N, double *dN, double *phi, double *dphi, double *rw) {
+    if (!h) return MOVFEM_E_BADARG;
+    CK(cudaSetDevice(h->device));
+    std::vector<ElemTables> T(1);
+    CK(cudaMemcpy(T.data(), h->d_tab, sizeof(ElemTables), cudaMemcpyDeviceToHost));
+    const MeshDims &m = h->m;
+    for (int g = 0; g < m.ngp; ++g) {
+        for (int k = 0; k < 4; ++k) rw[g * 4 + k] = T[0].rw[g][k];
+        for (int l = 0; l < m.mn; ++l) {
+            N[g * m.mn + l] = T[0].N[g][l];
+            for (int k = 0; k < 3; ++k) dN[(g * m.mn + l) * 3 + k] = T[0].dN[g][l][k];
+        }
+        for (int e = 0; e < m.me; ++e) {
+            phi[g * m.me + e] = T[0].phi[g][e];
+            for (int k = 0; k < 3; ++k) dphi[(g * m.me + e) * 3 + k] = T[0].dphi[g][e][k];
+        }
+    }
+    return MOVFEM_OK;
+}
+
+}  // extern "C"

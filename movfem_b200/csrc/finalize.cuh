@@ -1,0 +1,84 @@
+// movfem_b200/csrc/finalize.cuh -- deterministic gather-reduce, per-frequency A = K + i*w32*M,
+// the float32 round trip of ga_sort_sparse and the zero strip.
+//
+// Replaces:
+//   MoVFEM_3DMT.f90:221-263  local_vfem  (a(idd) += alocal ; b(...) += blocal)
+//   global_assembly.f90:43-79 assign_aij / assign_bi
+//   global_assembly.f90:152-181 ga_sort_sparse  (Q10: single-precision scratch, transposed values)
+//   global_assembly.f90:123-150 find_zeros / rem_zeros (Q11)
+//
+// Every matrix entry is summed by ONE thread over its <= 4 element contributions in ascending
+// element id -- the order in which the reference's serial loop executes a(idd)=a(idd)+aij -- so the
+// result does not depend on scheduling (no atomics).  Entries are already in delivery order
+// (upper triangle, row-major), so no sort is needed: ga_sort_sparse's net effect is this order
+// plus the float32 rounding, and "the lower-triangle value appears at the upper position".
+#pragma once
+#include "common.cuh"
+
+namespace movfem {
+
+constexpr int kFinThreads = 256;
+
+// mode 0 (T2): values rounded through float32, per-block count of surviving (non-zero) entries
+// mode 1 (T1): double values, nothing stripped
+__global__ void __launch_bounds__(kFinThreads)
+gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cptr, const uint32_t *__restrict__ src,
+                       const double *__restrict__ Ke, const double *__restrict__ Me, double2 *__restrict__ a,
+                       int *__restrict__ blk_nonzero, int mode) {
+    const int64_t i = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
+    int nzflag = 0;
+    if (i < nzu) {
+        const int64_t c0 = cptr[i], c1 = cptr[i + 1];
+        double k = 0.0, mm = 0.0;
+        for (int64_t c = c0; c < c1; ++c) {
+            const uint32_t s = src[c];
+            k = k + Ke[s];
+            mm = mm + Me[s];
+        }
+        double re = k, im = w32 * mm;
+        if (mode == 0) { re = f32r(re); im = f32r(im); }
+        a[i] = make_double2(re, im);
+        nzflag = !(re == 0.0 && im == 0.0);
+    }
+    const int cnt = __syncthreads_count(nzflag);
+    if (threadIdx.x == 0) blk_nonzero[blockIdx.x] = cnt;
+}
+
+// order-preserving compaction of the entries whose value is not exactly (0,0)
+__global__ void __launch_bounds__(kFinThreads)
+compact_kernel(int64_t nzu, const int64_t *__restrict__ blk_off, const int *__restrict__ irn, const int *__restrict__ jcn,
+               const double2 *__restrict__ a, int *__restrict__ irn_c, int *__restrict__ jcn_c, double2 *__restrict__ a_c) {
+    __shared__ int wsum[kFinThreads / 32];
+    const int64_t i = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
+    double2 v = make_double2(0.0, 0.0);
+    if (i < nzu) v = a[i];
+    const int keep = (i < nzu) && !(v.x == 0.0 && v.y == 0.0);
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = __popc(bal);
+    __syncthreads();
+    int off = __popc(bal & ((1u << lane) - 1));
+    for (int k = 0; k < w; ++k) off += wsum[k];
+    if (keep) {
+        const int64_t p = blk_off[blockIdx.x] + off;
+        irn_c[p] = irn[i]; jcn_c[p] = jcn[i]; a_c[p] = v;
+    }
+}
+
+// b(gne + (d-1)*nne) += blocal(d): sum of the <= 4 sharing elements in ascending element order
+__global__ void rhs_kernel(int nne, const int *__restrict__ rown, const double4 *__restrict__ be, double2 *__restrict__ rhs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nne) return;
+    double b0r = 0, b0i = 0, b1r = 0, b1i = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int o = rown[(int64_t)r * 4 + k];
+        if (o < 0) break;
+        const double4 v = be[o];
+        b0r = b0r + v.x; b0i = b0i + v.y; b1r = b1r + v.z; b1i = b1i + v.w;
+    }
+    rhs[r] = make_double2(b0r, b0i);
+    rhs[(int64_t)nne + r] = make_double2(b1r, b1i);
+}
+
+}  // namespace movfem
