@@ -118,6 +118,13 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega,
 int movfem_device_result(const movfem_handle *h, const int32_t **irn, const int32_t **jcn,
                          const double **a, const double **rhs, int64_t *nz /* syncs */);
 
+/* Forget the cached K_e/M_e of the unstretched elements: the next assemble recomputes every
+   element (what a single-frequency run does).  A sweep keeps them.            */
+int movfem_reset_cache(movfem_handle *h);
+
+/* Measured FP64 FMA-loop throughput of the device in TFLOP/s (roofline denominator). */
+int movfem_fp64_peak(int device, double *tflops);
+
 /* stream the handle launches on (cudaStream_t as void*); set before assembling. */
 int movfem_set_stream(movfem_handle *h, void *cuda_stream);
 int movfem_get_stats(const movfem_handle *h, movfem_stats *out);

@@ -541,6 +541,13 @@ int movfem_device_result(const movfem_handle *hc, const int32_t **irn, const int
             }
         }
     }
+    {
+        auto ms = [&](int a_, int b_) { float t = 0; cudaEventElapsedTime(&t, h->ev[a_], h->ev[b_]); return (double)t; };
+        h->stats.ms_h2d = 0; h->stats.ms_d2h = 0;
+        h->stats.ms_node = ms(EV_H2D, EV_NODE); h->stats.ms_element = ms(EV_NODE, EV_ELEM);
+        h->stats.ms_gather = ms(EV_ELEM, EV_GATHER); h->stats.ms_finalize = ms(EV_GATHER, EV_FINAL);
+        h->stats.ms_total = ms(EV_H2D, EV_FINAL); h->stats.nz = h->nz_last; h->stats.launches = h->launches;
+    }
     if (irn) *irn = h->compacted ? h->d_irn_c : h->d_irn;
     if (jcn) *jcn = h->compacted ? h->d_jcn_c : h->d_jcn;
     if (a) *a = reinterpret_cast<const double *>(h->compacted ? h->d_a_c : h->d_a);
@@ -572,10 +579,55 @@ int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega, const do
     CK(cudaStreamSynchronize(st));
     *nz_out = nz;
     auto ms = [&](int a_, int b_) { float t = 0; cudaEventElapsedTime(&t, h->ev[a_], h->ev[b_]); return (double)t; };
-    h->stats.ms_h2d = ms(EV_START, EV_H2D); h->stats.ms_node = ms(EV_H2D, EV_NODE); h->stats.ms_element = ms(EV_NODE, EV_ELEM);
-    h->stats.ms_gather = ms(EV_ELEM, EV_GATHER); h->stats.ms_finalize = ms(EV_GATHER, EV_FINAL); h->stats.ms_d2h = ms(EV_FINAL, EV_D2H);
+    h->stats.ms_h2d = ms(EV_START, EV_H2D); h->stats.ms_d2h = ms(EV_FINAL, EV_D2H);
     h->stats.ms_total = ms(EV_START, EV_D2H); h->stats.nz = nz; h->stats.launches = h->launches;
     return MOVFEM_OK;
+}
+
+// forget the cached K_e/M_e: the next assemble recomputes every element (a cold, single-frequency run)
+int movfem_reset_cache(movfem_handle *h) {
+    if (!h) return MOVFEM_E_BADARG;
+    h->km_valid = false;
+    return MOVFEM_OK;
+}
+
+// FP64 FMA-loop microbenchmark: the measured denominator of the FP64 roofline
+__global__ void fp64_peak_kernel(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = __fma_rn(a0, b, c); a1 = __fma_rn(a1, b, c); a2 = __fma_rn(a2, b, c); a3 = __fma_rn(a3, b, c);
+        a4 = __fma_rn(a4, b, c); a5 = __fma_rn(a5, b, c); a6 = __fma_rn(a6, b, c); a7 = __fma_rn(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int movfem_fp64_peak(int device, double *tflops) {
+    if (!tflops) return MOVFEM_E_BADARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return MOVFEM_E_NOGPU;
+    cudaSetDevice(device);
+    cudaDeviceProp p;
+    cudaGetDeviceProperties(&p, device);
+    const int blocks = p.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double *d = nullptr;
+    if (cudaMalloc(&d, sizeof(double) * blocks * threads) != cudaSuccess) return MOVFEM_E_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
+    return cudaGetLastError() == cudaSuccess ? MOVFEM_OK : MOVFEM_E_CUDA;
 }
 
 int movfem_get_stats(const movfem_handle *h, movfem_stats *out) {

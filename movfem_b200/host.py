@@ -65,6 +65,8 @@ def lib():
         L.movfem_last_error.argtypes = [vp]
         L.movfem_last_error.restype = C.c_char_p
         L.movfem_version.restype = C.c_char_p
+        L.movfem_reset_cache.argtypes = [vp]
+        L.movfem_fp64_peak.argtypes = [C.c_int, C.POINTER(dbl)]
         L.movfem_debug_element.argtypes = [vp, i32, vp, vp, vp]
         L.movfem_debug_tables.argtypes = [vp, vp, vp, vp, vp, vp]
         _LIB = L
@@ -74,8 +76,17 @@ def lib():
 EXPORTED_SYMBOLS = [
     "movfem_create", "movfem_destroy", "movfem_sizes", "movfem_get_gne", "movfem_get_pattern", "movfem_assemble",
     "movfem_assemble_device", "movfem_device_result", "movfem_set_stream", "movfem_get_stats", "movfem_last_error",
-    "movfem_version", "movfem_debug_element",
+    "movfem_version", "movfem_debug_element", "movfem_reset_cache", "movfem_fp64_peak",
 ]
+
+
+def fp64_peak_tflops(device: int = 0) -> float:
+    """Measured FP64 FMA-loop throughput (the FP64 roofline denominator)."""
+    v = C.c_double(0)
+    rc = lib().movfem_fp64_peak(device, C.byref(v))
+    if rc:
+        raise MovfemError(rc)
+    return v.value
 
 
 def _p(a):
@@ -159,6 +170,10 @@ class Assembly:
         nz = C.c_int64()
         self._check(lib().movfem_device_result(self._h, C.byref(irn), C.byref(jcn), C.byref(a), C.byref(rhs), C.byref(nz)))
         return irn.value, jcn.value, a.value, rhs.value, nz.value
+
+    def reset_cache(self):
+        """Next call recomputes every element's K_e/M_e (cold single-frequency assembly)."""
+        self._check(lib().movfem_reset_cache(self._h))
 
     def stats(self) -> dict:
         s = MovfemStats()
