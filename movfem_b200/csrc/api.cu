@@ -26,13 +26,16 @@ using namespace movfem;
 namespace {
 
 // ---- kernel configurations (tuned on B200) -------------------------------------
-//                    MN  ME NGP GCH EB THREADS PML
-using Cfg12  = ElemCfg<8, 12, 8, 4, 8, 96, false>;
-using Cfg12p = ElemCfg<8, 12, 8, 4, 8, 96, true>;
-using Cfg36  = ElemCfg<20, 36, 27, 3, 2, 96, false>;
-using Cfg36p = ElemCfg<20, 36, 27, 3, 2, 96, true>;
-using Cfg54  = ElemCfg<27, 54, 27, 3, 1, 128, false>;
-using Cfg54p = ElemCfg<27, 54, 27, 3, 1, 128, true>;
+//                     MN  ME NGP GCH EB THREADS MINB PML
+// EB / THREADS are chosen so that every phase fills whole warps (idle lanes cost FP64-pipe time):
+//   me=12: 16 el -> 128 (el,gp) / 192 (el,dof) / 96 tiles     me=36: 4 el -> 108 / 144 / 180
+//   me=54:  2 el ->  54 / 108 / 210
+using Cfg12  = ElemCfg<8, 12, 8, 2, 16, 192, 2, false>;
+using Cfg12p = ElemCfg<8, 12, 8, 2, 16, 192, 2, true>;
+using Cfg36  = ElemCfg<20, 36, 27, 3, 4, 192, 2, false>;
+using Cfg36p = ElemCfg<20, 36, 27, 3, 4, 192, 2, true>;
+using Cfg54  = ElemCfg<27, 54, 27, 3, 2, 224, 2, false>;
+using Cfg54p = ElemCfg<27, 54, 27, 3, 2, 224, 2, true>;
 
 enum { EV_START, EV_H2D, EV_NODE, EV_ELEM, EV_GATHER, EV_FINAL, EV_D2H, EV_COUNT };
 

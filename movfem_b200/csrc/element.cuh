@@ -95,9 +95,9 @@ struct ElemArgs {
     int skip_unless_changed;   // launch is a cache refresh: exit unless flags[1]
 };
 
-template <int MN_, int ME_, int NGP_, int GCH_, int EB_, int THREADS_, bool PML_>
+template <int MN_, int ME_, int NGP_, int GCH_, int EB_, int THREADS_, int MINB_, bool PML_>
 struct ElemCfg {
-    static constexpr int MN = MN_, ME = ME_, NGP = NGP_, GCH = GCH_, EB = EB_, THREADS = THREADS_;
+    static constexpr int MN = MN_, ME = ME_, NGP = NGP_, GCH = GCH_, EB = EB_, THREADS = THREADS_, MINB = MINB_;
     static constexpr bool PML = PML_;
     static constexpr int MEP = (ME + 3) / 4 * 4;
     static constexpr int NT = MEP / 4, NTILES = NT * (NT + 1) / 2;
@@ -105,13 +105,21 @@ struct ElemCfg {
     static constexpr int KR = PML ? 6 : 3;                 // rows of the curl operator
     static constexpr int NC = 2 * KR + 6;                  // C, DC, V, SV
     static constexpr int NDW = kNodeDoubles + 2;           // node record + x + y
-    static constexpr int GEO = PML ? 48 : 34;                // Ji 9 + D (21|6) + S 6 + w*src 12 (+1 pad: keeps s_B 16-byte aligned)
+    static constexpr int GEO = PML ? 48 : 34;              // Ji 9 + D (21|6) + S 6 + w*src 12 (+1 pad)
     static constexpr int NCHUNK = NGP / GCH;
-    static constexpr size_t SMEM = sizeof(double) * ((size_t)EB * MN * NDW + (size_t)EB * GCH * GEO + (size_t)EB * GCH * NC * MEP) +
+    // shared memory: node records [EB][MN][NDW] | geometry [EB][NGP][GEO] | B chunk [EB][GCH][NC][MEP]
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)EB * MN * NDW + (size_t)EB * NGP * GEO + (size_t)EB * GCH * NC * MEP) +
                                    sizeof(int) * EB * 4;
     static_assert(NGP % GCH == 0, "chunking");
     static_assert(THREADS >= EB * NTILES && THREADS >= EB * ME, "one tile / one DOF per thread");
 };
+
+// B rows are stored with the two 16-byte halves of every 4-DOF group swapped in alternate groups of
+// four, so that the 8 distinct groups a warp touches in one LDS.128 fall into distinct banks.
+__device__ __forceinline__ int swz(int j) {
+    const int grp = j >> 2, pos = j & 3;
+    return (grp << 2) + ((((pos >> 1) ^ ((grp >> 2) & 1)) << 1) | (pos & 1));
+}
 
 // gpml_h for one axis, boundary_conds.f90:94-123
 __device__ __forceinline__ double2 gpml_axis(const PmlParams &p, int flag, int axis, double r, double omega) {
@@ -150,26 +158,23 @@ __device__ __forceinline__ double2 cdivf(double2 a, double2 b) {   // Fortran ru
 }
 
 template <class CFG, bool DO_KM>
-__global__ void __launch_bounds__(CFG::THREADS) element_kernel(ElemArgs A) {
-    constexpr int MN = CFG::MN, ME = CFG::ME, MEP = CFG::MEP, GCH = CFG::GCH, EB = CFG::EB, NC = CFG::NC;
-    constexpr int KR = CFG::KR, GEO = CFG::GEO, NDW = CFG::NDW, NT = CFG::NT, NTILES = CFG::NTILES, NP = CFG::NP;
+__global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemArgs A) {
+    constexpr int MN = CFG::MN, ME = CFG::ME, MEP = CFG::MEP, GCH = CFG::GCH, EB = CFG::EB, NC = CFG::NC, NGP = CFG::NGP;
+    constexpr int KR = CFG::KR, GEO = CFG::GEO, NDW = CFG::NDW, NTILES = CFG::NTILES, NP = CFG::NP;
     constexpr bool PML = CFG::PML;
     if (A.skip_unless_changed && A.flags[1] == 0) return;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_nodes = reinterpret_cast<double *>(smem_raw);           // [EB][MN][NDW]
-    double *s_geo = s_nodes + EB * MN * NDW;                          // [EB][GCH][GEO]
-    double *s_B = s_geo + EB * GCH * GEO;                             // [EB][GCH][NC][MEP]
-    int *s_el = reinterpret_cast<int *>(s_B + EB * GCH * NC * MEP);   // [EB][4]: element id, flags
+    double *s_geo = s_nodes + EB * MN * NDW;                          // [EB][NGP][GEO]
+    double *s_B = s_geo + EB * NGP * GEO;                             // [EB][GCH][NC][MEP] (swizzled rows)
+    int *s_el = reinterpret_cast<int *>(s_B + EB * GCH * NC * MEP);   // [EB][4]: element id, GPML flags
 
     const ElemTables &T = *A.T;
     const MeshDims &m = A.m;
     const int tid = threadIdx.x;
     const int first = blockIdx.x * EB;
     const int nb = min(EB, A.nlist - first);
-    const int has_dmu = A.flags[0];
-    const double w32 = f32r(A.omega);                                  // cmplx(0.d0,-omega), problem.f90:112
-    const double psig = f32r(A.omega * kEps0);                         // pset_pmodel, problem.f90:250
 
     if (tid < EB) {
         const int e = tid < nb ? A.list[first + tid] : -1;
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(CFG::THREADS) element_kernel(ElemArgs A) {
         constexpr int PAD = MEP - ME;
         for (int i = tid; i < EB * GCH * NC * PAD; i += CFG::THREADS) {
             const int row = i / PAD, c = ME + i % PAD;
-            s_B[row * MEP + c] = 0.0;
+            s_B[row * MEP + swz(c)] = 0.0;
         }
     }
     __syncthreads();
@@ -205,31 +210,21 @@ __global__ void __launch_bounds__(CFG::THREADS) element_kernel(ElemArgs A) {
     }
     __syncthreads();
 
-    double accK[16], accM[16], bacc[4];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { accK[i] = 0.0; accM[i] = 0.0; }
-    bacc[0] = bacc[1] = bacc[2] = bacc[3] = 0.0;
-
-    // tile owned by this thread in the contraction
-    const int ts = tid / NTILES, tt = tid % NTILES;
-    int ti = 0, tj = 0;
+    // ---- phase B: one thread per (element, Gauss point): Jacobian, materials, GPML, source ----
     {
-        int rem = tt;
-        while (rem > ti) { rem -= ti + 1; ++ti; }
-        tj = rem;
-    }
-
-    for (int chunk = 0; chunk < CFG::NCHUNK; ++chunk) {
-        // ---- phase B: one thread per (element, Gauss point): Jacobian, materials, GPML, source ----
-        for (int i = tid; i < nb * GCH; i += CFG::THREADS) {
-            const int s = i / GCH, gc = i % GCH, g = chunk * GCH + gc;
+        const int has_dmu = A.flags[0];
+        const double w32 = f32r(A.omega);            // cmplx(0.d0,-omega), problem.f90:112
+        const double psig = f32r(A.omega * kEps0);   // pset_pmodel, problem.f90:250
+        for (int i = tid; i < nb * NGP; i += CFG::THREADS) {
+            const int s = i / NGP, g = i % NGP;
             const double *nd = s_nodes + s * MN * NDW;
-            double *geo = s_geo + (s * GCH + gc) * GEO;
+            double *geo = s_geo + (s * NGP + g) * GEO;
             // nf_jacobian, n_fem.f90:359-366: J(m,n) = sum_l dN_l/dxi_m * r_l(n), l ascending, no FMA
             double J[3][3];
 #pragma unroll
             for (int mm = 0; mm < 3; ++mm) {
                 double sx = 0.0, sy = 0.0, sz = 0.0;
+#pragma unroll 4
                 for (int l = 0; l < MN; ++l) {
                     const double dn = T.dN[g][l][mm];
                     sx = sx + dn * nd[l * NDW + kNodeDoubles];
@@ -256,33 +251,36 @@ __global__ void __launch_bounds__(CFG::THREADS) element_kernel(ElemArgs A) {
             Ji[8] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / ad;
 #pragma unroll
             for (int k = 0; k < 9; ++k) geo[k] = Ji[k];
-            // p_intmodels, problem.f90:139-142 (sequential accumulation, no FMA)
+            // p_intmodels, problem.f90:139-142: material tensors at the Gauss point
             double mu[6] = {0, 0, 0, 0, 0, 0}, sr[6] = {0, 0, 0, 0, 0, 0}, si[6] = {0, 0, 0, 0, 0, 0};
             double xg[3] = {0, 0, 0};
             double dm1r[3] = {0, 0, 0}, dm1i[3] = {0, 0, 0}, dm2r[3] = {0, 0, 0}, dm2i[3] = {0, 0, 0};
+#pragma unroll 2
             for (int l = 0; l < MN; ++l) {
                 const double ln = T.N[g][l];
                 const double *r = nd + l * NDW;
 #pragma unroll
                 for (int k = 0; k < 6; ++k) {
-                    mu[k] = mu[k] + ln * r[2 + k];
-                    sr[k] = sr[k] + ln * r[8 + k];
-                    if (PML) si[k] = si[k] + ln * r[14 + k];
+                    mu[k] = dfma(ln, r[2 + k], mu[k]);
+                    sr[k] = dfma(ln, r[8 + k], sr[k]);
+                    if (PML) si[k] = dfma(ln, r[14 + k], si[k]);
                 }
-                if (PML) {
+                if (PML) {   // g_rw, integration.f90:120-125 (reference order, no FMA: feeds the float32-rounded h)
                     xg[0] = xg[0] + ln * r[kNodeDoubles]; xg[1] = xg[1] + ln * r[kNodeDoubles + 1]; xg[2] = xg[2] + ln * r[0];
                 }
                 // p_dmpf, problem.f90:424-457: ln * (dsigma . Ep); Ep_1 = (0,-e) x^, Ep_2 = (0,+e) y^
-                const double e = r[1];
+                const double le = ln * r[1];
                 const double d0 = r[14] - psig, d3 = r[17] - psig;   // Im(dsigma) on the diagonal
-                // pol 1 uses column 1 (11,12,13), pol 2 column 2 (12,22,23)
-                dm1r[0] = dfma(ln, d0 * e, dm1r[0]);      dm1i[0] = dfma(ln, -(r[8] * e), dm1i[0]);
-                dm1r[1] = dfma(ln, r[15] * e, dm1r[1]);   dm1i[1] = dfma(ln, -(r[9] * e), dm1i[1]);
-                dm1r[2] = dfma(ln, r[16] * e, dm1r[2]);   dm1i[2] = dfma(ln, -(r[10] * e), dm1i[2]);
-                dm2r[0] = dfma(ln, -(r[15] * e), dm2r[0]); dm2i[0] = dfma(ln, r[9] * e, dm2i[0]);
-                dm2r[1] = dfma(ln, -(d3 * e), dm2r[1]);    dm2i[1] = dfma(ln, r[11] * e, dm2i[1]);
-                dm2r[2] = dfma(ln, -(r[18] * e), dm2r[2]); dm2i[2] = dfma(ln, r[12] * e, dm2i[2]);
+                dm1r[0] = dfma(le, d0, dm1r[0]);     dm1i[0] = dfma(le, r[8], dm1i[0]);
+                dm1r[1] = dfma(le, r[15], dm1r[1]);  dm1i[1] = dfma(le, r[9], dm1i[1]);
+                dm1r[2] = dfma(le, r[16], dm1r[2]);  dm1i[2] = dfma(le, r[10], dm1i[2]);
+                dm2r[0] = dfma(le, r[15], dm2r[0]);  dm2i[0] = dfma(le, r[9], dm2i[0]);
+                dm2r[1] = dfma(le, d3, dm2r[1]);     dm2i[1] = dfma(le, r[11], dm2i[1]);
+                dm2r[2] = dfma(le, r[18], dm2r[2]);  dm2i[2] = dfma(le, r[12], dm2i[2]);
             }
+            // signs: pol 1 dmpf = (+Im ds*e, -Re ds*e), pol 2 = (-Im ds*e, +Re ds*e)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { dm1i[k] = -dm1i[k]; dm2r[k] = -dm2r[k]; }
             double pc1[3] = {0, 0, 0}, pc2[3] = {0, 0, 0};
             if (has_dmu) {   // p_pcurl, problem.f90:362-374: grad N_l x (mu^-1 dmu Hp)_l
                 for (int l = 0; l < MN; ++l) {
@@ -337,21 +335,43 @@ __global__ void __launch_bounds__(CFG::THREADS) element_kernel(ElemArgs A) {
                 gp[mm * 2] = a1.x; gp[mm * 2 + 1] = a1.y; gp[6 + mm * 2] = a2.x; gp[6 + mm * 2 + 1] = a2.y;
             }
         }
-        __syncthreads();
+    }
+    __syncthreads();
 
+    double accK[16], accM[16], bacc[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { accK[i] = 0.0; accM[i] = 0.0; }
+    bacc[0] = bacc[1] = bacc[2] = bacc[3] = 0.0;
+
+    // tile owned by this thread in the contraction (lower triangle of 4x4 blocks)
+    const int ts = tid / NTILES, tt = tid % NTILES;
+    int ti = 0, tj = 0;
+    {
+        int rem = tt;
+        while (rem > ti) { rem -= ti + 1; ++ti; }
+        tj = rem;
+    }
+    // swizzled 16-byte half offsets of this thread's row / column groups (in doubles)
+    const int a_lo = 4 * ti + (((ti >> 2) & 1) << 1), a_hi = 4 * ti + ((((ti >> 2) & 1) ^ 1) << 1);
+    const int b_lo = 4 * tj + (((tj >> 2) & 1) << 1), b_hi = 4 * tj + ((((tj >> 2) & 1) ^ 1) << 1);
+    // DOF owned by this thread in the basis phase
+    const int cs = tid / ME, cdof = tid % ME;
+    const int cd = T.edir[cdof < ME ? cdof : 0], cpos = swz(cdof);
+
+    for (int chunk = 0; chunk < CFG::NCHUNK; ++chunk) {
         // ---- phase C: one thread per (element, DOF): basis, curl, D*B products, RHS ----
         if (tid < nb * ME) {
-            const int s = tid / ME, dof = tid % ME, d = T.edir[dof];
+#pragma unroll 1
             for (int gc = 0; gc < GCH; ++gc) {
                 const int g = chunk * GCH + gc;
-                const double *geo = s_geo + (s * GCH + gc) * GEO;
-                double *B = s_B + (size_t)(s * GCH + gc) * NC * MEP + dof;
-                const double phi = T.phi[g][dof];
-                const double dp0 = T.dphi[g][dof][0], dp1 = T.dphi[g][dof][1], dp2 = T.dphi[g][dof][2];
+                const double *geo = s_geo + (cs * NGP + g) * GEO;
+                double *B = s_B + (size_t)(cs * GCH + gc) * NC * MEP + cpos;
+                const double phi = T.phi[g][cdof];
+                const double dp0 = T.dphi[g][cdof][0], dp1 = T.dphi[g][cdof][1], dp2 = T.dphi[g][cdof][2];
                 double vij[3], V[3], dni[3];
 #pragma unroll
                 for (int mm = 0; mm < 3; ++mm) {
-                    vij[mm] = geo[mm * 3 + d];                      // grad_xi, v_fem.f90:518
+                    vij[mm] = geo[mm * 3 + cd];                     // grad_xi, v_fem.f90:518
                     V[mm] = phi * vij[mm];                          // vf_elem_ve, v_fem.f90:43
                     dni[mm] = geo[mm * 3] * dp0 + geo[mm * 3 + 1] * dp1 + geo[mm * 3 + 2] * dp2;   // mix_grad_ln
                 }
@@ -399,19 +419,22 @@ __global__ void __launch_bounds__(CFG::THREADS) element_kernel(ElemArgs A) {
                 }
             }
         }
+        if (!DO_KM) continue;
         __syncthreads();
 
         // ---- phase D: register-tiled lower-triangle contraction over this chunk ----
-        if (DO_KM && tid < nb * NTILES) {
+        if (tid < nb * NTILES) {
             const double *Bs = s_B + (size_t)ts * GCH * NC * MEP;
 #pragma unroll 1
             for (int gc = 0; gc < GCH; ++gc) {
                 const double *Bg = Bs + gc * NC * MEP;
 #pragma unroll
                 for (int k = 0; k < KR; ++k) {
-                    const double4 a = *reinterpret_cast<const double4 *>(Bg + (KR + k) * MEP + 4 * ti);   // D*C rows
-                    const double4 b = *reinterpret_cast<const double4 *>(Bg + k * MEP + 4 * tj);          // C cols
-                    const double av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+                    const double2 a0 = *reinterpret_cast<const double2 *>(Bg + (KR + k) * MEP + a_lo);   // D*C rows
+                    const double2 a1 = *reinterpret_cast<const double2 *>(Bg + (KR + k) * MEP + a_hi);
+                    const double2 b0 = *reinterpret_cast<const double2 *>(Bg + k * MEP + b_lo);          // C cols
+                    const double2 b1 = *reinterpret_cast<const double2 *>(Bg + k * MEP + b_hi);
+                    const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -419,9 +442,11 @@ __global__ void __launch_bounds__(CFG::THREADS) element_kernel(ElemArgs A) {
                 }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    const double4 a = *reinterpret_cast<const double4 *>(Bg + (2 * KR + 3 + k) * MEP + 4 * ti);   // S*V rows
-                    const double4 b = *reinterpret_cast<const double4 *>(Bg + (2 * KR + k) * MEP + 4 * tj);       // V cols
-                    const double av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+                    const double2 a0 = *reinterpret_cast<const double2 *>(Bg + (2 * KR + 3 + k) * MEP + a_lo);   // S*V rows
+                    const double2 a1 = *reinterpret_cast<const double2 *>(Bg + (2 * KR + 3 + k) * MEP + a_hi);
+                    const double2 b0 = *reinterpret_cast<const double2 *>(Bg + (2 * KR + k) * MEP + b_lo);       // V cols
+                    const double2 b1 = *reinterpret_cast<const double2 *>(Bg + (2 * KR + k) * MEP + b_hi);
+                    const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -450,9 +475,8 @@ __global__ void __launch_bounds__(CFG::THREADS) element_kernel(ElemArgs A) {
         }
     }
     if (tid < nb * ME) {
-        const int s = tid / ME, dof = tid % ME;
-        const int64_t e = s_el[s * 4];
-        reinterpret_cast<double4 *>(A.be)[e * ME + dof] = make_double4(bacc[0], bacc[1], bacc[2], bacc[3]);
+        const int64_t e = s_el[cs * 4];
+        reinterpret_cast<double4 *>(A.be)[e * ME + cdof] = make_double4(bacc[0], bacc[1], bacc[2], bacc[3]);
     }
 }
 
