@@ -26,16 +26,16 @@ using namespace movfem;
 namespace {
 
 // ---- kernel configurations (tuned on B200) -------------------------------------
-//                     MN  ME NGP GCH EB THREADS MINB PML
+//                     MN  ME MEP NGP GCH EB THREADS MINB PML
 // EB / THREADS are chosen so that every phase fills whole warps (idle lanes cost FP64-pipe time):
-//   me=12: 16 el -> 128 (el,gp) / 192 (el,dof) / 96 tiles     me=36: 4 el -> 108 / 144 / 180
-//   me=54:  2 el ->  54 / 108 / 210
-using Cfg12  = ElemCfg<8, 12, 8, 2, 16, 192, 2, false>;
-using Cfg12p = ElemCfg<8, 12, 8, 2, 16, 192, 2, true>;
-using Cfg36  = ElemCfg<20, 36, 27, 3, 4, 192, 2, false>;
-using Cfg36p = ElemCfg<20, 36, 27, 3, 4, 192, 2, true>;
-using Cfg54  = ElemCfg<27, 54, 27, 3, 2, 224, 2, false>;
-using Cfg54p = ElemCfg<27, 54, 27, 3, 2, 224, 2, true>;
+//   me=12: 16 el -> 128 (el,gp) / 192 (el,slot) / 96 tiles     me=36: 4 el -> 108 / 144 / 180
+//   me=54:  2 el ->  54 / 120 / 240                            (GPML variants: smaller batches, more smem)
+using Cfg12  = ElemCfg<8, 12, 12, 8, 4, 16, 192, 3, false>;
+using Cfg12p = ElemCfg<8, 12, 12, 8, 2, 16, 192, 2, true>;
+using Cfg36  = ElemCfg<20, 36, 36, 27, 3, 4, 192, 3, false>;
+using Cfg36p = ElemCfg<20, 36, 36, 27, 3, 2, 96, 2, true>;
+using Cfg54  = ElemCfg<27, 54, 60, 27, 3, 2, 256, 2, false>;
+using Cfg54p = ElemCfg<27, 54, 60, 27, 3, 1, 128, 2, true>;
 
 enum { EV_START, EV_H2D, EV_NODE, EV_ELEM, EV_GATHER, EV_FINAL, EV_D2H, EV_COUNT };
 
@@ -46,7 +46,7 @@ struct movfem_handle {
     int device;
     MeshDims m;
     PmlParams pml;
-    int NP, ngp;
+    int NP, ngp, num_sms;
     int nne;
     int64_t nzu, ncontrib, nnze_full;
     cudaStream_t stream;
@@ -152,6 +152,14 @@ void build_tables(const movfem_desc &d, const MeshDims &m, ElemTables &T, ShareT
         T.node_i[l] = i1[l] - 1; T.node_j[l] = j1[l] - 1;
     }
     for (int e = 0; e < d.me; ++e) T.edir[e] = ed[e] - 1;
+    // slot order: DOFs grouped by direction, every direction padded to a multiple of four
+    int ns = 0;
+    for (int dir = 0; dir < 3; ++dir) {
+        for (int e = 0; e < d.me; ++e)
+            if (T.edir[e] == dir) { T.slot_dof[ns] = e; T.slot_dir[ns] = dir; ++ns; }
+        while (ns % 4) { T.slot_dof[ns] = -1; T.slot_dir[ns] = dir; ++ns; }
+    }
+    T.nslots = ns;
 
     // sharing tables: global_assembly.f90:242-265 (me=12), 310-351 (me=36), 396-443 (me=54);
     // the same lists are the Dirichlet face lists of boundary_conds.f90:276-388
@@ -208,7 +216,11 @@ int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist)
     auto kern = element_kernel<CFG, DO_KM>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::SMEM));
     A.list = d_list; A.nlist = nlist;
-    const int grid = (nlist + CFG::EB - 1) / CFG::EB;
+    // persistent CTAs: one resident wave, each CTA strides over the element batches
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CFG::THREADS, CFG::SMEM));
+    const int nbatch = (nlist + CFG::EB - 1) / CFG::EB;
+    const int grid = std::max(1, std::min(nbatch, std::max(1, per_sm) * h->num_sms));
     kern<<<grid, CFG::THREADS, CFG::SMEM, h->stream>>>(A);
     h->launches += 1;
     CK(cudaGetLastError());
@@ -355,6 +367,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     h->NP = m.me * (m.me + 1) / 2; h->ngp = m.ngp;
 
     CK(cudaSetDevice(device));
+    CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     for (int i = 0; i < EV_COUNT; ++i) CK(cudaEventCreate(&h->ev[i]));

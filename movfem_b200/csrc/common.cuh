@@ -36,7 +36,7 @@ struct __align__(16) NodeRec {
 static_assert(sizeof(NodeRec) == 26 * 8, "NodeRec layout");
 constexpr int kNodeDoubles = 26;
 
-constexpr int kMaxGp = 27, kMaxMn = 27, kMaxMe = 54, kMaxMep = 56;
+constexpr int kMaxGp = 27, kMaxMn = 27, kMaxMe = 54, kMaxMep = 56, kMaxSlots = 60;
 
 // Reference-element tables at the Gauss points (global memory, read through L1).
 struct ElemTables {
@@ -48,6 +48,10 @@ struct ElemTables {
     int node_off[kMaxMn];                   // linear grid offset of local node from element base node
     int node_i[kMaxMn], node_j[kMaxMn];     // i1-1, j1-1 (n_fem.f90:36-59)
     int edir[kMaxMep];                      // direction of DOF, 0-based (v_fem.f90:491-504)
+    // DOFs permuted into direction-uniform groups of four (padded with -1): the contraction's slot order
+    int slot_dof[kMaxSlots];                // slot -> local DOF (0-based) or -1
+    int slot_dir[kMaxSlots];                // slot -> direction (0-based), defined for padding slots too
+    int nslots;
 };
 
 // DOF sharing tables (global_assembly.f90:242-265,310-351,396-443) and Dirichlet face lists

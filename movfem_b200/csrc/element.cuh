@@ -8,12 +8,23 @@
 //   integration.f90:60-265        int_elem_params, alocal/f1/f2, blocal/f3
 //
 // Formulation.  The reference evaluates one alocal(im,jm) at a time (36-term f1, 9-term f2, per
-// Gauss point, 3*me+mn+1 Jacobian rebuilds per point).  Here every Gauss point gets ONE Jacobian,
-// the me basis vectors / curls are formed once (bit-identical to the reference's cve1-cve2, ve),
-// and the element matrices are the two symmetric contractions
-//        K_e = sum_g C_g^T (w mu^-1) C_g         M_e = sum_g V_g^T (w Re[h1h2h3 sigma]) V_g
-// (6-row half-curl form with the 6x6 real GPML tensor inside the stretched layers), computed as
-// register-tiled 4x4 FP64 FMA blocks over the lower triangle from shared-memory B-matrices.
+// Gauss point, 3*me+mn+1 Jacobian rebuilds per point).  Here every Gauss point gets ONE Jacobian
+// J, G = J^-1 (both with the reference's exact operation order), and the edge basis
+// N_e = phi_e * grad(xi_d) = phi_e * G[:,d] is never formed per DOF.  Instead the tensor-product
+// structure is pushed into three small per-Gauss-point tensors:
+//
+//   mass    N_i . S N_j            = phi_i phi_j T[d_i][d_j],         T = G^T S G        (S = w Re[h1h2h3 sigma])
+//   curl    curl N_j = (G dphi_j) x (G e_d) = (1/det J) J^T (dphi_j x e_d) = (1/det J) J^T c_j
+//           curl N_i . D curl N_j  = c_i^T Q c_j,                      Q = (w/det^2) J mu^-1 J^T
+//           (c_j = dphi_j x e_d is a CONSTANT of the reference element with two non-zero components)
+//   source  N_j . (w h1h2h3 src_p) = phi_j R[d_j][p],                  R[d][p] = G[:,d] . (w h src_p)
+//
+// so that per (DOF pair, Gauss point) the element matrices cost 2 (K) + 1 (M) FMAs instead of the
+// 3 + 3 of the B^T D B form (and 143 flops of the reference's expanded f1/f2).  Inside the GPML
+// layers the stretched half-curls do not collapse to a curl; there K uses the 9x9 real tensor
+// P = H^T D6 H with H[a][(u,d)] = s_a G[x_a][u] G[y_a][d] and costs 3 FMAs per pair and point.
+// DOFs are permuted into direction-uniform groups of four, and the contraction runs as
+// register-tiled 4x4 FP64 FMA blocks over the lower triangle, one operand a constant table.
 // A_e = K_e + i*f32(omega)*M_e is formed later, per frequency (finalize.cuh), so K_e, M_e of the
 // unstretched elements are frequency independent and cached in HBM across a sweep.
 #pragma once
@@ -95,27 +106,32 @@ struct ElemArgs {
     int skip_unless_changed;   // launch is a cache refresh: exit unless flags[1]
 };
 
-template <int MN_, int ME_, int NGP_, int GCH_, int EB_, int THREADS_, int MINB_, bool PML_>
+template <int MN_, int ME_, int MEP_, int NGP_, int GCH_, int EB_, int THREADS_, int MINB_, bool PML_>
 struct ElemCfg {
-    static constexpr int MN = MN_, ME = ME_, NGP = NGP_, GCH = GCH_, EB = EB_, THREADS = THREADS_, MINB = MINB_;
+    static constexpr int MN = MN_, ME = ME_, MEP = MEP_, NGP = NGP_, GCH = GCH_, EB = EB_, THREADS = THREADS_, MINB = MINB_;
     static constexpr bool PML = PML_;
-    static constexpr int MEP = (ME + 3) / 4 * 4;
     static constexpr int NT = MEP / 4, NTILES = NT * (NT + 1) / 2;
     static constexpr int NP = ME * (ME + 1) / 2;
-    static constexpr int KR = PML ? 6 : 3;                 // rows of the curl operator
-    static constexpr int NC = 2 * KR + 6;                  // C, DC, V, SV
+    static constexpr int KA = PML ? 3 : 2;                 // K operand components per (slot, Gauss point)
+    static constexpr int NA = KA + 1;                      // a-table rows: K comps + phi
+    static constexpr int KB = PML ? 9 : 3;                 // bK components
+    static constexpr int NB = KB + 3;                      // B rows: bK + W[3]
     static constexpr int NDW = kNodeDoubles + 2;           // node record + x + y
-    static constexpr int GEO = PML ? 48 : 34;              // Ji 9 + D (21|6) + S 6 + w*src 12 (+1 pad)
+    static constexpr int GEO = (PML ? 45 : 6) + 6 + 12 + (PML ? 1 : 0);   // P|Q, T, R  (kept even)
     static constexpr int NCHUNK = NGP / GCH;
-    // shared memory: node records [EB][MN][NDW] | geometry [EB][NGP][GEO] | B chunk [EB][GCH][NC][MEP]
-    static constexpr size_t SMEM = sizeof(double) * ((size_t)EB * MN * NDW + (size_t)EB * NGP * GEO + (size_t)EB * GCH * NC * MEP) +
-                                   sizeof(int) * EB * 4;
+    // shared memory: a-table [NGP][NA][MEP] | geometry [EB][NGP][GEO] |
+    //                union{ node records [EB][MN][NDW] (phases A,B), B chunk [EB][GCH][NB][MEP] (phases C,D) }
+    static constexpr size_t ATAB_D = (size_t)NGP * NA * MEP, GEO_D = (size_t)EB * NGP * GEO;
+    static constexpr size_t NODES_D = (size_t)EB * MN * NDW, BCH_D = (size_t)EB * GCH * NB * MEP;
+    static constexpr size_t UNION_D = NODES_D > BCH_D ? NODES_D : BCH_D;
+    static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + UNION_D) + sizeof(int) * (EB * 4 + 2 * MEP);
     static_assert(NGP % GCH == 0, "chunking");
-    static_assert(THREADS >= EB * NTILES && THREADS >= EB * ME, "one tile / one DOF per thread");
+    static_assert(MEP % 4 == 0 && (ATAB_D % 2) == 0 && (GEO_D % 2) == 0, "16-byte alignment of the smem regions");
+    static_assert(THREADS >= EB * NTILES && THREADS >= EB * MEP, "one tile / one slot per thread");
 };
 
-// B rows are stored with the two 16-byte halves of every 4-DOF group swapped in alternate groups of
-// four, so that the 8 distinct groups a warp touches in one LDS.128 fall into distinct banks.
+// B / a-table rows are stored with the two 16-byte halves of every 4-slot group swapped in alternate
+// groups of four, so that the distinct groups a warp touches in one LDS.128 fall into distinct banks.
 __device__ __forceinline__ int swz(int j) {
     const int grp = j >> 2, pos = j & 3;
     return (grp << 2) + ((((pos >> 1) ^ ((grp >> 2) & 1)) << 1) | (pos & 1));
@@ -157,193 +173,56 @@ __device__ __forceinline__ double2 cdivf(double2 a, double2 b) {   // Fortran ru
     return make_double2(((a.y * ratio) + a.x) / div, (a.y - (a.x * ratio)) / div);
 }
 
+// index of (r,c) in a packed symmetric 3x3 (11,12,13,22,23,33)
+__host__ __device__ __forceinline__ constexpr int sym3(int r, int c) {
+    return r == c ? (r == 0 ? 0 : (r == 1 ? 3 : 5)) : ((r + c == 1) ? 1 : ((r + c == 2) ? 2 : 4));
+}
+// index of (r,c), r <= c, in a packed upper-triangular 9x9 stored row-major
+__host__ __device__ __forceinline__ constexpr int up9(int r, int c) { return r * 9 - r * (r - 1) / 2 + (c - r); }
+
 template <class CFG, bool DO_KM>
 __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemArgs A) {
-    constexpr int MN = CFG::MN, ME = CFG::ME, MEP = CFG::MEP, GCH = CFG::GCH, EB = CFG::EB, NC = CFG::NC, NGP = CFG::NGP;
-    constexpr int KR = CFG::KR, GEO = CFG::GEO, NDW = CFG::NDW, NTILES = CFG::NTILES, NP = CFG::NP;
+    constexpr int MN = CFG::MN, ME = CFG::ME, MEP = CFG::MEP, GCH = CFG::GCH, EB = CFG::EB, NGP = CFG::NGP;
+    constexpr int NA = CFG::NA, NB = CFG::NB, KA = CFG::KA, KB = CFG::KB;
+    constexpr int GEO = CFG::GEO, NDW = CFG::NDW, NTILES = CFG::NTILES, NP = CFG::NP;
     constexpr bool PML = CFG::PML;
+    constexpr int GQ = 0, GT = PML ? 45 : 6, GR = GT + 6;   // offsets inside one geometry record
     if (A.skip_unless_changed && A.flags[1] == 0) return;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_nodes = reinterpret_cast<double *>(smem_raw);           // [EB][MN][NDW]
-    double *s_geo = s_nodes + EB * MN * NDW;                          // [EB][NGP][GEO]
-    double *s_B = s_geo + EB * NGP * GEO;                             // [EB][GCH][NC][MEP] (swizzled rows)
-    int *s_el = reinterpret_cast<int *>(s_B + EB * GCH * NC * MEP);   // [EB][4]: element id, GPML flags
+    double *s_at = reinterpret_cast<double *>(smem_raw);              // [NGP][NA][MEP] constant operand (swizzled rows)
+    double *s_geo = s_at + CFG::ATAB_D;                               // [EB][NGP][GEO]
+    double *s_nodes = s_geo + CFG::GEO_D;                             // [EB][MN][NDW]   (dead after phase B)
+    double *s_B = s_nodes;                                            // [EB][GCH][NB][MEP] (swizzled rows), aliases s_nodes
+    int *s_el = reinterpret_cast<int *>(s_nodes + CFG::UNION_D);      // [EB][4]: element id, GPML flags
+    int *s_slot = s_el + EB * 4;                                      // [MEP] slot -> local DOF (0-based) or -1
+    int *s_sdir = s_slot + MEP;                                       // [MEP] slot -> direction (0-based)
 
     const ElemTables &T = *A.T;
     const MeshDims &m = A.m;
     const int tid = threadIdx.x;
-    const int first = blockIdx.x * EB;
-    const int nb = min(EB, A.nlist - first);
 
-    if (tid < EB) {
-        const int e = tid < nb ? A.list[first + tid] : -1;
-        s_el[tid * 4] = e;
-        int f[3] = {0, 0, 0};
-        if (PML && e >= 0) effective_pml(m, A.pml, e, f);
-        s_el[tid * 4 + 1] = f[0]; s_el[tid * 4 + 2] = f[1]; s_el[tid * 4 + 3] = f[2];
-    }
-    if constexpr (MEP > ME) {   // zero the padded DOF columns once
-        constexpr int PAD = MEP - ME;
-        for (int i = tid; i < EB * GCH * NC * PAD; i += CFG::THREADS) {
-            const int row = i / PAD, c = ME + i % PAD;
-            s_B[row * MEP + swz(c)] = 0.0;
+    // ---- once per CTA: the constant operand table of the contraction, in slot order ----
+    //   plain: rows 0,1 = c_i[perp(d_i)] = (dphi x e_d) components, row 2 = phi_i
+    //   GPML : rows 0..2 = dphi_i[u],                              row 3 = phi_i
+    for (int i = tid; i < NGP * MEP; i += CFG::THREADS) {
+        const int g = i / MEP, sl = i % MEP;
+        const int dof = T.slot_dof[sl], d = T.slot_dir[sl];
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        if (dof >= 0) {
+            const double d0 = T.dphi[g][dof][0], d1 = T.dphi[g][dof][1], d2 = T.dphi[g][dof][2];
+            if (PML) { v[0] = d0; v[1] = d1; v[2] = d2; }
+            else if (d == 0) { v[0] = d2; v[1] = -d1; }      // c = (0, dphi_z, -dphi_y): comps 1,2
+            else if (d == 1) { v[0] = -d2; v[1] = d0; }      // c = (-dphi_z, 0, dphi_x): comps 0,2
+            else { v[0] = d1; v[1] = -d0; }                  // c = (dphi_y, -dphi_x, 0): comps 0,1
+            v[KA] = T.phi[g][dof];
         }
+#pragma unroll
+        for (int k = 0; k < NA; ++k) s_at[(g * NA + k) * MEP + swz(sl)] = v[k];
     }
-    __syncthreads();
+    for (int i = tid; i < MEP; i += CFG::THREADS) { s_slot[i] = T.slot_dof[i]; s_sdir[i] = T.slot_dir[i]; }
 
-    // ---- phase A: gather the element's node records (16-byte pieces, coalesced per record) ----
-    for (int i = tid; i < nb * MN * (kNodeDoubles / 2 + 1); i += CFG::THREADS) {
-        const int part = i % (kNodeDoubles / 2 + 1), sl = i / (kNodeDoubles / 2 + 1);
-        const int l = sl % MN, s = sl / MN;
-        const int e = s_el[s * 4];
-        int ie, je, ke;
-        elem_ijk(m, e, ie, je, ke);
-        const int g1 = m.nord - 1;
-        double2 *dst = reinterpret_cast<double2 *>(s_nodes + (s * MN + l) * NDW);
-        if (part < kNodeDoubles / 2) {
-            const int64_t id = (int64_t)(ie - 1) * g1 * m.nyz + (int64_t)(je - 1) * g1 * m.nnz + (ke - 1) * g1 + T.node_off[l];
-            dst[part] = reinterpret_cast<const double2 *>(A.nodes + id)[part];
-        } else {
-            dst[part] = make_double2(A.xp[(ie - 1) * g1 + T.node_i[l]], A.yp[(je - 1) * g1 + T.node_j[l]]);
-        }
-    }
-    __syncthreads();
-
-    // ---- phase B: one thread per (element, Gauss point): Jacobian, materials, GPML, source ----
-    {
-        const int has_dmu = A.flags[0];
-        const double w32 = f32r(A.omega);            // cmplx(0.d0,-omega), problem.f90:112
-        const double psig = f32r(A.omega * kEps0);   // pset_pmodel, problem.f90:250
-        for (int i = tid; i < nb * NGP; i += CFG::THREADS) {
-            const int s = i / NGP, g = i % NGP;
-            const double *nd = s_nodes + s * MN * NDW;
-            double *geo = s_geo + (s * NGP + g) * GEO;
-            // nf_jacobian, n_fem.f90:359-366: J(m,n) = sum_l dN_l/dxi_m * r_l(n), l ascending, no FMA
-            double J[3][3];
-#pragma unroll
-            for (int mm = 0; mm < 3; ++mm) {
-                double sx = 0.0, sy = 0.0, sz = 0.0;
-#pragma unroll 4
-                for (int l = 0; l < MN; ++l) {
-                    const double dn = T.dN[g][l][mm];
-                    sx = sx + dn * nd[l * NDW + kNodeDoubles];
-                    sy = sy + dn * nd[l * NDW + kNodeDoubles + 1];
-                    sz = sz + dn * nd[l * NDW];
-                }
-                J[mm][0] = sx; J[mm][1] = sy; J[mm][2] = sz;
-            }
-            // nf_det, n_fem.f90:393-394 ; wgt, integration.f90:71
-            const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) + J[0][1] * (J[1][2] * J[2][0] - J[1][0] * J[2][2]) +
-                               J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
-            if (det == 0.0) atomicCAS(A.status, 0, -3);
-            const double w = det * T.rw[g][3];
-            const double ad = fabs(det);   // Q6
-            double Ji[9];
-            Ji[0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / ad;
-            Ji[1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / ad;
-            Ji[2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / ad;
-            Ji[3] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / ad;
-            Ji[4] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / ad;
-            Ji[5] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / ad;
-            Ji[6] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / ad;
-            Ji[7] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / ad;
-            Ji[8] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / ad;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) geo[k] = Ji[k];
-            // p_intmodels, problem.f90:139-142: material tensors at the Gauss point
-            double mu[6] = {0, 0, 0, 0, 0, 0}, sr[6] = {0, 0, 0, 0, 0, 0}, si[6] = {0, 0, 0, 0, 0, 0};
-            double xg[3] = {0, 0, 0};
-            double dm1r[3] = {0, 0, 0}, dm1i[3] = {0, 0, 0}, dm2r[3] = {0, 0, 0}, dm2i[3] = {0, 0, 0};
-#pragma unroll 2
-            for (int l = 0; l < MN; ++l) {
-                const double ln = T.N[g][l];
-                const double *r = nd + l * NDW;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    mu[k] = dfma(ln, r[2 + k], mu[k]);
-                    sr[k] = dfma(ln, r[8 + k], sr[k]);
-                    if (PML) si[k] = dfma(ln, r[14 + k], si[k]);
-                }
-                if (PML) {   // g_rw, integration.f90:120-125 (reference order, no FMA: feeds the float32-rounded h)
-                    xg[0] = xg[0] + ln * r[kNodeDoubles]; xg[1] = xg[1] + ln * r[kNodeDoubles + 1]; xg[2] = xg[2] + ln * r[0];
-                }
-                // p_dmpf, problem.f90:424-457: ln * (dsigma . Ep); Ep_1 = (0,-e) x^, Ep_2 = (0,+e) y^
-                const double le = ln * r[1];
-                const double d0 = r[14] - psig, d3 = r[17] - psig;   // Im(dsigma) on the diagonal
-                dm1r[0] = dfma(le, d0, dm1r[0]);     dm1i[0] = dfma(le, r[8], dm1i[0]);
-                dm1r[1] = dfma(le, r[15], dm1r[1]);  dm1i[1] = dfma(le, r[9], dm1i[1]);
-                dm1r[2] = dfma(le, r[16], dm1r[2]);  dm1i[2] = dfma(le, r[10], dm1i[2]);
-                dm2r[0] = dfma(le, r[15], dm2r[0]);  dm2i[0] = dfma(le, r[9], dm2i[0]);
-                dm2r[1] = dfma(le, d3, dm2r[1]);     dm2i[1] = dfma(le, r[11], dm2i[1]);
-                dm2r[2] = dfma(le, r[18], dm2r[2]);  dm2i[2] = dfma(le, r[12], dm2i[2]);
-            }
-            // signs: pol 1 dmpf = (+Im ds*e, -Re ds*e), pol 2 = (-Im ds*e, +Re ds*e)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { dm1i[k] = -dm1i[k]; dm2r[k] = -dm2r[k]; }
-            double pc1[3] = {0, 0, 0}, pc2[3] = {0, 0, 0};
-            if (has_dmu) {   // p_pcurl, problem.f90:362-374: grad N_l x (mu^-1 dmu Hp)_l
-                for (int l = 0; l < MN; ++l) {
-                    const double *r = nd + l * NDW;
-                    double dn[3];
-#pragma unroll
-                    for (int mm = 0; mm < 3; ++mm)
-                        dn[mm] = Ji[mm * 3] * T.dN[g][l][0] + Ji[mm * 3 + 1] * T.dN[g][l][1] + Ji[mm * 3 + 2] * T.dN[g][l][2];
-                    pc1[0] += r[22] * dn[1] - r[21] * dn[2]; pc1[1] += r[20] * dn[2] - r[22] * dn[0]; pc1[2] += r[21] * dn[0] - r[20] * dn[1];
-                    pc2[0] += r[25] * dn[1] - r[24] * dn[2]; pc2[1] += r[23] * dn[2] - r[25] * dn[0]; pc2[2] += r[24] * dn[0] - r[23] * dn[1];
-                }
-            }
-            // GPML stretch (boundary_conds.f90:84-186) with the LAGGING flags (Q17)
-            double2 hhh = make_double2(1.0, 0.0);
-            double G[6] = {1, 0, 0, 1, 0, 1};   // Re G11,G12,G13,G22,G23,G33 ; G_ij = h1h2h3/(h_i h_j)
-            if (PML) {
-                const double2 h1 = gpml_axis(A.pml, s_el[s * 4 + 1], 0, xg[0], A.omega);
-                const double2 h2 = gpml_axis(A.pml, s_el[s * 4 + 2], 1, xg[1], A.omega);
-                const double2 h3 = gpml_axis(A.pml, s_el[s * 4 + 3], 2, xg[2], A.omega);
-                hhh = cmul(cmul(h1, h2), h3);
-                G[0] = cdivf(cmul(h2, h3), h1).x; G[3] = cdivf(cmul(h1, h3), h2).x; G[5] = cdivf(cmul(h1, h2), h3).x;
-                G[1] = h3.x; G[2] = h2.x; G[4] = h1.x;
-            }
-            double *gp = geo + 9;
-            if (!PML) {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) gp[k] = w * mu[k];
-                gp += 6;
-            } else {
-                // D6[a][b] = w * mu^-1[p_a][p_b] * Re G[d_a][d_b]; a = (p,s): (1,1),(1,2),(2,1),(2,2),(3,1),(3,2)
-                // derivative axis d(a) = 2,3,3,1,1,2 (integration.f90:171-188)
-                const int pa[6] = {0, 0, 1, 1, 2, 2}, da[6] = {1, 2, 2, 0, 0, 1};
-                const int sym6[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
-                int q = 0;
-#pragma unroll
-                for (int a = 0; a < 6; ++a)
-#pragma unroll
-                    for (int b = a; b < 6; ++b) gp[q++] = w * mu[sym6[pa[a]][pa[b]]] * G[sym6[da[a]][da[b]]];
-                gp += 21;
-            }
-            // mass tensor: w * Re[h1h2h3 * sigma_g]  (integration.f90:228-236, Q3)
-#pragma unroll
-            for (int k = 0; k < 6; ++k) gp[k] = PML ? w * (hhh.x * sr[k] - hhh.y * si[k]) : w * sr[k];
-            gp += 6;
-            // p_source, problem.f90:112: (dmpf + pcrl) * cmplx32(0,-omega); then w*[h1h2h3] (integration.f90:258-263)
-            const double2 whh = make_double2(w * hhh.x, w * hhh.y);
-#pragma unroll
-            for (int mm = 0; mm < 3; ++mm) {
-                const double2 s1 = make_double2(dm1i[mm] * w32, -((dm1r[mm] + pc1[mm]) * w32));
-                const double2 s2 = make_double2(dm2i[mm] * w32, -((dm2r[mm] + pc2[mm]) * w32));
-                const double2 a1 = cmul(whh, s1), a2 = cmul(whh, s2);
-                gp[mm * 2] = a1.x; gp[mm * 2 + 1] = a1.y; gp[6 + mm * 2] = a2.x; gp[6 + mm * 2 + 1] = a2.y;
-            }
-        }
-    }
-    __syncthreads();
-
-    double accK[16], accM[16], bacc[4];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { accK[i] = 0.0; accM[i] = 0.0; }
-    bacc[0] = bacc[1] = bacc[2] = bacc[3] = 0.0;
-
-    // tile owned by this thread in the contraction (lower triangle of 4x4 blocks)
+    // tile owned by this thread in the contraction (lower triangle of 4x4 blocks in slot space)
     const int ts = tid / NTILES, tt = tid % NTILES;
     int ti = 0, tj = 0;
     {
@@ -354,129 +233,335 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
     // swizzled 16-byte half offsets of this thread's row / column groups (in doubles)
     const int a_lo = 4 * ti + (((ti >> 2) & 1) << 1), a_hi = 4 * ti + ((((ti >> 2) & 1) ^ 1) << 1);
     const int b_lo = 4 * tj + (((tj >> 2) & 1) << 1), b_hi = 4 * tj + ((((tj >> 2) & 1) ^ 1) << 1);
-    // DOF owned by this thread in the basis phase
-    const int cs = tid / ME, cdof = tid % ME;
-    const int cd = T.edir[cdof < ME ? cdof : 0], cpos = swz(cdof);
+    // slot owned by this thread in the basis phase
+    const int cs = tid / MEP, cslot = tid % MEP, cpos = swz(cslot);
 
-    for (int chunk = 0; chunk < CFG::NCHUNK; ++chunk) {
-        // ---- phase C: one thread per (element, DOF): basis, curl, D*B products, RHS ----
-        if (tid < nb * ME) {
-#pragma unroll 1
-            for (int gc = 0; gc < GCH; ++gc) {
-                const int g = chunk * GCH + gc;
-                const double *geo = s_geo + (cs * NGP + g) * GEO;
-                double *B = s_B + (size_t)(cs * GCH + gc) * NC * MEP + cpos;
-                const double phi = T.phi[g][cdof];
-                const double dp0 = T.dphi[g][cdof][0], dp1 = T.dphi[g][cdof][1], dp2 = T.dphi[g][cdof][2];
-                double vij[3], V[3], dni[3];
-#pragma unroll
-                for (int mm = 0; mm < 3; ++mm) {
-                    vij[mm] = geo[mm * 3 + cd];                     // grad_xi, v_fem.f90:518
-                    V[mm] = phi * vij[mm];                          // vf_elem_ve, v_fem.f90:43
-                    dni[mm] = geo[mm * 3] * dp0 + geo[mm * 3 + 1] * dp1 + geo[mm * 3 + 2] * dp2;   // mix_grad_ln
-                }
-                if (DO_KM) {
-                    // vf_elem_curl, v_fem.f90:57-59
-                    const double c11 = dni[1] * vij[2], c12 = dni[2] * vij[1];
-                    const double c21 = dni[2] * vij[0], c22 = dni[0] * vij[2];
-                    const double c31 = dni[0] * vij[1], c32 = dni[1] * vij[0];
-                    if (!PML) {
-                        const double *D = geo + 9;
-                        const double C0 = c11 - c12, C1 = c21 - c22, C2 = c31 - c32;
-                        B[0 * MEP] = C0; B[1 * MEP] = C1; B[2 * MEP] = C2;
-                        B[3 * MEP] = dfma(D[0], C0, dfma(D[1], C1, D[2] * C2));
-                        B[4 * MEP] = dfma(D[1], C0, dfma(D[3], C1, D[4] * C2));
-                        B[5 * MEP] = dfma(D[2], C0, dfma(D[4], C1, D[5] * C2));
-                    } else {
-                        const double *D = geo + 9;   // 21 packed upper entries of the symmetric 6x6
-                        const double C6[6] = {c11, -c12, c21, -c22, c31, -c32};
-                        double DC[6] = {0, 0, 0, 0, 0, 0};
-                        int q = 0;
-#pragma unroll
-                        for (int a = 0; a < 6; ++a)
-#pragma unroll
-                            for (int b = a; b < 6; ++b) {
-                                const double v = D[q++];
-                                DC[a] = dfma(v, C6[b], DC[a]);
-                                if (b != a) DC[b] = dfma(v, C6[a], DC[b]);
-                            }
-#pragma unroll
-                        for (int a = 0; a < 6; ++a) { B[a * MEP] = C6[a]; B[(6 + a) * MEP] = DC[a]; }
-                    }
-                    const double *S = geo + 9 + (PML ? 21 : 6);
-                    double *BV = B + 2 * KR * MEP;
-                    BV[0 * MEP] = V[0]; BV[1 * MEP] = V[1]; BV[2 * MEP] = V[2];
-                    BV[3 * MEP] = dfma(S[0], V[0], dfma(S[1], V[1], S[2] * V[2]));
-                    BV[4 * MEP] = dfma(S[1], V[0], dfma(S[3], V[1], S[4] * V[2]));
-                    BV[5 * MEP] = dfma(S[2], V[0], dfma(S[4], V[1], S[5] * V[2]));
-                }
-                // blocal / f3, integration.f90:96-104,258-263: sum_g w [h1h2h3] N . src_d
-                const double *ws = geo + 9 + (PML ? 21 : 6) + 6;
-#pragma unroll
-                for (int mm = 0; mm < 3; ++mm) {
-                    bacc[0] = dfma(V[mm], ws[mm * 2], bacc[0]);     bacc[1] = dfma(V[mm], ws[mm * 2 + 1], bacc[1]);
-                    bacc[2] = dfma(V[mm], ws[6 + mm * 2], bacc[2]); bacc[3] = dfma(V[mm], ws[6 + mm * 2 + 1], bacc[3]);
-                }
-            }
+    const int nbatch = (A.nlist + EB - 1) / EB;
+    for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+        const int first = batch * EB;
+        const int nb = min(EB, A.nlist - first);
+        __syncthreads();   // previous batch fully consumed (s_B / s_geo / s_el reuse); also publishes the tables
+        if (tid < EB) {
+            const int e = tid < nb ? A.list[first + tid] : -1;
+            s_el[tid * 4] = e;
+            int f[3] = {0, 0, 0};
+            if (PML && e >= 0) effective_pml(m, A.pml, e, f);
+            s_el[tid * 4 + 1] = f[0]; s_el[tid * 4 + 2] = f[1]; s_el[tid * 4 + 3] = f[2];
         }
-        if (!DO_KM) continue;
         __syncthreads();
 
-        // ---- phase D: register-tiled lower-triangle contraction over this chunk ----
-        if (tid < nb * NTILES) {
-            const double *Bs = s_B + (size_t)ts * GCH * NC * MEP;
-#pragma unroll 1
-            for (int gc = 0; gc < GCH; ++gc) {
-                const double *Bg = Bs + gc * NC * MEP;
-#pragma unroll
-                for (int k = 0; k < KR; ++k) {
-                    const double2 a0 = *reinterpret_cast<const double2 *>(Bg + (KR + k) * MEP + a_lo);   // D*C rows
-                    const double2 a1 = *reinterpret_cast<const double2 *>(Bg + (KR + k) * MEP + a_hi);
-                    const double2 b0 = *reinterpret_cast<const double2 *>(Bg + k * MEP + b_lo);          // C cols
-                    const double2 b1 = *reinterpret_cast<const double2 *>(Bg + k * MEP + b_hi);
-                    const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) accK[i * 4 + j] = dfma(av[i], bv[j], accK[i * 4 + j]);
-                }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const double2 a0 = *reinterpret_cast<const double2 *>(Bg + (2 * KR + 3 + k) * MEP + a_lo);   // S*V rows
-                    const double2 a1 = *reinterpret_cast<const double2 *>(Bg + (2 * KR + 3 + k) * MEP + a_hi);
-                    const double2 b0 = *reinterpret_cast<const double2 *>(Bg + (2 * KR + k) * MEP + b_lo);       // V cols
-                    const double2 b1 = *reinterpret_cast<const double2 *>(Bg + (2 * KR + k) * MEP + b_hi);
-                    const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) accM[i * 4 + j] = dfma(av[i], bv[j], accM[i * 4 + j]);
-                }
+        // ---- phase A: gather the element's node records (16-byte pieces, coalesced per record) ----
+        for (int i = tid; i < nb * MN * (kNodeDoubles / 2 + 1); i += CFG::THREADS) {
+            const int part = i % (kNodeDoubles / 2 + 1), sl = i / (kNodeDoubles / 2 + 1);
+            const int l = sl % MN, s = sl / MN;
+            const int e = s_el[s * 4];
+            int ie, je, ke;
+            elem_ijk(m, e, ie, je, ke);
+            const int g1 = m.nord - 1;
+            double2 *dst = reinterpret_cast<double2 *>(s_nodes + (s * MN + l) * NDW);
+            if (part < kNodeDoubles / 2) {
+                const int64_t id = (int64_t)(ie - 1) * g1 * m.nyz + (int64_t)(je - 1) * g1 * m.nnz + (ke - 1) * g1 + T.node_off[l];
+                dst[part] = reinterpret_cast<const double2 *>(A.nodes + id)[part];
+            } else {
+                dst[part] = make_double2(A.xp[(ie - 1) * g1 + T.node_i[l]], A.yp[(je - 1) * g1 + T.node_j[l]]);
             }
         }
-        if (chunk + 1 < CFG::NCHUNK) __syncthreads();
-    }
+        __syncthreads();
 
-    // ---- write-out: element-major, packed lower triangle by local index ----
-    if (DO_KM && tid < nb * NTILES) {
-        const int64_t e = s_el[ts * 4];
-        double *Ko = A.Ke + e * NP, *Mo = A.Me + e * NP;
+        // ---- phase B: one thread per (element, Gauss point): J, G, materials, GPML, source -> Q|P, T, R ----
+        {
+            const int has_dmu = A.flags[0];
+            const double w32 = f32r(A.omega);            // cmplx(0.d0,-omega), problem.f90:112
+            const double psig = f32r(A.omega * kEps0);   // pset_pmodel, problem.f90:250
+            for (int i = tid; i < nb * NGP; i += CFG::THREADS) {
+                const int s = i / NGP, g = i % NGP;
+                const double *nd = s_nodes + s * MN * NDW;
+                double *geo = s_geo + (s * NGP + g) * GEO;
+                // nf_jacobian, n_fem.f90:359-366: J(m,n) = sum_l dN_l/dxi_m * r_l(n), l ascending, no FMA
+                double J[3][3];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int im = 4 * ti + i;
+                for (int mm = 0; mm < 3; ++mm) {
+                    double sx = 0.0, sy = 0.0, sz = 0.0;
+#pragma unroll 4
+                    for (int l = 0; l < MN; ++l) {
+                        const double dn = T.dN[g][l][mm];
+                        sx = sx + dn * nd[l * NDW + kNodeDoubles];
+                        sy = sy + dn * nd[l * NDW + kNodeDoubles + 1];
+                        sz = sz + dn * nd[l * NDW];
+                    }
+                    J[mm][0] = sx; J[mm][1] = sy; J[mm][2] = sz;
+                }
+                // nf_det, n_fem.f90:393-394 ; wgt, integration.f90:71
+                const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) + J[0][1] * (J[1][2] * J[2][0] - J[1][0] * J[2][2]) +
+                                   J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+                if (det == 0.0) atomicCAS(A.status, 0, -3);
+                const double w = det * T.rw[g][3];
+                const double ad = fabs(det);   // Q6
+                double G[3][3];                // nf_ji: G[m][n] = d xi_n / d x_m
+                G[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / ad;
+                G[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / ad;
+                G[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / ad;
+                G[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / ad;
+                G[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / ad;
+                G[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / ad;
+                G[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / ad;
+                G[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / ad;
+                G[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / ad;
+                // p_intmodels, problem.f90:139-142: material tensors at the Gauss point
+                double mu[6] = {0, 0, 0, 0, 0, 0}, sr[6] = {0, 0, 0, 0, 0, 0}, si[6] = {0, 0, 0, 0, 0, 0};
+                double xg[3] = {0, 0, 0};
+                double dm1r[3] = {0, 0, 0}, dm1i[3] = {0, 0, 0}, dm2r[3] = {0, 0, 0}, dm2i[3] = {0, 0, 0};
+#pragma unroll 2
+                for (int l = 0; l < MN; ++l) {
+                    const double ln = T.N[g][l];
+                    const double *r = nd + l * NDW;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int jm = 4 * tj + j;
-                if (im < ME && jm <= im) {
-                    const int p = im * (im + 1) / 2 + jm;
-                    Ko[p] = accK[i * 4 + j]; Mo[p] = accM[i * 4 + j];
+                    for (int k = 0; k < 6; ++k) {
+                        mu[k] = dfma(ln, r[2 + k], mu[k]);
+                        sr[k] = dfma(ln, r[8 + k], sr[k]);
+                        if (PML) si[k] = dfma(ln, r[14 + k], si[k]);
+                    }
+                    if (PML) {   // g_rw, integration.f90:120-125 (reference order, no FMA: feeds the float32-rounded h)
+                        xg[0] = xg[0] + ln * r[kNodeDoubles]; xg[1] = xg[1] + ln * r[kNodeDoubles + 1]; xg[2] = xg[2] + ln * r[0];
+                    }
+                    // p_dmpf, problem.f90:424-457: ln * (dsigma . Ep); Ep_1 = (0,-e) x^, Ep_2 = (0,+e) y^
+                    const double le = ln * r[1];
+                    const double d0 = r[14] - psig, d3 = r[17] - psig;   // Im(dsigma) on the diagonal
+                    dm1r[0] = dfma(le, d0, dm1r[0]);     dm1i[0] = dfma(le, r[8], dm1i[0]);
+                    dm1r[1] = dfma(le, r[15], dm1r[1]);  dm1i[1] = dfma(le, r[9], dm1i[1]);
+                    dm1r[2] = dfma(le, r[16], dm1r[2]);  dm1i[2] = dfma(le, r[10], dm1i[2]);
+                    dm2r[0] = dfma(le, r[15], dm2r[0]);  dm2i[0] = dfma(le, r[9], dm2i[0]);
+                    dm2r[1] = dfma(le, d3, dm2r[1]);     dm2i[1] = dfma(le, r[11], dm2i[1]);
+                    dm2r[2] = dfma(le, r[18], dm2r[2]);  dm2i[2] = dfma(le, r[12], dm2i[2]);
+                }
+                // signs: pol 1 dmpf = (+Im ds*e, -Re ds*e), pol 2 = (-Im ds*e, +Re ds*e)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { dm1i[k] = -dm1i[k]; dm2r[k] = -dm2r[k]; }
+                double pc1[3] = {0, 0, 0}, pc2[3] = {0, 0, 0};
+                if (has_dmu) {   // p_pcurl, problem.f90:362-374: grad N_l x (mu^-1 dmu Hp)_l
+                    for (int l = 0; l < MN; ++l) {
+                        const double *r = nd + l * NDW;
+                        double dn[3];
+#pragma unroll
+                        for (int mm = 0; mm < 3; ++mm)
+                            dn[mm] = G[mm][0] * T.dN[g][l][0] + G[mm][1] * T.dN[g][l][1] + G[mm][2] * T.dN[g][l][2];
+                        pc1[0] += r[22] * dn[1] - r[21] * dn[2]; pc1[1] += r[20] * dn[2] - r[22] * dn[0]; pc1[2] += r[21] * dn[0] - r[20] * dn[1];
+                        pc2[0] += r[25] * dn[1] - r[24] * dn[2]; pc2[1] += r[23] * dn[2] - r[25] * dn[0]; pc2[2] += r[24] * dn[0] - r[23] * dn[1];
+                    }
+                }
+                // GPML stretch (boundary_conds.f90:84-186) with the LAGGING flags (Q17)
+                double2 hhh = make_double2(1.0, 0.0);
+                if (PML) {
+                    const double2 h1 = gpml_axis(A.pml, s_el[s * 4 + 1], 0, xg[0], A.omega);
+                    const double2 h2 = gpml_axis(A.pml, s_el[s * 4 + 2], 1, xg[1], A.omega);
+                    const double2 h3 = gpml_axis(A.pml, s_el[s * 4 + 3], 2, xg[2], A.omega);
+                    hhh = cmul(cmul(h1, h2), h3);
+                    // Re G_ij, G_ij = h1h2h3/(h_i h_j): the factor of the half-curl pair with derivative axes i,j
+                    double Gr[6];
+                    Gr[0] = cdivf(cmul(h2, h3), h1).x; Gr[3] = cdivf(cmul(h1, h3), h2).x; Gr[5] = cdivf(cmul(h1, h2), h3).x;
+                    Gr[1] = h3.x; Gr[2] = h2.x; Gr[4] = h1.x;
+                    // half-curl a = (p,s): derivative axis x_a, grad-xi component y_a, sign s_a (v_fem.f90:57-59,
+                    // integration.f90:171-188):  (1,1):(y,z,+) (1,2):(z,y,-) (2,1):(z,x,+) (2,2):(x,z,-) (3,1):(x,y,+) (3,2):(y,x,-)
+                    constexpr int xa[6] = {1, 2, 2, 0, 0, 1}, ya[6] = {2, 1, 0, 2, 1, 0}, pa[6] = {0, 0, 1, 1, 2, 2};
+                    constexpr double sa[6] = {1.0, -1.0, 1.0, -1.0, 1.0, -1.0};
+                    // D6[a][b] = w mu^-1[p_a][p_b] Re G[x_a][x_b]   (symmetric 6x6, 21 packed)
+                    double D6[6][6];
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+#pragma unroll
+                        for (int b = 0; b < 6; ++b) D6[a][b] = w * mu[sym3(pa[a], pa[b])] * Gr[sym3(xa[a], xa[b])];
+                    // P[(u,d)][(v,e)] = sum_ab H[a][u,d] D6[a][b] H[b][v,e],  H[a][u,d] = s_a G[x_a][u] G[y_a][d]
+                    double *P = geo + GQ;
+#pragma unroll 1
+                    for (int col = 0; col < 9; ++col) {
+                        const int v = col / 3, e2 = col % 3;
+                        double Hc[6], DH[6];
+#pragma unroll
+                        for (int b = 0; b < 6; ++b) Hc[b] = sa[b] * G[xa[b]][v] * G[ya[b]][e2];
+#pragma unroll
+                        for (int a = 0; a < 6; ++a) {
+                            double acc = 0.0;
+#pragma unroll
+                            for (int b = 0; b < 6; ++b) acc = dfma(D6[a][b], Hc[b], acc);
+                            DH[a] = acc;
+                        }
+#pragma unroll 1
+                        for (int row = 0; row <= col; ++row) {
+                            const int u = row / 3, d2 = row % 3;
+                            double acc = 0.0;
+#pragma unroll
+                            for (int a = 0; a < 6; ++a) acc = dfma(sa[a] * G[xa[a]][u] * G[ya[a]][d2], DH[a], acc);
+                            P[up9(row, col)] = acc;
+                        }
+                    }
+                } else {
+                    // Q = (w/det^2) J mu^-1 J^T  (curl N = (1/det J) J^T (dphi x e_d))
+                    const double f = w / (det * det);
+                    double Jm[3][3];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int q = 0; q < 3; ++q)
+                            Jm[a][q] = dfma(J[a][0], mu[sym3(0, q)], dfma(J[a][1], mu[sym3(1, q)], J[a][2] * mu[sym3(2, q)]));
+                    int q6 = 0;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int b = a; b < 3; ++b)
+                            geo[GQ + q6++] = f * dfma(Jm[a][0], J[b][0], dfma(Jm[a][1], J[b][1], Jm[a][2] * J[b][2]));
+                }
+                // T = G^T S G with the mass tensor S = w Re[h1h2h3 sigma_g] (integration.f90:228-236, Q3)
+                {
+                    double S[6], SG[3][3];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) S[k] = PML ? w * (hhh.x * sr[k] - hhh.y * si[k]) : w * sr[k];
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int d2 = 0; d2 < 3; ++d2)
+                            SG[a][d2] = dfma(S[sym3(a, 0)], G[0][d2], dfma(S[sym3(a, 1)], G[1][d2], S[sym3(a, 2)] * G[2][d2]));
+                    int q6 = 0;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int b = a; b < 3; ++b)
+                            geo[GT + q6++] = dfma(G[0][a], SG[0][b], dfma(G[1][a], SG[1][b], G[2][a] * SG[2][b]));
+                }
+                // R[d][pol] = G[:,d] . (w h1h2h3 src_pol);  src = (dmpf + pcrl) * cmplx32(0,-omega)  (problem.f90:112)
+                {
+                    const double2 whh = make_double2(w * hhh.x, w * hhh.y);
+                    double2 a1[3], a2[3];
+#pragma unroll
+                    for (int mm = 0; mm < 3; ++mm) {
+                        a1[mm] = cmul(whh, make_double2(dm1i[mm] * w32, -((dm1r[mm] + pc1[mm]) * w32)));
+                        a2[mm] = cmul(whh, make_double2(dm2i[mm] * w32, -((dm2r[mm] + pc2[mm]) * w32)));
+                    }
+#pragma unroll
+                    for (int d2 = 0; d2 < 3; ++d2) {
+                        geo[GR + d2 * 4 + 0] = dfma(G[0][d2], a1[0].x, dfma(G[1][d2], a1[1].x, G[2][d2] * a1[2].x));
+                        geo[GR + d2 * 4 + 1] = dfma(G[0][d2], a1[0].y, dfma(G[1][d2], a1[1].y, G[2][d2] * a1[2].y));
+                        geo[GR + d2 * 4 + 2] = dfma(G[0][d2], a2[0].x, dfma(G[1][d2], a2[1].x, G[2][d2] * a2[2].x));
+                        geo[GR + d2 * 4 + 3] = dfma(G[0][d2], a2[0].y, dfma(G[1][d2], a2[1].y, G[2][d2] * a2[2].y));
+                    }
                 }
             }
         }
-    }
-    if (tid < nb * ME) {
-        const int64_t e = s_el[cs * 4];
-        reinterpret_cast<double4 *>(A.be)[e * ME + cdof] = make_double4(bacc[0], bacc[1], bacc[2], bacc[3]);
+        __syncthreads();
+
+        double accK[16], accM[16], bacc[4];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { accK[i] = 0.0; accM[i] = 0.0; }
+        bacc[0] = bacc[1] = bacc[2] = bacc[3] = 0.0;
+        const int cdof = s_slot[cslot], cd = s_sdir[cslot];
+
+        for (int chunk = 0; chunk < CFG::NCHUNK; ++chunk) {
+            // ---- phase C: one thread per (element, slot): bK = Q c_j | P dphi_j, W = phi_j T[:,d_j], RHS ----
+            if (tid < nb * MEP) {
+#pragma unroll 1
+                for (int gc = 0; gc < GCH; ++gc) {
+                    const int g = chunk * GCH + gc;
+                    const double *geo = s_geo + (cs * NGP + g) * GEO;
+                    const double *at = s_at + (size_t)g * NA * MEP + cpos;
+                    double *B = s_B + (size_t)(cs * GCH + gc) * NB * MEP + cpos;
+                    const double phi = at[KA * MEP];
+                    if (DO_KM) {
+                        if (!PML) {
+                            // c_j has its two non-zero components on the axes perpendicular to d_j
+                            const int m1 = cd == 0 ? 1 : 0, m2 = cd == 2 ? 1 : 2;
+                            const double c1 = at[0], c2 = at[MEP];
+                            const double *Q = geo + GQ;
+#pragma unroll
+                            for (int p = 0; p < 3; ++p) B[p * MEP] = dfma(Q[sym3(p, m1)], c1, Q[sym3(p, m2)] * c2);
+                        } else {
+                            const double dp[3] = {at[0], at[MEP], at[2 * MEP]};
+                            const double *P = geo + GQ;
+#pragma unroll
+                            for (int r = 0; r < 9; ++r) {          // r = (u,d)
+                                double acc = 0.0;
+#pragma unroll
+                                for (int v = 0; v < 3; ++v) {      // column (v, d_j)
+                                    const int c = v * 3 + cd;
+                                    const int lo = r < c ? r : c, hi = r < c ? c : r;
+                                    acc = dfma(P[up9(lo, hi)], dp[v], acc);
+                                }
+                                B[r * MEP] = acc;
+                            }
+                        }
+                        const double *Tt = geo + GT;
+#pragma unroll
+                        for (int d2 = 0; d2 < 3; ++d2) B[(KB + d2) * MEP] = phi * Tt[sym3(d2, cd)];
+                    }
+                    // blocal / f3, integration.f90:96-104,258-263
+                    const double *R = geo + GR + cd * 4;
+                    bacc[0] = dfma(phi, R[0], bacc[0]); bacc[1] = dfma(phi, R[1], bacc[1]);
+                    bacc[2] = dfma(phi, R[2], bacc[2]); bacc[3] = dfma(phi, R[3], bacc[3]);
+                }
+            }
+            if (!DO_KM) continue;
+            __syncthreads();
+
+            // ---- phase D: register-tiled lower-triangle contraction over this chunk ----
+            if (tid < nb * NTILES) {
+                const double *Bs = s_B + (size_t)ts * GCH * NB * MEP;
+                const int dI = s_sdir[4 * ti];                            // direction of this thread's row group
+                // bK rows paired with a-rows 0,1(,2): plain = the two axes perpendicular to d_i; GPML = (u, d_i)
+                const int r0 = PML ? dI : (dI == 0 ? 1 : 0);
+                const int r1 = PML ? 3 + dI : (dI == 2 ? 1 : 2);
+#pragma unroll 1
+                for (int gc = 0; gc < GCH; ++gc) {
+                    const double *Bg = Bs + gc * NB * MEP;
+                    const double *Ag = s_at + (size_t)(chunk * GCH + gc) * NA * MEP;
+#pragma unroll
+                    for (int k = 0; k < KA; ++k) {
+                        const int rb = k == 0 ? r0 : (k == 1 ? r1 : 6 + dI);
+                        const double2 a0 = *reinterpret_cast<const double2 *>(Ag + k * MEP + a_lo);
+                        const double2 a1 = *reinterpret_cast<const double2 *>(Ag + k * MEP + a_hi);
+                        const double2 b0 = *reinterpret_cast<const double2 *>(Bg + rb * MEP + b_lo);
+                        const double2 b1 = *reinterpret_cast<const double2 *>(Bg + rb * MEP + b_hi);
+                        const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) accK[i * 4 + j] = dfma(av[i], bv[j], accK[i * 4 + j]);
+                    }
+                    {
+                        const double2 a0 = *reinterpret_cast<const double2 *>(Ag + KA * MEP + a_lo);          // phi_i
+                        const double2 a1 = *reinterpret_cast<const double2 *>(Ag + KA * MEP + a_hi);
+                        const double2 b0 = *reinterpret_cast<const double2 *>(Bg + (KB + dI) * MEP + b_lo);   // W_j[d_i]
+                        const double2 b1 = *reinterpret_cast<const double2 *>(Bg + (KB + dI) * MEP + b_hi);
+                        const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) accM[i * 4 + j] = dfma(av[i], bv[j], accM[i * 4 + j]);
+                    }
+                }
+            }
+            if (chunk + 1 < CFG::NCHUNK) __syncthreads();
+        }
+
+        // ---- write-out: element-major, packed lower triangle by LOCAL DOF index ----
+        if (DO_KM && tid < nb * NTILES) {
+            const int64_t e = s_el[ts * 4];
+            double *Ko = A.Ke + e * NP, *Mo = A.Me + e * NP;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int si = 4 * ti + i, im = s_slot[si];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int sj = 4 * tj + j, jm = s_slot[sj];
+                    if (im >= 0 && jm >= 0 && sj <= si) {
+                        const int hi = im > jm ? im : jm, lo = im > jm ? jm : im;
+                        const int p = hi * (hi + 1) / 2 + lo;
+                        Ko[p] = accK[i * 4 + j]; Mo[p] = accM[i * 4 + j];
+                    }
+                }
+            }
+        }
+        if (tid < nb * MEP && cdof >= 0) {
+            const int64_t e = s_el[cs * 4];
+            reinterpret_cast<double4 *>(A.be)[e * ME + cdof] = make_double4(bacc[0], bacc[1], bacc[2], bacc[3]);
+        }
     }
 }
 
