@@ -1,0 +1,100 @@
+"""CPU tests: the C-ABI library loads and exports what include/movfem_b200.h declares; host-side logic."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from movfem_b200 import abi, host, mesh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    txt = open(os.path.join(ROOT, "include", "movfem_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(movfem_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(host.build())
+    names = _header_functions()
+    assert "movfem_create" in names and "movfem_assemble" in names and len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/movfem_b200.h but not exported"
+    assert set(host.EXPORTED_SYMBOLS) <= set(names)
+    assert b"sm_100a" in host.lib().movfem_version()
+
+
+def test_desc_layout_matches_header():
+    """ctypes mirror vs the C struct: field order from the header, size from the compiler's rules."""
+    txt = open(os.path.join(ROOT, "include", "movfem_b200.h")).read()
+    body = re.search(r"typedef struct movfem_desc \{(.*?)\} movfem_desc;", txt, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.replace("const double *", "").replace("int32_t", "").replace("double", "").split(",")
+        fields += [n.strip().lstrip("*") for n in names]
+    assert fields == [f for f, _ in abi.MovfemDesc._fields_]
+    assert C.sizeof(abi.MovfemDesc) == 14 * 4 + 3 * 8 + 4 * 8 + 2 * 4
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(host.MovfemError) as ei:
+        host.Assembly(mesh.config(1, scale=0.2))
+    assert ei.value.code == abi.MOVFEM_E_NOGPU
+
+
+def test_bad_descriptors_are_rejected_before_touching_cuda():
+    m = mesh.config(1, scale=0.2)
+    d = m.desc()
+    h = C.c_void_p()
+    d.me = 13
+    assert host.lib().movfem_create(C.byref(d), 0, C.byref(h)) == abi.MOVFEM_E_BADARG
+    d = m.desc(); d.bd_inimod = 2; d.dirichlet = 1
+    assert host.lib().movfem_create(C.byref(d), 0, C.byref(h)) == abi.MOVFEM_E_UNSUPPORTED
+    assert host.lib().movfem_create(None, 0, C.byref(h)) == abi.MOVFEM_E_BADARG
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under movfem_b200/ may import, link or call it."""
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|liboracle|oracle_[a-z]+\s*\(|#include\s+\"[^\"]*oracle", re.M)
+    for dp, _, files in os.walk(os.path.join(ROOT, "movfem_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".f90")) or f == "Makefile":
+                s = open(os.path.join(dp, f), errors="ignore").read()
+                assert not pat.search(s), f
+
+
+def test_config_sizes_match_survey():
+    for n, (nx, ny, nz, mn) in {1: (58, 58, 43, 8), 2: (40, 40, 30, 20), 3: (24, 24, 18, 27), 4: (100, 100, 60, 8)}.items():
+        m = mesh.config(n)
+        assert (m.g_nx - 1, m.g_ny - 1, m.g_nz - 1, m.mn) == (nx, ny, nz, mn)
+        assert m.g_zp.size == m.g_xp.size * m.g_yp.size * ((m.g_nz - 1) * (m.nord - 1) + 1)
+    m = mesh.config(1)
+    dx = np.diff(m.g_xp)
+    np.testing.assert_allclose(dx[:4], 1.3 * 1990 * np.array([4, 3, 2, 1]))     # geometry.f90:268-317
+    np.testing.assert_allclose(dx[4:-4], 1990.0)
+    assert mesh.config(4).freqs.size == 32
+
+
+def test_update_sigma_reproduces_q12():
+    """geometry.f90:144-153 indexes g_sigma(i,j), i<=npt, j<=6 on a (6,npt) array: only the first npt+30
+    linear entries are refreshed; real parts never change."""
+    m = mesh.config(4, scale=0.12)
+    s1, s5 = m.sigma_for(1), m.sigma_for(5)
+    assert np.array_equal(s1.real, s5.real)
+    flat1, flat5 = s1.reshape(-1), s5.reshape(-1)
+    n = m.npt + 30
+    changed = np.flatnonzero(flat1.imag != flat5.imag)
+    assert changed.size > 0 and changed.max() < n
+    w5 = np.float64(np.float32(mesh.EPS0 * m.omega(5)))
+    assert np.all(flat5.imag[:n][flat5.imag[:n] != 0] == w5)
+    assert np.all(flat5.imag[n:][flat5.imag[n:] != 0] == np.float64(np.float32(mesh.EPS0 * m.omega(1))))

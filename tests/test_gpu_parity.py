@@ -1,0 +1,201 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars (north_star / SURVEY 8c): gne, nne, nnze and the structural pattern bit-exact; matrix (tap T1) and RHS
+values <= 1e-12 normwise relative in complex128; tap T2 (what ZMUMPS receives) has identical IRN/JCN/nz and
+float32 values equal up to the rounding flips a 1e-16 double difference can cause on noise-level entries.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from movfem_b200 import abi, host, mesh
+from oracle.oracle import Oracle
+from parity_util import compare_assembly, rel_err
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+TOL = 1e-12
+
+
+def _check(r, allow_noise_pattern=False):
+    assert r["nne"][0] == r["nne"][1] and r["nnze"][0] == r["nnze"][1] and r["nz_upper"][0] == r["nz_upper"][1], r
+    assert r["pattern_equal"], r
+    assert r["t1_idx_equal"] and r["t1_rel"] <= TOL and r["rhs_rel"] <= TOL, r
+    if r["t2_idx_equal"]:
+        assert r["t2_rel"] <= TOL, r
+    else:   # entries present on one side only must be numerical noise (exact-zero set)
+        assert allow_noise_pattern, r
+        assert r["t2_only_graft"][1] <= TOL and r["t2_only_oracle"][1] <= TOL and r["t2_rel"] <= 1e-6, r
+    assert r["rhs_rel_t2"] <= TOL
+
+
+def _small(mn, dirichlet, sch, **kw):
+    return mesh.build_model(f"small_mn{mn}", 6, 5, mn, 1000., 1100., 900., 2, 2, 1, dirichlet=dirichlet, gpml_sch=sch, freqs=(0.5, 3.0),
+                            sigma_fn=mesh._layered((1500., 1500., 500., 1500.)), topo_amp=50.0, **kw)
+
+
+def test_device_tables_bitwise_equal_oracle():
+    """The product's reference-element tables (N, dN, phi, dphi, Gauss points incl. float32 literals and the
+    n_fem.f90:193 typo) carry the same bits as the oracle's independent copy."""
+    for mn in (8, 20, 27):
+        m = _small(mn, 0, 1)
+        asm, o = host.Assembly(m), Oracle(m)
+        a, b = asm.debug_tables(), o.tables()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (mn, k)
+        asm.close()
+
+
+@pytest.mark.parametrize("mn", [8, 20, 27])
+@pytest.mark.parametrize("dirichlet,sch", [(1, 1), (0, 0), (0, 1)])
+def test_parity_small(mn, dirichlet, sch):
+    m = _small(mn, dirichlet, sch)
+    asm, o = host.Assembly(m), Oracle(m)
+    assert np.array_equal(asm.gne(), o.gne())
+    _check(compare_assembly(asm, o, m, ifreq=1, faithful=(mn == 8)))
+    # second frequency of the sequential loop: Q12 (partial sigma update), Q17 (element 1 sees stale flags),
+    # cached K_e/M_e of the unstretched elements
+    _check(compare_assembly(asm, o, m, ifreq=2))
+    asm.close()
+
+
+def test_parity_anisotropic_sigma_and_mu():
+    """config 3 (full 6-component sigma) plus a non-trivial permeability: exercises the curl part of the
+    secondary source (problem.f90:362-420), which vanishes for mu = mu0."""
+    m = mesh.config(3, scale=0.3)
+    rng = np.random.default_rng(7)
+    mur = 1.0 + 0.5 * rng.random(m.npt)
+    m.g_mu[:, [0, 3, 5]] = mesh.MU0 * mur[:, None]
+    m.g_mu[:, 1] = 0.05 * mesh.MU0 * rng.standard_normal(m.npt)
+    asm, o = host.Assembly(m), Oracle(m)
+    _check(compare_assembly(asm, o, m))
+    asm.close()
+
+
+@pytest.mark.parametrize("name", ["small_mn8_gpml_zhou", "small_mn8_dirichlet", "small_mn20_gpml_fang", "small_mn27_gpml_zhou"])
+def test_golden_fixtures(name):
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden
+    m = make_golden.make_model(**make_golden.CASES[name])
+    ref = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    asm = host.Assembly(m)
+    assert np.array_equal(asm.gne(), ref["gne"]) and asm.nne == int(ref["nne"]) and asm.nnze == int(ref["nnze"])
+    for ifreq in (1, 2):
+        irn, jcn, a, rhs, nz = asm.global_vfem(ifreq, m.omega(ifreq), m.sigma_for(ifreq))
+        assert nz == ref[f"a{ifreq}"].size
+        assert np.array_equal(irn[:nz], ref[f"irn{ifreq}"]) and np.array_equal(jcn[:nz], ref[f"jcn{ifreq}"])
+        assert rel_err(a[:nz], ref[f"a{ifreq}"]) <= TOL and rel_err(rhs, ref[f"rhs{ifreq}"]) <= TOL
+    asm.close()
+
+
+@pytest.mark.parametrize("dirichlet", [0, 1])
+def test_config1_full_size(dirichlet):
+    """BASELINE configs[0]: the shipped 58x58x43 example, GPML as shipped and Dirichlet."""
+    m = mesh.config(1, dirichlet=dirichlet)
+    asm, o = host.Assembly(m), Oracle(m)
+    assert (asm.nne, asm.nnze) == ((450819, 14437635) if not dirichlet else (417411, 13355403))
+    assert np.array_equal(asm.gne(), o.gne())
+    _check(compare_assembly(asm, o, m))
+    asm.close()
+
+
+@pytest.mark.parametrize("n,scale", [(2, 0.3), (3, 0.35), (5, 0.1)])
+def test_configs_scaled(n, scale):
+    """configs 2, 3 and 5 (topography, exercises Q5) on sub-meshes the oracle finishes in seconds."""
+    m = mesh.config(n, scale=scale)
+    asm, o = host.Assembly(m), Oracle(m)
+    _check(compare_assembly(asm, o, m), allow_noise_pattern=True)
+    asm.close()
+
+
+def test_config4_sweep_cached_equals_cold_and_oracle():
+    """Frequency sweep on a reduced config 4: K_e/M_e cached across frequencies give the same bits
+    as a cold assembly, and every frequency matches the oracle's sequential loop."""
+    m = mesh.config(4, scale=0.12)
+    asm, o = host.Assembly(m), Oracle(m)
+    for ifreq in (1, 2, 17, 32):
+        om, sg = m.omega(ifreq), m.sigma_for(ifreq)
+        warm = asm.global_vfem(ifreq, om, sg)
+        asm.reset_cache()
+        cold = asm.global_vfem(ifreq, om, sg)
+        nz = warm[4]
+        assert nz == cold[4]
+        for k in range(3):
+            assert np.array_equal(warm[k][:nz], cold[k][:nz])
+        assert np.array_equal(warm[3], cold[3])
+        if ifreq > 1:
+            o.set_in_pml((1, 1, 1))          # state the sequential loop would have left behind (Q17)
+        r = o.assemble(om, sg)
+        assert nz == r["nz"] and np.array_equal(warm[0][:nz], r["irn"]) and np.array_equal(warm[1][:nz], r["jcn"])
+        assert rel_err(warm[2][:nz], r["a"]) <= TOL and rel_err(warm[3], r["rhs"]) <= TOL
+    asm.close()
+
+
+def test_full_size_properties_config2():
+    """BASELINE configs[1] at full size (48000 20-node elements), through size-independent properties:
+    determinism (bit-identical reruns), T2 == float32 round trip of T1 minus exact zeros, sorted upper
+    triangle, nz == (nnze+nne)/2 when nothing is stripped, K/M cache idempotence."""
+    m = mesh.config(2)
+    asm = host.Assembly(m)
+    om, sg = m.omega(1), m.sigma_for(1)
+    i1, j1, a1, b1, n1 = [x.copy() if isinstance(x, np.ndarray) else x for x in asm.global_vfem(1, om, sg, mode=abi.MODE_T1)]
+    i2, j2, a2, b2, n2 = asm.global_vfem(1, om, sg, mode=abi.MODE_T2)            # cached K/M
+    asm.reset_cache()
+    i3, j3, a3, b3, n3 = [x.copy() if isinstance(x, np.ndarray) else x for x in asm.global_vfem(1, om, sg, mode=abi.MODE_T2)]
+    assert n1 == asm.nz_upper == (asm.nnze + asm.nne) // 2
+    assert n2 == n3 and np.array_equal(a2[:n2], a3[:n3]) and np.array_equal(b2, b3)
+    r32 = a1.real.astype(np.float32).astype(np.float64) + 1j * a1.imag.astype(np.float32).astype(np.float64)
+    keep = r32 != 0
+    assert n2 == int(keep.sum()) and np.array_equal(a2[:n2], r32[keep])
+    assert np.array_equal(i2[:n2], i1[keep]) and np.array_equal(j2[:n2], j1[keep])
+    key = i1.astype(np.int64) * (asm.nne + 1) + j1
+    assert np.all(np.diff(key) > 0) and np.all(i1 <= j1) and i1.min() == 1 and j1.max() == asm.nne
+    assert np.all(np.isfinite(a1.view(np.float64))) and np.all(np.isfinite(b1.view(np.float64)))
+    asm.close()
+
+
+def test_error_codes_replace_stops():
+    m = _small(8, 1, 1)
+    asm = host.Assembly(m)
+    sg = m.sigma_for(1)
+    bad = sg.copy(); bad[5, :] = 0                      # singular sigma tensor: problem.f90:260-265 'stop'
+    with pytest.raises(host.MovfemError) as ei:
+        asm.global_vfem(1, m.omega(1), bad)
+    assert ei.value.code == abi.MOVFEM_E_SINGULAR_MODEL
+    irn, jcn, a, rhs, nz = asm.global_vfem(1, m.omega(1), sg)      # the handle stays usable
+    assert nz == asm.nz_upper
+    with pytest.raises(host.MovfemError) as ei:
+        asm.global_vfem(1, m.omega(1), sg, irn=np.zeros(3, np.int32))
+    assert ei.value.code == abi.MOVFEM_E_CAPACITY
+    asm.close()
+    m2 = _small(8, 1, 1)
+    m2.g_zp[:] = 0.0                                    # flat mesh: det J = 0 -> n_fem.f90:374-377 'stop'
+    asm = host.Assembly(m2)
+    with pytest.raises(host.MovfemError) as ei:
+        asm.global_vfem(1, m2.omega(1), m2.sigma_for(1))
+    assert ei.value.code == abi.MOVFEM_E_SINGULAR_JAC
+    asm.close()
+
+
+def test_device_resident_api():
+    import torch
+    m = _small(20, 0, 0)
+    asm = host.Assembly(m)
+    stream = torch.cuda.Stream()
+    asm.set_stream(stream.cuda_stream)
+    sg = m.sigma_for(1)
+    d_sigma = torch.from_numpy(sg.view(np.float64).reshape(-1).copy()).cuda()
+    asm.assemble_device(1, m.omega(1), d_sigma.data_ptr(), abi.MODE_T2)
+    p_irn, p_jcn, p_a, p_rhs, nz = asm.device_result()
+    irn, jcn, a, rhs, nz2 = asm.global_vfem(1, m.omega(1), sg)
+    assert nz == nz2 and p_a and p_rhs
+    import ctypes
+    buf = np.empty(nz, np.complex128)
+    torch.cuda.synchronize()
+    rt = ctypes.CDLL("/usr/local/cuda/lib64/libcudart.so")
+    rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    rc = rt.cudaMemcpy(buf.ctypes.data, p_a, nz * 16, 2)
+    assert int(rc) == 0 and np.array_equal(buf, a[:nz])
+    asm.close()
