@@ -8,11 +8,12 @@ namespace movfem {
 // ---------------------------------------------------------------------------------------------
 // Arithmetic policy.  The library is compiled with -fmad=false: every `a*b+c` written with plain
 // operators is an IEEE multiply followed by an IEEE add, exactly like the reference built with
-// `gfortran -O` on x86-64.  Geometry, basis and material interpolation are written that way, in
-// the reference's evaluation order, so the per-Gauss-point B-matrices carry the reference's
-// bits.  Fused multiply-adds are used only where they are asked for explicitly (dfma below):
-// the D*B products, the B^T(DB) contractions and the RHS -- the FP64-throughput-critical part,
-// which agrees with the reference to rounding (<= 1e-12 relative, north_star).
+// `gfortran -O` on x86-64.  The Jacobian, its inverse, det, the quadrature weight and the GPML
+// coordinate are written that way, in the reference's evaluation order, so they carry the
+// reference's bits (and with them its exact zeros and round-off residues, which decide what
+// rem_zeros strips).  Fused multiply-adds are used only where asked for explicitly (dfma below):
+// material interpolation, the per-Gauss-point tensors, the contractions and the RHS -- the
+// FP64-throughput-critical part, which agrees with the reference to rounding (<= 1e-12, north_star).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
 

@@ -1,0 +1,145 @@
+! movfem_cuda.f90 -- ISO_C_BINDING shim: calls libmovfem_b200.so from MoVFEM_3DMT.f90.
+!
+! NOT compiled in this repository's environment (no Fortran compiler in the image); it is the binding a
+! maintainer adds to MoVFEM_3DMT/src and lists in the Makefile.  Every interface below is the Fortran view
+! of one prototype in include/movfem_b200.h.  See INTEGRATION.md for the three edits to MoVFEM_3DMT.f90.
+!
+! It replaces, on rank 0 only (MoVFEM_3DMT.f90:63):
+!   ga_init -> ga_cgne / ga_nzindx                      (global_assembly.f90:38-39)   by movfem_cuda_init
+!   global_vfem + find_zeros / rem_zeros                (MoVFEM_3DMT.f90:82-97)       by movfem_cuda_assemble
+module movfem_cuda
+    use, intrinsic :: iso_c_binding
+    use kind_param
+    implicit none
+    private
+    public :: movfem_cuda_init, movfem_cuda_assemble, movfem_cuda_finalize, movfem_nz_upper
+
+    ! struct movfem_desc of include/movfem_b200.h, field for field
+    type, bind(C) :: movfem_desc
+        integer(c_int32_t) :: g_nx, g_ny, g_nz, nord, mn, me, nextd, nzl_top
+        integer(c_int32_t) :: dirichlet, bd_inimod, gpml_sch, sym, ndir, pe_sch
+        real(c_double)     :: a0, b0, nn
+        type(c_ptr)        :: g_xp, g_yp, g_zp, g_mu
+        integer(c_int32_t) :: ie_lo, ie_hi
+    end type movfem_desc
+
+    type(c_ptr), save          :: handle = c_null_ptr
+    integer(c_int64_t), save   :: movfem_nz_upper = 0     ! capacity irn/jcn/a need (<= nnze)
+    integer(c_int32_t), parameter :: MODE_T2 = 0
+
+    interface
+        integer(c_int) function movfem_create(desc, device, h) bind(C, name='movfem_create')
+            import :: c_int, c_ptr, movfem_desc
+            type(movfem_desc), intent(in) :: desc
+            integer(c_int), value         :: device
+            type(c_ptr), intent(out)      :: h
+        end function
+        subroutine movfem_destroy(h) bind(C, name='movfem_destroy')
+            import :: c_ptr
+            type(c_ptr), value :: h
+        end subroutine
+        integer(c_int) function movfem_sizes(h, nne, nnze_full, nz_upper) bind(C, name='movfem_sizes')
+            import :: c_int, c_ptr, c_int32_t, c_int64_t
+            type(c_ptr), value              :: h
+            integer(c_int32_t), intent(out) :: nne
+            integer(c_int64_t), intent(out) :: nnze_full, nz_upper
+        end function
+        integer(c_int) function movfem_get_gne(h, gne) bind(C, name='movfem_get_gne')
+            import :: c_int, c_ptr, c_int32_t
+            type(c_ptr), value                :: h
+            integer(c_int32_t), intent(out)   :: gne(*)          ! gne(ne,me), column-major as in Fortran
+        end function
+        integer(c_int) function movfem_assemble(h, freq_index, omega, g_sigma, irn, jcn, a, rhs, nz_out, mode) &
+                bind(C, name='movfem_assemble')
+            import :: c_int, c_ptr, c_int32_t, c_int64_t, c_double, c_double_complex
+            type(c_ptr), value                         :: h
+            integer(c_int32_t), value                  :: freq_index
+            real(c_double), value                      :: omega
+            complex(c_double_complex), intent(in)      :: g_sigma(*)   ! (6,g_npt)
+            integer(c_int32_t), intent(out)            :: irn(*), jcn(*)
+            complex(c_double_complex), intent(out)     :: a(*), rhs(*)
+            integer(c_int64_t), intent(out)            :: nz_out
+            integer(c_int32_t), value                  :: mode
+        end function
+        function movfem_last_error(h) bind(C, name='movfem_last_error') result(msg)
+            import :: c_ptr
+            type(c_ptr), value :: h
+            type(c_ptr)        :: msg
+        end function
+    end interface
+
+contains
+
+    ! Called from ga_init (global_assembly.f90:26) in place of ga_cgne / ga_nzindx.  Fills the module
+    ! variables the rest of the program consumes: nne, nnze (MoVFEM_3DMT.f90:72-78), gne (solution.f90:331-336).
+    subroutine movfem_cuda_init()
+        use geometry, only: g_nx, g_ny, g_nz, g_nordx, nextd, g_nsf, g_nzl, g_xp, g_yp, g_zp, g_mu
+        use n_fem, only: nf_mn
+        use v_fem, only: vf_me
+        use problem, only: ndir, pe_sch
+        use boundary_conds, only: dirichlet, bd_inimod, gpml_sch, a0, b0, nn
+        use global_assembly, only: nne, nnze, gne, sym
+        type(movfem_desc) :: d
+        integer(c_int) :: rc
+        integer(c_int32_t) :: nne_c
+        integer(c_int64_t) :: nnze_c
+        d%g_nx = g_nx; d%g_ny = g_ny; d%g_nz = g_nz; d%nord = g_nordx
+        d%mn = nf_mn; d%me = vf_me; d%nextd = nextd; d%nzl_top = g_nzl(g_nsf)
+        d%dirichlet = merge(1, 0, dirichlet); d%bd_inimod = bd_inimod; d%gpml_sch = gpml_sch
+        d%sym = merge(1, 0, sym); d%ndir = ndir; d%pe_sch = pe_sch
+        d%a0 = a0; d%b0 = b0; d%nn = nn
+        d%g_xp = c_loc(g_xp); d%g_yp = c_loc(g_yp); d%g_zp = c_loc(g_zp); d%g_mu = c_loc(g_mu)   ! arrays need TARGET
+        d%ie_lo = 0; d%ie_hi = 0
+        rc = movfem_create(d, 0_c_int, handle)
+        if (rc /= 0) call die('movfem_create', rc)
+        rc = movfem_sizes(handle, nne_c, nnze_c, movfem_nz_upper)
+        if (rc /= 0) call die('movfem_sizes', rc)
+        if (nnze_c > huge(nnze)) call die('nnze exceeds default integer (SURVEY Q16): size arrays with movfem_nz_upper', -6)
+        nne = nne_c; nnze = int(nnze_c)
+        allocate(gne((g_nx-1)*(g_ny-1)*(g_nz-1), vf_me))
+        rc = movfem_get_gne(handle, gne)
+        if (rc /= 0) call die('movfem_get_gne', rc)
+    end subroutine movfem_cuda_init
+
+    ! Replaces  call global_vfem(irn,jcn,a,rhs)  and the find_zeros/rem_zeros block (MoVFEM_3DMT.f90:82-97).
+    ! ii is the loop index of the frequency loop (MoVFEM_3DMT.f90:62); nz returns mumps_par%nz.
+    subroutine movfem_cuda_assemble(ii, irn, jcn, a, rhs, nz)
+        use geometry, only: omega, g_sigma
+        integer, intent(in)                          :: ii
+        integer, intent(inout)                       :: irn(*), jcn(*)
+        complex(kind=double), intent(inout)          :: a(*), rhs(*)
+        integer, intent(out)                         :: nz
+        integer(c_int64_t) :: nz_c
+        integer(c_int) :: rc
+        rc = movfem_assemble(handle, int(ii, c_int32_t), omega, g_sigma, irn, jcn, a, rhs, nz_c, MODE_T2)
+        if (rc /= 0) call die('movfem_assemble', rc)
+        nz = int(nz_c)
+    end subroutine movfem_cuda_assemble
+
+    subroutine movfem_cuda_finalize()
+        if (c_associated(handle)) call movfem_destroy(handle)
+        handle = c_null_ptr
+    end subroutine movfem_cuda_finalize
+
+    ! the reference stops on inconsistencies (global_assembly.f90:56-57, n_fem.f90:374-377, problem.f90:260-271)
+    subroutine die(what, rc)
+        character(*), intent(in) :: what
+        integer(c_int), intent(in) :: rc
+        character(kind=c_char), pointer :: s(:)
+        type(c_ptr) :: p
+        integer :: i
+        print *, trim(what), ' failed with code ', rc
+        if (c_associated(handle)) then
+            p = movfem_last_error(handle)
+            if (c_associated(p)) then
+                call c_f_pointer(p, s, [512])
+                do i = 1, 512
+                    if (s(i) == c_null_char) exit
+                    write(*, '(a)', advance='no') s(i)
+                end do
+                print *
+            end if
+        end if
+        stop
+    end subroutine die
+end module movfem_cuda

@@ -6,9 +6,9 @@
  * CHECKER and the timed CPU baseline.  It is never linked into, imported by or called from the
  * product (movfem_b200/): the product fails loudly when its CUDA library is missing.
  *
- * PARITY PIN STATUS: the reference ships no tests, golden vectors or sample outputs and no
- * Fortran compiler exists in this image, so the reference itself cannot be run.
- * This oracle is pinned to (i) the numeric element-matrix known answers of SURVEY App. B item 4
+ * PARITY PIN STATUS: **parity unpinned** by reference runs -- the reference ships no tests, golden
+ * vectors or sample outputs and no Fortran compiler exists in this image, so the
+ * reference itself cannot be run (no oracle/_ref).  What pins this oracle instead: (i) the numeric element-matrix known answers of SURVEY App. B item 4
  * (obtained by executing a mechanical translation of the reference's own shape tables),
  * (ii) the exact nne / nnze counts of SURVEY section 6 (emulated c_gne12 / ga_nzindx),
  * (iii) mathematical invariants (App. B items 3 and 5).  See tests/test_oracle_pins.py.
