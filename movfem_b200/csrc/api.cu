@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -26,16 +27,16 @@ using namespace movfem;
 namespace {
 
 // ---- kernel configurations (tuned on B200) -------------------------------------
-//                     MN  ME MEP NGP GCH EB THREADS MINB PML
+//                     MN  ME MEP NGP EB THREADS MINB PML
 // EB / THREADS are chosen so that every phase fills whole warps (idle lanes cost FP64-pipe time):
 //   me=12: 16 el -> 128 (el,gp) / 192 (el,slot) / 96 tiles     me=36: 4 el -> 108 / 144 / 180
 //   me=54:  2 el ->  54 / 120 / 240                            (GPML variants: smaller batches, more smem)
-using Cfg12  = ElemCfg<8, 12, 12, 8, 4, 16, 192, 3, false>;
-using Cfg12p = ElemCfg<8, 12, 12, 8, 2, 16, 192, 2, true>;
-using Cfg36  = ElemCfg<20, 36, 36, 27, 3, 4, 192, 3, false>;
-using Cfg36p = ElemCfg<20, 36, 36, 27, 3, 2, 96, 2, true>;
-using Cfg54  = ElemCfg<27, 54, 60, 27, 3, 2, 256, 2, false>;
-using Cfg54p = ElemCfg<27, 54, 60, 27, 3, 1, 128, 2, true>;
+using Cfg12  = ElemCfg<8, 12, 12, 8, 16, 192, 2, false>;
+using Cfg12p = ElemCfg<8, 12, 12, 8, 16, 192, 2, true>;
+using Cfg36  = ElemCfg<20, 36, 36, 27, 4, 192, 2, false>;
+using Cfg36p = ElemCfg<20, 36, 36, 27, 2, 96, 2, true>;
+using Cfg54  = ElemCfg<27, 54, 60, 27, 2, 256, 2, false>;
+using Cfg54p = ElemCfg<27, 54, 60, 27, 1, 128, 2, true>;
 
 enum { EV_START, EV_H2D, EV_NODE, EV_ELEM, EV_GATHER, EV_FINAL, EV_D2H, EV_COUNT };
 
@@ -47,6 +48,7 @@ struct movfem_handle {
     MeshDims m;
     PmlParams pml;
     int NP, ngp, num_sms;
+    double h_Ntab[kMaxGp * kMaxMn];   // N[g][l] packed with stride mn (kernel-parameter copy)
     int nne;
     int64_t nzu, ncontrib, nnze_full;
     cudaStream_t stream;
@@ -160,6 +162,11 @@ void build_tables(const movfem_desc &d, const MeshDims &m, ElemTables &T, ShareT
         while (ns % 4) { T.slot_dof[ns] = -1; T.slot_dir[ns] = dir; ++ns; }
     }
     T.nslots = ns;
+    for (int l = 0; l < d.mn; ++l)
+        for (int g = 0; g < m.ngp; ++g) {
+            for (int k = 0; k < 3; ++k) T.dNt[(l * 4 + k) * 32 + g] = T.dN[g][l][k];
+            T.dNt[(l * 4 + 3) * 32 + g] = T.N[g][l];
+        }
 
     // sharing tables: global_assembly.f90:242-265 (me=12), 310-351 (me=36), 396-443 (me=54);
     // the same lists are the Dirichlet face lists of boundary_conds.f90:276-388
@@ -391,6 +398,8 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
         build_tables(*d, m, T[0], S);
         CK(dmalloc(&h->d_tab, 1)); CK(dmalloc(&h->d_share, 1));
         CK(cudaMemcpy(h->d_tab, T.data(), sizeof(ElemTables), cudaMemcpyHostToDevice));
+        for (int g = 0; g < m.ngp; ++g)
+            for (int l = 0; l < m.mn; ++l) h->h_Ntab[g * m.mn + l] = T[0].N[g][l];
         CK(cudaMemcpy(h->d_share, &S, sizeof(ShareTables), cudaMemcpyHostToDevice));
     }
     init_pml(*d, m, h->pml);
@@ -497,6 +506,9 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
     A.m = m; A.pml = h->pml; A.omega = omega; A.T = h->d_tab; A.nodes = h->d_nodes; A.xp = h->d_xp; A.yp = h->d_yp;
     A.list = nullptr; A.nlist = 0; A.Ke = h->d_Ke; A.Me = h->d_Me; A.be = h->d_be; A.status = h->d_status; A.flags = h->d_flags;
     A.skip_unless_changed = 0;
+    A.phase_mask = 15;
+    std::memcpy(A.Ntab, h->h_Ntab, sizeof(A.Ntab));
+    if (const char *pm = getenv("MOVFEM_PHASE_MASK")) A.phase_mask = atoi(pm);   // profiling aid only
     int rc;
     const bool full = !h->km_valid;
     if (m.me == 12) rc = run_elements<Cfg12, Cfg12p>(h, A, full);

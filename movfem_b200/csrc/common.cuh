@@ -53,6 +53,7 @@ struct ElemTables {
     int slot_dof[kMaxSlots];                // slot -> local DOF (0-based) or -1
     int slot_dir[kMaxSlots];                // slot -> direction (0-based), defined for padding slots too
     int nslots;
+    double dNt[kMaxMn * 4 * 32];            // [l][4][32]: dN/dxi_m (m=0..2) and N (3) with the Gauss point fastest
 };
 
 // DOF sharing tables (global_assembly.f90:242-265,310-351,396-443) and Dirichlet face lists

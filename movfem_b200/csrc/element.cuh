@@ -104,30 +104,36 @@ struct ElemArgs {
     int *status;
     const int *flags;     // flags[0] any dmu, flags[1] Re sigma changed
     int skip_unless_changed;   // launch is a cache refresh: exit unless flags[1]
+    int phase_mask;            // profiling aid (MOVFEM_PHASE_MASK): bit0 B, bit1 C, bit2 D, bit3 write-out; default 15
+    // nodal shape functions at the Gauss points, N[g][l], in the kernel parameter = constant bank: the
+    // material interpolation reads them as uniform constant operands, costing no shared-memory bandwidth
+    double Ntab[kMaxGp * kMaxMn];
 };
 
-template <int MN_, int ME_, int MEP_, int NGP_, int GCH_, int EB_, int THREADS_, int MINB_, bool PML_>
+// columns interpolated to the Gauss points by phase B1 (record offsets into NodeRec, see common.cuh):
+//   0-5 mu^-1, 6-11 Re sigma, 12-14 e*Im(dsigma col 1), 15-17 e*Re(sigma col 1), 18-20 e*Im(dsigma col 2),
+//   21-23 e*Re(sigma col 2), [GPML only] 24-29 Im sigma
+__constant__ int kColOff[30] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 8, 9, 10, 15, 17, 18, 9, 11, 12, 14, 15, 16, 17, 18, 19};
+__constant__ int kColFlag[30] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 1, 1, 1, 1, 1, 1, 3, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0};   // bit0: times e, bit1: minus psig first
+
+template <int MN_, int ME_, int MEP_, int NGP_, int EB_, int THREADS_, int MINB_, bool PML_>
 struct ElemCfg {
-    static constexpr int MN = MN_, ME = ME_, MEP = MEP_, NGP = NGP_, GCH = GCH_, EB = EB_, THREADS = THREADS_, MINB = MINB_;
+    static constexpr int MN = MN_, ME = ME_, MEP = MEP_, NGP = NGP_, EB = EB_, THREADS = THREADS_, MINB = MINB_;
     static constexpr bool PML = PML_;
     static constexpr int NT = MEP / 4, NTILES = NT * (NT + 1) / 2;
     static constexpr int NP = ME * (ME + 1) / 2;
     static constexpr int KA = PML ? 3 : 2;                 // K operand components per (slot, Gauss point)
     static constexpr int NA = KA + 1;                      // a-table rows: K comps + phi
-    static constexpr int KB = PML ? 9 : 3;                 // bK components
-    static constexpr int NB = KB + 3;                      // B rows: bK + W[3]
     static constexpr int NDW = kNodeDoubles + 2;           // node record + x + y
     static constexpr int GEO = (PML ? 45 : 6) + 6 + 12 + (PML ? 1 : 0);   // P|Q, T, R  (kept even)
-    static constexpr int NCHUNK = NGP / GCH;
-    // shared memory: a-table [NGP][NA][MEP] | geometry [EB][NGP][GEO] |
-    //                union{ node records [EB][MN][NDW] (phases A,B), B chunk [EB][GCH][NB][MEP] (phases C,D) }
+    static constexpr int NCOL = PML ? 30 : 24;             // columns interpolated by phase B1 (<= GEO: stored in place)
+    // shared memory: a-table [NGP][NA][MEP] | geometry [EB][NGP][GEO] | node records [EB][MN][NDW]
     static constexpr size_t ATAB_D = (size_t)NGP * NA * MEP, GEO_D = (size_t)EB * NGP * GEO;
-    static constexpr size_t NODES_D = (size_t)EB * MN * NDW, BCH_D = (size_t)EB * GCH * NB * MEP;
-    static constexpr size_t UNION_D = NODES_D > BCH_D ? NODES_D : BCH_D;
-    static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + UNION_D) + sizeof(int) * (EB * 4 + 2 * MEP);
-    static_assert(NGP % GCH == 0, "chunking");
+    static constexpr size_t NODES_D = (size_t)EB * MN * NDW;
+    static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + NODES_D) + sizeof(int) * (EB * 4 + 2 * MEP);
     static_assert(MEP % 4 == 0 && (ATAB_D % 2) == 0 && (GEO_D % 2) == 0, "16-byte alignment of the smem regions");
     static_assert(THREADS >= EB * NTILES && THREADS >= EB * MEP, "one tile / one slot per thread");
+    static_assert(NCOL <= GEO, "interpolated columns are overwritten in place by the geometry record");
 };
 
 // B / a-table rows are stored with the two 16-byte halves of every 4-slot group swapped in alternate
@@ -182,8 +188,8 @@ __host__ __device__ __forceinline__ constexpr int up9(int r, int c) { return r *
 
 template <class CFG, bool DO_KM>
 __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemArgs A) {
-    constexpr int MN = CFG::MN, ME = CFG::ME, MEP = CFG::MEP, GCH = CFG::GCH, EB = CFG::EB, NGP = CFG::NGP;
-    constexpr int NA = CFG::NA, NB = CFG::NB, KA = CFG::KA, KB = CFG::KB;
+    constexpr int MN = CFG::MN, ME = CFG::ME, MEP = CFG::MEP, EB = CFG::EB, NGP = CFG::NGP;
+    constexpr int NA = CFG::NA, KA = CFG::KA;
     constexpr int GEO = CFG::GEO, NDW = CFG::NDW, NTILES = CFG::NTILES, NP = CFG::NP;
     constexpr bool PML = CFG::PML;
     constexpr int GQ = 0, GT = PML ? 45 : 6, GR = GT + 6;   // offsets inside one geometry record
@@ -192,11 +198,11 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_at = reinterpret_cast<double *>(smem_raw);              // [NGP][NA][MEP] constant operand (swizzled rows)
     double *s_geo = s_at + CFG::ATAB_D;                               // [EB][NGP][GEO]
-    double *s_nodes = s_geo + CFG::GEO_D;                             // [EB][MN][NDW]   (dead after phase B)
-    double *s_B = s_nodes;                                            // [EB][GCH][NB][MEP] (swizzled rows), aliases s_nodes
-    int *s_el = reinterpret_cast<int *>(s_nodes + CFG::UNION_D);      // [EB][4]: element id, GPML flags
+    double *s_nodes = s_geo + CFG::GEO_D;                             // [EB][MN][NDW]
+    int *s_el = reinterpret_cast<int *>(s_nodes + CFG::NODES_D);      // [EB][4]: element id, GPML flags
     int *s_slot = s_el + EB * 4;                                      // [MEP] slot -> local DOF (0-based) or -1
     int *s_sdir = s_slot + MEP;                                       // [MEP] slot -> direction (0-based)
+    const double *__restrict__ g_dN = A.T->dNt;                       // [MN][4][32]: dN/dxi (0..2), N (3); Gauss point fastest (L1)
 
     const ElemTables &T = *A.T;
     const MeshDims &m = A.m;
@@ -237,10 +243,31 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
     const int cs = tid / MEP, cslot = tid % MEP, cpos = swz(cslot);
 
     const int nbatch = (A.nlist + EB - 1) / EB;
+    // asynchronous gather of one batch's node records into s_nodes (16-byte cp.async pieces, coalesced per record)
+    auto request_nodes = [&](int b) {
+        const int first = b * EB, nb = min(EB, A.nlist - first);
+        const int g1 = m.nord - 1;
+        for (int i = tid; i < nb * MN * (kNodeDoubles / 2 + 1); i += CFG::THREADS) {
+            const int part = i % (kNodeDoubles / 2 + 1), sl = i / (kNodeDoubles / 2 + 1);
+            const int l = sl % MN, s = sl / MN;
+            const int e = A.list[first + s];
+            int ie, je, ke;
+            elem_ijk(m, e, ie, je, ke);
+            double2 *dst = reinterpret_cast<double2 *>(s_nodes + (s * MN + l) * NDW) + part;
+            if (part < kNodeDoubles / 2) {
+                const int64_t id = (int64_t)(ie - 1) * g1 * m.nyz + (int64_t)(je - 1) * g1 * m.nnz + (ke - 1) * g1 + T.node_off[l];
+                const double2 *src = reinterpret_cast<const double2 *>(A.nodes + id) + part;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+            } else {
+                *dst = make_double2(A.xp[(ie - 1) * g1 + T.node_i[l]], A.yp[(je - 1) * g1 + T.node_j[l]]);
+            }
+        }
+    };
+    if ((int)blockIdx.x < nbatch) request_nodes(blockIdx.x);
     for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
         const int first = batch * EB;
         const int nb = min(EB, A.nlist - first);
-        __syncthreads();   // previous batch fully consumed (s_B / s_geo / s_el reuse); also publishes the tables
+        __syncthreads();   // previous batch fully consumed (s_geo / s_el reuse); also publishes the tables
         if (tid < EB) {
             const int e = tid < nb ? A.list[first + tid] : -1;
             s_el[tid * 4] = e;
@@ -248,31 +275,62 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
             if (PML && e >= 0) effective_pml(m, A.pml, e, f);
             s_el[tid * 4 + 1] = f[0]; s_el[tid * 4 + 2] = f[1]; s_el[tid * 4 + 3] = f[2];
         }
+
+        // ---- phase A: the node records of this batch were requested with cp.async while the previous batch was in
+        //      its contraction (s_nodes is dead after phase B2); wait for them here ----
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
 
-        // ---- phase A: gather the element's node records (16-byte pieces, coalesced per record) ----
-        for (int i = tid; i < nb * MN * (kNodeDoubles / 2 + 1); i += CFG::THREADS) {
-            const int part = i % (kNodeDoubles / 2 + 1), sl = i / (kNodeDoubles / 2 + 1);
-            const int l = sl % MN, s = sl / MN;
-            const int e = s_el[s * 4];
-            int ie, je, ke;
-            elem_ijk(m, e, ie, je, ke);
-            const int g1 = m.nord - 1;
-            double2 *dst = reinterpret_cast<double2 *>(s_nodes + (s * MN + l) * NDW);
-            if (part < kNodeDoubles / 2) {
-                const int64_t id = (int64_t)(ie - 1) * g1 * m.nyz + (int64_t)(je - 1) * g1 * m.nnz + (ke - 1) * g1 + T.node_off[l];
-                dst[part] = reinterpret_cast<const double2 *>(A.nodes + id)[part];
-            } else {
-                dst[part] = make_double2(A.xp[(ie - 1) * g1 + T.node_i[l]], A.yp[(je - 1) * g1 + T.node_j[l]]);
-            }
+        // ---- phase B1: one thread per (element, column): interpolate node data to the Gauss points ----
+        // (p_intmodels problem.f90:139-142 and the N_l-weighted part of p_source problem.f90:424-457).  The
+        // thread keeps its column of the MN node records in registers; N[g][l] comes from the constant bank.
+        if (A.phase_mask & 1) {
+            const double psig = f32r(A.omega * kEps0);   // pset_pmodel, problem.f90:250
+            // warp w handles Gauss-point range `part` of (element, column) pairs (w % PW)*32 + lane, so that the
+            // range is warp-uniform and N[g][l] is an immediate constant-bank operand of the fully unrolled FMAs
+            constexpr int NW = CFG::THREADS / 32, PW = (EB * CFG::NCOL + 31) / 32;
+            constexpr int GS = PW >= NW ? 1 : (NW / PW >= 4 ? 4 : (NW / PW >= 2 ? 2 : 1));
+            const int wid = tid >> 5, lane = tid & 31;
+            const int part = GS == 1 ? 0 : wid / PW;
+            const int stride = GS == 1 ? CFG::THREADS : PW * 32;
+            if (part < GS)
+                for (int it = GS == 1 ? tid : (wid % PW) * 32 + lane; it < nb * CFG::NCOL; it += stride) {
+                    const int s = it / CFG::NCOL, c = it % CFG::NCOL;
+                    const double *nd = s_nodes + s * MN * NDW;
+                    const int off = kColOff[c], flag = kColFlag[c];
+                    double v[MN];
+#pragma unroll
+                    for (int l = 0; l < MN; ++l) {
+                        double x = nd[l * NDW + off];
+                        if (flag & 2) x = x - psig;              // Im(dsigma) on the diagonal (pdelta_model)
+                        if (flag & 1) x = x * nd[l * NDW + 1];   // times e_l = f32(omega b0 z_l): |Ep| at the node
+                        v[l] = x;
+                    }
+                    double *out = s_geo + (size_t)s * NGP * GEO + c;
+#define MOVFEM_B1_RANGE(G0, G1)                                                              \
+    _Pragma("unroll") for (int g = (G0); g < (G1); ++g) {                                    \
+        double acc = 0.0;                                                                    \
+        _Pragma("unroll") for (int l = 0; l < MN; ++l) acc = dfma(A.Ntab[g * MN + l], v[l], acc); \
+        out[g * GEO] = acc;                                                                  \
+    }
+                    if constexpr (GS == 1) { MOVFEM_B1_RANGE(0, NGP) }
+                    else if constexpr (GS == 2) {
+                        if (part == 0) { MOVFEM_B1_RANGE(0, NGP / 2) } else { MOVFEM_B1_RANGE(NGP / 2, NGP) }
+                    } else {
+                        if (part == 0) { MOVFEM_B1_RANGE(0, NGP / 4) }
+                        else if (part == 1) { MOVFEM_B1_RANGE(NGP / 4, NGP / 2) }
+                        else if (part == 2) { MOVFEM_B1_RANGE(NGP / 2, 3 * NGP / 4) }
+                        else { MOVFEM_B1_RANGE(3 * NGP / 4, NGP) }
+                    }
+#undef MOVFEM_B1_RANGE
+                }
         }
         __syncthreads();
 
-        // ---- phase B: one thread per (element, Gauss point): J, G, materials, GPML, source -> Q|P, T, R ----
-        {
+        // ---- phase B2: one thread per (element, Gauss point): J, G, GPML, source -> Q|P, T, R (in place) ----
+        if (A.phase_mask & 1) {
             const int has_dmu = A.flags[0];
             const double w32 = f32r(A.omega);            // cmplx(0.d0,-omega), problem.f90:112
-            const double psig = f32r(A.omega * kEps0);   // pset_pmodel, problem.f90:250
             for (int i = tid; i < nb * NGP; i += CFG::THREADS) {
                 const int s = i / NGP, g = i % NGP;
                 const double *nd = s_nodes + s * MN * NDW;
@@ -284,7 +342,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
                     double sx = 0.0, sy = 0.0, sz = 0.0;
 #pragma unroll 4
                     for (int l = 0; l < MN; ++l) {
-                        const double dn = T.dN[g][l][mm];
+                        const double dn = g_dN[(l * 4 + mm) * 32 + g];
                         sx = sx + dn * nd[l * NDW + kNodeDoubles];
                         sy = sy + dn * nd[l * NDW + kNodeDoubles + 1];
                         sz = sz + dn * nd[l * NDW];
@@ -307,44 +365,30 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
                 G[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / ad;
                 G[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / ad;
                 G[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / ad;
-                // p_intmodels, problem.f90:139-142: material tensors at the Gauss point
-                double mu[6] = {0, 0, 0, 0, 0, 0}, sr[6] = {0, 0, 0, 0, 0, 0}, si[6] = {0, 0, 0, 0, 0, 0};
-                double xg[3] = {0, 0, 0};
-                double dm1r[3] = {0, 0, 0}, dm1i[3] = {0, 0, 0}, dm2r[3] = {0, 0, 0}, dm2i[3] = {0, 0, 0};
-#pragma unroll 2
-                for (int l = 0; l < MN; ++l) {
-                    const double ln = T.N[g][l];
-                    const double *r = nd + l * NDW;
+                // interpolated columns of phase B1 (this thread's record is overwritten below)
+                double mu[6], sr[6], si[6] = {0, 0, 0, 0, 0, 0};
+                double dm1r[3], dm1i[3], dm2r[3], dm2i[3];
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        mu[k] = dfma(ln, r[2 + k], mu[k]);
-                        sr[k] = dfma(ln, r[8 + k], sr[k]);
-                        if (PML) si[k] = dfma(ln, r[14 + k], si[k]);
-                    }
-                    if (PML) {   // g_rw, integration.f90:120-125 (reference order, no FMA: feeds the float32-rounded h)
-                        xg[0] = xg[0] + ln * r[kNodeDoubles]; xg[1] = xg[1] + ln * r[kNodeDoubles + 1]; xg[2] = xg[2] + ln * r[0];
-                    }
-                    // p_dmpf, problem.f90:424-457: ln * (dsigma . Ep); Ep_1 = (0,-e) x^, Ep_2 = (0,+e) y^
-                    const double le = ln * r[1];
-                    const double d0 = r[14] - psig, d3 = r[17] - psig;   // Im(dsigma) on the diagonal
-                    dm1r[0] = dfma(le, d0, dm1r[0]);     dm1i[0] = dfma(le, r[8], dm1i[0]);
-                    dm1r[1] = dfma(le, r[15], dm1r[1]);  dm1i[1] = dfma(le, r[9], dm1i[1]);
-                    dm1r[2] = dfma(le, r[16], dm1r[2]);  dm1i[2] = dfma(le, r[10], dm1i[2]);
-                    dm2r[0] = dfma(le, r[15], dm2r[0]);  dm2i[0] = dfma(le, r[9], dm2i[0]);
-                    dm2r[1] = dfma(le, d3, dm2r[1]);     dm2i[1] = dfma(le, r[11], dm2i[1]);
-                    dm2r[2] = dfma(le, r[18], dm2r[2]);  dm2i[2] = dfma(le, r[12], dm2i[2]);
-                }
+                for (int k = 0; k < 6; ++k) { mu[k] = geo[k]; sr[k] = geo[6 + k]; if (PML) si[k] = geo[24 + k]; }
                 // signs: pol 1 dmpf = (+Im ds*e, -Re ds*e), pol 2 = (-Im ds*e, +Re ds*e)
 #pragma unroll
-                for (int k = 0; k < 3; ++k) { dm1i[k] = -dm1i[k]; dm2r[k] = -dm2r[k]; }
+                for (int k = 0; k < 3; ++k) { dm1r[k] = geo[12 + k]; dm1i[k] = -geo[15 + k]; dm2r[k] = -geo[18 + k]; dm2i[k] = geo[21 + k]; }
+                double xg[3] = {0, 0, 0};
+                if (PML) {   // g_rw, integration.f90:120-125 (reference order, no FMA: feeds the float32-rounded h)
+                    for (int l = 0; l < MN; ++l) {
+                        const double ln = g_dN[(l * 4 + 3) * 32 + g];
+                        const double *r = nd + l * NDW;
+                        xg[0] = xg[0] + ln * r[kNodeDoubles]; xg[1] = xg[1] + ln * r[kNodeDoubles + 1]; xg[2] = xg[2] + ln * r[0];
+                    }
+                }
                 double pc1[3] = {0, 0, 0}, pc2[3] = {0, 0, 0};
                 if (has_dmu) {   // p_pcurl, problem.f90:362-374: grad N_l x (mu^-1 dmu Hp)_l
                     for (int l = 0; l < MN; ++l) {
                         const double *r = nd + l * NDW;
+                        const double t0 = g_dN[(l * 4 + 0) * 32 + g], t1 = g_dN[(l * 4 + 1) * 32 + g], t2 = g_dN[(l * 4 + 2) * 32 + g];
                         double dn[3];
 #pragma unroll
-                        for (int mm = 0; mm < 3; ++mm)
-                            dn[mm] = G[mm][0] * T.dN[g][l][0] + G[mm][1] * T.dN[g][l][1] + G[mm][2] * T.dN[g][l][2];
+                        for (int mm = 0; mm < 3; ++mm) dn[mm] = G[mm][0] * t0 + G[mm][1] * t1 + G[mm][2] * t2;
                         pc1[0] += r[22] * dn[1] - r[21] * dn[2]; pc1[1] += r[20] * dn[2] - r[22] * dn[0]; pc1[2] += r[21] * dn[0] - r[20] * dn[1];
                         pc2[0] += r[25] * dn[1] - r[24] * dn[2]; pc2[1] += r[23] * dn[2] - r[25] * dn[0]; pc2[2] += r[24] * dn[0] - r[23] * dn[1];
                     }
@@ -448,100 +492,119 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
         }
         __syncthreads();
 
-        double accK[16], accM[16], bacc[4];
+        if (batch + (int)gridDim.x < nbatch) request_nodes(batch + gridDim.x);   // lands during the contraction
+
+        // ---- RHS: one thread per (element, slot): blocal / f3, integration.f90:96-104,258-263 ----
+        const int cdof = s_slot[cslot], cd = s_sdir[cslot];
+        double bacc[4] = {0.0, 0.0, 0.0, 0.0};
+        if ((A.phase_mask & 2) && tid < nb * MEP) {
+#pragma unroll 3
+            for (int g = 0; g < NGP; ++g) {
+                const double phi = s_at[(size_t)(g * NA + KA) * MEP + cpos];
+                const double *R = s_geo + (cs * NGP + g) * GEO + GR + cd * 4;
+                bacc[0] = dfma(phi, R[0], bacc[0]); bacc[1] = dfma(phi, R[1], bacc[1]);
+                bacc[2] = dfma(phi, R[2], bacc[2]); bacc[3] = dfma(phi, R[3], bacc[3]);
+            }
+        }
+
+        // ---- contraction: register-tiled 4x4 blocks over the lower triangle in slot space.  The thread forms the
+        //      element-dependent operand of its four COLUMN slots on the fly from a 2x2 block of Q (3x3 block of P
+        //      in the GPML layers) and one entry of T; the row operand is the constant table. ----
+        double accK[16], accM[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { accK[i] = 0.0; accM[i] = 0.0; }
-        bacc[0] = bacc[1] = bacc[2] = bacc[3] = 0.0;
-        const int cdof = s_slot[cslot], cd = s_sdir[cslot];
-
-        for (int chunk = 0; chunk < CFG::NCHUNK; ++chunk) {
-            // ---- phase C: one thread per (element, slot): bK = Q c_j | P dphi_j, W = phi_j T[:,d_j], RHS ----
-            if (tid < nb * MEP) {
-#pragma unroll 1
-                for (int gc = 0; gc < GCH; ++gc) {
-                    const int g = chunk * GCH + gc;
-                    const double *geo = s_geo + (cs * NGP + g) * GEO;
-                    const double *at = s_at + (size_t)g * NA * MEP + cpos;
-                    double *B = s_B + (size_t)(cs * GCH + gc) * NB * MEP + cpos;
-                    const double phi = at[KA * MEP];
-                    if (DO_KM) {
-                        if (!PML) {
-                            // c_j has its two non-zero components on the axes perpendicular to d_j
-                            const int m1 = cd == 0 ? 1 : 0, m2 = cd == 2 ? 1 : 2;
-                            const double c1 = at[0], c2 = at[MEP];
-                            const double *Q = geo + GQ;
-#pragma unroll
-                            for (int p = 0; p < 3; ++p) B[p * MEP] = dfma(Q[sym3(p, m1)], c1, Q[sym3(p, m2)] * c2);
-                        } else {
-                            const double dp[3] = {at[0], at[MEP], at[2 * MEP]};
-                            const double *P = geo + GQ;
-#pragma unroll
-                            for (int r = 0; r < 9; ++r) {          // r = (u,d)
-                                double acc = 0.0;
-#pragma unroll
-                                for (int v = 0; v < 3; ++v) {      // column (v, d_j)
-                                    const int c = v * 3 + cd;
-                                    const int lo = r < c ? r : c, hi = r < c ? c : r;
-                                    acc = dfma(P[up9(lo, hi)], dp[v], acc);
-                                }
-                                B[r * MEP] = acc;
-                            }
-                        }
-                        const double *Tt = geo + GT;
-#pragma unroll
-                        for (int d2 = 0; d2 < 3; ++d2) B[(KB + d2) * MEP] = phi * Tt[sym3(d2, cd)];
-                    }
-                    // blocal / f3, integration.f90:96-104,258-263
-                    const double *R = geo + GR + cd * 4;
-                    bacc[0] = dfma(phi, R[0], bacc[0]); bacc[1] = dfma(phi, R[1], bacc[1]);
-                    bacc[2] = dfma(phi, R[2], bacc[2]); bacc[3] = dfma(phi, R[3], bacc[3]);
-                }
-            }
-            if (!DO_KM) continue;
-            __syncthreads();
-
-            // ---- phase D: register-tiled lower-triangle contraction over this chunk ----
-            if (tid < nb * NTILES) {
-                const double *Bs = s_B + (size_t)ts * GCH * NB * MEP;
-                const int dI = s_sdir[4 * ti];                            // direction of this thread's row group
-                // bK rows paired with a-rows 0,1(,2): plain = the two axes perpendicular to d_i; GPML = (u, d_i)
-                const int r0 = PML ? dI : (dI == 0 ? 1 : 0);
-                const int r1 = PML ? 3 + dI : (dI == 2 ? 1 : 2);
-#pragma unroll 1
-                for (int gc = 0; gc < GCH; ++gc) {
-                    const double *Bg = Bs + gc * NB * MEP;
-                    const double *Ag = s_at + (size_t)(chunk * GCH + gc) * NA * MEP;
-#pragma unroll
-                    for (int k = 0; k < KA; ++k) {
-                        const int rb = k == 0 ? r0 : (k == 1 ? r1 : 6 + dI);
-                        const double2 a0 = *reinterpret_cast<const double2 *>(Ag + k * MEP + a_lo);
-                        const double2 a1 = *reinterpret_cast<const double2 *>(Ag + k * MEP + a_hi);
-                        const double2 b0 = *reinterpret_cast<const double2 *>(Bg + rb * MEP + b_lo);
-                        const double2 b1 = *reinterpret_cast<const double2 *>(Bg + rb * MEP + b_hi);
-                        const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) accK[i * 4 + j] = dfma(av[i], bv[j], accK[i * 4 + j]);
+        if (DO_KM && (A.phase_mask & 4) && tid < nb * NTILES) {
+            const int dI = s_sdir[4 * ti], dJ = s_sdir[4 * tj];
+            const double *geo0 = s_geo + (size_t)ts * NGP * GEO;
+            const int it = GT + sym3(dI, dJ);
+            if (!PML) {
+                // axes perpendicular to the row / column direction: the non-zero components of c_i, c_j
+                const int r0 = dI == 0 ? 1 : 0, r1 = dI == 2 ? 1 : 2, m0 = dJ == 0 ? 1 : 0, m1 = dJ == 2 ? 1 : 2;
+                const int i00 = GQ + sym3(r0, m0), i01 = GQ + sym3(r0, m1), i10 = GQ + sym3(r1, m0), i11 = GQ + sym3(r1, m1);
+#pragma unroll 2
+                for (int g = 0; g < NGP; ++g) {
+                    const double *Ag = s_at + (size_t)g * NA * MEP;
+                    const double *geo = geo0 + g * GEO;
+                    const double q00 = geo[i00], q01 = geo[i01], q10 = geo[i10], q11 = geo[i11], t = geo[it];
+                    double a1[4], a2[4], a3[4], b1[4], b2[4], bw[4];
+                    {
+                        const double2 x0 = *reinterpret_cast<const double2 *>(Ag + a_lo), x1 = *reinterpret_cast<const double2 *>(Ag + a_hi);
+                        const double2 y0 = *reinterpret_cast<const double2 *>(Ag + MEP + a_lo), y1 = *reinterpret_cast<const double2 *>(Ag + MEP + a_hi);
+                        const double2 z0 = *reinterpret_cast<const double2 *>(Ag + 2 * MEP + a_lo), z1 = *reinterpret_cast<const double2 *>(Ag + 2 * MEP + a_hi);
+                        a1[0] = x0.x; a1[1] = x0.y; a1[2] = x1.x; a1[3] = x1.y;
+                        a2[0] = y0.x; a2[1] = y0.y; a2[2] = y1.x; a2[3] = y1.y;
+                        a3[0] = z0.x; a3[1] = z0.y; a3[2] = z1.x; a3[3] = z1.y;
                     }
                     {
-                        const double2 a0 = *reinterpret_cast<const double2 *>(Ag + KA * MEP + a_lo);          // phi_i
-                        const double2 a1 = *reinterpret_cast<const double2 *>(Ag + KA * MEP + a_hi);
-                        const double2 b0 = *reinterpret_cast<const double2 *>(Bg + (KB + dI) * MEP + b_lo);   // W_j[d_i]
-                        const double2 b1 = *reinterpret_cast<const double2 *>(Bg + (KB + dI) * MEP + b_hi);
-                        const double av[4] = {a0.x, a0.y, a1.x, a1.y}, bv[4] = {b0.x, b0.y, b1.x, b1.y};
+                        const double2 x0 = *reinterpret_cast<const double2 *>(Ag + b_lo), x1 = *reinterpret_cast<const double2 *>(Ag + b_hi);
+                        const double2 y0 = *reinterpret_cast<const double2 *>(Ag + MEP + b_lo), y1 = *reinterpret_cast<const double2 *>(Ag + MEP + b_hi);
+                        const double2 z0 = *reinterpret_cast<const double2 *>(Ag + 2 * MEP + b_lo), z1 = *reinterpret_cast<const double2 *>(Ag + 2 * MEP + b_hi);
+                        const double c1[4] = {x0.x, x0.y, x1.x, x1.y}, c2[4] = {y0.x, y0.y, y1.x, y1.y}, ph[4] = {z0.x, z0.y, z1.x, z1.y};
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) accM[i * 4 + j] = dfma(av[i], bv[j], accM[i * 4 + j]);
+                        for (int j = 0; j < 4; ++j) {
+                            b1[j] = dfma(q00, c1[j], q01 * c2[j]);     // (Q c_j)[r0]
+                            b2[j] = dfma(q10, c1[j], q11 * c2[j]);     // (Q c_j)[r1]
+                            bw[j] = ph[j] * t;                         // phi_j T[d_i][d_j]
+                        }
                     }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            accK[i * 4 + j] = dfma(a1[i], b1[j], dfma(a2[i], b2[j], accK[i * 4 + j]));
+                            accM[i * 4 + j] = dfma(a3[i], bw[j], accM[i * 4 + j]);
+                        }
+                }
+            } else {
+                int ip[9];
+#pragma unroll
+                for (int u = 0; u < 3; ++u)
+#pragma unroll
+                    for (int v = 0; v < 3; ++v) {
+                        const int r = u * 3 + dI, c = v * 3 + dJ;
+                        ip[u * 3 + v] = GQ + (r <= c ? up9(r, c) : up9(c, r));
+                    }
+#pragma unroll 1
+                for (int g = 0; g < NGP; ++g) {
+                    const double *Ag = s_at + (size_t)g * NA * MEP;
+                    const double *geo = geo0 + g * GEO;
+                    double P[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) P[k] = geo[ip[k]];
+                    const double t = geo[it];
+                    double a[4][4], b[3][4], bw[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const double2 x0 = *reinterpret_cast<const double2 *>(Ag + k * MEP + a_lo), x1 = *reinterpret_cast<const double2 *>(Ag + k * MEP + a_hi);
+                        a[k][0] = x0.x; a[k][1] = x0.y; a[k][2] = x1.x; a[k][3] = x1.y;
+                    }
+                    {
+                        double c[4][4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const double2 x0 = *reinterpret_cast<const double2 *>(Ag + k * MEP + b_lo), x1 = *reinterpret_cast<const double2 *>(Ag + k * MEP + b_hi);
+                            c[k][0] = x0.x; c[k][1] = x0.y; c[k][2] = x1.x; c[k][3] = x1.y;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                            for (int u = 0; u < 3; ++u) b[u][j] = dfma(P[u * 3], c[0][j], dfma(P[u * 3 + 1], c[1][j], P[u * 3 + 2] * c[2][j]));
+                            bw[j] = c[3][j] * t;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            accK[i * 4 + j] = dfma(a[0][i], b[0][j], dfma(a[1][i], b[1][j], dfma(a[2][i], b[2][j], accK[i * 4 + j])));
+                            accM[i * 4 + j] = dfma(a[3][i], bw[j], accM[i * 4 + j]);
+                        }
                 }
             }
-            if (chunk + 1 < CFG::NCHUNK) __syncthreads();
         }
 
         // ---- write-out: element-major, packed lower triangle by LOCAL DOF index ----
-        if (DO_KM && tid < nb * NTILES) {
+        if (DO_KM && (A.phase_mask & 8) && tid < nb * NTILES) {
             const int64_t e = s_el[ts * 4];
             double *Ko = A.Ke + e * NP, *Mo = A.Me + e * NP;
 #pragma unroll
