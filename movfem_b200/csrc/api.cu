@@ -34,9 +34,9 @@ namespace {
 using Cfg12  = ElemCfg<8, 12, 12, 8, 16, 192, 2, false>;
 using Cfg12p = ElemCfg<8, 12, 12, 8, 16, 192, 2, true>;
 using Cfg36  = ElemCfg<20, 36, 36, 27, 4, 192, 2, false>;
-using Cfg36p = ElemCfg<20, 36, 36, 27, 2, 96, 2, true>;
+using Cfg36p = ElemCfg<20, 36, 36, 27, 4, 192, 2, true>;
 using Cfg54  = ElemCfg<27, 54, 60, 27, 2, 256, 2, false>;
-using Cfg54p = ElemCfg<27, 54, 60, 27, 1, 128, 2, true>;
+using Cfg54p = ElemCfg<27, 54, 60, 27, 2, 256, 2, true>;
 
 enum { EV_START, EV_H2D, EV_NODE, EV_ELEM, EV_GATHER, EV_FINAL, EV_D2H, EV_COUNT };
 
@@ -64,7 +64,8 @@ struct movfem_handle {
     int *d_irn, *d_jcn, *d_irn_c, *d_jcn_c, *d_rown;
     int64_t *d_cptr;
     uint32_t *d_src;
-    double *d_Ke, *d_Me, *d_be;
+    double2 *d_KM;
+    double *d_be;
     double2 *d_a, *d_a_c, *d_rhs;
     int *d_list_plain, *d_list_pml;
     int n_plain, n_pml;
@@ -257,7 +258,7 @@ int run_elements(movfem_handle *h, ElemArgs &A, bool full) {
 void free_all(movfem_handle *h) {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_xp, h->d_yp, h->d_zp, h->d_mu, h->d_sigma, h->d_nodes, h->d_tab, h->d_share, h->d_gne, h->d_ownE,
-                    h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_src, h->d_Ke, h->d_Me,
+                    h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_src, h->d_KM,
                     h->d_be, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum,
                     h->d_status, h->d_flags};
     for (void *p : ptrs)
@@ -430,7 +431,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     }
 
     // work / result arrays
-    CK(dmalloc(&h->d_Ke, (size_t)m.ne * h->NP)); CK(dmalloc(&h->d_Me, (size_t)m.ne * h->NP));
+    CK(dmalloc(&h->d_KM, (size_t)m.ne * h->NP));
     CK(dmalloc(&h->d_be, (size_t)m.ne * m.me * 4));
     CK(dmalloc(&h->d_a, (size_t)h->nzu)); CK(dmalloc(&h->d_a_c, (size_t)h->nzu));
     CK(dmalloc(&h->d_irn_c, (size_t)h->nzu)); CK(dmalloc(&h->d_jcn_c, (size_t)h->nzu));
@@ -504,7 +505,7 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
 
     ElemArgs A;
     A.m = m; A.pml = h->pml; A.omega = omega; A.T = h->d_tab; A.nodes = h->d_nodes; A.xp = h->d_xp; A.yp = h->d_yp;
-    A.list = nullptr; A.nlist = 0; A.Ke = h->d_Ke; A.Me = h->d_Me; A.be = h->d_be; A.status = h->d_status; A.flags = h->d_flags;
+    A.list = nullptr; A.nlist = 0; A.KM = h->d_KM; A.be = h->d_be; A.status = h->d_status; A.flags = h->d_flags;
     A.skip_unless_changed = 0;
     A.phase_mask = 15;
     std::memcpy(A.Ntab, h->h_Ntab, sizeof(A.Ntab));
@@ -518,7 +519,7 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
     h->km_valid = true;
     CK(cudaEventRecord(h->ev[EV_ELEM], st));
 
-    gather_finalize_kernel<<<h->nblk_fin, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cptr, h->d_src, h->d_Ke, h->d_Me, h->d_a,
+    gather_finalize_kernel<<<h->nblk_fin, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cptr, h->d_src, h->d_KM, h->d_a,
                                                               h->d_blkcnt, mode == MOVFEM_MODE_T1 ? 1 : 0);
     rhs_kernel<<<(h->nne + 127) / 128, 128, 0, st>>>(h->nne, h->d_rown, reinterpret_cast<const double4 *>(h->d_be), h->d_rhs);
     h->launches += 2;
@@ -670,8 +671,9 @@ int movfem_debug_element(movfem_handle *h, int32_t ide, double *Ke, double *Me, 
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     const size_t e = (size_t)ide - 1;
-    if (Ke) CK(cudaMemcpy(Ke, h->d_Ke + e * h->NP, sizeof(double) * h->NP, cudaMemcpyDeviceToHost));
-    if (Me) CK(cudaMemcpy(Me, h->d_Me + e * h->NP, sizeof(double) * h->NP, cudaMemcpyDeviceToHost));
+    std::vector<double2> km(h->NP);
+    CK(cudaMemcpy(km.data(), h->d_KM + e * h->NP, sizeof(double2) * h->NP, cudaMemcpyDeviceToHost));
+    for (int p = 0; p < h->NP; ++p) { if (Ke) Ke[p] = km[p].x; if (Me) Me[p] = km[p].y; }
     if (be) CK(cudaMemcpy(be, h->d_be + e * h->m.me * 4, sizeof(double) * h->m.me * 4, cudaMemcpyDeviceToHost));
     return MOVFEM_OK;
 }

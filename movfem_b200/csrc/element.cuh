@@ -99,7 +99,7 @@ struct ElemArgs {
     const double *xp, *yp;
     const int *list;      // element ids (0-based) this launch handles
     int nlist;
-    double *Ke, *Me;      // [ne][NP]
+    double2 *KM;          // [ne][NP] (K_e, M_e) interleaved: one 16-byte access per local pair
     double *be;           // [ne][ME][4]  (re,im) x 2 polarisations
     int *status;
     const int *flags;     // flags[0] any dmu, flags[1] Re sigma changed
@@ -408,13 +408,11 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
                     // integration.f90:171-188):  (1,1):(y,z,+) (1,2):(z,y,-) (2,1):(z,x,+) (2,2):(x,z,-) (3,1):(x,y,+) (3,2):(y,x,-)
                     constexpr int xa[6] = {1, 2, 2, 0, 0, 1}, ya[6] = {2, 1, 0, 2, 1, 0}, pa[6] = {0, 0, 1, 1, 2, 2};
                     constexpr double sa[6] = {1.0, -1.0, 1.0, -1.0, 1.0, -1.0};
-                    // D6[a][b] = w mu^-1[p_a][p_b] Re G[x_a][x_b]   (symmetric 6x6, 21 packed)
-                    double D6[6][6];
-#pragma unroll
-                    for (int a = 0; a < 6; ++a)
-#pragma unroll
-                        for (int b = 0; b < 6; ++b) D6[a][b] = w * mu[sym3(pa[a], pa[b])] * Gr[sym3(xa[a], xa[b])];
+                    // D6[a][b] = w mu^-1[p_a][p_b] Re G[x_a][x_b]   (symmetric 6x6; formed on the fly)
                     // P[(u,d)][(v,e)] = sum_ab H[a][u,d] D6[a][b] H[b][v,e],  H[a][u,d] = s_a G[x_a][u] G[y_a][d]
+                    double wmu[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) wmu[k] = w * mu[k];
                     double *P = geo + GQ;
 #pragma unroll 1
                     for (int col = 0; col < 9; ++col) {
@@ -426,7 +424,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
                         for (int a = 0; a < 6; ++a) {
                             double acc = 0.0;
 #pragma unroll
-                            for (int b = 0; b < 6; ++b) acc = dfma(D6[a][b], Hc[b], acc);
+                            for (int b = 0; b < 6; ++b) acc = dfma(wmu[sym3(pa[a], pa[b])] * Gr[sym3(xa[a], xa[b])], Hc[b], acc);
                             DH[a] = acc;
                         }
 #pragma unroll 1
@@ -606,7 +604,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
         // ---- write-out: element-major, packed lower triangle by LOCAL DOF index ----
         if (DO_KM && (A.phase_mask & 8) && tid < nb * NTILES) {
             const int64_t e = s_el[ts * 4];
-            double *Ko = A.Ke + e * NP, *Mo = A.Me + e * NP;
+            double2 *KMo = A.KM + e * NP;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int si = 4 * ti + i, im = s_slot[si];
@@ -616,7 +614,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
                     if (im >= 0 && jm >= 0 && sj <= si) {
                         const int hi = im > jm ? im : jm, lo = im > jm ? jm : im;
                         const int p = hi * (hi + 1) / 2 + lo;
-                        Ko[p] = accK[i * 4 + j]; Mo[p] = accM[i * 4 + j];
+                        KMo[p] = make_double2(accK[i * 4 + j], accM[i * 4 + j]);
                     }
                 }
             }

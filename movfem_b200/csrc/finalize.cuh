@@ -23,7 +23,7 @@ constexpr int kFinThreads = 256;
 // mode 1 (T1): double values, nothing stripped
 __global__ void __launch_bounds__(kFinThreads)
 gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cptr, const uint32_t *__restrict__ src,
-                       const double *__restrict__ Ke, const double *__restrict__ Me, double2 *__restrict__ a,
+                       const double2 *__restrict__ KM, double2 *__restrict__ a,
                        int *__restrict__ blk_nonzero, int mode) {
     const int64_t i = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
     int nzflag = 0;
@@ -31,9 +31,9 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cptr
         const int64_t c0 = cptr[i], c1 = cptr[i + 1];
         double k = 0.0, mm = 0.0;
         for (int64_t c = c0; c < c1; ++c) {
-            const uint32_t s = src[c];
-            k = k + Ke[s];
-            mm = mm + Me[s];
+            const double2 v = KM[src[c]];
+            k = k + v.x;
+            mm = mm + v.y;
         }
         double re = k, im = w32 * mm;
         if (mode == 0) { re = f32r(re); im = f32r(im); }
