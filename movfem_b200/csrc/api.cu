@@ -31,9 +31,9 @@ namespace {
 // EB / THREADS are chosen so that every phase fills whole warps (idle lanes cost FP64-pipe time):
 //   me=12: 16 el -> 128 (el,gp) / 192 (el,slot) / 96 tiles     me=36: 4 el -> 108 / 144 / 180
 //   me=54:  2 el ->  54 / 120 / 240                            (GPML variants: smaller batches, more smem)
-using Cfg12  = ElemCfg<8, 12, 12, 8, 16, 192, 2, false>;
+using Cfg12  = ElemCfg<8, 12, 12, 8, 16, 192, 3, false>;
 using Cfg12p = ElemCfg<8, 12, 12, 8, 16, 192, 2, true>;
-using Cfg36  = ElemCfg<20, 36, 36, 27, 4, 192, 2, false>;
+using Cfg36  = ElemCfg<20, 36, 36, 27, 4, 192, 3, false>;
 using Cfg36p = ElemCfg<20, 36, 36, 27, 4, 192, 2, true>;
 using Cfg54  = ElemCfg<27, 54, 60, 27, 2, 256, 2, false>;
 using Cfg54p = ElemCfg<27, 54, 60, 27, 2, 256, 2, true>;

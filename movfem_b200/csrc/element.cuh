@@ -129,7 +129,8 @@ struct ElemCfg {
     static constexpr int NCOL = PML ? 30 : 24;             // columns interpolated by phase B1 (<= GEO: stored in place)
     // shared memory: a-table [NGP][NA][MEP] | geometry [EB][NGP][GEO] | node records [EB][MN][NDW]
     static constexpr size_t ATAB_D = (size_t)NGP * NA * MEP, GEO_D = (size_t)EB * NGP * GEO;
-    static constexpr size_t NODES_D = (size_t)EB * MN * NDW;
+    static constexpr int NSTR = MN * NDW + 2;              // per-element stride of the node records (+16 B: bank shift)
+    static constexpr size_t NODES_D = (size_t)EB * NSTR;
     static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + NODES_D) + sizeof(int) * (EB * 4 + 2 * MEP);
     static_assert(MEP % 4 == 0 && (ATAB_D % 2) == 0 && (GEO_D % 2) == 0, "16-byte alignment of the smem regions");
     static_assert(THREADS >= EB * NTILES && THREADS >= EB * MEP, "one tile / one slot per thread");
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
             const int e = A.list[first + s];
             int ie, je, ke;
             elem_ijk(m, e, ie, je, ke);
-            double2 *dst = reinterpret_cast<double2 *>(s_nodes + (s * MN + l) * NDW) + part;
+            double2 *dst = reinterpret_cast<double2 *>(s_nodes + s * CFG::NSTR + l * NDW) + part;
             if (part < kNodeDoubles / 2) {
                 const int64_t id = (int64_t)(ie - 1) * g1 * m.nyz + (int64_t)(je - 1) * g1 * m.nnz + (ke - 1) * g1 + T.node_off[l];
                 const double2 *src = reinterpret_cast<const double2 *>(A.nodes + id) + part;
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
             if (part < GS)
                 for (int it = GS == 1 ? tid : (wid % PW) * 32 + lane; it < nb * CFG::NCOL; it += stride) {
                     const int s = it / CFG::NCOL, c = it % CFG::NCOL;
-                    const double *nd = s_nodes + s * MN * NDW;
+                    const double *nd = s_nodes + s * CFG::NSTR;
                     const int off = kColOff[c], flag = kColFlag[c];
                     double v[MN];
 #pragma unroll
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
             const double w32 = f32r(A.omega);            // cmplx(0.d0,-omega), problem.f90:112
             for (int i = tid; i < nb * NGP; i += CFG::THREADS) {
                 const int s = i / NGP, g = i % NGP;
-                const double *nd = s_nodes + s * MN * NDW;
+                const double *nd = s_nodes + s * CFG::NSTR;
                 double *geo = s_geo + (s * NGP + g) * GEO;
                 // nf_jacobian, n_fem.f90:359-366: J(m,n) = sum_l dN_l/dxi_m * r_l(n), l ascending, no FMA
                 double J[3][3];
@@ -519,39 +520,47 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
                 // axes perpendicular to the row / column direction: the non-zero components of c_i, c_j
                 const int r0 = dI == 0 ? 1 : 0, r1 = dI == 2 ? 1 : 2, m0 = dJ == 0 ? 1 : 0, m1 = dJ == 2 ? 1 : 2;
                 const int i00 = GQ + sym3(r0, m0), i01 = GQ + sym3(r0, m1), i10 = GQ + sym3(r1, m0), i11 = GQ + sym3(r1, m1);
-#pragma unroll 2
+                // K pass and M pass are separate loops over the Gauss points: 16 live accumulators each instead of 32,
+                // which keeps the kernel at 3 resident CTAs per SM without spilling
+#pragma unroll 3
                 for (int g = 0; g < NGP; ++g) {
                     const double *Ag = s_at + (size_t)g * NA * MEP;
                     const double *geo = geo0 + g * GEO;
-                    const double q00 = geo[i00], q01 = geo[i01], q10 = geo[i10], q11 = geo[i11], t = geo[it];
-                    double a1[4], a2[4], a3[4], b1[4], b2[4], bw[4];
+                    const double q00 = geo[i00], q01 = geo[i01], q10 = geo[i10], q11 = geo[i11];
+                    double a1[4], a2[4], b1[4], b2[4];
                     {
                         const double2 x0 = *reinterpret_cast<const double2 *>(Ag + a_lo), x1 = *reinterpret_cast<const double2 *>(Ag + a_hi);
                         const double2 y0 = *reinterpret_cast<const double2 *>(Ag + MEP + a_lo), y1 = *reinterpret_cast<const double2 *>(Ag + MEP + a_hi);
-                        const double2 z0 = *reinterpret_cast<const double2 *>(Ag + 2 * MEP + a_lo), z1 = *reinterpret_cast<const double2 *>(Ag + 2 * MEP + a_hi);
                         a1[0] = x0.x; a1[1] = x0.y; a1[2] = x1.x; a1[3] = x1.y;
                         a2[0] = y0.x; a2[1] = y0.y; a2[2] = y1.x; a2[3] = y1.y;
-                        a3[0] = z0.x; a3[1] = z0.y; a3[2] = z1.x; a3[3] = z1.y;
                     }
                     {
                         const double2 x0 = *reinterpret_cast<const double2 *>(Ag + b_lo), x1 = *reinterpret_cast<const double2 *>(Ag + b_hi);
                         const double2 y0 = *reinterpret_cast<const double2 *>(Ag + MEP + b_lo), y1 = *reinterpret_cast<const double2 *>(Ag + MEP + b_hi);
-                        const double2 z0 = *reinterpret_cast<const double2 *>(Ag + 2 * MEP + b_lo), z1 = *reinterpret_cast<const double2 *>(Ag + 2 * MEP + b_hi);
-                        const double c1[4] = {x0.x, x0.y, x1.x, x1.y}, c2[4] = {y0.x, y0.y, y1.x, y1.y}, ph[4] = {z0.x, z0.y, z1.x, z1.y};
+                        const double c1[4] = {x0.x, x0.y, x1.x, x1.y}, c2[4] = {y0.x, y0.y, y1.x, y1.y};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             b1[j] = dfma(q00, c1[j], q01 * c2[j]);     // (Q c_j)[r0]
                             b2[j] = dfma(q10, c1[j], q11 * c2[j]);     // (Q c_j)[r1]
-                            bw[j] = ph[j] * t;                         // phi_j T[d_i][d_j]
                         }
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            accK[i * 4 + j] = dfma(a1[i], b1[j], dfma(a2[i], b2[j], accK[i * 4 + j]));
-                            accM[i * 4 + j] = dfma(a3[i], bw[j], accM[i * 4 + j]);
-                        }
+                        for (int j = 0; j < 4; ++j) accK[i * 4 + j] = dfma(a1[i], b1[j], dfma(a2[i], b2[j], accK[i * 4 + j]));
+                }
+#pragma unroll 3
+                for (int g = 0; g < NGP; ++g) {
+                    const double *Ag = s_at + (size_t)(g * NA + 2) * MEP;
+                    const double t = geo0[g * GEO + it];
+                    const double2 z0 = *reinterpret_cast<const double2 *>(Ag + a_lo), z1 = *reinterpret_cast<const double2 *>(Ag + a_hi);
+                    const double2 w0 = *reinterpret_cast<const double2 *>(Ag + b_lo), w1 = *reinterpret_cast<const double2 *>(Ag + b_hi);
+                    const double a3[4] = {z0.x, z0.y, z1.x, z1.y};
+                    const double bw[4] = {w0.x * t, w0.y * t, w1.x * t, w1.y * t};    // phi_j T[d_i][d_j]
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) accM[i * 4 + j] = dfma(a3[i], bw[j], accM[i * 4 + j]);
                 }
             } else {
                 int ip[9];
