@@ -33,6 +33,9 @@ from movfem_b200 import abi, mesh  # noqa: E402
 WORKLOAD = 2     # BASELINE.json configs[1]
 FLOPS_PER_ELEMENT = {12: 10944, 36: 250776, 54: 533628}   # 2*ngp*(18*me + 3*me*(me+1))
 BYTES_PER_NNZ_UPDATE = 32                                  # read K 8 + M 8, write A 16
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
+# (profiles/r01_ncu_full_top_kernels.json, profiles/r01_summary.md); None for other workloads
+NCU_TRAFFIC_BYTES = {"element_kernel": 41.2e6 + 368.3e6 + 20.6e6 + 118.5e6, "gather_finalize_kernel": 836.9e6 + 374.1e6}
 
 
 def rank_env():
@@ -153,9 +156,10 @@ def run_graft(args):
     sampler = None
     with torch.cuda.stream(stream):
         for it in range(args.warmup + args.steps):
+            if it == 0:
+                sampler = ClockSampler(local_rank); sampler.start()     # spans warm-up, the timed region and the e2e loop
             if it == args.warmup:
                 torch.cuda.synchronize(dev); barrier(); torch.cuda.synchronize(dev)
-                sampler = ClockSampler(local_rank); sampler.start()
                 t_wall0 = time.perf_counter()
             flush.zero_()                                   # evict L2 between iterations
             asm.reset_cache()                               # every step is a cold, full assembly
@@ -171,7 +175,6 @@ def run_graft(args):
                 launches += int(st["launches"]) + 1         # + the L2 flush fill
         torch.cuda.synchronize(dev); barrier(); torch.cuda.synchronize(dev)
         t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -204,6 +207,7 @@ def run_graft(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
     e2e_stats = asm.stats()
+    clocks = sampler.stop()
     h2d = sigma_np.size * 16
     d2h = nz_e2e * 24 + asm.nne * 32
 
@@ -231,11 +235,12 @@ def run_graft(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "element_kernel (plain + GPML launches)", "achieved": ach, "peak": fp64_peak,
-                         "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None, "traffic": NCU_TRAFFIC_BYTES["element_kernel"],
+                         "traffic_note": "bytes per step over both element launches, ncu capture of round 1 (profiles/)",
                          "peak_source": "FP64 FMA-loop microbenchmark run in this process (movfem_fp64_peak); nominal 37.2",
                          "flops_per_element": FLOPS_PER_ELEMENT[model.me], "ms_kernel": ms_el},
             "roofline_hbm": {"bound": "hbm", "kernel": "gather_finalize_kernel", "achieved": ga_bytes / (ms_ga * 1e-3) * 1e-9, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": ga_bytes / (ms_ga * 1e-3) * 1e-9 / hbm_peak, "traffic": None,
+                             "unit": "GB/s", "frac": ga_bytes / (ms_ga * 1e-3) * 1e-9 / hbm_peak, "traffic": NCU_TRAFFIC_BYTES["gather_finalize_kernel"],
                              "peak_source": f"MEASURED_PEAKS.json ({hbm_src})", "bytes_per_nnz": BYTES_PER_NNZ_UPDATE, "ms_kernel": ms_ga},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -260,7 +265,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--ref-elements", type=int, default=1200, help="elements in the bounded CPU sample")
+    ap.add_argument("--ref-elements", type=int, default=4000, help="elements in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -51,7 +51,7 @@ struct movfem_handle {
     double h_Ntab[kMaxGp * kMaxMn];   // N[g][l] packed with stride mn (kernel-parameter copy)
     int nne;
     int64_t nzu, ncontrib, nnze_full;
-    cudaStream_t stream;
+    cudaStream_t stream, copy_stream;   // copy_stream: speculative D2H of the static IRN/JCN, overlapped with the kernels
     bool own_stream;
     // device memory
     double *d_xp, *d_yp, *d_zp, *d_mu;
@@ -267,6 +267,7 @@ void free_all(movfem_handle *h) {
     if (h->h_count) cudaFreeHost(h->h_count);
     for (int i = 0; i < EV_COUNT; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
 }
 
@@ -378,6 +379,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < EV_COUNT; ++i) CK(cudaEventCreate(&h->ev[i]));
     CK(cudaMallocHost((void **)&h->h_status, 4 * sizeof(int)));
     CK(cudaMallocHost((void **)&h->h_count, sizeof(int64_t)));
@@ -592,18 +594,25 @@ int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega, const do
     const MeshDims &m = h->m;
     cudaStream_t st = h->stream;
     CK(cudaEventRecord(h->ev[EV_START], st));
+    // IRN/JCN of the structural pattern never change: start their D2H now, on the copy stream, so that it overlaps
+    // the H2D of g_sigma (PCIe is full duplex) and the kernels.  If rem_zeros strips entries (rare) they are re-sent.
+    CK(cudaMemcpyAsync(irn, h->d_irn, sizeof(int) * (size_t)h->nzu, cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(cudaMemcpyAsync(jcn, h->d_jcn, sizeof(int) * (size_t)h->nzu, cudaMemcpyDeviceToHost, h->copy_stream));
     CK(cudaMemcpyAsync(h->d_sigma, g_sigma, sizeof(double2) * (size_t)6 * m.npt, cudaMemcpyHostToDevice, st));
     int rc = movfem_assemble_device(h, freq_index, omega, reinterpret_cast<const double *>(h->d_sigma), mode);
-    if (rc) return rc;
+    if (rc) { cudaStreamSynchronize(h->copy_stream); return rc; }
     const int32_t *d_irn, *d_jcn;
     const double *d_a, *d_rhs;
     int64_t nz = 0;
     rc = movfem_device_result(h, &d_irn, &d_jcn, &d_a, &d_rhs, &nz);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(irn, d_irn, sizeof(int) * (size_t)nz, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(jcn, d_jcn, sizeof(int) * (size_t)nz, cudaMemcpyDeviceToHost, st));
+    if (rc) { cudaStreamSynchronize(h->copy_stream); return rc; }
     CK(cudaMemcpyAsync(a, d_a, sizeof(double2) * (size_t)nz, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(rhs, d_rhs, sizeof(double2) * (size_t)2 * h->nne, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(h->copy_stream));
+    if (h->compacted) {   // find_zeros > 0: the delivered pattern is the compacted one
+        CK(cudaMemcpyAsync(irn, d_irn, sizeof(int) * (size_t)nz, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(jcn, d_jcn, sizeof(int) * (size_t)nz, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaEventRecord(h->ev[EV_D2H], st));
     CK(cudaStreamSynchronize(st));
     *nz_out = nz;
