@@ -87,6 +87,13 @@ void movfem_destroy(movfem_handle *h);
    structural upper-triangle count (capacity the graft actually needs).                      */
 int movfem_sizes(const movfem_handle *h, int32_t *nne, int64_t *nnze_full, int64_t *nz_upper);
 
+/* Rows owned by the handle: 1-based first row and count.  The whole matrix unless the descriptor asked for an
+   x-slab (ie_lo..ie_hi): a slab handle owns the rows whose first-encounter element lies in the slab -- a contiguous
+   range, because DOFs are numbered in (ie,je,ke) order (global_assembly.f90:237-296) -- computes the +x neighbour
+   layer itself (no exchange) and delivers only those rows; movfem_sizes then reports the LOCAL nz_upper and 0 for
+   nnze_full, and movfem_assemble fills only rows row_lo..row_lo+nrows-1 of each RHS column.               */
+int movfem_slab_rows(const movfem_handle *h, int32_t *row_lo, int32_t *nrows);
+
 /* gne(ne,me), column-major, Fortran values (1-based, -face for Dirichlet edges):
    global_assembly.f90:183-195.  solution.f90:331-336 consumes it after the solve.           */
 int movfem_get_gne(const movfem_handle *h, int32_t *gne);

@@ -49,7 +49,9 @@ struct movfem_handle {
     PmlParams pml;
     int NP, ngp, num_sms;
     double h_Ntab[kMaxGp * kMaxMn];   // N[g][l] packed with stride mn (kernel-parameter copy)
-    int nne;
+    int nne;                 // global number of unknowns
+    int row_lo, nrows;       // rows owned by this handle (whole matrix unless a slab was requested)
+    int e_base, e_own_end, e_end;   // elements [e_base, e_own_end) are owned, [e_own_end, e_end) is the +x halo
     int64_t nzu, ncontrib, nnze_full;
     cudaStream_t stream, copy_stream;   // copy_stream: speculative D2H of the static IRN/JCN, overlapped with the kernels
     bool own_stream;
@@ -286,6 +288,12 @@ int build_pattern(movfem_handle *h) {
     CK(cudaMemcpy(&nne64, d_base + m.ne, sizeof(int64_t), cudaMemcpyDeviceToHost));
     if (nne64 <= 0 || nne64 > 0x1fffffff) { set_err(h, "nne=%lld out of range", (long long)nne64); return MOVFEM_E_CAPACITY; }
     h->nne = (int)nne64;
+    {
+        int64_t rb[2];
+        CK(cudaMemcpy(&rb[0], d_base + h->e_base, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&rb[1], d_base + h->e_own_end, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        h->row_lo = (int)rb[0]; h->nrows = (int)(rb[1] - rb[0]);
+    }
     CK(dmalloc(&h->d_gne, (size_t)m.ne * m.me));
     CK(dmalloc(&h->d_ownE, (size_t)h->nne));
     CK(dmalloc(&h->d_ownL, (size_t)h->nne));
@@ -298,25 +306,26 @@ int build_pattern(movfem_handle *h) {
 
     int *d_rowcnt = nullptr, *d_rowcand = nullptr;
     int64_t *d_rowptr = nullptr, *d_cbase = nullptr;
-    CK(dmalloc(&d_rowcnt, (size_t)h->nne));
-    CK(dmalloc(&d_rowcand, (size_t)h->nne));
-    CK(dmalloc(&d_rowptr, (size_t)h->nne + 1));
-    CK(dmalloc(&d_cbase, (size_t)h->nne + 1));
-    const int rgrid = (h->nne + kRowWarps - 1) / kRowWarps;
+    CK(dmalloc(&d_rowcnt, (size_t)h->nrows));
+    CK(dmalloc(&d_rowcand, (size_t)h->nrows));
+    CK(dmalloc(&d_rowptr, (size_t)h->nrows + 1));
+    CK(dmalloc(&d_cbase, (size_t)h->nrows + 1));
+    const int rgrid = std::max(1, (h->nrows + kRowWarps - 1) / kRowWarps);
     if (m.me == 12)
-        row_kernel<64, false><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->nne, h->NP,
+        row_kernel<64, false><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->row_lo, h->nrows, h->e_base, h->NP,
                                                                      d_rowcnt, d_rowcand, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     else
-        row_kernel<256, false><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->nne, h->NP,
+        row_kernel<256, false><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->row_lo, h->nrows, h->e_base, h->NP,
                                                                       d_rowcnt, d_rowcand, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     h->launches += 1;
     CK(cudaGetLastError());
-    if ((rc = scan_counts(h, d_rowcnt, h->nne, d_rowptr))) return rc;
-    if ((rc = scan_counts(h, d_rowcand, h->nne, d_cbase))) return rc;
-    CK(cudaMemcpy(&h->nzu, d_rowptr + h->nne, sizeof(int64_t), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(&h->ncontrib, d_cbase + h->nne, sizeof(int64_t), cudaMemcpyDeviceToHost));
-    h->nnze_full = 2 * h->nzu - h->nne;   // structurally symmetric pattern, every row has its diagonal
-    if (h->nzu > 0x7fffffffLL || h->ncontrib > 0xffffffffLL || (int64_t)m.ne * h->NP > 0xffffffffLL) {
+    if ((rc = scan_counts(h, d_rowcnt, h->nrows, d_rowptr))) return rc;
+    if ((rc = scan_counts(h, d_rowcand, h->nrows, d_cbase))) return rc;
+    CK(cudaMemcpy(&h->nzu, d_rowptr + h->nrows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&h->ncontrib, d_cbase + h->nrows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    // structurally symmetric pattern, every row has its diagonal; unknown for a slab handle (0)
+    h->nnze_full = (h->nrows == h->nne) ? 2 * h->nzu - h->nne : 0;
+    if (h->nzu > 0x7fffffffLL || h->ncontrib > 0xffffffffLL || (int64_t)(h->e_end - h->e_base) * h->NP > 0xffffffffLL) {
         set_err(h, "pattern too large for 32-bit slots: nz_upper=%lld contributions=%lld", (long long)h->nzu, (long long)h->ncontrib);
         return MOVFEM_E_CAPACITY;
     }
@@ -324,12 +333,12 @@ int build_pattern(movfem_handle *h) {
     CK(dmalloc(&h->d_jcn, (size_t)h->nzu));
     CK(dmalloc(&h->d_cptr, (size_t)h->nzu + 1));
     CK(dmalloc(&h->d_src, (size_t)h->ncontrib));
-    CK(dmalloc(&h->d_rown, (size_t)h->nne * 4));
+    CK(dmalloc(&h->d_rown, (size_t)h->nrows * 4));
     if (m.me == 12)
-        row_kernel<64, true><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->nne, h->NP, nullptr,
+        row_kernel<64, true><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->row_lo, h->nrows, h->e_base, h->NP, nullptr,
                                                                     nullptr, d_rowptr, d_cbase, h->d_irn, h->d_jcn, h->d_cptr, h->d_src, h->d_rown);
     else
-        row_kernel<256, true><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->nne, h->NP, nullptr,
+        row_kernel<256, true><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->row_lo, h->nrows, h->e_base, h->NP, nullptr,
                                                                      nullptr, d_rowptr, d_cbase, h->d_irn, h->d_jcn, h->d_cptr, h->d_src, h->d_rown);
     h->launches += 1;
     CK(cudaGetLastError());
@@ -356,7 +365,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     if (d->g_nx < 2 || d->g_ny < 2 || d->g_nz < 2 || !d->g_xp || !d->g_yp || !d->g_zp || !d->g_mu) return MOVFEM_E_BADARG;
     if (d->ndir != 2 || d->pe_sch != 1 || d->sym != 1) return MOVFEM_E_UNSUPPORTED;   // the driver hard-codes these
     if (d->dirichlet && d->bd_inimod != 1) return MOVFEM_E_UNSUPPORTED;
-    if (d->ie_lo != 0 || d->ie_hi != 0) return MOVFEM_E_UNSUPPORTED;
+    if ((d->ie_lo != 0 || d->ie_hi != 0) && !(d->ie_lo >= 1 && d->ie_lo <= d->ie_hi && d->ie_hi <= d->g_nx - 1)) return MOVFEM_E_BADARG;
     if (!d->dirichlet && (d->nextd < 1 || 2 * d->nextd > std::min(d->g_nx, std::min(d->g_ny, d->g_nz)) - 1)) return MOVFEM_E_BADARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return MOVFEM_E_NOGPU;
@@ -374,6 +383,11 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     if (ne64 > 0x7fffffffLL / 64 * 8 || npt64 > 0x7fffffffLL) { set_err(h, "mesh too large"); return MOVFEM_E_CAPACITY; }
     m.ne = (int)ne64; m.npt = (int)npt64; m.dirichlet = d->dirichlet ? 1 : 0;
     h->NP = m.me * (m.me + 1) / 2; h->ngp = m.ngp;
+    {   // x-slab: DOFs are numbered in (ie,je,ke) first-encounter order, so a range of ie owns a contiguous
+        // range of rows; the +x neighbour layer is computed too so that every owned row is summed locally
+        const int lo = d->ie_lo ? d->ie_lo : 1, hi = d->ie_hi ? d->ie_hi : m.nx;
+        h->e_base = (lo - 1) * m.ny * m.nz; h->e_own_end = hi * m.ny * m.nz; h->e_end = std::min(hi + 1, m.nx) * m.ny * m.nz;
+    }
 
     CK(cudaSetDevice(device));
     CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -417,8 +431,8 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     // always goes through the stretched kernel (its flags are a per-call input)
     {
         std::vector<int> plain, pmlv;
-        plain.reserve(m.ne);
-        for (int e = 0; e < m.ne; ++e) {
+        plain.reserve(h->e_end - h->e_base);
+        for (int e = h->e_base; e < h->e_end; ++e) {
             bool st = false;
             if (!m.dirichlet) {
                 if (e == 0) st = true;
@@ -433,11 +447,11 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     }
 
     // work / result arrays
-    CK(dmalloc(&h->d_KM, (size_t)m.ne * h->NP));
-    CK(dmalloc(&h->d_be, (size_t)m.ne * m.me * 4));
+    CK(dmalloc(&h->d_KM, (size_t)(h->e_end - h->e_base) * h->NP));
+    CK(dmalloc(&h->d_be, (size_t)(h->e_end - h->e_base) * m.me * 4));
     CK(dmalloc(&h->d_a, (size_t)h->nzu)); CK(dmalloc(&h->d_a_c, (size_t)h->nzu));
     CK(dmalloc(&h->d_irn_c, (size_t)h->nzu)); CK(dmalloc(&h->d_jcn_c, (size_t)h->nzu));
-    CK(dmalloc(&h->d_rhs, (size_t)2 * h->nne));
+    CK(dmalloc(&h->d_rhs, (size_t)2 * std::max(h->nrows, 1)));
     h->nblk_fin = (int)((h->nzu + kFinThreads - 1) / kFinThreads);
     CK(dmalloc(&h->d_blkcnt, (size_t)h->nblk_fin)); CK(dmalloc(&h->d_blkoff, (size_t)h->nblk_fin + 1));
     CK(dmalloc(&h->d_finbsum, (size_t)(h->nblk_fin + kScanTile - 1) / kScanTile + 1));
@@ -456,6 +470,13 @@ int movfem_sizes(const movfem_handle *h, int32_t *nne, int64_t *nnze_full, int64
     if (nne) *nne = h->nne;
     if (nnze_full) *nnze_full = h->nnze_full;
     if (nz_upper) *nz_upper = h->nzu;
+    return MOVFEM_OK;
+}
+
+int movfem_slab_rows(const movfem_handle *h, int32_t *row_lo, int32_t *nrows) {
+    if (!h) return MOVFEM_E_BADARG;
+    if (row_lo) *row_lo = h->row_lo + 1;   // 1-based first owned row
+    if (nrows) *nrows = h->nrows;
     return MOVFEM_OK;
 }
 
@@ -507,7 +528,7 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
 
     ElemArgs A;
     A.m = m; A.pml = h->pml; A.omega = omega; A.T = h->d_tab; A.nodes = h->d_nodes; A.xp = h->d_xp; A.yp = h->d_yp;
-    A.list = nullptr; A.nlist = 0; A.KM = h->d_KM; A.be = h->d_be; A.status = h->d_status; A.flags = h->d_flags;
+    A.list = nullptr; A.nlist = 0; A.e_base = h->e_base; A.KM = h->d_KM; A.be = h->d_be; A.status = h->d_status; A.flags = h->d_flags;
     A.skip_unless_changed = 0;
     A.phase_mask = 15;
     std::memcpy(A.Ntab, h->h_Ntab, sizeof(A.Ntab));
@@ -523,7 +544,7 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
 
     gather_finalize_kernel<<<h->nblk_fin, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cptr, h->d_src, h->d_KM, h->d_a,
                                                               h->d_blkcnt, mode == MOVFEM_MODE_T1 ? 1 : 0);
-    rhs_kernel<<<(h->nne + 127) / 128, 128, 0, st>>>(h->nne, h->d_rown, reinterpret_cast<const double4 *>(h->d_be), h->d_rhs);
+    rhs_kernel<<<(h->nrows + 127) / 128, 128, 0, st>>>(h->nrows, h->d_rown, reinterpret_cast<const double4 *>(h->d_be), h->d_rhs);
     h->launches += 2;
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[EV_GATHER], st));
@@ -607,7 +628,11 @@ int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega, const do
     rc = movfem_device_result(h, &d_irn, &d_jcn, &d_a, &d_rhs, &nz);
     if (rc) { cudaStreamSynchronize(h->copy_stream); return rc; }
     CK(cudaMemcpyAsync(a, d_a, sizeof(double2) * (size_t)nz, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(rhs, d_rhs, sizeof(double2) * (size_t)2 * h->nne, cudaMemcpyDeviceToHost, st));
+    // RHS: the caller's array is rhs(ndir*nne), column d at offset (d-1)*nne (global_assembly.f90:70-74); a slab handle
+    // fills only its own rows, so several handles can complete one array
+    for (int dd = 0; dd < 2; ++dd)
+        CK(cudaMemcpyAsync(rhs + 2 * ((size_t)dd * h->nne + h->row_lo), d_rhs + 2 * (size_t)dd * h->nrows, sizeof(double2) * (size_t)h->nrows,
+                           cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(h->copy_stream));
     if (h->compacted) {   // find_zeros > 0: the delivered pattern is the compacted one
         CK(cudaMemcpyAsync(irn, d_irn, sizeof(int) * (size_t)nz, cudaMemcpyDeviceToHost, st));
@@ -676,10 +701,10 @@ int movfem_get_stats(const movfem_handle *h, movfem_stats *out) {
 
 // parity tap: K_e, M_e (packed lower by local index) and b_e of one element after the last assemble
 int movfem_debug_element(movfem_handle *h, int32_t ide, double *Ke, double *Me, double *be) {
-    if (!h || ide < 1 || ide > h->m.ne) return MOVFEM_E_BADARG;
+    if (!h || ide < 1 + h->e_base || ide > h->e_end) return MOVFEM_E_BADARG;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    const size_t e = (size_t)ide - 1;
+    const size_t e = (size_t)ide - 1 - h->e_base;
     std::vector<double2> km(h->NP);
     CK(cudaMemcpy(km.data(), h->d_KM + e * h->NP, sizeof(double2) * h->NP, cudaMemcpyDeviceToHost));
     for (int p = 0; p < h->NP; ++p) { if (Ke) Ke[p] = km[p].x; if (Me) Me[p] = km[p].y; }

@@ -99,6 +99,7 @@ struct ElemArgs {
     const double *xp, *yp;
     const int *list;      // element ids (0-based) this launch handles
     int nlist;
+    int e_base;           // first element stored in KM / be (slab handles keep only their slab + halo)
     double2 *KM;          // [ne][NP] (K_e, M_e) interleaved: one 16-byte access per local pair
     double *be;           // [ne][ME][4]  (re,im) x 2 polarisations
     int *status;
@@ -613,7 +614,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
         // ---- write-out: element-major, packed lower triangle by LOCAL DOF index ----
         if (DO_KM && (A.phase_mask & 8) && tid < nb * NTILES) {
             const int64_t e = s_el[ts * 4];
-            double2 *KMo = A.KM + e * NP;
+            double2 *KMo = A.KM + (e - A.e_base) * NP;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int si = 4 * ti + i, im = s_slot[si];
@@ -630,7 +631,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
         }
         if (tid < nb * MEP && cdof >= 0) {
             const int64_t e = s_el[cs * 4];
-            reinterpret_cast<double4 *>(A.be)[e * ME + cdof] = make_double4(bacc[0], bacc[1], bacc[2], bacc[3]);
+            reinterpret_cast<double4 *>(A.be)[(e - A.e_base) * ME + cdof] = make_double4(bacc[0], bacc[1], bacc[2], bacc[3]);
         }
     }
 }

@@ -66,9 +66,9 @@ compact_kernel(int64_t nzu, const int64_t *__restrict__ blk_off, const int *__re
 }
 
 // b(gne + (d-1)*nne) += blocal(d): sum of the <= 4 sharing elements in ascending element order
-__global__ void rhs_kernel(int nne, const int *__restrict__ rown, const double4 *__restrict__ be, double2 *__restrict__ rhs) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nne) return;
+__global__ void rhs_kernel(int nrows, const int *__restrict__ rown, const double4 *__restrict__ be, double2 *__restrict__ rhs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;   // row local to the handle's slab; rhs is [2][nrows]
+    if (r >= nrows) return;
     double b0r = 0, b0i = 0, b1r = 0, b1i = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -78,7 +78,7 @@ __global__ void rhs_kernel(int nne, const int *__restrict__ rown, const double4 
         b0r = b0r + v.x; b0i = b0i + v.y; b1r = b1r + v.z; b1i = b1i + v.w;
     }
     rhs[r] = make_double2(b0r, b0i);
-    rhs[(int64_t)nne + r] = make_double2(b1r, b1i);
+    rhs[(int64_t)nrows + r] = make_double2(b1r, b1i);
 }
 
 }  // namespace movfem

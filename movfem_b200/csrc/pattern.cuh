@@ -181,14 +181,15 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t *k, int lane) {
 template <int CAP, bool FILL>
 __global__ void __launch_bounds__(kRowWarps * 32)
 row_kernel(MeshDims m, const ShareTables *__restrict__ stp, const int *__restrict__ gne, const int *__restrict__ ownE,
-           const uint8_t *__restrict__ ownL, int nne, int NP, int *__restrict__ rowcnt, int *__restrict__ rowcand,
+           const uint8_t *__restrict__ ownL, int row_lo, int nrows, int e_base, int NP, int *__restrict__ rowcnt, int *__restrict__ rowcand,
            const int64_t *__restrict__ row_ptr, const int64_t *__restrict__ cbase, int *__restrict__ irn,
            int *__restrict__ jcn, int64_t *__restrict__ cptr, uint32_t *__restrict__ src, int *__restrict__ rown) {
     __shared__ uint64_t s_keys[kRowWarps][CAP];
     __shared__ int s_el[kRowWarps][4], s_ll[kRowWarps][4], s_n[kRowWarps];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * kRowWarps + w;
-    if (r >= nne) return;
+    const int rl = blockIdx.x * kRowWarps + w;      // row index local to this handle's slab
+    if (rl >= nrows) return;
+    const int r = row_lo + rl;                      // global row (0-based DOF id)
     const ShareTables &st = *stp;
     uint64_t *keys = s_keys[w];
     if (lane == 0) {
@@ -239,19 +240,19 @@ row_kernel(MeshDims m, const ShareTables *__restrict__ stp, const int *__restric
         const unsigned fb = __ballot_sync(0xffffffffu, first), vb = __ballot_sync(0xffffffffu, valid);
         if (FILL && valid) {
             const int k = (int)((key >> 8) & 0xff), jm = (int)(key & 0xff), c = (int)(key >> 16);
-            const int64_t cpos = cbase[r] + idx;   // valid keys sort to the front, so idx is the rank
-            src[cpos] = (uint32_t)((int64_t)s_el[w][k] * NP + pair_index(s_ll[w][k] - 1, jm));
+            const int64_t cpos = cbase[rl] + idx;   // valid keys sort to the front, so idx is the rank
+            src[cpos] = (uint32_t)((int64_t)(s_el[w][k] - e_base) * NP + pair_index(s_ll[w][k] - 1, jm));
             if (first) {
-                const int64_t pos = row_ptr[r] + nuniq + __popc(fb & ((1u << lane) - 1));
+                const int64_t pos = row_ptr[rl] + nuniq + __popc(fb & ((1u << lane) - 1));
                 irn[pos] = r + 1; jcn[pos] = c; cptr[pos] = cpos;
             }
         }
         nuniq += __popc(fb); ncand += __popc(vb);
     }
     if (lane == 0) {
-        if (!FILL) { rowcnt[r] = nuniq; rowcand[r] = ncand; }
+        if (!FILL) { rowcnt[rl] = nuniq; rowcand[rl] = ncand; }
         else
-            for (int i = 0; i < 4; ++i) rown[(int64_t)r * 4 + i] = s_el[w][i] < 0 ? -1 : s_el[w][i] * me + (s_ll[w][i] - 1);
+            for (int i = 0; i < 4; ++i) rown[(int64_t)rl * 4 + i] = s_el[w][i] < 0 ? -1 : (s_el[w][i] - e_base) * me + (s_ll[w][i] - 1);
     }
 }
 

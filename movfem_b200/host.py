@@ -55,6 +55,7 @@ def lib():
         L.movfem_destroy.argtypes = [vp]
         L.movfem_destroy.restype = None
         L.movfem_sizes.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
+        L.movfem_slab_rows.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
         L.movfem_get_gne.argtypes = [vp, vp]
         L.movfem_get_pattern.argtypes = [vp, vp, vp]
         L.movfem_assemble.argtypes = [vp, i32, dbl, vp, vp, vp, vp, vp, C.POINTER(i64), i32]
@@ -76,7 +77,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "movfem_create", "movfem_destroy", "movfem_sizes", "movfem_get_gne", "movfem_get_pattern", "movfem_assemble",
     "movfem_assemble_device", "movfem_device_result", "movfem_set_stream", "movfem_get_stats", "movfem_last_error",
-    "movfem_version", "movfem_debug_element", "movfem_reset_cache", "movfem_fp64_peak",
+    "movfem_version", "movfem_debug_element", "movfem_reset_cache", "movfem_fp64_peak", "movfem_slab_rows",
 ]
 
 
@@ -111,6 +112,9 @@ class Assembly:
         lib().movfem_sizes(self._h, C.byref(nne), C.byref(nnze), C.byref(nzu))
         self.nne, self.nnze, self.nz_upper = nne.value, nnze.value, nzu.value
         self.me, self.mn, self.ne = model.me, model.mn, model.ne
+        lo, n = C.c_int32(), C.c_int32()
+        lib().movfem_slab_rows(self._h, C.byref(lo), C.byref(n))
+        self.row_lo, self.nrows = lo.value, n.value          # 1-based first owned row, count (x-slab handles)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -199,3 +199,34 @@ def test_device_resident_api():
     rc = rt.cudaMemcpy(buf.ctypes.data, p_a, nz * 16, 2)
     assert int(rc) == 0 and np.array_equal(buf, a[:nz])
     asm.close()
+
+
+@pytest.mark.parametrize("mn,dirichlet", [(8, 0), (20, 1), (27, 0)])
+def test_x_slab_handles_concatenate_to_the_full_assembly(mn, dirichlet):
+    """SURVEY 8e slab sharding: handles that own ranges of ie (plus a +x halo they compute themselves) deliver
+    disjoint, contiguous row ranges; concatenated in slab order they are bit-identical to the single-handle result."""
+    import copy
+    from movfem_b200.sharding import slab_partition
+    m = mesh.build_model("slab", 7, 4, mn, 1000., 1100., 900., 2, 2, 1, dirichlet=dirichlet, gpml_sch=0, freqs=(0.5,),
+                         sigma_fn=mesh._layered((1500., 1500., 500., 1500.)), topo_amp=30.0)
+    om, sg = m.omega(1), m.sigma_for(1)
+    full = host.Assembly(m)
+    irn, jcn, a, rhs, nz = full.global_vfem(1, om, sg)
+    world = 3
+    parts, rhs_acc, row_next = [], np.zeros(2 * full.nne, np.complex128), 1
+    for r in range(world):
+        ms = copy.copy(m)
+        ms.ie_lo, ms.ie_hi = slab_partition(m.g_nx - 1, r, world)
+        sl = host.Assembly(ms)
+        assert sl.nne == full.nne and sl.row_lo == row_next
+        row_next += sl.nrows
+        i2, j2, a2, _, n2 = sl.global_vfem(1, om, sg, rhs=rhs_acc)
+        assert n2 == sl.nz_upper and (n2 == 0 or (i2[:n2].min() >= sl.row_lo and i2[:n2].max() < sl.row_lo + sl.nrows))
+        parts.append((i2[:n2].copy(), j2[:n2].copy(), a2[:n2].copy()))
+        sl.close()
+    assert row_next == full.nne + 1
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), irn[:nz])
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), jcn[:nz])
+    assert np.array_equal(np.concatenate([p[2] for p in parts]), a[:nz])
+    assert np.array_equal(rhs_acc, rhs)
+    full.close()
