@@ -449,8 +449,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     // work / result arrays
     CK(dmalloc(&h->d_KM, (size_t)(h->e_end - h->e_base) * h->NP));
     CK(dmalloc(&h->d_be, (size_t)(h->e_end - h->e_base) * m.me * 4));
-    CK(dmalloc(&h->d_a, (size_t)h->nzu)); CK(dmalloc(&h->d_a_c, (size_t)h->nzu));
-    CK(dmalloc(&h->d_irn_c, (size_t)h->nzu)); CK(dmalloc(&h->d_jcn_c, (size_t)h->nzu));
+    CK(dmalloc(&h->d_a, (size_t)h->nzu));   // the compacted copies (a_c, irn_c, jcn_c) are allocated on first use
     CK(dmalloc(&h->d_rhs, (size_t)2 * std::max(h->nrows, 1)));
     h->nblk_fin = (int)((h->nzu + kFinThreads - 1) / kFinThreads);
     CK(dmalloc(&h->d_blkcnt, (size_t)h->nblk_fin)); CK(dmalloc(&h->d_blkoff, (size_t)h->nblk_fin + 1));
@@ -584,6 +583,9 @@ int movfem_device_result(const movfem_handle *hc, const int32_t **irn, const int
         else {
             h->nz_last = *h->h_count;
             if (h->nz_last != h->nzu) {   // find_zeros > 0: rem_zeros (global_assembly.f90:134-150)
+                if (!h->d_a_c) {
+                    CK(dmalloc(&h->d_a_c, (size_t)h->nzu)); CK(dmalloc(&h->d_irn_c, (size_t)h->nzu)); CK(dmalloc(&h->d_jcn_c, (size_t)h->nzu));
+                }
                 compact_kernel<<<h->nblk_fin, kFinThreads, 0, h->stream>>>(h->nzu, h->d_blkoff, h->d_irn, h->d_jcn, h->d_a, h->d_irn_c,
                                                                           h->d_jcn_c, h->d_a_c);
                 h->launches += 1;
