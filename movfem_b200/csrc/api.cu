@@ -51,6 +51,7 @@ struct movfem_handle {
     double h_Ntab[kMaxGp * kMaxMn];   // N[g][l] packed with stride mn (kernel-parameter copy)
     int nne;                 // global number of unknowns
     int row_lo, nrows;       // rows owned by this handle (whole matrix unless a slab was requested)
+    int node_lo, node_hi;    // node id range [lo, hi) touched by the slab's elements
     int e_base, e_own_end, e_end;   // elements [e_base, e_own_end) are owned, [e_own_end, e_end) is the +x halo
     int64_t nzu, ncontrib, nnze_full;
     cudaStream_t stream, copy_stream;   // copy_stream: speculative D2H of the static IRN/JCN, overlapped with the kernels
@@ -387,6 +388,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
         // range of rows; the +x neighbour layer is computed too so that every owned row is summed locally
         const int lo = d->ie_lo ? d->ie_lo : 1, hi = d->ie_hi ? d->ie_hi : m.nx;
         h->e_base = (lo - 1) * m.ny * m.nz; h->e_own_end = hi * m.ny * m.nz; h->e_end = std::min(hi + 1, m.nx) * m.ny * m.nz;
+        h->node_lo = (lo - 1) * (m.nord - 1) * m.nyz; h->node_hi = std::min(hi + 1, m.nx) * (m.nord - 1) * m.nyz + m.nyz;
     }
 
     CK(cudaSetDevice(device));
@@ -519,7 +521,7 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
     }
     CK(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), st));
     CK(cudaEventRecord(h->ev[EV_H2D], st));
-    node_kernel<<<(m.npt + 127) / 128, 128, 0, st>>>(m.npt, omega, h->d_zp, h->d_mu, reinterpret_cast<const double2 *>(g_sigma_dev),
+    node_kernel<<<(h->node_hi - h->node_lo + 127) / 128, 128, 0, st>>>(h->node_lo, h->node_hi, omega, h->d_zp, h->d_mu, reinterpret_cast<const double2 *>(g_sigma_dev),
                                                     h->d_nodes, h->d_status, h->d_flags, h->km_valid ? 1 : 0);
     h->launches += 1;
     CK(cudaGetLastError());
@@ -621,7 +623,8 @@ int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega, const do
     // the H2D of g_sigma (PCIe is full duplex) and the kernels.  If rem_zeros strips entries (rare) they are re-sent.
     CK(cudaMemcpyAsync(irn, h->d_irn, sizeof(int) * (size_t)h->nzu, cudaMemcpyDeviceToHost, h->copy_stream));
     CK(cudaMemcpyAsync(jcn, h->d_jcn, sizeof(int) * (size_t)h->nzu, cudaMemcpyDeviceToHost, h->copy_stream));
-    CK(cudaMemcpyAsync(h->d_sigma, g_sigma, sizeof(double2) * (size_t)6 * m.npt, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_sigma + (size_t)6 * h->node_lo, reinterpret_cast<const double2 *>(g_sigma) + (size_t)6 * h->node_lo,
+                       sizeof(double2) * (size_t)6 * (h->node_hi - h->node_lo), cudaMemcpyHostToDevice, st));
     int rc = movfem_assemble_device(h, freq_index, omega, reinterpret_cast<const double *>(h->d_sigma), mode);
     if (rc) { cudaStreamSynchronize(h->copy_stream); return rc; }
     const int32_t *d_irn, *d_jcn;

@@ -35,10 +35,10 @@ namespace movfem {
 // ------------------------------------------------------------------------------------------
 // node kernel: problem.f90:257-358 per grid node instead of per (element, node)
 // ------------------------------------------------------------------------------------------
-__global__ void node_kernel(int npt, double omega, const double *__restrict__ zp, const double *__restrict__ mu,
+__global__ void node_kernel(int n0, int npt, double omega, const double *__restrict__ zp, const double *__restrict__ mu,
                             const double2 *__restrict__ sigma, NodeRec *__restrict__ out, int *__restrict__ status,
                             int *__restrict__ flags /* [0]: any dmu != 0, [1]: Re sigma changed */, int check_re) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;   // [n0, npt): the node planes this handle's slab touches
     if (i >= npt) return;
     double a[6];
     double2 s[6];
