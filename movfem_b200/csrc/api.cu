@@ -17,6 +17,7 @@
 
 #include "../../include/movfem_b200.h"
 #include "common.cuh"
+#include "contract.cuh"
 #include "element.cuh"
 #include "finalize.cuh"
 #include "pattern.cuh"
@@ -27,16 +28,22 @@ using namespace movfem;
 namespace {
 
 // ---- kernel configurations (tuned on B200) -------------------------------------
-//                     MN  ME MEP NGP EB THREADS MINB PML
-// EB / THREADS are chosen so that every phase fills whole warps (idle lanes cost FP64-pipe time):
-//   me=12: 16 el -> 128 (el,gp) / 192 (el,slot) / 96 tiles     me=36: 4 el -> 108 / 144 / 180
-//   me=54:  2 el ->  54 / 120 / 240                            (GPML variants: smaller batches, more smem)
-using Cfg12  = ElemCfg<8, 12, 12, 8, 16, 192, 3, false>;
-using Cfg12p = ElemCfg<8, 12, 12, 8, 16, 192, 2, true>;
-using Cfg36  = ElemCfg<20, 36, 36, 27, 4, 192, 3, false>;
-using Cfg36p = ElemCfg<20, 36, 36, 27, 4, 192, 2, true>;
-using Cfg54  = ElemCfg<27, 54, 60, 27, 2, 256, 2, false>;
-using Cfg54p = ElemCfg<27, 54, 60, 27, 2, 256, 2, true>;
+// geometry_kernel:     MN  ME MEP NGP EB THREADS MINB PML     (EB x NGP threads in phase B2, EB x NCOL in B1)
+using Geo12  = ElemCfg<8, 12, 12, 8, 16, 128, 4, false>;
+using Geo12p = ElemCfg<8, 12, 12, 8, 16, 128, 3, true>;
+using Geo36  = ElemCfg<20, 36, 36, 27, 8, 224, 2, false>;
+using Geo36p = ElemCfg<20, 36, 36, 27, 8, 224, 1, true>;
+using Geo54  = ElemCfg<27, 54, 60, 27, 4, 128, 3, false>;
+using Geo54p = ElemCfg<27, 54, 60, 27, 4, 128, 2, true>;
+// contract_kernel:          ME MEP NGP PML   W STAGES    (W consumer warps + 1 producer warp; ring of STAGES class blocks)
+using Con12  = ContractCfg<12, 12, 8, false, 6, 6>;
+using Con12p = ContractCfg<12, 12, 8, true, 6, 3>;
+using Con36  = ContractCfg<36, 36, 27, false, 15, 5>;
+using Con36p = ContractCfg<36, 36, 27, true, 9, 2>;
+using Con54  = ContractCfg<54, 60, 27, false, 15, 4>;
+using Con54p = ContractCfg<54, 60, 27, true, 12, 2>;
+
+constexpr size_t kScratchCap = (size_t)512 << 20;   // Q|P,T scratch: larger lists are processed in chunks
 
 enum { EV_START, EV_H2D, EV_NODE, EV_ELEM, EV_GATHER, EV_FINAL, EV_D2H, EV_COUNT };
 
@@ -69,6 +76,9 @@ struct movfem_handle {
     uint32_t *d_src;
     double2 *d_KM;
     double *d_be;
+    double *d_qt;            // Q|P,T scratch between geometry_kernel and contract_kernel
+    size_t qt_bytes;
+    ContractTables ct;       // constant-bank tables of this element type
     double2 *d_a, *d_a_c, *d_rhs;
     int *d_list_plain, *d_list_pml;
     int n_plain, n_pml;
@@ -221,40 +231,114 @@ void init_pml(const movfem_desc &d, const MeshDims &m, PmlParams &p) {
     p.omegar[0] = 2.0 * kPi * f1; p.omegar[1] = 2.0 * kPi * f2;
 }
 
-template <class CFG, bool DO_KM>
-int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist) {
-    if (nlist <= 0) return 0;
-    auto kern = element_kernel<CFG, DO_KM>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::SMEM));
-    A.list = d_list; A.nlist = nlist;
-    // persistent CTAs: one resident wave, each CTA strides over the element batches
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CFG::THREADS, CFG::SMEM));
-    const int nbatch = (nlist + CFG::EB - 1) / CFG::EB;
-    const int grid = std::max(1, std::min(nbatch, std::max(1, per_sm) * h->num_sms));
-    kern<<<grid, CFG::THREADS, CFG::SMEM, h->stream>>>(A);
-    h->launches += 1;
-    CK(cudaGetLastError());
+// ---- constant-bank tables of the contraction ------------------------------------------------------------------
+// c_ct holds the tables of ONE element type per device.  A process normally assembles one element type; when handles
+// of different types alternate, the switch waits for the device to drain before the symbol is overwritten.
+int g_ct_owner[64];   // element type (me) resident in c_ct, per device; 0 = none
+
+void build_contract_tables(const MeshDims &m, const ElemTables &T, ContractTables &C) {
+    std::memset(&C, 0, sizeof(C));
+    const int mep = T.nslots, nt = mep / 4;
+    for (int g = 0; g < m.ngp; ++g)
+        for (int sl = 0; sl < mep; ++sl) {
+            const int dof = T.slot_dof[sl];
+            for (int k = 0; k < 3; ++k) C.at[(g * 4 + k) * mep + sl] = dof >= 0 ? T.dphi[g][dof][k] : 0.0;
+            C.at[(g * 4 + 3) * mep + sl] = dof >= 0 ? T.phi[g][dof] : 0.0;
+        }
+    for (int sl = 0; sl < kMaxSlots; ++sl) C.slot_dof[sl] = sl < mep ? (short)T.slot_dof[sl] : (short)-1;
+    // tiles of the lower triangle (4x4 slot blocks), sorted by direction-pair class
+    int nt_out = 0;
+    for (int c = 0; c < 6; ++c) {
+        C.cls_begin[c] = (short)nt_out;
+        for (int ti = 0; ti < nt; ++ti)
+            for (int tj = 0; tj <= ti; ++tj)
+                if (T.slot_dir[4 * ti] == cls_dI(c) && T.slot_dir[4 * tj] == cls_dJ(c)) {
+                    C.tile_ti[nt_out] = (unsigned char)ti; C.tile_tj[nt_out] = (unsigned char)tj; ++nt_out;
+                }
+    }
+    C.cls_begin[6] = (short)nt_out;
+    // scratch components a class streams: plain Q[r0|r1(dI)][m0|m1(dJ)] (components 0-5, sym3 order) and T[dI][dJ]
+    // (6-11); GPML P[(u,dI)][(v,dJ)] (0-44, up9 order) and T (45-50)
+    for (int c = 0; c < 6; ++c) {
+        const int dI = cls_dI(c), dJ = cls_dJ(c);
+        const int r0 = dI == 0 ? 1 : 0, r1 = dI == 2 ? 1 : 2, m0 = dJ == 0 ? 1 : 0, m1 = dJ == 2 ? 1 : 2;
+        C.comp[0][c][0] = (unsigned char)sym3(r0, m0); C.comp[0][c][1] = (unsigned char)sym3(r0, m1);
+        C.comp[0][c][2] = (unsigned char)sym3(r1, m0); C.comp[0][c][3] = (unsigned char)sym3(r1, m1);
+        C.comp[0][c][4] = (unsigned char)(6 + sym3(dI, dJ));
+        for (int u = 0; u < 3; ++u)
+            for (int v = 0; v < 3; ++v) {
+                const int r = u * 3 + dI, cc = v * 3 + dJ;
+                C.comp[1][c][u * 3 + v] = (unsigned char)(r <= cc ? up9(r, cc) : up9(cc, r));
+            }
+        C.comp[1][c][9] = (unsigned char)(45 + sym3(dI, dJ));
+    }
+}
+
+int const_table_acquire(movfem_handle *h) {
+    if (h->device >= 64) return MOVFEM_E_BADARG;
+    if (g_ct_owner[h->device] == h->m.me) return 0;
+    CK(cudaDeviceSynchronize());   // no kernel of another element type may still be reading c_ct
+    CK(cudaMemcpyToSymbol(c_ct, &h->ct, sizeof(ContractTables)));
+    g_ct_owner[h->device] = h->m.me;
     return 0;
 }
 
-template <class CP, class CQ>
+// geometry (+ RHS) and contraction of one element list, in chunks that fit the scratch
+template <class GEO, class CON, bool DO_QT>
+int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist, int skip_unless_changed) {
+    if (nlist <= 0) return 0;
+    auto gk = geometry_kernel<GEO, DO_QT>;
+    auto ck = contract_kernel<CON>;
+    CK(cudaFuncSetAttribute(gk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEO::SMEM));
+    int g_per_sm = 0, c_per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_per_sm, gk, GEO::THREADS, GEO::SMEM));
+    if (DO_QT) {
+        CK(cudaFuncSetAttribute(ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CON::SMEM));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_per_sm, ck, CON::THREADS, CON::SMEM));
+        int rc = const_table_acquire(h);
+        if (rc) return rc;
+    }
+    // chunks: equal sizes, whole 32-element batches, each chunk's scratch within the buffer
+    const size_t per_batch = sizeof(double) * (size_t)CON::NCMP * CON::CB;
+    const int64_t max_batches = std::max<int64_t>(1, (int64_t)(h->qt_bytes / per_batch));
+    const int64_t nbatch_all = (nlist + 31) / 32;
+    const int64_t nchunks = DO_QT ? (nbatch_all + max_batches - 1) / max_batches : 1;
+    const int64_t chunk_b = (nbatch_all + nchunks - 1) / nchunks;
+    A.skip_unless_changed = skip_unless_changed;
+    for (int64_t cb = 0; cb < nbatch_all; cb += chunk_b) {
+        const int off = (int)(cb * 32), n = (int)std::min<int64_t>(nlist - off, chunk_b * 32);
+        A.list = d_list + off; A.nlist = n; A.qt = DO_QT ? h->d_qt : nullptr;
+        const int ngb = (n + GEO::EB - 1) / GEO::EB;
+        gk<<<std::max(1, std::min(ngb, std::max(1, g_per_sm) * h->num_sms)), GEO::THREADS, GEO::SMEM, h->stream>>>(A);
+        h->launches += 1;
+        CK(cudaGetLastError());
+        if (DO_QT) {
+            ContractArgs C;
+            C.qt = h->d_qt; C.list = A.list; C.nlist = n; C.e_base = h->e_base; C.KM = h->d_KM; C.flags = h->d_flags;
+            C.skip_unless_changed = skip_unless_changed;
+            const int ncb = (n + 31) / 32;
+            ck<<<std::max(1, std::min(ncb, std::max(1, c_per_sm) * h->num_sms)), CON::THREADS, CON::SMEM, h->stream>>>(C);
+            h->launches += 1;
+            CK(cudaGetLastError());
+        }
+    }
+    return 0;
+}
+
+template <class GP, class CP, class GQ, class CQ>
 int run_elements(movfem_handle *h, ElemArgs &A, bool full) {
     int rc;
     // unstretched elements: K_e, M_e are frequency independent -> computed on the first
     // frequency and whenever Re(sigma) changed; their RHS is rebuilt every frequency
     if (full) {
-        A.skip_unless_changed = 0;
-        if ((rc = launch_elements<CP, true>(h, A, h->d_list_plain, h->n_plain))) return rc;
+        if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 0))) return rc;
     } else {
-        A.skip_unless_changed = 0;
-        if ((rc = launch_elements<CP, false>(h, A, h->d_list_plain, h->n_plain))) return rc;
-        A.skip_unless_changed = 1;   // refresh K/M only if the node kernel saw Re(sigma) change
-        if ((rc = launch_elements<CP, true>(h, A, h->d_list_plain, h->n_plain))) return rc;
-        A.skip_unless_changed = 0;
+        if ((rc = launch_elements<GP, CP, false>(h, A, h->d_list_plain, h->n_plain, 0))) return rc;
+        // refresh K/M only if the node kernel saw Re(sigma) change
+        if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 1))) return rc;
     }
     // stretched (GPML) elements depend on omega through h: always recomputed
-    if ((rc = launch_elements<CQ, true>(h, A, h->d_list_pml, h->n_pml))) return rc;
+    if ((rc = launch_elements<GQ, CQ, true>(h, A, h->d_list_pml, h->n_pml, 0))) return rc;
     return 0;
 }
 
@@ -262,7 +346,7 @@ void free_all(movfem_handle *h) {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_xp, h->d_yp, h->d_zp, h->d_mu, h->d_sigma, h->d_nodes, h->d_tab, h->d_share, h->d_gne, h->d_ownE,
                     h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_src, h->d_KM,
-                    h->d_be, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum,
+                    h->d_be, h->d_qt, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum,
                     h->d_status, h->d_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -420,6 +504,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
         for (int g = 0; g < m.ngp; ++g)
             for (int l = 0; l < m.mn; ++l) h->h_Ntab[g * m.mn + l] = T[0].N[g][l];
         CK(cudaMemcpy(h->d_share, &S, sizeof(ShareTables), cudaMemcpyHostToDevice));
+        build_contract_tables(m, T[0], h->ct);
     }
     init_pml(*d, m, h->pml);
 
@@ -451,6 +536,13 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     // work / result arrays
     CK(dmalloc(&h->d_KM, (size_t)(h->e_end - h->e_base) * h->NP));
     CK(dmalloc(&h->d_be, (size_t)(h->e_end - h->e_base) * m.me * 4));
+    {   // Q|P,T scratch: whole 32-element batches of the larger of the two lists, capped (launch_elements chunks)
+        const size_t cb = sizeof(double) * (size_t)m.ngp * 32;
+        const size_t need = std::max((size_t)((h->n_plain + 31) / 32) * 12 * cb, (size_t)((h->n_pml + 31) / 32) * 51 * cb);
+        h->qt_bytes = std::max(std::min(need, kScratchCap), (size_t)51 * cb);
+        CK(cudaMalloc((void **)&h->d_qt, h->qt_bytes));
+        CK(cudaMemset(h->d_qt, 0, h->qt_bytes));   // lanes past the end of a ragged last batch read zeros, not NaNs
+    }
     CK(dmalloc(&h->d_a, (size_t)h->nzu));   // the compacted copies (a_c, irn_c, jcn_c) are allocated on first use
     CK(dmalloc(&h->d_rhs, (size_t)2 * std::max(h->nrows, 1)));
     h->nblk_fin = (int)((h->nzu + kFinThreads - 1) / kFinThreads);
@@ -529,16 +621,15 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
 
     ElemArgs A;
     A.m = m; A.pml = h->pml; A.omega = omega; A.T = h->d_tab; A.nodes = h->d_nodes; A.xp = h->d_xp; A.yp = h->d_yp;
-    A.list = nullptr; A.nlist = 0; A.e_base = h->e_base; A.KM = h->d_KM; A.be = h->d_be; A.status = h->d_status; A.flags = h->d_flags;
+    A.list = nullptr; A.nlist = 0; A.e_base = h->e_base; A.qt = nullptr; A.be = h->d_be; A.status = h->d_status; A.flags = h->d_flags;
     A.skip_unless_changed = 0;
-    A.phase_mask = 15;
-    std::memcpy(A.Ntab, h->h_Ntab, sizeof(A.Ntab));
+    A.phase_mask = 3;
     if (const char *pm = getenv("MOVFEM_PHASE_MASK")) A.phase_mask = atoi(pm);   // profiling aid only
     int rc;
     const bool full = !h->km_valid;
-    if (m.me == 12) rc = run_elements<Cfg12, Cfg12p>(h, A, full);
-    else if (m.me == 36) rc = run_elements<Cfg36, Cfg36p>(h, A, full);
-    else rc = run_elements<Cfg54, Cfg54p>(h, A, full);
+    if (m.me == 12) rc = run_elements<Geo12, Con12, Geo12p, Con12p>(h, A, full);
+    else if (m.me == 36) rc = run_elements<Geo36, Con36, Geo36p, Con36p>(h, A, full);
+    else rc = run_elements<Geo54, Con54, Geo54p, Con54p>(h, A, full);
     if (rc) return rc;
     h->km_valid = true;
     CK(cudaEventRecord(h->ev[EV_ELEM], st));

@@ -23,8 +23,9 @@
 // 3 + 3 of the B^T D B form (and 143 flops of the reference's expanded f1/f2).  Inside the GPML
 // layers the stretched half-curls do not collapse to a curl; there K uses the 9x9 real tensor
 // P = H^T D6 H with H[a][(u,d)] = s_a G[x_a][u] G[y_a][d] and costs 3 FMAs per pair and point.
-// DOFs are permuted into direction-uniform groups of four, and the contraction runs as
-// register-tiled 4x4 FP64 FMA blocks over the lower triangle, one operand a constant table.
+//
+// geometry_kernel (this file) produces Q|P, T per (element, Gauss point) into an L2-resident scratch and the
+// element RHS b_e; contract_kernel (contract.cuh) turns the scratch into K_e, M_e.
 // A_e = K_e + i*f32(omega)*M_e is formed later, per frequency (finalize.cuh), so K_e, M_e of the
 // unstretched elements are frequency independent and cached in HBM across a sweep.
 #pragma once
@@ -100,15 +101,12 @@ struct ElemArgs {
     const int *list;      // element ids (0-based) this launch handles
     int nlist;
     int e_base;           // first element stored in KM / be (slab handles keep only their slab + halo)
-    double2 *KM;          // [ne][NP] (K_e, M_e) interleaved: one 16-byte access per local pair
+    double *qt;           // scratch [nbatch32][NCMP][NGP][32]: Q|P and T per (element, Gauss point), see contract.cuh
     double *be;           // [ne][ME][4]  (re,im) x 2 polarisations
     int *status;
     const int *flags;     // flags[0] any dmu, flags[1] Re sigma changed
     int skip_unless_changed;   // launch is a cache refresh: exit unless flags[1]
-    int phase_mask;            // profiling aid (MOVFEM_PHASE_MASK): bit0 B, bit1 C, bit2 D, bit3 write-out; default 15
-    // nodal shape functions at the Gauss points, N[g][l], in the kernel parameter = constant bank: the
-    // material interpolation reads them as uniform constant operands, costing no shared-memory bandwidth
-    double Ntab[kMaxGp * kMaxMn];
+    int phase_mask;            // profiling aid (MOVFEM_PHASE_MASK): bit0 B, bit1 RHS; default 3
 };
 
 // columns interpolated to the Gauss points by phase B1 (record offsets into NodeRec, see common.cuh):
@@ -121,29 +119,19 @@ template <int MN_, int ME_, int MEP_, int NGP_, int EB_, int THREADS_, int MINB_
 struct ElemCfg {
     static constexpr int MN = MN_, ME = ME_, MEP = MEP_, NGP = NGP_, EB = EB_, THREADS = THREADS_, MINB = MINB_;
     static constexpr bool PML = PML_;
-    static constexpr int NT = MEP / 4, NTILES = NT * (NT + 1) / 2;
-    static constexpr int NP = ME * (ME + 1) / 2;
-    static constexpr int KA = PML ? 3 : 2;                 // K operand components per (slot, Gauss point)
-    static constexpr int NA = KA + 1;                      // a-table rows: K comps + phi
     static constexpr int NDW = kNodeDoubles + 2;           // node record + x + y
-    static constexpr int GEO = (PML ? 45 : 6) + 6 + 12 + (PML ? 1 : 0);   // P|Q, T, R  (kept even)
-    static constexpr int NCOL = PML ? 30 : 24;             // columns interpolated by phase B1 (<= GEO: stored in place)
-    // shared memory: a-table [NGP][NA][MEP] | geometry [EB][NGP][GEO] | node records [EB][MN][NDW]
-    static constexpr size_t ATAB_D = (size_t)NGP * NA * MEP, GEO_D = (size_t)EB * NGP * GEO;
+    static constexpr int NCOL = PML ? 30 : 24;             // columns interpolated by phase B1
+    static constexpr int GEO = NCOL;                       // per (element, Gauss point) record: the columns, then R (12) in place
+    static constexpr int NCMP = PML ? 51 : 12;             // scratch components: P(45)|Q(6), T(6)
+    static constexpr int MNP = (MN + 1) & ~1;              // row stride of the N table (16-byte aligned rows)
+    // shared memory: phi table [NGP][MEP] + N table [NGP][MNP] | records [EB][NGP][GEO] | node records [EB][MN][NDW]
+    static constexpr size_t ATAB_D = (size_t)NGP * MEP + (size_t)NGP * MNP, GEO_D = (size_t)EB * NGP * GEO;
     static constexpr int NSTR = MN * NDW + 2;              // per-element stride of the node records (+16 B: bank shift)
     static constexpr size_t NODES_D = (size_t)EB * NSTR;
     static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + NODES_D) + sizeof(int) * (EB * 4 + 2 * MEP);
-    static_assert(MEP % 4 == 0 && (ATAB_D % 2) == 0 && (GEO_D % 2) == 0, "16-byte alignment of the smem regions");
-    static_assert(THREADS >= EB * NTILES && THREADS >= EB * MEP, "one tile / one slot per thread");
-    static_assert(NCOL <= GEO, "interpolated columns are overwritten in place by the geometry record");
+    static_assert((ATAB_D % 2) == 0 && (GEO_D % 2) == 0, "16-byte alignment of the smem regions");
+    static_assert(32 % EB == 0, "a batch of the contraction (32 lanes) is a whole number of geometry batches");
 };
-
-// B / a-table rows are stored with the two 16-byte halves of every 4-slot group swapped in alternate
-// groups of four, so that the distinct groups a warp touches in one LDS.128 fall into distinct banks.
-__device__ __forceinline__ int swz(int j) {
-    const int grp = j >> 2, pos = j & 3;
-    return (grp << 2) + ((((pos >> 1) ^ ((grp >> 2) & 1)) << 1) | (pos & 1));
-}
 
 // gpml_h for one axis, boundary_conds.f90:94-123
 __device__ __forceinline__ double2 gpml_axis(const PmlParams &p, int flag, int axis, double r, double omega) {
@@ -188,18 +176,22 @@ __host__ __device__ __forceinline__ constexpr int sym3(int r, int c) {
 // index of (r,c), r <= c, in a packed upper-triangular 9x9 stored row-major
 __host__ __device__ __forceinline__ constexpr int up9(int r, int c) { return r * 9 - r * (r - 1) / 2 + (c - r); }
 
-template <class CFG, bool DO_KM>
-__global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemArgs A) {
+// DO_QT = false: RHS-only variant for the unstretched elements of a later frequency of a sweep (their K_e, M_e are
+// cached): only the source columns are interpolated and Q, T are neither formed nor written.
+template <class CFG, bool DO_QT>
+__global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemArgs A) {
     constexpr int MN = CFG::MN, ME = CFG::ME, MEP = CFG::MEP, EB = CFG::EB, NGP = CFG::NGP;
-    constexpr int NA = CFG::NA, KA = CFG::KA;
-    constexpr int GEO = CFG::GEO, NDW = CFG::NDW, NTILES = CFG::NTILES, NP = CFG::NP;
+    constexpr int GEO = CFG::GEO, NDW = CFG::NDW, NCMP = CFG::NCMP;
     constexpr bool PML = CFG::PML;
-    constexpr int GQ = 0, GT = PML ? 45 : 6, GR = GT + 6;   // offsets inside one geometry record
+    constexpr int GR = 0;                                   // R overwrites the record's first 12 columns
+    constexpr int CLO = DO_QT ? 0 : 12, CHI = DO_QT ? CFG::NCOL : 24, NCOLA = CHI - CLO;   // active columns
+    static_assert(DO_QT || !PML, "stretched elements are always recomputed in full");
     if (A.skip_unless_changed && A.flags[1] == 0) return;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_at = reinterpret_cast<double *>(smem_raw);              // [NGP][NA][MEP] constant operand (swizzled rows)
-    double *s_geo = s_at + CFG::ATAB_D;                               // [EB][NGP][GEO]
+    double *s_phi = reinterpret_cast<double *>(smem_raw);             // [NGP][MEP] phi in slot order
+    double *s_N = s_phi + NGP * MEP;                                  // [NGP][MNP] nodal shape functions N[g][l]
+    double *s_geo = s_phi + CFG::ATAB_D;                              // [EB][NGP][GEO]
     double *s_nodes = s_geo + CFG::GEO_D;                             // [EB][MN][NDW]
     int *s_el = reinterpret_cast<int *>(s_nodes + CFG::NODES_D);      // [EB][4]: element id, GPML flags
     int *s_slot = s_el + EB * 4;                                      // [MEP] slot -> local DOF (0-based) or -1
@@ -210,39 +202,16 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
     const MeshDims &m = A.m;
     const int tid = threadIdx.x;
 
-    // ---- once per CTA: the constant operand table of the contraction, in slot order ----
-    //   plain: rows 0,1 = c_i[perp(d_i)] = (dphi x e_d) components, row 2 = phi_i
-    //   GPML : rows 0..2 = dphi_i[u],                              row 3 = phi_i
     for (int i = tid; i < NGP * MEP; i += CFG::THREADS) {
         const int g = i / MEP, sl = i % MEP;
-        const int dof = T.slot_dof[sl], d = T.slot_dir[sl];
-        double v[4] = {0.0, 0.0, 0.0, 0.0};
-        if (dof >= 0) {
-            const double d0 = T.dphi[g][dof][0], d1 = T.dphi[g][dof][1], d2 = T.dphi[g][dof][2];
-            if (PML) { v[0] = d0; v[1] = d1; v[2] = d2; }
-            else if (d == 0) { v[0] = d2; v[1] = -d1; }      // c = (0, dphi_z, -dphi_y): comps 1,2
-            else if (d == 1) { v[0] = -d2; v[1] = d0; }      // c = (-dphi_z, 0, dphi_x): comps 0,2
-            else { v[0] = d1; v[1] = -d0; }                  // c = (dphi_y, -dphi_x, 0): comps 0,1
-            v[KA] = T.phi[g][dof];
-        }
-#pragma unroll
-        for (int k = 0; k < NA; ++k) s_at[(g * NA + k) * MEP + swz(sl)] = v[k];
+        const int dof = T.slot_dof[sl];
+        s_phi[i] = dof >= 0 ? T.phi[g][dof] : 0.0;
     }
     for (int i = tid; i < MEP; i += CFG::THREADS) { s_slot[i] = T.slot_dof[i]; s_sdir[i] = T.slot_dir[i]; }
-
-    // tile owned by this thread in the contraction (lower triangle of 4x4 blocks in slot space)
-    const int ts = tid / NTILES, tt = tid % NTILES;
-    int ti = 0, tj = 0;
-    {
-        int rem = tt;
-        while (rem > ti) { rem -= ti + 1; ++ti; }
-        tj = rem;
+    for (int i = tid; i < NGP * CFG::MNP; i += CFG::THREADS) {
+        const int g = i / CFG::MNP, l = i % CFG::MNP;
+        s_N[i] = l < MN ? T.N[g][l] : 0.0;
     }
-    // swizzled 16-byte half offsets of this thread's row / column groups (in doubles)
-    const int a_lo = 4 * ti + (((ti >> 2) & 1) << 1), a_hi = 4 * ti + ((((ti >> 2) & 1) ^ 1) << 1);
-    const int b_lo = 4 * tj + (((tj >> 2) & 1) << 1), b_hi = 4 * tj + ((((tj >> 2) & 1) ^ 1) << 1);
-    // slot owned by this thread in the basis phase
-    const int cs = tid / MEP, cslot = tid % MEP, cpos = swz(cslot);
 
     const int nbatch = (A.nlist + EB - 1) / EB;
     // asynchronous gather of one batch's node records into s_nodes (16-byte cp.async pieces, coalesced per record)
@@ -279,25 +248,25 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
         }
 
         // ---- phase A: the node records of this batch were requested with cp.async while the previous batch was in
-        //      its contraction (s_nodes is dead after phase B2); wait for them here ----
+        //      its RHS phase (s_nodes is dead after phase B2); wait for them here ----
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
 
         // ---- phase B1: one thread per (element, column): interpolate node data to the Gauss points ----
         // (p_intmodels problem.f90:139-142 and the N_l-weighted part of p_source problem.f90:424-457).  The
-        // thread keeps its column of the MN node records in registers; N[g][l] comes from the constant bank.
+        // thread keeps its column of the MN node records in registers; N[g][l] is warp-uniform and read from shared
+        // memory with broadcast 128-bit loads (constant-bank operands are slower: tools/micro/ldcu_bench.cu).
         if (A.phase_mask & 1) {
             const double psig = f32r(A.omega * kEps0);   // pset_pmodel, problem.f90:250
-            // warp w handles Gauss-point range `part` of (element, column) pairs (w % PW)*32 + lane, so that the
-            // range is warp-uniform and N[g][l] is an immediate constant-bank operand of the fully unrolled FMAs
-            constexpr int NW = CFG::THREADS / 32, PW = (EB * CFG::NCOL + 31) / 32;
+            // warp w handles Gauss-point range `part` of (element, column) pairs (w % PW)*32 + lane
+            constexpr int NW = CFG::THREADS / 32, PW = (EB * NCOLA + 31) / 32;
             constexpr int GS = PW >= NW ? 1 : (NW / PW >= 4 ? 4 : (NW / PW >= 2 ? 2 : 1));
             const int wid = tid >> 5, lane = tid & 31;
             const int part = GS == 1 ? 0 : wid / PW;
             const int stride = GS == 1 ? CFG::THREADS : PW * 32;
             if (part < GS)
-                for (int it = GS == 1 ? tid : (wid % PW) * 32 + lane; it < nb * CFG::NCOL; it += stride) {
-                    const int s = it / CFG::NCOL, c = it % CFG::NCOL;
+                for (int it = GS == 1 ? tid : (wid % PW) * 32 + lane; it < nb * NCOLA; it += stride) {
+                    const int s = it / NCOLA, c = CLO + it % NCOLA;
                     const double *nd = s_nodes + s * CFG::NSTR;
                     const int off = kColOff[c], flag = kColFlag[c];
                     double v[MN];
@@ -312,7 +281,11 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
 #define MOVFEM_B1_RANGE(G0, G1)                                                              \
     _Pragma("unroll") for (int g = (G0); g < (G1); ++g) {                                    \
         double acc = 0.0;                                                                    \
-        _Pragma("unroll") for (int l = 0; l < MN; ++l) acc = dfma(A.Ntab[g * MN + l], v[l], acc); \
+        _Pragma("unroll") for (int l = 0; l + 1 < MN; l += 2) {                              \
+            const double2 n2 = *reinterpret_cast<const double2 *>(s_N + g * CFG::MNP + l);   \
+            acc = dfma(n2.x, v[l], acc); acc = dfma(n2.y, v[l + 1], acc);                    \
+        }                                                                                    \
+        if (MN & 1) acc = dfma(s_N[g * CFG::MNP + MN - 1], v[MN - 1], acc);                  \
         out[g * GEO] = acc;                                                                  \
     }
                     if constexpr (GS == 1) { MOVFEM_B1_RANGE(0, NGP) }
@@ -329,14 +302,18 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
         }
         __syncthreads();
 
-        // ---- phase B2: one thread per (element, Gauss point): J, G, GPML, source -> Q|P, T, R (in place) ----
+        // ---- phase B2: one thread per (Gauss point, element): J, G, GPML, source -> Q|P, T (scratch), R (in place) ----
         if (A.phase_mask & 1) {
             const int has_dmu = A.flags[0];
             const double w32 = f32r(A.omega);            // cmplx(0.d0,-omega), problem.f90:112
             for (int i = tid; i < nb * NGP; i += CFG::THREADS) {
-                const int s = i / NGP, g = i % NGP;
+                const int g = i / nb, s = i % nb;       // element fastest: runs of EB lanes in the scratch
                 const double *nd = s_nodes + s * CFG::NSTR;
                 double *geo = s_geo + (s * NGP + g) * GEO;
+                // scratch position of this (element, Gauss point): qt[batch32][component][g][lane]
+                const int pos = first + s;
+                double *qo = A.qt + ((size_t)(pos >> 5) * NCMP * NGP + g) * 32 + (pos & 31);
+                constexpr size_t QS = (size_t)NGP * 32;   // component stride
                 // nf_jacobian, n_fem.f90:359-366: J(m,n) = sum_l dN_l/dxi_m * r_l(n), l ascending, no FMA
                 double J[3][3];
 #pragma unroll
@@ -370,8 +347,10 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
                 // interpolated columns of phase B1 (this thread's record is overwritten below)
                 double mu[6], sr[6], si[6] = {0, 0, 0, 0, 0, 0};
                 double dm1r[3], dm1i[3], dm2r[3], dm2i[3];
+                if (DO_QT) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) { mu[k] = geo[k]; sr[k] = geo[6 + k]; if (PML) si[k] = geo[24 + k]; }
+                    for (int k = 0; k < 6; ++k) { mu[k] = geo[k]; sr[k] = geo[6 + k]; if (PML) si[k] = geo[24 + k]; }
+                }
                 // signs: pol 1 dmpf = (+Im ds*e, -Re ds*e), pol 2 = (-Im ds*e, +Re ds*e)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { dm1r[k] = geo[12 + k]; dm1i[k] = -geo[15 + k]; dm2r[k] = -geo[18 + k]; dm2i[k] = geo[21 + k]; }
@@ -415,7 +394,6 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
                     double wmu[6];
 #pragma unroll
                     for (int k = 0; k < 6; ++k) wmu[k] = w * mu[k];
-                    double *P = geo + GQ;
 #pragma unroll 1
                     for (int col = 0; col < 9; ++col) {
                         const int v = col / 3, e2 = col % 3;
@@ -435,10 +413,10 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
                             double acc = 0.0;
 #pragma unroll
                             for (int a = 0; a < 6; ++a) acc = dfma(sa[a] * G[xa[a]][u] * G[ya[a]][d2], DH[a], acc);
-                            P[up9(row, col)] = acc;
+                            qo[up9(row, col) * QS] = acc;
                         }
                     }
-                } else {
+                } else if (DO_QT) {
                     // Q = (w/det^2) J mu^-1 J^T  (curl N = (1/det J) J^T (dphi x e_d))
                     const double f = w / (det * det);
                     double Jm[3][3];
@@ -452,10 +430,10 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
                     for (int a = 0; a < 3; ++a)
 #pragma unroll
                         for (int b = a; b < 3; ++b)
-                            geo[GQ + q6++] = f * dfma(Jm[a][0], J[b][0], dfma(Jm[a][1], J[b][1], Jm[a][2] * J[b][2]));
+                            qo[(q6++) * QS] = f * dfma(Jm[a][0], J[b][0], dfma(Jm[a][1], J[b][1], Jm[a][2] * J[b][2]));
                 }
                 // T = G^T S G with the mass tensor S = w Re[h1h2h3 sigma_g] (integration.f90:228-236, Q3)
-                {
+                if (DO_QT) {
                     double S[6], SG[3][3];
 #pragma unroll
                     for (int k = 0; k < 6; ++k) S[k] = PML ? w * (hhh.x * sr[k] - hhh.y * si[k]) : w * sr[k];
@@ -469,7 +447,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
                     for (int a = 0; a < 3; ++a)
 #pragma unroll
                         for (int b = a; b < 3; ++b)
-                            geo[GT + q6++] = dfma(G[0][a], SG[0][b], dfma(G[1][a], SG[1][b], G[2][a] * SG[2][b]));
+                            qo[((PML ? 45 : 6) + q6++) * QS] = dfma(G[0][a], SG[0][b], dfma(G[1][a], SG[1][b], G[2][a] * SG[2][b]));
                 }
                 // R[d][pol] = G[:,d] . (w h1h2h3 src_pol);  src = (dmpf + pcrl) * cmplx32(0,-omega)  (problem.f90:112)
                 {
@@ -492,146 +470,26 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) element_kernel(ElemAr
         }
         __syncthreads();
 
-        if (batch + (int)gridDim.x < nbatch) request_nodes(batch + gridDim.x);   // lands during the contraction
+        if (batch + (int)gridDim.x < nbatch) request_nodes(batch + gridDim.x);   // lands during the RHS phase / next wait
 
         // ---- RHS: one thread per (element, slot): blocal / f3, integration.f90:96-104,258-263 ----
-        const int cdof = s_slot[cslot], cd = s_sdir[cslot];
-        double bacc[4] = {0.0, 0.0, 0.0, 0.0};
-        if ((A.phase_mask & 2) && tid < nb * MEP) {
-#pragma unroll 3
-            for (int g = 0; g < NGP; ++g) {
-                const double phi = s_at[(size_t)(g * NA + KA) * MEP + cpos];
-                const double *R = s_geo + (cs * NGP + g) * GEO + GR + cd * 4;
-                bacc[0] = dfma(phi, R[0], bacc[0]); bacc[1] = dfma(phi, R[1], bacc[1]);
-                bacc[2] = dfma(phi, R[2], bacc[2]); bacc[3] = dfma(phi, R[3], bacc[3]);
-            }
-        }
-
-        // ---- contraction: register-tiled 4x4 blocks over the lower triangle in slot space.  The thread forms the
-        //      element-dependent operand of its four COLUMN slots on the fly from a 2x2 block of Q (3x3 block of P
-        //      in the GPML layers) and one entry of T; the row operand is the constant table. ----
-        double accK[16], accM[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { accK[i] = 0.0; accM[i] = 0.0; }
-        if (DO_KM && (A.phase_mask & 4) && tid < nb * NTILES) {
-            const int dI = s_sdir[4 * ti], dJ = s_sdir[4 * tj];
-            const double *geo0 = s_geo + (size_t)ts * NGP * GEO;
-            const int it = GT + sym3(dI, dJ);
-            if (!PML) {
-                // axes perpendicular to the row / column direction: the non-zero components of c_i, c_j
-                const int r0 = dI == 0 ? 1 : 0, r1 = dI == 2 ? 1 : 2, m0 = dJ == 0 ? 1 : 0, m1 = dJ == 2 ? 1 : 2;
-                const int i00 = GQ + sym3(r0, m0), i01 = GQ + sym3(r0, m1), i10 = GQ + sym3(r1, m0), i11 = GQ + sym3(r1, m1);
-                // K pass and M pass are separate loops over the Gauss points: 16 live accumulators each instead of 32,
-                // which keeps the kernel at 3 resident CTAs per SM without spilling
+        if (A.phase_mask & 2) {
+            for (int i = tid; i < nb * MEP; i += CFG::THREADS) {
+                const int cs = i / MEP, cslot = i % MEP;
+                const int cdof = s_slot[cslot], cd = s_sdir[cslot];
+                double bacc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 3
                 for (int g = 0; g < NGP; ++g) {
-                    const double *Ag = s_at + (size_t)g * NA * MEP;
-                    const double *geo = geo0 + g * GEO;
-                    const double q00 = geo[i00], q01 = geo[i01], q10 = geo[i10], q11 = geo[i11];
-                    double a1[4], a2[4], b1[4], b2[4];
-                    {
-                        const double2 x0 = *reinterpret_cast<const double2 *>(Ag + a_lo), x1 = *reinterpret_cast<const double2 *>(Ag + a_hi);
-                        const double2 y0 = *reinterpret_cast<const double2 *>(Ag + MEP + a_lo), y1 = *reinterpret_cast<const double2 *>(Ag + MEP + a_hi);
-                        a1[0] = x0.x; a1[1] = x0.y; a1[2] = x1.x; a1[3] = x1.y;
-                        a2[0] = y0.x; a2[1] = y0.y; a2[2] = y1.x; a2[3] = y1.y;
-                    }
-                    {
-                        const double2 x0 = *reinterpret_cast<const double2 *>(Ag + b_lo), x1 = *reinterpret_cast<const double2 *>(Ag + b_hi);
-                        const double2 y0 = *reinterpret_cast<const double2 *>(Ag + MEP + b_lo), y1 = *reinterpret_cast<const double2 *>(Ag + MEP + b_hi);
-                        const double c1[4] = {x0.x, x0.y, x1.x, x1.y}, c2[4] = {y0.x, y0.y, y1.x, y1.y};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            b1[j] = dfma(q00, c1[j], q01 * c2[j]);     // (Q c_j)[r0]
-                            b2[j] = dfma(q10, c1[j], q11 * c2[j]);     // (Q c_j)[r1]
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) accK[i * 4 + j] = dfma(a1[i], b1[j], dfma(a2[i], b2[j], accK[i * 4 + j]));
+                    const double phi = s_phi[g * MEP + cslot];
+                    const double *R = s_geo + (cs * NGP + g) * GEO + GR + cd * 4;
+                    bacc[0] = dfma(phi, R[0], bacc[0]); bacc[1] = dfma(phi, R[1], bacc[1]);
+                    bacc[2] = dfma(phi, R[2], bacc[2]); bacc[3] = dfma(phi, R[3], bacc[3]);
                 }
-#pragma unroll 3
-                for (int g = 0; g < NGP; ++g) {
-                    const double *Ag = s_at + (size_t)(g * NA + 2) * MEP;
-                    const double t = geo0[g * GEO + it];
-                    const double2 z0 = *reinterpret_cast<const double2 *>(Ag + a_lo), z1 = *reinterpret_cast<const double2 *>(Ag + a_hi);
-                    const double2 w0 = *reinterpret_cast<const double2 *>(Ag + b_lo), w1 = *reinterpret_cast<const double2 *>(Ag + b_hi);
-                    const double a3[4] = {z0.x, z0.y, z1.x, z1.y};
-                    const double bw[4] = {w0.x * t, w0.y * t, w1.x * t, w1.y * t};    // phi_j T[d_i][d_j]
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) accM[i * 4 + j] = dfma(a3[i], bw[j], accM[i * 4 + j]);
-                }
-            } else {
-                int ip[9];
-#pragma unroll
-                for (int u = 0; u < 3; ++u)
-#pragma unroll
-                    for (int v = 0; v < 3; ++v) {
-                        const int r = u * 3 + dI, c = v * 3 + dJ;
-                        ip[u * 3 + v] = GQ + (r <= c ? up9(r, c) : up9(c, r));
-                    }
-#pragma unroll 1
-                for (int g = 0; g < NGP; ++g) {
-                    const double *Ag = s_at + (size_t)g * NA * MEP;
-                    const double *geo = geo0 + g * GEO;
-                    double P[9];
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) P[k] = geo[ip[k]];
-                    const double t = geo[it];
-                    double a[4][4], b[3][4], bw[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const double2 x0 = *reinterpret_cast<const double2 *>(Ag + k * MEP + a_lo), x1 = *reinterpret_cast<const double2 *>(Ag + k * MEP + a_hi);
-                        a[k][0] = x0.x; a[k][1] = x0.y; a[k][2] = x1.x; a[k][3] = x1.y;
-                    }
-                    {
-                        double c[4][4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const double2 x0 = *reinterpret_cast<const double2 *>(Ag + k * MEP + b_lo), x1 = *reinterpret_cast<const double2 *>(Ag + k * MEP + b_hi);
-                            c[k][0] = x0.x; c[k][1] = x0.y; c[k][2] = x1.x; c[k][3] = x1.y;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                            for (int u = 0; u < 3; ++u) b[u][j] = dfma(P[u * 3], c[0][j], dfma(P[u * 3 + 1], c[1][j], P[u * 3 + 2] * c[2][j]));
-                            bw[j] = c[3][j] * t;
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            accK[i * 4 + j] = dfma(a[0][i], b[0][j], dfma(a[1][i], b[1][j], dfma(a[2][i], b[2][j], accK[i * 4 + j])));
-                            accM[i * 4 + j] = dfma(a[3][i], bw[j], accM[i * 4 + j]);
-                        }
+                if (cdof >= 0) {
+                    const int64_t e = s_el[cs * 4];
+                    reinterpret_cast<double4 *>(A.be)[(e - A.e_base) * ME + cdof] = make_double4(bacc[0], bacc[1], bacc[2], bacc[3]);
                 }
             }
-        }
-
-        // ---- write-out: element-major, packed lower triangle by LOCAL DOF index ----
-        if (DO_KM && (A.phase_mask & 8) && tid < nb * NTILES) {
-            const int64_t e = s_el[ts * 4];
-            double2 *KMo = A.KM + (e - A.e_base) * NP;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int si = 4 * ti + i, im = s_slot[si];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int sj = 4 * tj + j, jm = s_slot[sj];
-                    if (im >= 0 && jm >= 0 && sj <= si) {
-                        const int hi = im > jm ? im : jm, lo = im > jm ? jm : im;
-                        const int p = hi * (hi + 1) / 2 + lo;
-                        KMo[p] = make_double2(accK[i * 4 + j], accM[i * 4 + j]);
-                    }
-                }
-            }
-        }
-        if (tid < nb * MEP && cdof >= 0) {
-            const int64_t e = s_el[cs * 4];
-            reinterpret_cast<double4 *>(A.be)[(e - A.e_base) * ME + cdof] = make_double4(bacc[0], bacc[1], bacc[2], bacc[3]);
         }
     }
 }
