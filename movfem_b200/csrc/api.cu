@@ -82,6 +82,9 @@ struct movfem_handle {
     double2 *d_a, *d_a_c, *d_rhs;
     int *d_list_plain, *d_list_pml;
     int n_plain, n_pml;
+    int *d_kmrow;            // element (slab-local) -> row of the K/M store: plain list first, each list padded to 32
+    std::vector<int> kmrow;
+    int64_t km_rows;
     int *d_blkcnt;
     int64_t *d_blkoff, *d_finbsum;
     int nblk_fin;
@@ -285,7 +288,7 @@ int const_table_acquire(movfem_handle *h) {
 
 // geometry (+ RHS) and contraction of one element list, in chunks that fit the scratch
 template <class GEO, class CON, bool DO_QT>
-int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist, int skip_unless_changed) {
+int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist, int64_t km_row0, int skip_unless_changed) {
     if (nlist <= 0) return 0;
     auto gk = geometry_kernel<GEO, DO_QT>;
     auto ck = contract_kernel<CON>;
@@ -314,7 +317,7 @@ int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist,
         CK(cudaGetLastError());
         if (DO_QT) {
             ContractArgs C;
-            C.qt = h->d_qt; C.list = A.list; C.nlist = n; C.e_base = h->e_base; C.KM = h->d_KM; C.flags = h->d_flags;
+            C.qt = h->d_qt; C.nlist = n; C.KM = h->d_KM + (size_t)(km_row0 + off) * h->NP; C.flags = h->d_flags;
             C.skip_unless_changed = skip_unless_changed;
             const int ncb = (n + 31) / 32;
             ck<<<std::max(1, std::min(ncb, std::max(1, c_per_sm) * h->num_sms)), CON::THREADS, CON::SMEM, h->stream>>>(C);
@@ -331,14 +334,14 @@ int run_elements(movfem_handle *h, ElemArgs &A, bool full) {
     // unstretched elements: K_e, M_e are frequency independent -> computed on the first
     // frequency and whenever Re(sigma) changed; their RHS is rebuilt every frequency
     if (full) {
-        if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 0))) return rc;
+        if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 0, 0))) return rc;
     } else {
-        if ((rc = launch_elements<GP, CP, false>(h, A, h->d_list_plain, h->n_plain, 0))) return rc;
+        if ((rc = launch_elements<GP, CP, false>(h, A, h->d_list_plain, h->n_plain, 0, 0))) return rc;
         // refresh K/M only if the node kernel saw Re(sigma) change
-        if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 1))) return rc;
+        if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 0, 1))) return rc;
     }
     // stretched (GPML) elements depend on omega through h: always recomputed
-    if ((rc = launch_elements<GQ, CQ, true>(h, A, h->d_list_pml, h->n_pml, 0))) return rc;
+    if ((rc = launch_elements<GQ, CQ, true>(h, A, h->d_list_pml, h->n_pml, (h->n_plain + 31) / 32 * 32, 0))) return rc;
     return 0;
 }
 
@@ -346,7 +349,7 @@ void free_all(movfem_handle *h) {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_xp, h->d_yp, h->d_zp, h->d_mu, h->d_sigma, h->d_nodes, h->d_tab, h->d_share, h->d_gne, h->d_ownE,
                     h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_src, h->d_KM,
-                    h->d_be, h->d_qt, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum,
+                    h->d_be, h->d_qt, h->d_kmrow, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum,
                     h->d_status, h->d_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -398,10 +401,10 @@ int build_pattern(movfem_handle *h) {
     const int rgrid = std::max(1, (h->nrows + kRowWarps - 1) / kRowWarps);
     if (m.me == 12)
         row_kernel<64, false><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->row_lo, h->nrows, h->e_base, h->NP,
-                                                                     d_rowcnt, d_rowcand, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+                                                                     d_rowcnt, d_rowcand, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     else
         row_kernel<256, false><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->row_lo, h->nrows, h->e_base, h->NP,
-                                                                      d_rowcnt, d_rowcand, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+                                                                      d_rowcnt, d_rowcand, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     h->launches += 1;
     CK(cudaGetLastError());
     if ((rc = scan_counts(h, d_rowcnt, h->nrows, d_rowptr))) return rc;
@@ -410,7 +413,7 @@ int build_pattern(movfem_handle *h) {
     CK(cudaMemcpy(&h->ncontrib, d_cbase + h->nrows, sizeof(int64_t), cudaMemcpyDeviceToHost));
     // structurally symmetric pattern, every row has its diagonal; unknown for a slab handle (0)
     h->nnze_full = (h->nrows == h->nne) ? 2 * h->nzu - h->nne : 0;
-    if (h->nzu > 0x7fffffffLL || h->ncontrib > 0xffffffffLL || (int64_t)(h->e_end - h->e_base) * h->NP > 0xffffffffLL) {
+    if (h->nzu > 0x7fffffffLL || h->ncontrib > 0xffffffffLL || h->km_rows * h->NP > 0xffffffffLL) {
         set_err(h, "pattern too large for 32-bit slots: nz_upper=%lld contributions=%lld", (long long)h->nzu, (long long)h->ncontrib);
         return MOVFEM_E_CAPACITY;
     }
@@ -421,10 +424,10 @@ int build_pattern(movfem_handle *h) {
     CK(dmalloc(&h->d_rown, (size_t)h->nrows * 4));
     if (m.me == 12)
         row_kernel<64, true><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->row_lo, h->nrows, h->e_base, h->NP, nullptr,
-                                                                    nullptr, d_rowptr, d_cbase, h->d_irn, h->d_jcn, h->d_cptr, h->d_src, h->d_rown);
+                                                                    nullptr, d_rowptr, d_cbase, h->d_irn, h->d_jcn, h->d_cptr, h->d_src, h->d_rown, h->d_kmrow);
     else
         row_kernel<256, true><<<rgrid, kRowWarps * 32, 0, h->stream>>>(m, h->d_share, h->d_gne, h->d_ownE, h->d_ownL, h->row_lo, h->nrows, h->e_base, h->NP, nullptr,
-                                                                     nullptr, d_rowptr, d_cbase, h->d_irn, h->d_jcn, h->d_cptr, h->d_src, h->d_rown);
+                                                                     nullptr, d_rowptr, d_cbase, h->d_irn, h->d_jcn, h->d_cptr, h->d_src, h->d_rown, h->d_kmrow);
     h->launches += 1;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->d_cptr + h->nzu, &h->ncontrib, sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
@@ -511,9 +514,6 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     CK(dmalloc(&h->d_status, 1)); CK(dmalloc(&h->d_flags, 2));
     CK(cudaMemset(h->d_status, 0, sizeof(int))); CK(cudaMemset(h->d_flags, 0, 2 * sizeof(int)));
 
-    int rc = build_pattern(h);
-    if (rc) return rc;
-
     // element lists: stretched = predecessor in loop order carries a GPML flag (Q17); element (1,1,1)
     // always goes through the stretched kernel (its flags are a per-call input)
     {
@@ -531,10 +531,22 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
         CK(dmalloc(&h->d_list_plain, plain.size())); CK(dmalloc(&h->d_list_pml, pmlv.size()));
         if (!plain.empty()) CK(cudaMemcpy(h->d_list_plain, plain.data(), sizeof(int) * plain.size(), cudaMemcpyHostToDevice));
         if (!pmlv.empty()) CK(cudaMemcpy(h->d_list_pml, pmlv.data(), sizeof(int) * pmlv.size(), cudaMemcpyHostToDevice));
+        // rows of the K/M store: list position, the plain list first, each list padded to whole 32-element batches
+        const int pml_row0 = (h->n_plain + 31) / 32 * 32;
+        h->km_rows = (int64_t)pml_row0 + (h->n_pml + 31) / 32 * 32;
+        h->kmrow.resize(h->e_end - h->e_base);
+        for (size_t i = 0; i < plain.size(); ++i) h->kmrow[plain[i] - h->e_base] = (int)i;
+        for (size_t i = 0; i < pmlv.size(); ++i) h->kmrow[pmlv[i] - h->e_base] = pml_row0 + (int)i;
+        CK(dmalloc(&h->d_kmrow, h->kmrow.size()));
+        CK(cudaMemcpy(h->d_kmrow, h->kmrow.data(), sizeof(int) * h->kmrow.size(), cudaMemcpyHostToDevice));
     }
 
+
+    int rc = build_pattern(h);
+    if (rc) return rc;
+
     // work / result arrays
-    CK(dmalloc(&h->d_KM, (size_t)(h->e_end - h->e_base) * h->NP));
+    CK(dmalloc(&h->d_KM, (size_t)h->km_rows * h->NP));
     CK(dmalloc(&h->d_be, (size_t)(h->e_end - h->e_base) * m.me * 4));
     {   // Q|P,T scratch: whole 32-element batches of the larger of the two lists, capped (launch_elements chunks)
         const size_t cb = sizeof(double) * (size_t)m.ngp * 32;
@@ -802,7 +814,9 @@ int movfem_debug_element(movfem_handle *h, int32_t ide, double *Ke, double *Me, 
     CK(cudaStreamSynchronize(h->stream));
     const size_t e = (size_t)ide - 1 - h->e_base;
     std::vector<double2> km(h->NP);
-    CK(cudaMemcpy(km.data(), h->d_KM + e * h->NP, sizeof(double2) * h->NP, cudaMemcpyDeviceToHost));
+    const int kr = h->kmrow[e];
+    CK(cudaMemcpy2D(km.data(), sizeof(double2), h->d_KM + ((size_t)(kr >> 5) * h->NP << 5) + (kr & 31), 32 * sizeof(double2), sizeof(double2), h->NP,
+                    cudaMemcpyDeviceToHost));
     for (int p = 0; p < h->NP; ++p) { if (Ke) Ke[p] = km[p].x; if (Me) Me[p] = km[p].y; }
     if (be) CK(cudaMemcpy(be, h->d_be + e * h->m.me * 4, sizeof(double) * h->m.me * 4, cudaMemcpyDeviceToHost));
     return MOVFEM_OK;

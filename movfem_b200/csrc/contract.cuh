@@ -21,7 +21,8 @@
 // streams, per (batch, class), the 5 (10) component blocks that class needs into a shared-memory ring with
 // cp.async.bulk (TMA 1-D bulk copies, 6.9 kB each) signalled through mbarriers; W consumer warps walk the classes
 // in order, each taking the tiles t = w (mod W) of the class, and hand the ring slot back through a second mbarrier.
-// Results go out element-major, packed lower triangle by LOCAL DOF index, (K,M) interleaved as double2.
+// Results go out as (K,M) double2, packed lower triangle by LOCAL DOF index, the 32 elements of a batch interleaved
+// ([batch][pair][lane]) so that every store instruction of a warp writes 512 contiguous bytes.
 #pragma once
 #include "common.cuh"
 
@@ -45,10 +46,8 @@ __host__ __device__ __forceinline__ constexpr int cls_dJ(int c) { return c == 0 
 
 struct ContractArgs {
     const double *qt;     // [nbatch][NCMP][NGP][32]
-    const int *list;      // element ids (0-based) in scratch order
-    int nlist;
-    int e_base;
-    double2 *KM;          // [ne][NP]
+    int nlist;            // elements in this launch (scratch order = K/M row order)
+    double2 *KM;          // K/M store at this launch's first row: [batch][NP][32 lanes]
     const int *flags;     // flags[1]: Re sigma changed (cache refresh launches)
     int skip_unless_changed;
 };
@@ -144,9 +143,8 @@ __global__ void __launch_bounds__(CFG::THREADS, 1) contract_kernel(ContractArgs 
     // ---- consumers ----
     int n = 0;
     for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
-        const int pos = b * 32 + lane;
-        const int64_t el = pos < A.nlist ? (int64_t)A.list[pos] : -1;
-        double2 *KMo = A.KM + (el - A.e_base) * NP;
+        const bool live = b * 32 + lane < A.nlist;
+        double2 *KMo = A.KM + (size_t)b * NP * 32 + lane;
 #pragma unroll 1
         for (int c = 0; c < 6; ++c, ++n) {
             const int slot = n % STAGES, round = n / STAGES;
@@ -223,8 +221,8 @@ __global__ void __launch_bounds__(CFG::THREADS, 1) contract_kernel(ContractArgs 
                         }
                     }
                 }
-                // write-out: element-major, packed lower triangle by LOCAL DOF index
-                if (el >= 0) {
+                // write-out: packed lower triangle by LOCAL DOF index, 32 elements interleaved -> 512-byte coalesced stores
+                if (live) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int si = 4 * ti + i, im = c_ct.slot_dof[si];
@@ -233,7 +231,7 @@ __global__ void __launch_bounds__(CFG::THREADS, 1) contract_kernel(ContractArgs 
                             const int sj = 4 * tj + j, jm = c_ct.slot_dof[sj];
                             if (im >= 0 && jm >= 0 && sj <= si) {
                                 const int hi = im > jm ? im : jm, lo = im > jm ? jm : im;
-                                KMo[hi * (hi + 1) / 2 + lo] = make_double2(accK[i * 4 + j], accM[i * 4 + j]);
+                                KMo[(hi * (hi + 1) / 2 + lo) * 32] = make_double2(accK[i * 4 + j], accM[i * 4 + j]);
                             }
                         }
                     }

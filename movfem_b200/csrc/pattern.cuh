@@ -176,14 +176,15 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t *k, int lane) {
  *             rowcand[r] = number of element contributions to them.
  * FILL=true : cols / irn / jcn (1-based) per entry, cptr (first contribution of each entry), src (the
  *             contributions of each entry in ASCENDING ELEMENT ORDER = the reference's summation order,
- *             encoded as element*NP + packed pair), rown (the <=4 (element, local DOF) owners of row r).
+ *             encoded as the index into the K/M store), rown (the <=4 (element, local DOF) owners of row r).
  */
 template <int CAP, bool FILL>
 __global__ void __launch_bounds__(kRowWarps * 32)
 row_kernel(MeshDims m, const ShareTables *__restrict__ stp, const int *__restrict__ gne, const int *__restrict__ ownE,
            const uint8_t *__restrict__ ownL, int row_lo, int nrows, int e_base, int NP, int *__restrict__ rowcnt, int *__restrict__ rowcand,
            const int64_t *__restrict__ row_ptr, const int64_t *__restrict__ cbase, int *__restrict__ irn,
-           int *__restrict__ jcn, int64_t *__restrict__ cptr, uint32_t *__restrict__ src, int *__restrict__ rown) {
+           int *__restrict__ jcn, int64_t *__restrict__ cptr, uint32_t *__restrict__ src, int *__restrict__ rown,
+           const int *__restrict__ kmrow /* element (slab-local) -> row of the K/M store, see contract.cuh */) {
     __shared__ uint64_t s_keys[kRowWarps][CAP];
     __shared__ int s_el[kRowWarps][4], s_ll[kRowWarps][4], s_n[kRowWarps];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -241,7 +242,9 @@ row_kernel(MeshDims m, const ShareTables *__restrict__ stp, const int *__restric
         if (FILL && valid) {
             const int k = (int)((key >> 8) & 0xff), jm = (int)(key & 0xff), c = (int)(key >> 16);
             const int64_t cpos = cbase[rl] + idx;   // valid keys sort to the front, so idx is the rank
-            src[cpos] = (uint32_t)((int64_t)(s_el[w][k] - e_base) * NP + pair_index(s_ll[w][k] - 1, jm));
+            // K/M store layout [row / 32][packed pair][row % 32] (32 elements interleaved: coalesced by the contraction)
+            const int kr = kmrow[s_el[w][k] - e_base];
+            src[cpos] = (uint32_t)((((int64_t)(kr >> 5) * NP + pair_index(s_ll[w][k] - 1, jm)) << 5) + (kr & 31));
             if (first) {
                 const int64_t pos = row_ptr[rl] + nuniq + __popc(fb & ((1u << lane) - 1));
                 irn[pos] = r + 1; jcn[pos] = c; cptr[pos] = cpos;
