@@ -119,13 +119,15 @@ template <int MN_, int ME_, int MEP_, int NGP_, int EB_, int THREADS_, int MINB_
 struct ElemCfg {
     static constexpr int MN = MN_, ME = ME_, MEP = MEP_, NGP = NGP_, EB = EB_, THREADS = THREADS_, MINB = MINB_;
     static constexpr bool PML = PML_;
-    static constexpr int NDW = kNodeDoubles + 2;           // node record + x + y
+    static constexpr int NREC = 20;                        // doubles of the node record staged in smem (z,e,mu^-1,Re/Im sigma; not vc)
+    static constexpr int NDW = NREC + 2;                   // staged record + x + y
     static constexpr int NCOL = PML ? 30 : 24;             // columns interpolated by phase B1
     static constexpr int GEO = NCOL;                       // per (element, Gauss point) record: the columns, then R (12) in place
     static constexpr int NCMP = PML ? 51 : 12;             // scratch components: P(45)|Q(6), T(6)
     static constexpr int MNP = (MN + 1) & ~1;              // row stride of the N table (16-byte aligned rows)
-    // shared memory: phi table [NGP][MEP] + N table [NGP][MNP] | records [EB][NGP][GEO] | node records [EB][MN][NDW]
-    static constexpr size_t ATAB_D = (size_t)NGP * MEP + (size_t)NGP * MNP, GEO_D = (size_t)EB * NGP * GEO;
+    static constexpr int NGPP = (NGP + 1) & ~1;            // row stride of the dN table
+    // shared memory: phi [NGP][MEP] + N [NGP][MNP] + dN|N [MN][4][NGPP] | records [EB][NGP][GEO] | node records [EB][MN][NDW]
+    static constexpr size_t ATAB_D = (size_t)NGP * MEP + (size_t)NGP * MNP + (size_t)MN * 4 * NGPP, GEO_D = (size_t)EB * NGP * GEO;
     static constexpr int NSTR = MN * NDW + 2;              // per-element stride of the node records (+16 B: bank shift)
     static constexpr size_t NODES_D = (size_t)EB * NSTR;
     static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + NODES_D) + sizeof(int) * (EB * 4 + 2 * MEP);
@@ -191,12 +193,13 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_phi = reinterpret_cast<double *>(smem_raw);             // [NGP][MEP] phi in slot order
     double *s_N = s_phi + NGP * MEP;                                  // [NGP][MNP] nodal shape functions N[g][l]
+    double *s_dN = s_N + NGP * CFG::MNP;                              // [MN][4][NGPP]: dN/dxi (0..2), N (3); Gauss point fastest
     double *s_geo = s_phi + CFG::ATAB_D;                              // [EB][NGP][GEO]
     double *s_nodes = s_geo + CFG::GEO_D;                             // [EB][MN][NDW]
     int *s_el = reinterpret_cast<int *>(s_nodes + CFG::NODES_D);      // [EB][4]: element id, GPML flags
     int *s_slot = s_el + EB * 4;                                      // [MEP] slot -> local DOF (0-based) or -1
     int *s_sdir = s_slot + MEP;                                       // [MEP] slot -> direction (0-based)
-    const double *__restrict__ g_dN = A.T->dNt;                       // [MN][4][32]: dN/dxi (0..2), N (3); Gauss point fastest (L1)
+    constexpr int NGPP = CFG::NGPP, NREC = CFG::NREC;
 
     const ElemTables &T = *A.T;
     const MeshDims &m = A.m;
@@ -212,20 +215,24 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         const int g = i / CFG::MNP, l = i % CFG::MNP;
         s_N[i] = l < MN ? T.N[g][l] : 0.0;
     }
+    for (int i = tid; i < MN * 4 * NGPP; i += CFG::THREADS) {
+        const int g = i % NGPP, lm = i / NGPP;
+        s_dN[i] = g < NGP ? T.dNt[lm * 32 + g] : 0.0;
+    }
 
     const int nbatch = (A.nlist + EB - 1) / EB;
     // asynchronous gather of one batch's node records into s_nodes (16-byte cp.async pieces, coalesced per record)
     auto request_nodes = [&](int b) {
         const int first = b * EB, nb = min(EB, A.nlist - first);
         const int g1 = m.nord - 1;
-        for (int i = tid; i < nb * MN * (kNodeDoubles / 2 + 1); i += CFG::THREADS) {
-            const int part = i % (kNodeDoubles / 2 + 1), sl = i / (kNodeDoubles / 2 + 1);
+        for (int i = tid; i < nb * MN * (NREC / 2 + 1); i += CFG::THREADS) {
+            const int part = i % (NREC / 2 + 1), sl = i / (NREC / 2 + 1);
             const int l = sl % MN, s = sl / MN;
             const int e = A.list[first + s];
             int ie, je, ke;
             elem_ijk(m, e, ie, je, ke);
             double2 *dst = reinterpret_cast<double2 *>(s_nodes + s * CFG::NSTR + l * NDW) + part;
-            if (part < kNodeDoubles / 2) {
+            if (part < NREC / 2) {
                 const int64_t id = (int64_t)(ie - 1) * g1 * m.nyz + (int64_t)(je - 1) * g1 * m.nnz + (ke - 1) * g1 + T.node_off[l];
                 const double2 *src = reinterpret_cast<const double2 *>(A.nodes + id) + part;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
@@ -259,34 +266,43 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         if (A.phase_mask & 1) {
             const double psig = f32r(A.omega * kEps0);   // pset_pmodel, problem.f90:250
             // warp w handles Gauss-point range `part` of (element, column) pairs (w % PW)*32 + lane
-            constexpr int NW = CFG::THREADS / 32, PW = (EB * NCOLA + 31) / 32;
+            // two columns per thread: every broadcast N[g][l] pair feeds four FMAs
+            constexpr int NCH = NCOLA / 2;
+            constexpr int NW = CFG::THREADS / 32, PW = (EB * NCH + 31) / 32;
             constexpr int GS = PW >= NW ? 1 : (NW / PW >= 4 ? 4 : (NW / PW >= 2 ? 2 : 1));
             const int wid = tid >> 5, lane = tid & 31;
             const int part = GS == 1 ? 0 : wid / PW;
             const int stride = GS == 1 ? CFG::THREADS : PW * 32;
             if (part < GS)
-                for (int it = GS == 1 ? tid : (wid % PW) * 32 + lane; it < nb * NCOLA; it += stride) {
-                    const int s = it / NCOLA, c = CLO + it % NCOLA;
+                for (int it = GS == 1 ? tid : (wid % PW) * 32 + lane; it < nb * NCH; it += stride) {
+                    const int s = it / NCH, c0 = CLO + it % NCH, c1 = c0 + NCH;
                     const double *nd = s_nodes + s * CFG::NSTR;
-                    const int off = kColOff[c], flag = kColFlag[c];
-                    double v[MN];
+                    const int off0 = kColOff[c0], flag0 = kColFlag[c0], off1 = kColOff[c1], flag1 = kColFlag[c1];
+                    double v[MN], u[MN];
 #pragma unroll
                     for (int l = 0; l < MN; ++l) {
-                        double x = nd[l * NDW + off];
-                        if (flag & 2) x = x - psig;              // Im(dsigma) on the diagonal (pdelta_model)
-                        if (flag & 1) x = x * nd[l * NDW + 1];   // times e_l = f32(omega b0 z_l): |Ep| at the node
-                        v[l] = x;
+                        double x = nd[l * NDW + off0], y = nd[l * NDW + off1];
+                        const double el = nd[l * NDW + 1];
+                        if (flag0 & 2) x = x - psig;             // Im(dsigma) on the diagonal (pdelta_model)
+                        if (flag0 & 1) x = x * el;               // times e_l = f32(omega b0 z_l): |Ep| at the node
+                        if (flag1 & 2) y = y - psig;
+                        if (flag1 & 1) y = y * el;
+                        v[l] = x; u[l] = y;
                     }
-                    double *out = s_geo + (size_t)s * NGP * GEO + c;
+                    double *out = s_geo + (size_t)s * NGP * GEO;
 #define MOVFEM_B1_RANGE(G0, G1)                                                              \
     _Pragma("unroll") for (int g = (G0); g < (G1); ++g) {                                    \
-        double acc = 0.0;                                                                    \
+        double acc = 0.0, bcc = 0.0;                                                         \
         _Pragma("unroll") for (int l = 0; l + 1 < MN; l += 2) {                              \
             const double2 n2 = *reinterpret_cast<const double2 *>(s_N + g * CFG::MNP + l);   \
             acc = dfma(n2.x, v[l], acc); acc = dfma(n2.y, v[l + 1], acc);                    \
+            bcc = dfma(n2.x, u[l], bcc); bcc = dfma(n2.y, u[l + 1], bcc);                    \
         }                                                                                    \
-        if (MN & 1) acc = dfma(s_N[g * CFG::MNP + MN - 1], v[MN - 1], acc);                  \
-        out[g * GEO] = acc;                                                                  \
+        if (MN & 1) {                                                                        \
+            const double nl = s_N[g * CFG::MNP + MN - 1];                                    \
+            acc = dfma(nl, v[MN - 1], acc); bcc = dfma(nl, u[MN - 1], bcc);                  \
+        }                                                                                    \
+        out[g * GEO + c0] = acc; out[g * GEO + c1] = bcc;                                    \
     }
                     if constexpr (GS == 1) { MOVFEM_B1_RANGE(0, NGP) }
                     else if constexpr (GS == 2) {
@@ -321,9 +337,9 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                     double sx = 0.0, sy = 0.0, sz = 0.0;
 #pragma unroll 4
                     for (int l = 0; l < MN; ++l) {
-                        const double dn = g_dN[(l * 4 + mm) * 32 + g];
-                        sx = sx + dn * nd[l * NDW + kNodeDoubles];
-                        sy = sy + dn * nd[l * NDW + kNodeDoubles + 1];
+                        const double dn = s_dN[(l * 4 + mm) * NGPP + g];
+                        sx = sx + dn * nd[l * NDW + NREC];
+                        sy = sy + dn * nd[l * NDW + NREC + 1];
                         sz = sz + dn * nd[l * NDW];
                     }
                     J[mm][0] = sx; J[mm][1] = sy; J[mm][2] = sz;
@@ -357,21 +373,25 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                 double xg[3] = {0, 0, 0};
                 if (PML) {   // g_rw, integration.f90:120-125 (reference order, no FMA: feeds the float32-rounded h)
                     for (int l = 0; l < MN; ++l) {
-                        const double ln = g_dN[(l * 4 + 3) * 32 + g];
+                        const double ln = s_dN[(l * 4 + 3) * NGPP + g];
                         const double *r = nd + l * NDW;
-                        xg[0] = xg[0] + ln * r[kNodeDoubles]; xg[1] = xg[1] + ln * r[kNodeDoubles + 1]; xg[2] = xg[2] + ln * r[0];
+                        xg[0] = xg[0] + ln * r[NREC]; xg[1] = xg[1] + ln * r[NREC + 1]; xg[2] = xg[2] + ln * r[0];
                     }
                 }
                 double pc1[3] = {0, 0, 0}, pc2[3] = {0, 0, 0};
-                if (has_dmu) {   // p_pcurl, problem.f90:362-374: grad N_l x (mu^-1 dmu Hp)_l
+                if (has_dmu) {   // p_pcurl, problem.f90:362-374: grad N_l x (mu^-1 dmu Hp)_l  (mu != mu0 only: vc is read from L2)
+                    int ie, je, ke;
+                    elem_ijk(m, s_el[s * 4], ie, je, ke);
+                    const int g1 = m.nord - 1;
+                    const int64_t id0 = (int64_t)(ie - 1) * g1 * m.nyz + (int64_t)(je - 1) * g1 * m.nnz + (ke - 1) * g1;
                     for (int l = 0; l < MN; ++l) {
-                        const double *r = nd + l * NDW;
-                        const double t0 = g_dN[(l * 4 + 0) * 32 + g], t1 = g_dN[(l * 4 + 1) * 32 + g], t2 = g_dN[(l * 4 + 2) * 32 + g];
+                        const double *vc = A.nodes[id0 + T.node_off[l]].vc;
+                        const double t0 = s_dN[(l * 4 + 0) * NGPP + g], t1 = s_dN[(l * 4 + 1) * NGPP + g], t2 = s_dN[(l * 4 + 2) * NGPP + g];
                         double dn[3];
 #pragma unroll
                         for (int mm = 0; mm < 3; ++mm) dn[mm] = G[mm][0] * t0 + G[mm][1] * t1 + G[mm][2] * t2;
-                        pc1[0] += r[22] * dn[1] - r[21] * dn[2]; pc1[1] += r[20] * dn[2] - r[22] * dn[0]; pc1[2] += r[21] * dn[0] - r[20] * dn[1];
-                        pc2[0] += r[25] * dn[1] - r[24] * dn[2]; pc2[1] += r[23] * dn[2] - r[25] * dn[0]; pc2[2] += r[24] * dn[0] - r[23] * dn[1];
+                        pc1[0] += vc[2] * dn[1] - vc[1] * dn[2]; pc1[1] += vc[0] * dn[2] - vc[2] * dn[0]; pc1[2] += vc[1] * dn[0] - vc[0] * dn[1];
+                        pc2[0] += vc[5] * dn[1] - vc[4] * dn[2]; pc2[1] += vc[3] * dn[2] - vc[5] * dn[0]; pc2[2] += vc[4] * dn[0] - vc[3] * dn[1];
                     }
                 }
                 // GPML stretch (boundary_conds.f90:84-186) with the LAGGING flags (Q17)
@@ -391,10 +411,16 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                     constexpr double sa[6] = {1.0, -1.0, 1.0, -1.0, 1.0, -1.0};
                     // D6[a][b] = w mu^-1[p_a][p_b] Re G[x_a][x_b]   (symmetric 6x6; formed on the fly)
                     // P[(u,d)][(v,e)] = sum_ab H[a][u,d] D6[a][b] H[b][v,e],  H[a][u,d] = s_a G[x_a][u] G[y_a][d]
-                    double wmu[6];
+                    // evaluated per column (v,e) as DH = D6 H[:,(v,e)], then P[(u,d)][(v,e)] = (G^T W G)[u][d] with the
+                    // antisymmetric-pattern W[x_a][y_a] = s_a DH[a]; everything statically indexed (registers)
+                    double wmu[6], D6[21];
 #pragma unroll
                     for (int k = 0; k < 6; ++k) wmu[k] = w * mu[k];
-#pragma unroll 1
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+#pragma unroll
+                        for (int b = a; b < 6; ++b) D6[a * 6 - a * (a - 1) / 2 + (b - a)] = wmu[sym3(pa[a], pa[b])] * Gr[sym3(xa[a], xa[b])];
+#pragma unroll
                     for (int col = 0; col < 9; ++col) {
                         const int v = col / 3, e2 = col % 3;
                         double Hc[6], DH[6];
@@ -404,16 +430,24 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                         for (int a = 0; a < 6; ++a) {
                             double acc = 0.0;
 #pragma unroll
-                            for (int b = 0; b < 6; ++b) acc = dfma(wmu[sym3(pa[a], pa[b])] * Gr[sym3(xa[a], xa[b])], Hc[b], acc);
+                            for (int b = 0; b < 6; ++b) {
+                                const int lo = a < b ? a : b, hi = a < b ? b : a;
+                                acc = dfma(D6[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)], Hc[b], acc);
+                            }
                             DH[a] = acc;
                         }
-#pragma unroll 1
+                        // E[x][d] = sum_y W[x][y] G[y][d];  W01=+DH4 W02=-DH3 W10=-DH5 W12=+DH0 W20=+DH2 W21=-DH1
+                        double E[3][3];
+#pragma unroll
+                        for (int d2 = 0; d2 < 3; ++d2) {
+                            E[0][d2] = dfma(DH[4], G[1][d2], -(DH[3] * G[2][d2]));
+                            E[1][d2] = dfma(DH[0], G[2][d2], -(DH[5] * G[0][d2]));
+                            E[2][d2] = dfma(DH[2], G[0][d2], -(DH[1] * G[1][d2]));
+                        }
+#pragma unroll
                         for (int row = 0; row <= col; ++row) {
                             const int u = row / 3, d2 = row % 3;
-                            double acc = 0.0;
-#pragma unroll
-                            for (int a = 0; a < 6; ++a) acc = dfma(sa[a] * G[xa[a]][u] * G[ya[a]][d2], DH[a], acc);
-                            qo[up9(row, col) * QS] = acc;
+                            qo[up9(row, col) * QS] = dfma(G[0][u], E[0][d2], dfma(G[1][u], E[1][d2], G[2][u] * E[2][d2]));
                         }
                     }
                 } else if (DO_QT) {
