@@ -130,7 +130,7 @@ struct ElemCfg {
     static constexpr size_t ATAB_D = (size_t)NGP * MEP + (size_t)NGP * MNP + (size_t)MN * 4 * NGPP, GEO_D = (size_t)EB * NGP * GEO;
     static constexpr int NSTR = MN * NDW + 2;              // per-element stride of the node records (+16 B: bank shift)
     static constexpr size_t NODES_D = (size_t)EB * NSTR;
-    static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + NODES_D) + sizeof(int) * (EB * 4 + 2 * MEP);
+    static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + NODES_D + EB) + sizeof(int) * (EB * 4 + 2 * MEP + 2 * EB + 3 * MN);
     static_assert((ATAB_D % 2) == 0 && (GEO_D % 2) == 0, "16-byte alignment of the smem regions");
     static_assert(32 % EB == 0, "a batch of the contraction (32 lanes) is a whole number of geometry batches");
 };
@@ -196,9 +196,12 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
     double *s_dN = s_N + NGP * CFG::MNP;                              // [MN][4][NGPP]: dN/dxi (0..2), N (3); Gauss point fastest
     double *s_geo = s_phi + CFG::ATAB_D;                              // [EB][NGP][GEO]
     double *s_nodes = s_geo + CFG::GEO_D;                             // [EB][MN][NDW]
-    int *s_el = reinterpret_cast<int *>(s_nodes + CFG::NODES_D);      // [EB][4]: element id, GPML flags
+    int64_t *s_rbase = reinterpret_cast<int64_t *>(s_nodes + CFG::NODES_D);   // [EB] base node id of the batch being prefetched
+    int *s_el = reinterpret_cast<int *>(s_rbase + EB);                // [EB][4]: element id, GPML flags
     int *s_slot = s_el + EB * 4;                                      // [MEP] slot -> local DOF (0-based) or -1
     int *s_sdir = s_slot + MEP;                                       // [MEP] slot -> direction (0-based)
+    int *s_rxy = s_sdir + MEP;                                        // [EB][2] x / y line index of the prefetched elements' base node
+    int *s_noff = s_rxy + 2 * EB;                                     // [MN][3] node offset, i1-1, j1-1
     constexpr int NGPP = CFG::NGPP, NREC = CFG::NREC;
 
     const ElemTables &T = *A.T;
@@ -211,6 +214,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         s_phi[i] = dof >= 0 ? T.phi[g][dof] : 0.0;
     }
     for (int i = tid; i < MEP; i += CFG::THREADS) { s_slot[i] = T.slot_dof[i]; s_sdir[i] = T.slot_dir[i]; }
+    for (int i = tid; i < MN; i += CFG::THREADS) { s_noff[i * 3] = T.node_off[i]; s_noff[i * 3 + 1] = T.node_i[i]; s_noff[i * 3 + 2] = T.node_j[i]; }
     for (int i = tid; i < NGP * CFG::MNP; i += CFG::THREADS) {
         const int g = i / CFG::MNP, l = i % CFG::MNP;
         s_N[i] = l < MN ? T.N[g][l] : 0.0;
@@ -222,25 +226,33 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
 
     const int nbatch = (A.nlist + EB - 1) / EB;
     // asynchronous gather of one batch's node records into s_nodes (16-byte cp.async pieces, coalesced per record)
-    auto request_nodes = [&](int b) {
+    // (threads < EB first resolve the batch's elements to base node ids: prepare_request, one barrier earlier)
+    auto prepare_request = [&](int b) {
         const int first = b * EB, nb = min(EB, A.nlist - first);
-        const int g1 = m.nord - 1;
+        if (tid < nb) {
+            int ie, je, ke;
+            elem_ijk(m, A.list[first + tid], ie, je, ke);
+            const int g1 = m.nord - 1;
+            s_rbase[tid] = (int64_t)(ie - 1) * g1 * m.nyz + (int64_t)(je - 1) * g1 * m.nnz + (ke - 1) * g1;
+            s_rxy[tid * 2] = (ie - 1) * g1; s_rxy[tid * 2 + 1] = (je - 1) * g1;
+        }
+    };
+    auto request_nodes = [&](int b) {
+        const int nb = min(EB, A.nlist - b * EB);
         for (int i = tid; i < nb * MN * (NREC / 2 + 1); i += CFG::THREADS) {
             const int part = i % (NREC / 2 + 1), sl = i / (NREC / 2 + 1);
             const int l = sl % MN, s = sl / MN;
-            const int e = A.list[first + s];
-            int ie, je, ke;
-            elem_ijk(m, e, ie, je, ke);
             double2 *dst = reinterpret_cast<double2 *>(s_nodes + s * CFG::NSTR + l * NDW) + part;
             if (part < NREC / 2) {
-                const int64_t id = (int64_t)(ie - 1) * g1 * m.nyz + (int64_t)(je - 1) * g1 * m.nnz + (ke - 1) * g1 + T.node_off[l];
-                const double2 *src = reinterpret_cast<const double2 *>(A.nodes + id) + part;
+                const double2 *src = reinterpret_cast<const double2 *>(A.nodes + (s_rbase[s] + s_noff[l * 3])) + part;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
             } else {
-                *dst = make_double2(A.xp[(ie - 1) * g1 + T.node_i[l]], A.yp[(je - 1) * g1 + T.node_j[l]]);
+                *dst = make_double2(A.xp[s_rxy[s * 2] + s_noff[l * 3 + 1]], A.yp[s_rxy[s * 2 + 1] + s_noff[l * 3 + 2]]);
             }
         }
     };
+    if ((int)blockIdx.x < nbatch) prepare_request(blockIdx.x);
+    __syncthreads();
     if ((int)blockIdx.x < nbatch) request_nodes(blockIdx.x);
     for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
         const int first = batch * EB;
@@ -319,6 +331,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         __syncthreads();
 
         // ---- phase B2: one thread per (Gauss point, element): J, G, GPML, source -> Q|P, T (scratch), R (in place) ----
+        if (batch + (int)gridDim.x < nbatch) prepare_request(batch + gridDim.x);
         if (A.phase_mask & 1) {
             const int has_dmu = A.flags[0];
             const double w32 = f32r(A.omega);            // cmplx(0.d0,-omega), problem.f90:112
@@ -512,10 +525,11 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                 const int cs = i / MEP, cslot = i % MEP;
                 const int cdof = s_slot[cslot], cd = s_sdir[cslot];
                 double bacc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 3
+                const double *R0 = s_geo + cs * NGP * GEO + GR + cd * 4, *ph = s_phi + cslot;
+#pragma unroll
                 for (int g = 0; g < NGP; ++g) {
-                    const double phi = s_phi[g * MEP + cslot];
-                    const double *R = s_geo + (cs * NGP + g) * GEO + GR + cd * 4;
+                    const double phi = ph[g * MEP];
+                    const double *R = R0 + g * GEO;
                     bacc[0] = dfma(phi, R[0], bacc[0]); bacc[1] = dfma(phi, R[1], bacc[1]);
                     bacc[2] = dfma(phi, R[2], bacc[2]); bacc[3] = dfma(phi, R[3], bacc[3]);
                 }
