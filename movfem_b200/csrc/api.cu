@@ -320,7 +320,7 @@ int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist,
             C.qt = h->d_qt; C.nlist = n; C.KM = h->d_KM + (size_t)(km_row0 + off) * h->NP; C.flags = h->d_flags;
             C.skip_unless_changed = skip_unless_changed;
             const int ncb = (n + 31) / 32;
-            ck<<<std::max(1, std::min(ncb, std::max(1, c_per_sm) * h->num_sms)), CON::THREADS, CON::SMEM, h->stream>>>(C);
+            ck<<<std::max(1, std::min(ncb * 6, std::max(1, c_per_sm) * h->num_sms)), CON::THREADS, CON::SMEM, h->stream>>>(C);
             h->launches += 1;
             CK(cudaGetLastError());
         }

@@ -120,34 +120,38 @@ __global__ void __launch_bounds__(CFG::THREADS, 1) contract_kernel(ContractArgs 
     }
     __syncthreads();
 
+    // Work items are (batch, class) pairs; every CTA takes a contiguous range of the item sequence, so the grid is
+    // balanced to within one class block instead of one 32-element batch.  Inside the CTA the tiles of its items form
+    // one stream and warp w takes the stream positions = w (mod W).
+    const int64_t nitems = (int64_t)nbatch * 6;
+    const int n0 = (int)(nitems * blockIdx.x / gridDim.x), n1 = (int)(nitems * (blockIdx.x + 1) / gridDim.x);
     if (warp == W) {
-        // ---- producer: one lane streams the class blocks of this CTA's batches through the ring ----
+        // ---- producer: one lane streams the class blocks of this CTA's items through the ring ----
         if (lane == 0) {
-            int n = 0;
-            for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
+            for (int n = n0; n < n1; ++n) {
+                const int b = n / 6, c = n - b * 6, k = n - n0;
                 const double *src = A.qt + (size_t)b * NCMP * CB;
-                for (int c = 0; c < 6; ++c, ++n) {
-                    const int slot = n % STAGES, round = n / STAGES;
-                    if (round > 0) mbar_wait(&empty[slot], (unsigned)((round - 1) & 1));
-                    mbar_expect_tx(&full[slot], (unsigned)(STAGE_D * sizeof(double)));
-                    double *dst = s_stage + (size_t)slot * STAGE_D;
+                const int slot = k % STAGES, round = k / STAGES;
+                if (round > 0) mbar_wait(&empty[slot], (unsigned)((round - 1) & 1));
+                mbar_expect_tx(&full[slot], (unsigned)(STAGE_D * sizeof(double)));
+                double *dst = s_stage + (size_t)slot * STAGE_D;
 #pragma unroll 1
-                    for (int k = 0; k < NC; ++k)
-                        bulk_g2s(dst + k * CB, src + (size_t)c_ct.comp[PML ? 1 : 0][c][k] * CB, (unsigned)(CB * sizeof(double)), &full[slot]);
-                }
+                for (int q = 0; q < NC; ++q)
+                    bulk_g2s(dst + q * CB, src + (size_t)c_ct.comp[PML ? 1 : 0][c][q] * CB, (unsigned)(CB * sizeof(double)), &full[slot]);
             }
         }
         return;
     }
 
     // ---- consumers ----
-    int n = 0;
-    for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
-        const bool live = b * 32 + lane < A.nlist;
-        double2 *KMo = A.KM + (size_t)b * NP * 32 + lane;
+    const int pos0 = (n0 / 6) * CFG::NTILES + c_ct.cls_begin[n0 % 6];   // stream position of the CTA's first tile
+    {
 #pragma unroll 1
-        for (int c = 0; c < 6; ++c, ++n) {
-            const int slot = n % STAGES, round = n / STAGES;
+        for (int n = n0; n < n1; ++n) {
+            const int b = n / 6, c = n - b * 6, k = n - n0;
+            const bool live = b * 32 + lane < A.nlist;
+            double2 *KMo = A.KM + (size_t)b * NP * 32 + lane;
+            const int slot = k % STAGES, round = k / STAGES;
             mbar_wait(&full[slot], (unsigned)(round & 1));
             const double *S = s_stage + (size_t)slot * STAGE_D + lane;
             const int dI = cls_dI(c), dJ = cls_dJ(c);
@@ -157,7 +161,8 @@ __global__ void __launch_bounds__(CFG::THREADS, 1) contract_kernel(ContractArgs 
             const int k1I = dI == 2 ? 1 : 2, k2I = dI == 0 ? 1 : 0, k1J = dJ == 2 ? 1 : 2, k2J = dJ == 0 ? 1 : 0;
             const double tau = ((dI == 1) != (dJ == 1)) ? -1.0 : 1.0;
 #pragma unroll 1
-            for (int t = t_lo + ((warp - t_lo % W + W) % W); t < t_hi; t += W) {
+            const int first = (b * CFG::NTILES + t_lo - pos0) % W;   // warp that owns the class's first tile
+            for (int t = t_lo + ((warp - first + W) % W); t < t_hi; t += W) {
                 const int ti = c_ct.tile_ti[t], tj = c_ct.tile_tj[t];
                 double accK[16], accM[16];
 #pragma unroll

@@ -519,23 +519,35 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
 
         if (batch + (int)gridDim.x < nbatch) request_nodes(batch + gridDim.x);   // lands during the RHS phase / next wait
 
-        // ---- RHS: one thread per (element, slot): blocal / f3, integration.f90:96-104,258-263 ----
+        // ---- RHS: one thread per (element, group of four slots of one direction): blocal / f3,
+        //      integration.f90:96-104,258-263.  R[d] is loaded once per Gauss point for the four slots. ----
         if (A.phase_mask & 2) {
-            for (int i = tid; i < nb * MEP; i += CFG::THREADS) {
-                const int cs = i / MEP, cslot = i % MEP;
-                const int cdof = s_slot[cslot], cd = s_sdir[cslot];
-                double bacc[4] = {0.0, 0.0, 0.0, 0.0};
-                const double *R0 = s_geo + cs * NGP * GEO + GR + cd * 4, *ph = s_phi + cslot;
+            constexpr int NQ = MEP / 4;
+            for (int i = tid; i < nb * NQ; i += CFG::THREADS) {
+                const int cs = i / NQ, q4 = (i % NQ) * 4;
+                const int cd = s_sdir[q4];
+                double bacc[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) bacc[k][c] = 0.0;
+                const double *R0 = s_geo + cs * NGP * GEO + GR + cd * 4, *ph = s_phi + q4;
 #pragma unroll
                 for (int g = 0; g < NGP; ++g) {
-                    const double phi = ph[g * MEP];
-                    const double *R = R0 + g * GEO;
-                    bacc[0] = dfma(phi, R[0], bacc[0]); bacc[1] = dfma(phi, R[1], bacc[1]);
-                    bacc[2] = dfma(phi, R[2], bacc[2]); bacc[3] = dfma(phi, R[3], bacc[3]);
+                    const double2 p01 = *reinterpret_cast<const double2 *>(ph + g * MEP), p23 = *reinterpret_cast<const double2 *>(ph + g * MEP + 2);
+                    const double2 r01 = *reinterpret_cast<const double2 *>(R0 + g * GEO), r23 = *reinterpret_cast<const double2 *>(R0 + g * GEO + 2);
+                    const double phi[4] = {p01.x, p01.y, p23.x, p23.y}, R[4] = {r01.x, r01.y, r23.x, r23.y};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) bacc[k][c] = dfma(phi[k], R[c], bacc[k][c]);
                 }
-                if (cdof >= 0) {
-                    const int64_t e = s_el[cs * 4];
-                    reinterpret_cast<double4 *>(A.be)[(e - A.e_base) * ME + cdof] = make_double4(bacc[0], bacc[1], bacc[2], bacc[3]);
+                const int64_t e = s_el[cs * 4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int cdof = s_slot[q4 + k];
+                    if (cdof >= 0)
+                        reinterpret_cast<double4 *>(A.be)[(e - A.e_base) * ME + cdof] = make_double4(bacc[k][0], bacc[k][1], bacc[k][2], bacc[k][3]);
                 }
             }
         }
