@@ -35,7 +35,13 @@ FLOPS_PER_ELEMENT = {12: 10944, 36: 250776, 54: 533628}   # 2*ngp*(18
 BYTES_PER_NNZ_UPDATE = 32                                  # read K 8 + M 8, write A 16
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
 # (profiles/r01_ncu_full_top_kernels.json, profiles/r01_summary.md); None for other workloads
-NCU_TRAFFIC_BYTES = {"element_kernel": 41.2e6 + 368.3e6 + 20.6e6 + 118.5e6, "gather_finalize_kernel": 836.9e6 + 374.1e6}
+NCU_TRAFFIC_BYTES = {"contract_kernel": None, "geometry_kernel": None, "gather_finalize_kernel": None}   # filled from profiles/r01_ncu_full.json
+try:
+    with open(os.path.join(HERE, "profiles", "r01_ncu_full.json")) as _f:
+        for _k, _v in json.load(_f).get("dram_bytes_per_step", {}).items():
+            NCU_TRAFFIC_BYTES[_k] = _v
+except Exception:
+    pass
 
 
 def rank_env():
@@ -151,7 +157,7 @@ def run_graft(args):
 
     # ---------------- device-timed loop ----------------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    phase = {"ms_node": [], "ms_element": [], "ms_gather": [], "ms_finalize": []}
+    phase = {"ms_node": [], "ms_element": [], "ms_geometry": [], "ms_contract": [], "ms_gather": [], "ms_finalize": []}
     launches = 0
     sampler = None
     with torch.cuda.stream(stream):
@@ -215,8 +221,10 @@ def run_graft(args):
         hbm_peak, hbm_src = measured_peaks()
         fp64_peak = host.fp64_peak_tflops(local_rank)
         ms_el = float(np.mean(phase["ms_element"])); ms_ga = float(np.mean(phase["ms_gather"]))
+        ms_con = float(np.mean(phase["ms_contract"])); ms_geo = float(np.mean(phase["ms_geometry"]))
         flops = FLOPS_PER_ELEMENT[model.me] * model.ne
-        ach = flops / (ms_el * 1e-3) * 1e-12
+        ach = flops / (ms_con * 1e-3) * 1e-12          # the contraction kernel executes exactly the flops SURVEY 8d counts
+        ach_path = flops / (ms_el * 1e-3) * 1e-12      # same count over geometry + contraction
         ga_bytes = BYTES_PER_NNZ_UPDATE * asm.nz_upper
         line = {
             "metric": "elements_assembled_per_s", "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps,
@@ -234,11 +242,15 @@ def run_graft(args):
                     "api": "movfem_assemble (C ABI) with pinned host buffers"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "kernel": "element_kernel (plain + GPML launches)", "achieved": ach, "peak": fp64_peak,
-                         "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None, "traffic": NCU_TRAFFIC_BYTES["element_kernel"],
-                         "traffic_note": "bytes per step over both element launches, ncu capture of round 1 (profiles/)",
+            "roofline": {"bound": "fp64", "kernel": "contract_kernel (plain + GPML launches): the B^T D B contractions SURVEY 8d counts",
+                         "achieved": ach, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None, "traffic": NCU_TRAFFIC_BYTES["contract_kernel"],
+                         "traffic_note": "dram bytes per step over both launches, ncu --set full capture (profiles/r01_ncu_full.json)",
                          "peak_source": "FP64 FMA-loop microbenchmark run in this process (movfem_fp64_peak); nominal 37.2",
-                         "flops_per_element": FLOPS_PER_ELEMENT[model.me], "ms_kernel": ms_el},
+                         "flops_per_element": FLOPS_PER_ELEMENT[model.me], "ms_kernel": ms_con,
+                         "element_path": {"kernels": "geometry_kernel + contract_kernel", "ms": ms_el, "ms_geometry": ms_geo, "achieved": ach_path,
+                                          "frac": ach_path / fp64_peak if fp64_peak else None,
+                                          "note": "same algorithmic flop count over the whole per-element path (geometry flops are not counted)"}},
             "roofline_hbm": {"bound": "hbm", "kernel": "gather_finalize_kernel", "achieved": ga_bytes / (ms_ga * 1e-3) * 1e-9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": ga_bytes / (ms_ga * 1e-3) * 1e-9 / hbm_peak, "traffic": NCU_TRAFFIC_BYTES["gather_finalize_kernel"],
                              "peak_source": f"MEASURED_PEAKS.json ({hbm_src})", "bytes_per_nnz": BYTES_PER_NNZ_UPDATE, "ms_kernel": ms_ga},

@@ -76,6 +76,8 @@ typedef struct movfem_stats {
     double ms_h2d, ms_node, ms_element, ms_gather, ms_finalize, ms_d2h, ms_total;
     int64_t nz;           /* entries delivered                                  */
     int64_t launches;     /* kernels launched by the call                       */
+    double ms_geometry;   /* part of ms_element: geometry_kernel launches        */
+    double ms_contract;   /* part of ms_element: contract_kernel launches        */
 } movfem_stats;
 
 /* Create: uploads the mesh once, builds gne + pattern ON THE DEVICE

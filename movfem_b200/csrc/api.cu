@@ -98,6 +98,8 @@ struct movfem_handle {
     int64_t nz_last;
     int32_t mode_last;
     cudaEvent_t ev[EV_COUNT];
+    std::vector<cudaEvent_t> kev;   // per-launch events of the element kernels: (begin, end) pairs
+    std::vector<int> kev_kind;      // 0 geometry, 1 contraction
     movfem_stats stats;
     int64_t launches;
     char err[512];
@@ -286,6 +288,19 @@ int const_table_acquire(movfem_handle *h) {
     return 0;
 }
 
+// event pair around one element-kernel launch (profiling: ms_geometry / ms_contract of movfem_stats)
+int kernel_event(movfem_handle *h, int kind, bool begin) {
+    const size_t idx = begin ? 2 * h->kev_kind.size() : 2 * h->kev_kind.size() - 1;
+    while (h->kev.size() <= idx) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        h->kev.push_back(e);
+    }
+    if (begin) h->kev_kind.push_back(kind);
+    CK(cudaEventRecord(h->kev[idx], h->stream));
+    return 0;
+}
+
 // geometry (+ RHS) and contraction of one element list, in chunks that fit the scratch
 template <class GEO, class CON, bool DO_QT>
 int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist, int64_t km_row0, int skip_unless_changed) {
@@ -312,17 +327,21 @@ int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist,
         const int off = (int)(cb * 32), n = (int)std::min<int64_t>(nlist - off, chunk_b * 32);
         A.list = d_list + off; A.nlist = n; A.qt = DO_QT ? h->d_qt : nullptr;
         const int ngb = (n + GEO::EB - 1) / GEO::EB;
+        if (kernel_event(h, 0, true)) return MOVFEM_E_CUDA;
         gk<<<std::max(1, std::min(ngb, std::max(1, g_per_sm) * h->num_sms)), GEO::THREADS, GEO::SMEM, h->stream>>>(A);
         h->launches += 1;
         CK(cudaGetLastError());
+        if (kernel_event(h, 0, false)) return MOVFEM_E_CUDA;
         if (DO_QT) {
             ContractArgs C;
             C.qt = h->d_qt; C.nlist = n; C.KM = h->d_KM + (size_t)(km_row0 + off) * h->NP; C.flags = h->d_flags;
             C.skip_unless_changed = skip_unless_changed;
             const int ncb = (n + 31) / 32;
+            if (kernel_event(h, 1, true)) return MOVFEM_E_CUDA;
             ck<<<std::max(1, std::min(ncb * 6, std::max(1, c_per_sm) * h->num_sms)), CON::THREADS, CON::SMEM, h->stream>>>(C);
             h->launches += 1;
             CK(cudaGetLastError());
+            if (kernel_event(h, 1, false)) return MOVFEM_E_CUDA;
         }
     }
     return 0;
@@ -357,6 +376,7 @@ void free_all(movfem_handle *h) {
     if (h->h_count) cudaFreeHost(h->h_count);
     for (int i = 0; i < EV_COUNT; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
 }
@@ -617,6 +637,7 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
     const MeshDims &m = h->m;
     cudaStream_t st = h->stream;
     h->launches = 0;
+    h->kev_kind.clear();
     // Q17: element (1,1,1) sees the SAVEd in_pml: zeros on the first assembled frequency, the flags
     // of the last element afterwards
     if (!m.dirichlet) {
@@ -706,6 +727,12 @@ int movfem_device_result(const movfem_handle *hc, const int32_t **irn, const int
         h->stats.ms_node = ms(EV_H2D, EV_NODE); h->stats.ms_element = ms(EV_NODE, EV_ELEM);
         h->stats.ms_gather = ms(EV_ELEM, EV_GATHER); h->stats.ms_finalize = ms(EV_GATHER, EV_FINAL);
         h->stats.ms_total = ms(EV_H2D, EV_FINAL); h->stats.nz = h->nz_last; h->stats.launches = h->launches;
+        h->stats.ms_geometry = h->stats.ms_contract = 0;
+        for (size_t k = 0; k < h->kev_kind.size(); ++k) {
+            float t = 0;
+            cudaEventElapsedTime(&t, h->kev[2 * k], h->kev[2 * k + 1]);
+            (h->kev_kind[k] ? h->stats.ms_contract : h->stats.ms_geometry) += t;
+        }
     }
     if (irn) *irn = h->compacted ? h->d_irn_c : h->d_irn;
     if (jcn) *jcn = h->compacted ? h->d_jcn_c : h->d_jcn;

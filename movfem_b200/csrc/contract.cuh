@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(CFG::THREADS, 1) contract_kernel(ContractArgs 
                     for (int i = 0; i < 16; ++i) accK[i] *= tau;
                 } else {
                     const double *Y = s_tab + 4 * ti, *X = s_tab + 4 * tj;
-#pragma unroll 1
+#pragma unroll 3
                     for (int g = 0; g < NGP; ++g) {
                         const int o = g * 4 * MEP;
                         double P[9];

@@ -122,7 +122,9 @@ struct ElemCfg {
     static constexpr int NREC = 20;                        // doubles of the node record staged in smem (z,e,mu^-1,Re/Im sigma; not vc)
     static constexpr int NDW = NREC + 2;                   // staged record + x + y
     static constexpr int NCOL = PML ? 30 : 24;             // columns interpolated by phase B1
-    static constexpr int GEO = NCOL;                       // per (element, Gauss point) record: the columns, then R (12) in place
+    // per (Gauss point, element) record: the columns, then R (12) in place; stored [g][element] with an odd number of
+    // 16-byte chunks per record, so the 8 lanes of a quarter warp (8 elements) hit distinct bank groups
+    static constexpr int GEO = (NCOL / 2) % 2 ? NCOL : NCOL + 2;
     static constexpr int NCMP = PML ? 51 : 12;             // scratch components: P(45)|Q(6), T(6)
     static constexpr int MNP = (MN + 1) & ~1;              // row stride of the N table (16-byte aligned rows)
     static constexpr int NGPP = (NGP + 1) & ~1;            // row stride of the dN table
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
     double *s_phi = reinterpret_cast<double *>(smem_raw);             // [NGP][MEP] phi in slot order
     double *s_N = s_phi + NGP * MEP;                                  // [NGP][MNP] nodal shape functions N[g][l]
     double *s_dN = s_N + NGP * CFG::MNP;                              // [MN][4][NGPP]: dN/dxi (0..2), N (3); Gauss point fastest
-    double *s_geo = s_phi + CFG::ATAB_D;                              // [EB][NGP][GEO]
+    double *s_geo = s_phi + CFG::ATAB_D;                              // [NGP][EB][GEO]
     double *s_nodes = s_geo + CFG::GEO_D;                             // [EB][MN][NDW]
     int64_t *s_rbase = reinterpret_cast<int64_t *>(s_nodes + CFG::NODES_D);   // [EB] base node id of the batch being prefetched
     int *s_el = reinterpret_cast<int *>(s_rbase + EB);                // [EB][4]: element id, GPML flags
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                         if (flag1 & 1) y = y * el;
                         v[l] = x; u[l] = y;
                     }
-                    double *out = s_geo + (size_t)s * NGP * GEO;
+                    double *out = s_geo + (size_t)s * GEO;
 #define MOVFEM_B1_RANGE(G0, G1)                                                              \
     _Pragma("unroll") for (int g = (G0); g < (G1); ++g) {                                    \
         double acc = 0.0, bcc = 0.0;                                                         \
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
             const double nl = s_N[g * CFG::MNP + MN - 1];                                    \
             acc = dfma(nl, v[MN - 1], acc); bcc = dfma(nl, u[MN - 1], bcc);                  \
         }                                                                                    \
-        out[g * GEO + c0] = acc; out[g * GEO + c1] = bcc;                                    \
+        out[g * EB * GEO + c0] = acc; out[g * EB * GEO + c1] = bcc;                                    \
     }
                     if constexpr (GS == 1) { MOVFEM_B1_RANGE(0, NGP) }
                     else if constexpr (GS == 2) {
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
             for (int i = tid; i < nb * NGP; i += CFG::THREADS) {
                 const int g = i / nb, s = i % nb;       // element fastest: runs of EB lanes in the scratch
                 const double *nd = s_nodes + s * CFG::NSTR;
-                double *geo = s_geo + (s * NGP + g) * GEO;
+                double *geo = s_geo + (g * EB + s) * GEO;
                 // scratch position of this (element, Gauss point): qt[batch32][component][g][lane]
                 const int pos = first + s;
                 double *qo = A.qt + ((size_t)(pos >> 5) * NCMP * NGP + g) * 32 + (pos & 31);
@@ -531,11 +533,11 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                 for (int k = 0; k < 4; ++k)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) bacc[k][c] = 0.0;
-                const double *R0 = s_geo + cs * NGP * GEO + GR + cd * 4, *ph = s_phi + q4;
+                const double *R0 = s_geo + cs * GEO + GR + cd * 4, *ph = s_phi + q4;
 #pragma unroll
                 for (int g = 0; g < NGP; ++g) {
                     const double2 p01 = *reinterpret_cast<const double2 *>(ph + g * MEP), p23 = *reinterpret_cast<const double2 *>(ph + g * MEP + 2);
-                    const double2 r01 = *reinterpret_cast<const double2 *>(R0 + g * GEO), r23 = *reinterpret_cast<const double2 *>(R0 + g * GEO + 2);
+                    const double2 r01 = *reinterpret_cast<const double2 *>(R0 + g * EB * GEO), r23 = *reinterpret_cast<const double2 *>(R0 + g * EB * GEO + 2);
                     const double phi[4] = {p01.x, p01.y, p23.x, p23.y}, R[4] = {r01.x, r01.y, r23.x, r23.y};
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
