@@ -31,8 +31,8 @@ namespace {
 // geometry_kernel:     MN  ME MEP NGP EB THREADS MINB PML     (EB x NGP threads in phase B2, EB x NCOL in B1)
 using Geo12  = ElemCfg<8, 12, 12, 8, 16, 128, 4, false>;
 using Geo12p = ElemCfg<8, 12, 12, 8, 16, 128, 3, true>;
-using Geo36  = ElemCfg<20, 36, 36, 27, 8, 224, 2, false>;
-using Geo36p = ElemCfg<20, 36, 36, 27, 8, 224, 2, true>;
+using Geo36  = ElemCfg<20, 36, 36, 27, 8, 256, 2, false>;
+using Geo36p = ElemCfg<20, 36, 36, 27, 8, 256, 2, true>;
 using Geo54  = ElemCfg<27, 54, 60, 27, 4, 128, 3, false>;
 using Geo54p = ElemCfg<27, 54, 60, 27, 4, 128, 2, true>;
 // contract_kernel:          ME MEP NGP PML   W STAGES    (W consumer warps + 1 producer warp; ring of STAGES class blocks)

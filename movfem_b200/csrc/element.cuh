@@ -226,6 +226,27 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         s_dN[i] = g < NGP ? T.dNt[lm * 32 + g] : 0.0;
     }
 
+    // phase-B1 GEMM fragments (mma.m8n8k4: A row = lane/4, k = lane%4; B k = lane%4, n = lane/4; C row = lane/4, cols 2(lane%4)+{0,1})
+    constexpr int NW = CFG::THREADS / 32, MB = (NGP + 7) / 8, MH = MB > 1 ? 2 : 1, MBH = MB / MH, KB = (MN + 3) / 4, NB = (NCOLA + 7) / 8;
+    static_assert(MB % MH == 0 && NW % MH == 0, "a warp always owns the same half of the Gauss-point blocks");
+    const int lane = tid & 31;
+    const int b1_mh = (tid >> 5) % MH;
+    const double psig = f32r(A.omega * kEps0);   // pset_pmodel, problem.f90:250
+    double b1_a[MBH][KB];
+    int b1_off[NB], b1_flag[NB];
+#pragma unroll
+    for (int mi = 0; mi < MBH; ++mi)
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+            const int g = 8 * (b1_mh * MBH + mi) + (lane >> 2), l = 4 * kb + (lane & 3);
+            b1_a[mi][kb] = (g < NGP && l < MN) ? T.N[g][l] : 0.0;
+        }
+#pragma unroll
+    for (int nbk = 0; nbk < NB; ++nbk) {
+        const int c = CLO + 8 * nbk + (lane >> 2);
+        b1_off[nbk] = c < CHI ? kColOff[c] : -1; b1_flag[nbk] = c < CHI ? kColFlag[c] : 0;
+    }
+
     const int nbatch = (A.nlist + EB - 1) / EB;
     // asynchronous gather of one batch's node records into s_nodes (16-byte cp.async pieces, coalesced per record)
     // (threads < EB first resolve the batch's elements to base node ids: prepare_request, one barrier earlier)
@@ -273,62 +294,52 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
 
-        // ---- phase B1: one thread per (element, column): interpolate node data to the Gauss points ----
-        // (p_intmodels problem.f90:139-142 and the N_l-weighted part of p_source problem.f90:424-457).  The
-        // thread keeps its column of the MN node records in registers; N[g][l] is warp-uniform and read from shared
-        // memory with broadcast 128-bit loads (constant-bank operands are slower: tools/micro/ldcu_bench.cu).
+        // ---- phase B1: interpolate node data to the Gauss points (p_intmodels problem.f90:139-142 and the N_l-weighted
+        //      part of p_source problem.f90:424-457): per element the small GEMM  out[g][c] = sum_l N[g][l] V[l][c]
+        //      (NGP x MN) x (MN x NCOL) on the FP64 tensor-core path, mma.sync.m8n8k4.f64.  A = N is a constant of the
+        //      element type and stays in registers for the whole kernel (the warp always owns the same Gauss-point
+        //      blocks); B = the node-record columns, read straight from the staged records with their per-column
+        //      transform; one warp per (element, half of the Gauss-point blocks). ----
         if (A.phase_mask & 1) {
-            const double psig = f32r(A.omega * kEps0);   // pset_pmodel, problem.f90:250
-            // warp w handles Gauss-point range `part` of (element, column) pairs (w % PW)*32 + lane
-            // two columns per thread: every broadcast N[g][l] pair feeds four FMAs
-            constexpr int NCH = NCOLA / 2;
-            constexpr int NW = CFG::THREADS / 32, PW = (EB * NCH + 31) / 32;
-            constexpr int GS = PW >= NW ? 1 : (NW / PW >= 4 ? 4 : (NW / PW >= 2 ? 2 : 1));
-            const int wid = tid >> 5, lane = tid & 31;
-            const int part = GS == 1 ? 0 : wid / PW;
-            const int stride = GS == 1 ? CFG::THREADS : PW * 32;
-            if (part < GS)
-                for (int it = GS == 1 ? tid : (wid % PW) * 32 + lane; it < nb * NCH; it += stride) {
-                    const int s = it / NCH, c0 = CLO + it % NCH, c1 = c0 + NCH;
-                    const double *nd = s_nodes + s * CFG::NSTR;
-                    const int off0 = kColOff[c0], flag0 = kColFlag[c0], off1 = kColOff[c1], flag1 = kColFlag[c1];
-                    double v[MN], u[MN];
+            const int wid = tid >> 5;
+            for (int task = wid; task < nb * MH; task += NW) {
+                const int s = task / MH;
+                const double *nd = s_nodes + s * CFG::NSTR;
+                double acc[MBH][NB][2];
 #pragma unroll
-                    for (int l = 0; l < MN; ++l) {
-                        double x = nd[l * NDW + off0], y = nd[l * NDW + off1];
-                        const double el = nd[l * NDW + 1];
-                        if (flag0 & 2) x = x - psig;             // Im(dsigma) on the diagonal (pdelta_model)
-                        if (flag0 & 1) x = x * el;               // times e_l = f32(omega b0 z_l): |Ep| at the node
-                        if (flag1 & 2) y = y - psig;
-                        if (flag1 & 1) y = y * el;
-                        v[l] = x; u[l] = y;
+                for (int mi = 0; mi < MBH; ++mi)
+#pragma unroll
+                    for (int nbk = 0; nbk < NB; ++nbk) acc[mi][nbk][0] = acc[mi][nbk][1] = 0.0;
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    const int l = 4 * kb + (lane & 3);
+                    const bool lv = l < MN;
+                    const double el = lv ? nd[l * NDW + 1] : 0.0;
+#pragma unroll
+                    for (int nbk = 0; nbk < NB; ++nbk) {
+                        double bv = 0.0;
+                        if (lv && b1_off[nbk] >= 0) {
+                            bv = nd[l * NDW + b1_off[nbk]];
+                            if (b1_flag[nbk] & 2) bv = bv - psig;       // Im(dsigma) on the diagonal (pdelta_model)
+                            if (b1_flag[nbk] & 1) bv = bv * el;         // times e_l = f32(omega b0 z_l): |Ep| at the node
+                        }
+#pragma unroll
+                        for (int mi = 0; mi < MBH; ++mi)
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                         : "+d"(acc[mi][nbk][0]), "+d"(acc[mi][nbk][1]) : "d"(b1_a[mi][kb]), "d"(bv));
                     }
-                    double *out = s_geo + (size_t)s * GEO;
-#define MOVFEM_B1_RANGE(G0, G1)                                                              \
-    _Pragma("unroll") for (int g = (G0); g < (G1); ++g) {                                    \
-        double acc = 0.0, bcc = 0.0;                                                         \
-        _Pragma("unroll") for (int l = 0; l + 1 < MN; l += 2) {                              \
-            const double2 n2 = *reinterpret_cast<const double2 *>(s_N + g * CFG::MNP + l);   \
-            acc = dfma(n2.x, v[l], acc); acc = dfma(n2.y, v[l + 1], acc);                    \
-            bcc = dfma(n2.x, u[l], bcc); bcc = dfma(n2.y, u[l + 1], bcc);                    \
-        }                                                                                    \
-        if (MN & 1) {                                                                        \
-            const double nl = s_N[g * CFG::MNP + MN - 1];                                    \
-            acc = dfma(nl, v[MN - 1], acc); bcc = dfma(nl, u[MN - 1], bcc);                  \
-        }                                                                                    \
-        out[g * EB * GEO + c0] = acc; out[g * EB * GEO + c1] = bcc;                                    \
-    }
-                    if constexpr (GS == 1) { MOVFEM_B1_RANGE(0, NGP) }
-                    else if constexpr (GS == 2) {
-                        if (part == 0) { MOVFEM_B1_RANGE(0, NGP / 2) } else { MOVFEM_B1_RANGE(NGP / 2, NGP) }
-                    } else {
-                        if (part == 0) { MOVFEM_B1_RANGE(0, NGP / 4) }
-                        else if (part == 1) { MOVFEM_B1_RANGE(NGP / 4, NGP / 2) }
-                        else if (part == 2) { MOVFEM_B1_RANGE(NGP / 2, 3 * NGP / 4) }
-                        else { MOVFEM_B1_RANGE(3 * NGP / 4, NGP) }
-                    }
-#undef MOVFEM_B1_RANGE
                 }
+#pragma unroll
+                for (int mi = 0; mi < MBH; ++mi) {
+                    const int g = 8 * (b1_mh * MBH + mi) + (lane >> 2);
+#pragma unroll
+                    for (int nbk = 0; nbk < NB; ++nbk) {
+                        const int c = CLO + 8 * nbk + 2 * (lane & 3);
+                        if (g < NGP && c < CHI)   // NCOL and CLO are even: the pair (c, c+1) is in range together
+                            *reinterpret_cast<double2 *>(s_geo + (size_t)(g * EB + s) * GEO + c) = make_double2(acc[mi][nbk][0], acc[mi][nbk][1]);
+                    }
+                }
+            }
         }
         __syncthreads();
 
