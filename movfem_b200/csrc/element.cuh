@@ -115,6 +115,11 @@ struct ElemArgs {
 __constant__ int kColOff[30] = {2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 8, 9, 10, 15, 17, 18, 9, 11, 12, 14, 15, 16, 17, 18, 19};
 __constant__ int kColFlag[30] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 1, 1, 1, 1, 1, 1, 3, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0};   // bit0: times e, bit1: minus psig first
 
+// x / y line index of local node l in the 27-node numbering (n_fem.f90:36-59, i1-1 / j1-1 for nord = 3; the 8- and
+// 20-node tables are prefixes, with 2 -> nord-1)
+__device__ constexpr int kNodeI27[27] = {2, 2, 0, 0, 2, 2, 0, 0, 2, 1, 0, 1, 2, 1, 0, 1, 2, 2, 0, 0, 2, 1, 0, 1, 1, 1, 1};
+__device__ constexpr int kNodeJ27[27] = {0, 2, 2, 0, 0, 2, 2, 0, 1, 2, 1, 0, 1, 2, 1, 0, 0, 2, 2, 0, 1, 2, 1, 0, 1, 1, 1};
+
 template <int MN_, int ME_, int MEP_, int NGP_, int EB_, int THREADS_, int MINB_, bool PML_>
 struct ElemCfg {
     static constexpr int MN = MN_, ME = ME_, MEP = MEP_, NGP = NGP_, EB = EB_, THREADS = THREADS_, MINB = MINB_;
@@ -128,11 +133,11 @@ struct ElemCfg {
     static constexpr int NCMP = PML ? 51 : 12;             // scratch components: P(45)|Q(6), T(6)
     static constexpr int MNP = (MN + 1) & ~1;              // row stride of the N table (16-byte aligned rows)
     static constexpr int NGPP = (NGP + 1) & ~1;            // row stride of the dN table
-    // shared memory: phi [NGP][MEP] + N [NGP][MNP] + dN|N [MN][4][NGPP] | records [EB][NGP][GEO] | node records [EB][MN][NDW]
-    static constexpr size_t ATAB_D = (size_t)NGP * MEP + (size_t)NGP * MNP + (size_t)MN * 4 * NGPP, GEO_D = (size_t)EB * NGP * GEO;
+    // shared memory: phi [NGP][MEP] + dN|N [MN][4][NGPP] | records [EB][NGP][GEO] | node records [EB][MN][NDW]
+    static constexpr size_t ATAB_D = (size_t)NGP * MEP + (size_t)MN * 4 * NGPP, GEO_D = (size_t)EB * NGP * GEO;
     static constexpr int NSTR = MN * NDW + 2;              // per-element stride of the node records (+16 B: bank shift)
     static constexpr size_t NODES_D = (size_t)EB * NSTR;
-    static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + NODES_D + EB) + sizeof(int) * (EB * 4 + 2 * MEP + 2 * EB + 3 * MN);
+    static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + NODES_D + EB + 1) + sizeof(int) * (EB * 4 + 2 * MEP + 2 * EB + 3 * MN);
     static_assert((ATAB_D % 2) == 0 && (GEO_D % 2) == 0, "16-byte alignment of the smem regions");
     static_assert(32 % EB == 0, "a batch of the contraction (32 lanes) is a whole number of geometry batches");
 };
@@ -194,12 +199,12 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_phi = reinterpret_cast<double *>(smem_raw);             // [NGP][MEP] phi in slot order
-    double *s_N = s_phi + NGP * MEP;                                  // [NGP][MNP] nodal shape functions N[g][l]
-    double *s_dN = s_N + NGP * CFG::MNP;                              // [MN][4][NGPP]: dN/dxi (0..2), N (3); Gauss point fastest
+    double *s_dN = s_phi + NGP * MEP;                              // [MN][4][NGPP]: dN/dxi (0..2), N (3); Gauss point fastest
     double *s_geo = s_phi + CFG::ATAB_D;                              // [NGP][EB][GEO]
     double *s_nodes = s_geo + CFG::GEO_D;                             // [EB][MN][NDW]
     int64_t *s_rbase = reinterpret_cast<int64_t *>(s_nodes + CFG::NODES_D);   // [EB] base node id of the batch being prefetched
-    int *s_el = reinterpret_cast<int *>(s_rbase + EB);                // [EB][4]: element id, GPML flags
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_rbase + EB);     // mbarrier of the node-record bulk copies
+    int *s_el = reinterpret_cast<int *>(s_bar + 1);                   // [EB][4]: element id, GPML flags
     int *s_slot = s_el + EB * 4;                                      // [MEP] slot -> local DOF (0-based) or -1
     int *s_sdir = s_slot + MEP;                                       // [MEP] slot -> direction (0-based)
     int *s_rxy = s_sdir + MEP;                                        // [EB][2] x / y line index of the prefetched elements' base node
@@ -217,10 +222,6 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
     }
     for (int i = tid; i < MEP; i += CFG::THREADS) { s_slot[i] = T.slot_dof[i]; s_sdir[i] = T.slot_dir[i]; }
     for (int i = tid; i < MN; i += CFG::THREADS) { s_noff[i * 3] = T.node_off[i]; s_noff[i * 3 + 1] = T.node_i[i]; s_noff[i * 3 + 2] = T.node_j[i]; }
-    for (int i = tid; i < NGP * CFG::MNP; i += CFG::THREADS) {
-        const int g = i / CFG::MNP, l = i % CFG::MNP;
-        s_N[i] = l < MN ? T.N[g][l] : 0.0;
-    }
     for (int i = tid; i < MN * 4 * NGPP; i += CFG::THREADS) {
         const int g = i % NGPP, lm = i / NGPP;
         s_dN[i] = g < NGP ? T.dNt[lm * 32 + g] : 0.0;
@@ -260,23 +261,23 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
             s_rxy[tid * 2] = (ie - 1) * g1; s_rxy[tid * 2 + 1] = (je - 1) * g1;
         }
     };
+    // one 160-byte bulk copy (TMA 1-D) per node record, completion counted on s_bar; x,y lines by plain stores
     auto request_nodes = [&](int b) {
         const int nb = min(EB, A.nlist - b * EB);
-        for (int i = tid; i < nb * MN * (NREC / 2 + 1); i += CFG::THREADS) {
-            const int part = i % (NREC / 2 + 1), sl = i / (NREC / 2 + 1);
-            const int l = sl % MN, s = sl / MN;
-            double2 *dst = reinterpret_cast<double2 *>(s_nodes + s * CFG::NSTR + l * NDW) + part;
-            if (part < NREC / 2) {
-                const double2 *src = reinterpret_cast<const double2 *>(A.nodes + (s_rbase[s] + s_noff[l * 3])) + part;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-            } else {
-                *dst = make_double2(A.xp[s_rxy[s * 2] + s_noff[l * 3 + 1]], A.yp[s_rxy[s * 2 + 1] + s_noff[l * 3 + 2]]);
-            }
+        if (tid == 0) mbar_expect_tx(s_bar, (unsigned)(nb * MN * NREC * sizeof(double)));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of s_nodes vs the async writes
+        for (int i = tid; i < nb * MN; i += CFG::THREADS) {
+            const int l = i % MN, s = i / MN;
+            double *dst = s_nodes + s * CFG::NSTR + l * NDW;
+            bulk_g2s(dst, A.nodes + (s_rbase[s] + s_noff[l * 3]), (unsigned)(NREC * sizeof(double)), s_bar);
+            *reinterpret_cast<double2 *>(dst + NREC) = make_double2(A.xp[s_rxy[s * 2] + s_noff[l * 3 + 1]], A.yp[s_rxy[s * 2 + 1] + s_noff[l * 3 + 2]]);
         }
     };
+    if (tid == 0) { mbar_init(s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if ((int)blockIdx.x < nbatch) prepare_request(blockIdx.x);
     __syncthreads();
     if ((int)blockIdx.x < nbatch) request_nodes(blockIdx.x);
+    unsigned node_phase = 0;
     for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
         const int first = batch * EB;
         const int nb = min(EB, A.nlist - first);
@@ -289,9 +290,10 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
             s_el[tid * 4 + 1] = f[0]; s_el[tid * 4 + 2] = f[1]; s_el[tid * 4 + 3] = f[2];
         }
 
-        // ---- phase A: the node records of this batch were requested with cp.async while the previous batch was in
+        // ---- phase A: the node records of this batch were requested with bulk copies while the previous batch was in
         //      its RHS phase (s_nodes is dead after phase B2); wait for them here ----
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        mbar_wait(s_bar, node_phase);
+        node_phase ^= 1;
         __syncthreads();
 
         // ---- phase B1: interpolate node data to the Gauss points (p_intmodels problem.f90:139-142 and the N_l-weighted
@@ -356,36 +358,42 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                 const int pos = first + s;
                 double *qo = A.qt + ((size_t)(pos >> 5) * NCMP * NGP + g) * 32 + (pos & 31);
                 constexpr size_t QS = (size_t)NGP * 32;   // component stride
-                // nf_jacobian, n_fem.f90:359-366: J(m,n) = sum_l dN_l/dxi_m * r_l(n), l ascending, no FMA
-                double J[3][3];
+                // nf_jacobian, n_fem.f90:359-366: J(m,n) = sum_l dN_l/dxi_m * r_l(n), l ascending, no FMA.  x and y are
+                // tensor-product lines (2 or 3 distinct values per element): loaded once, selected per node at compile time
+                constexpr int NORD = MN == 8 ? 2 : 3;
+                double xs[3], ys[3];
+                xs[0] = nd[2 * NDW + NREC]; xs[NORD - 1] = nd[NREC]; ys[0] = nd[NREC + 1]; ys[NORD - 1] = nd[NDW + NREC + 1];
+                if (NORD == 3) { xs[1] = nd[9 * NDW + NREC]; ys[1] = nd[8 * NDW + NREC + 1]; }
+                double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, xg[3] = {0, 0, 0};
 #pragma unroll
-                for (int mm = 0; mm < 3; ++mm) {
-                    double sx = 0.0, sy = 0.0, sz = 0.0;
-#pragma unroll 4
-                    for (int l = 0; l < MN; ++l) {
+                for (int l = 0; l < MN; ++l) {
+                    const double x = xs[kNodeI27[l] * (NORD - 1) / 2], y = ys[kNodeJ27[l] * (NORD - 1) / 2], z = nd[l * NDW];
+#pragma unroll
+                    for (int mm = 0; mm < 3; ++mm) {
                         const double dn = s_dN[(l * 4 + mm) * NGPP + g];
-                        sx = sx + dn * nd[l * NDW + NREC];
-                        sy = sy + dn * nd[l * NDW + NREC + 1];
-                        sz = sz + dn * nd[l * NDW];
+                        J[mm][0] = J[mm][0] + dn * x; J[mm][1] = J[mm][1] + dn * y; J[mm][2] = J[mm][2] + dn * z;
                     }
-                    J[mm][0] = sx; J[mm][1] = sy; J[mm][2] = sz;
+                    if (PML) {   // g_rw, integration.f90:120-125 (reference order, no FMA: feeds the float32-rounded h)
+                        const double ln = s_dN[(l * 4 + 3) * NGPP + g];
+                        xg[0] = xg[0] + ln * x; xg[1] = xg[1] + ln * y; xg[2] = xg[2] + ln * z;
+                    }
                 }
                 // nf_det, n_fem.f90:393-394 ; wgt, integration.f90:71
                 const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) + J[0][1] * (J[1][2] * J[2][0] - J[1][0] * J[2][2]) +
                                    J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
                 if (det == 0.0) atomicCAS(A.status, 0, -3);
                 const double w = det * T.rw[g][3];
-                const double ad = fabs(det);   // Q6
+                const double rad = 1.0 / fabs(det);   // Q6: nf_ji = adj(J)/abs(det); one reciprocal (G only feeds fused products)
                 double G[3][3];                // nf_ji: G[m][n] = d xi_n / d x_m
-                G[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / ad;
-                G[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / ad;
-                G[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / ad;
-                G[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / ad;
-                G[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / ad;
-                G[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / ad;
-                G[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / ad;
-                G[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / ad;
-                G[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / ad;
+                G[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * rad;
+                G[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * rad;
+                G[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * rad;
+                G[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * rad;
+                G[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * rad;
+                G[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * rad;
+                G[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * rad;
+                G[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * rad;
+                G[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * rad;
                 // interpolated columns of phase B1 (this thread's record is overwritten below)
                 double mu[6], sr[6], si[6] = {0, 0, 0, 0, 0, 0};
                 double dm1r[3], dm1i[3], dm2r[3], dm2i[3];
@@ -396,14 +404,6 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                 // signs: pol 1 dmpf = (+Im ds*e, -Re ds*e), pol 2 = (-Im ds*e, +Re ds*e)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { dm1r[k] = geo[12 + k]; dm1i[k] = -geo[15 + k]; dm2r[k] = -geo[18 + k]; dm2i[k] = geo[21 + k]; }
-                double xg[3] = {0, 0, 0};
-                if (PML) {   // g_rw, integration.f90:120-125 (reference order, no FMA: feeds the float32-rounded h)
-                    for (int l = 0; l < MN; ++l) {
-                        const double ln = s_dN[(l * 4 + 3) * NGPP + g];
-                        const double *r = nd + l * NDW;
-                        xg[0] = xg[0] + ln * r[NREC]; xg[1] = xg[1] + ln * r[NREC + 1]; xg[2] = xg[2] + ln * r[0];
-                    }
-                }
                 double pc1[3] = {0, 0, 0}, pc2[3] = {0, 0, 0};
                 if (has_dmu) {   // p_pcurl, problem.f90:362-374: grad N_l x (mu^-1 dmu Hp)_l  (mu != mu0 only: vc is read from L2)
                     int ie, je, ke;
