@@ -39,7 +39,7 @@ using Geo54p = ElemCfg<27, 54, 60, 27, 4, 128, 2, true>;
 using Con12  = ContractCfg<12, 12, 8, false, 6, 6>;
 using Con12p = ContractCfg<12, 12, 8, true, 6, 3>;
 using Con36  = ContractCfg<36, 36, 27, false, 15, 5>;
-using Con36p = ContractCfg<36, 36, 27, true, 9, 2>;
+using Con36p = ContractCfg<36, 36, 27, true, 12, 2>;
 using Con54  = ContractCfg<54, 60, 27, false, 15, 4>;
 using Con54p = ContractCfg<54, 60, 27, true, 12, 2>;
 
@@ -72,7 +72,9 @@ struct movfem_handle {
     int *d_gne, *d_ownE;
     uint8_t *d_ownL;
     int *d_irn, *d_jcn, *d_irn_c, *d_jcn_c, *d_rown;
-    int64_t *d_cptr;
+    int64_t *d_cptr;         // transient (pattern build); replaced by the compressed d_cblk / d_off16
+    int64_t *d_cblk;
+    uint16_t *d_off16;
     uint32_t *d_src;
     double2 *d_KM;
     double *d_be;
@@ -367,7 +369,7 @@ int run_elements(movfem_handle *h, ElemArgs &A, bool full) {
 void free_all(movfem_handle *h) {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_xp, h->d_yp, h->d_zp, h->d_mu, h->d_sigma, h->d_nodes, h->d_tab, h->d_share, h->d_gne, h->d_ownE,
-                    h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_src, h->d_KM,
+                    h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_cblk, h->d_off16, h->d_src, h->d_KM,
                     h->d_be, h->d_qt, h->d_kmrow, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum,
                     h->d_status, h->d_flags};
     for (void *p : ptrs)
@@ -451,7 +453,17 @@ int build_pattern(movfem_handle *h) {
     h->launches += 1;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h->d_cptr + h->nzu, &h->ncontrib, sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    {   // compress the contribution pointers (8 B/entry -> 2 B/entry + 8 B per 256 entries) and drop the 64-bit array
+        const int nblk = (int)((h->nzu + kFinThreads - 1) / kFinThreads);
+        CK(dmalloc(&h->d_cblk, (size_t)nblk + 1));
+        CK(dmalloc(&h->d_off16, (size_t)h->nzu));
+        if (nblk > 0) compress_cptr_kernel<<<nblk, kFinThreads, 0, h->stream>>>(h->nzu, h->d_cptr, h->d_cblk, h->d_off16);
+        h->launches += 1;
+        CK(cudaGetLastError());
+    }
     CK(cudaStreamSynchronize(h->stream));
+    CK(cudaFree(h->d_cptr));
+    h->d_cptr = nullptr;
     CK(cudaFree(d_rowcnt)); CK(cudaFree(d_rowcand)); CK(cudaFree(d_rowptr)); CK(cudaFree(d_cbase));
     return 0;
 }
@@ -667,7 +679,7 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
     h->km_valid = true;
     CK(cudaEventRecord(h->ev[EV_ELEM], st));
 
-    gather_finalize_kernel<<<h->nblk_fin, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cptr, h->d_src, h->d_KM, h->d_a,
+    gather_finalize_kernel<<<h->nblk_fin, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cblk, h->d_off16, h->d_src, h->d_KM, h->d_a,
                                                               h->d_blkcnt, mode == MOVFEM_MODE_T1 ? 1 : 0);
     rhs_kernel<<<(h->nrows + 127) / 128, 128, 0, st>>>(h->nrows, h->d_rown, reinterpret_cast<const double4 *>(h->d_be), h->d_rhs);
     h->launches += 2;

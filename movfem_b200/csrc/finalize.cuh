@@ -19,19 +19,52 @@ namespace movfem {
 
 constexpr int kFinThreads = 256;
 
+// Contribution index, compressed once per mesh: per block of kFinThreads entries the 64-bit position of its first
+// contribution (cblk) and per entry a 16-bit offset from it (an entry has <= 4 contributions, so a block has <= 1024).
+__global__ void __launch_bounds__(kFinThreads)
+compress_cptr_kernel(int64_t nzu, const int64_t *__restrict__ cptr, int64_t *__restrict__ cblk, uint16_t *__restrict__ off16) {
+    const int64_t i = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
+    const int64_t b0 = cptr[(int64_t)blockIdx.x * kFinThreads];
+    if (threadIdx.x == 0) {
+        cblk[blockIdx.x] = b0;
+        if (blockIdx.x == gridDim.x - 1) cblk[gridDim.x] = cptr[nzu];
+    }
+    if (i < nzu) off16[i] = (uint16_t)(cptr[i] - b0);
+}
+
 // mode 0 (T2): values rounded through float32, per-block count of surviving (non-zero) entries
 // mode 1 (T1): double values, nothing stripped
+// Phase 1: the block's <= 1024 contributions are fetched by all threads (independent random 16-byte reads, up to four
+// in flight per thread) into shared memory; phase 2: one thread per entry sums its contributions in ascending order.
 __global__ void __launch_bounds__(kFinThreads)
-gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cptr, const uint32_t *__restrict__ src,
-                       const double2 *__restrict__ KM, double2 *__restrict__ a,
+gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk, const uint16_t *__restrict__ off16,
+                       const uint32_t *__restrict__ src, const double2 *__restrict__ KM, double2 *__restrict__ a,
                        int *__restrict__ blk_nonzero, int mode) {
+    __shared__ double2 vals[4 * kFinThreads];
+    __shared__ uint16_t offs[kFinThreads + 1];
     const int64_t i = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
+    const int64_t c0 = cblk[blockIdx.x];
+    const int n = (int)(cblk[blockIdx.x + 1] - c0);
+    if (i < nzu) offs[threadIdx.x] = off16[i];
+    uint32_t sidx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = threadIdx.x + k * kFinThreads;
+        sidx[k] = c < n ? src[c0 + c] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = threadIdx.x + k * kFinThreads;
+        if (c < n) vals[c] = KM[sidx[k]];
+    }
+    __syncthreads();
     int nzflag = 0;
     if (i < nzu) {
-        const int64_t c0 = cptr[i], c1 = cptr[i + 1];
+        const int lo = offs[threadIdx.x];
+        const int hi = (threadIdx.x + 1 < kFinThreads && i + 1 < nzu) ? offs[threadIdx.x + 1] : n;
         double k = 0.0, mm = 0.0;
-        for (int64_t c = c0; c < c1; ++c) {
-            const double2 v = KM[src[c]];
+        for (int c = lo; c < hi; ++c) {
+            const double2 v = vals[c];
             k = k + v.x;
             mm = mm + v.y;
         }
