@@ -41,7 +41,7 @@ using Con12p = ContractCfg<12, 12, 8, true, 6, 3>;
 using Con36  = ContractCfg<36, 36, 27, false, 15, 5>;
 using Con36p = ContractCfg<36, 36, 27, true, 12, 2>;
 using Con54  = ContractCfg<54, 60, 27, false, 15, 4>;
-using Con54p = ContractCfg<54, 60, 27, true, 12, 2>;
+using Con54p = ContractCfg<54, 60, 27, true, 15, 2>;
 
 constexpr size_t kScratchCap = (size_t)512 << 20;   // Q|P,T scratch: larger lists are processed in chunks
 
