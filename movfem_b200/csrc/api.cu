@@ -36,8 +36,8 @@ using Geo36p = ElemCfg<20, 36, 36, 27, 8, 256, 2, true>;
 using Geo54  = ElemCfg<27, 54, 60, 27, 4, 128, 3, false>;
 using Geo54p = ElemCfg<27, 54, 60, 27, 4, 128, 2, true>;
 // contract_kernel:          ME MEP NGP PML   W STAGES    (W consumer warps + 1 producer warp; ring of STAGES class blocks)
-using Con12  = ContractCfg<12, 12, 8, false, 6, 6>;
-using Con12p = ContractCfg<12, 12, 8, true, 6, 3>;
+using Con12  = ContractCfg<12, 12, 8, false, 6, 6, 2>;
+using Con12p = ContractCfg<12, 12, 8, true, 6, 3, 2>;
 using Con36  = ContractCfg<36, 36, 27, false, 15, 5>;
 using Con36p = ContractCfg<36, 36, 27, true, 12, 2>;
 using Con54  = ContractCfg<54, 60, 27, false, 15, 4>;

@@ -58,9 +58,9 @@ __device__ __forceinline__ void ld4(double (&v)[4], const double *p) {
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
-template <int ME_, int MEP_, int NGP_, bool PML_, int W_, int STAGES_>
+template <int ME_, int MEP_, int NGP_, bool PML_, int W_, int STAGES_, int MINB_ = 1>
 struct ContractCfg {
-    static constexpr int ME = ME_, MEP = MEP_, NGP = NGP_, W = W_, STAGES = STAGES_;
+    static constexpr int ME = ME_, MEP = MEP_, NGP = NGP_, W = W_, STAGES = STAGES_, MINB = MINB_;
     static constexpr bool PML = PML_;
     static constexpr int NC = PML ? 10 : 5;          // component blocks per stage
     static constexpr int NCMP = PML ? 51 : 12;       // scratch components per (element, Gauss point): P(45)|Q(6), T(6)
@@ -73,7 +73,7 @@ struct ContractCfg {
 };
 
 template <class CFG>
-__global__ void __launch_bounds__(CFG::THREADS, 1) contract_kernel(ContractArgs A) {
+__global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(ContractArgs A) {
     constexpr int MEP = CFG::MEP, NGP = CFG::NGP, W = CFG::W, STAGES = CFG::STAGES, NC = CFG::NC, NCMP = CFG::NCMP;
     constexpr int CB = CFG::CB, STAGE_D = CFG::STAGE_D, NP = CFG::NP;
     constexpr bool PML = CFG::PML;
