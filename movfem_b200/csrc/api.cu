@@ -583,7 +583,9 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     {   // Q|P,T scratch: whole 32-element batches of the larger of the two lists, capped (launch_elements chunks)
         const size_t cb = sizeof(double) * (size_t)m.ngp * 32;
         const size_t need = std::max((size_t)((h->n_plain + 31) / 32) * 12 * cb, (size_t)((h->n_pml + 31) / 32) * 51 * cb);
-        h->qt_bytes = std::max(std::min(need, kScratchCap), (size_t)51 * cb);
+        size_t cap = kScratchCap;
+        if (const char *mb = getenv("MOVFEM_SCRATCH_MB")) cap = (size_t)std::max(1, atoi(mb)) << 20;   // test aid: force chunking
+        h->qt_bytes = std::max(std::min(need, cap), (size_t)51 * cb);
         CK(cudaMalloc((void **)&h->d_qt, h->qt_bytes));
         CK(cudaMemset(h->d_qt, 0, h->qt_bytes));   // lanes past the end of a ragged last batch read zeros, not NaNs
     }

@@ -61,6 +61,24 @@ def test_parity_small(mn, dirichlet, sch):
     asm.close()
 
 
+def test_parity_chunked_scratch(monkeypatch):
+    """The Q|P,T scratch between geometry_kernel and contract_kernel is processed in chunks when an element list
+    does not fit it (config 5 sizes).  Force a 1 MiB scratch so a small mesh runs through many chunks, ragged last
+    batch included, and must reproduce the oracle (and the unchunked run) exactly as before."""
+    m = _small(20, 0, 0)
+    asm0 = host.Assembly(m)
+    monkeypatch.setenv("MOVFEM_SCRATCH_MB", "1")
+    asm1, o = host.Assembly(m), Oracle(m)
+    monkeypatch.delenv("MOVFEM_SCRATCH_MB")
+    _check(compare_assembly(asm1, o, m, ifreq=1))
+    r0 = asm0.global_vfem(1, m.omega(1), m.sigma_for(1), mode=abi.MODE_T1)
+    r1 = asm1.global_vfem(1, m.omega(1), m.sigma_for(1), mode=abi.MODE_T1)
+    for x, y in zip(r0[:4], r1[:4]):
+        assert np.array_equal(x, y)           # chunking changes nothing, bit for bit
+    assert asm1.stats()["launches"] > asm0.stats()["launches"]
+    asm0.close(); asm1.close()
+
+
 def test_parity_anisotropic_sigma_and_mu():
     """config 3 (full 6-component sigma) plus a non-trivial permeability: exercises the curl part of the
     secondary source (problem.f90:362-420), which vanishes for mu = mu0."""
