@@ -1009,4 +1009,113 @@ void oracle_effective_pml(const oracle_ctx *h, int ide, int *f) {
     effective_pml(*h->c, ide, first, f);
 }
 
+/*
+ * Post-processing of a solved system (TEST INFRASTRUCTURE for the north_star's end-to-end criterion):
+ * solution.f90:18-69 node_solution / z_rho_phi, :207-256 get_elem_sol (pe_sch=1), :304-343 get_er, :370-413 get_hr,
+ * :440-505 hor_fields / get_impedance / get_res_phase / inv_matrix.
+ *   x[2*nne]        solution of both polarisations (column d at offset (d-1)*nne), complex
+ *   esol,hsol[2*npt][3] total E and H at the grid nodes (row idd-1 = node + (edir-1)*npt), complex
+ *   z[npt][4] complex, rho[npt][4], phi[npt][4]
+ */
+int oracle_node_solution(const oracle_ctx *h, double omega, const double *g_sigma_, const double *x_, double *esol_, double *hsol_,
+                         double *z_, double *rho_, double *phi_) {
+    const Ctx &c = *h->c;
+    const C *x = (const C *)x_;
+    C *esol = (C *)esol_, *hsol = (C *)hsol_, *z = (C *)z_;
+    const int g = c.d.nord, npt = c.npt, nne = c.nne, ne = c.ne, me = c.me, mn = c.mn;
+    auto G = [&](int ide, int im) -> int { return c.gne[(size_t)(im - 1) * ne + (ide - 1)]; };
+    std::vector<char> valued_e((size_t)2 * npt, 0), valued_h((size_t)2 * npt, 0);
+    for (size_t i = 0; i < (size_t)6 * npt; ++i) { esol[i] = mk(0, 0); hsol[i] = mk(0, 0); }
+    double as[3];
+    for (int j = 1; j <= g; ++j) as[j - 1] = -1 + (double)(j - 1) * (2 / (double)(g - 1));   // gqg_nodes, geometry.f90:720-739
+    Elem *E = new Elem;
+    elem_setup(*E, c, omega, (const C *)g_sigma_, 0);
+    for (int ie = 1; ie <= c.nx; ++ie)
+        for (int je = 1; je <= c.ny; ++je)
+            for (int ke = 1; ke <= c.nz; ++ke) {
+                const int eno = (ie - 1) * c.nyz * (g - 1) + (je - 1) * c.nnz * (g - 1) + (ke - 1) * (g - 1) + 1;
+                const int ide = (ie - 1) * c.ny * c.nz + (je - 1) * c.nz + ke;
+                nf_get_r(*E, ie, je, ke, eno);
+                p_elem_fields(*E);
+                if (E->status) { const int st = E->status; delete E; return st; }
+                for (int edir = 1; edir <= 2; ++edir) {
+                    // get_elem_sol, pe_sch = 1: E first (secondary + primary), then H from the nodal E of this element
+                    for (int i1 = 1; i1 <= g; ++i1)
+                        for (int j1 = 1; j1 <= g; ++j1)
+                            for (int k1 = 1; k1 <= g; ++k1) {
+                                const int idd = eno + (i1 - 1) * c.nyz + (j1 - 1) * c.nnz + (k1 - 1) + (edir - 1) * npt;
+                                if (valued_e[idd - 1]) continue;
+                                const double r[3] = {as[i1 - 1], as[j1 - 1], as[k1 - 1]};
+                                C ef[3] = {mk(0, 0), mk(0, 0), mk(0, 0)};            // get_er
+                                for (int im = 1; im <= me; ++im) {
+                                    C f = mk(0, 0);
+                                    if (G(ide, im) >= 0) f = x[(size_t)G(ide, im) - 1 + (size_t)(edir - 1) * nne];   // f_boundary == 0 (bd_inimod 1)
+                                    double ve[3];
+                                    vf_elem_ve(*E, im, r, ve);
+                                    ef[0] = ef[0] + f * ve[0]; ef[1] = ef[1] + f * ve[1]; ef[2] = ef[2] + f * ve[2];
+                                }
+                                C ep[3] = {mk(0, 0), mk(0, 0), mk(0, 0)};            // get_ep, problem.f90:151-168
+                                for (int i = 1; i <= mn; ++i) {
+                                    const int j = i + (edir - 1) * mn;
+                                    const double ln = c.shape.nf_ln(i, r[0], r[1], r[2]);
+                                    for (int m = 0; m < 3; ++m) ep[m] = ep[m] + E->pe_ep[j - 1][m] * ln;
+                                }
+                                for (int m = 0; m < 3; ++m) esol[(size_t)(idd - 1) * 3 + m] = ef[m] + ep[m];
+                                valued_e[idd - 1] = 1;
+                            }
+                    for (int i1 = 1; i1 <= g; ++i1)
+                        for (int j1 = 1; j1 <= g; ++j1)
+                            for (int k1 = 1; k1 <= g; ++k1) {
+                                const int idd = eno + (i1 - 1) * c.nyz + (j1 - 1) * c.nnz + (k1 - 1) + (edir - 1) * npt;
+                                if (valued_h[idd - 1]) continue;
+                                const double r[3] = {as[i1 - 1], as[j1 - 1], as[k1 - 1]};
+                                C ef[3] = {mk(0, 0), mk(0, 0), mk(0, 0)};            // get_hr
+                                for (int im = 1; im <= mn; ++im) {
+                                    const C *f2 = esol + ((size_t)E->nf_index[im - 1] - 1 + (size_t)(edir - 1) * npt) * 3;
+                                    double dn[3];
+                                    nf_grad_ln(*E, im, r, dn);
+                                    ef[0] = ef[0] + (f2[2] * dn[1] - f2[1] * dn[2]);
+                                    ef[1] = ef[1] + (f2[0] * dn[2] - f2[2] * dn[0]);
+                                    ef[2] = ef[2] + (f2[1] * dn[0] - f2[0] * dn[1]);
+                                }
+                                C mf1[6];
+                                for (int k = 0; k < 6; ++k) mf1[k] = mk(0, 0);
+                                for (int i = 1; i <= mn; ++i) {                      // p_intmodels, problem.f90:139-142
+                                    const double ln = c.shape.nf_ln(i, r[0], r[1], r[2]);
+                                    for (int k = 0; k < 6; ++k) mf1[k] = mf1[k] + mk(ln * E->pe_inmu[i - 1][k], 0.0);
+                                }
+                                C md[6];
+                                for (int k = 0; k < 6; ++k) md[k] = cmplx32(0.0, -1.0 / omega) * mf1[k];   // cmplx() without KIND (Q2)
+                                C *ho = hsol + (size_t)(idd - 1) * 3;
+                                ho[0] = md[0] * ef[0] + md[1] * ef[1] + md[2] * ef[2];
+                                ho[1] = md[1] * ef[0] + md[3] * ef[1] + md[4] * ef[2];
+                                ho[2] = md[2] * ef[0] + md[4] * ef[1] + md[5] * ef[2];
+                                valued_h[idd - 1] = 1;
+                            }
+                }
+            }
+    delete E;
+    // z_rho_phi
+    const double mu0 = 4 * PI * 1.e-7;
+    for (int id = 0; id < npt; ++id) {
+        const C e[4] = {esol[(size_t)id * 3], esol[((size_t)id + npt) * 3], esol[(size_t)id * 3 + 1], esol[((size_t)id + npt) * 3 + 1]};
+        const C hh[4] = {hsol[(size_t)id * 3], hsol[((size_t)id + npt) * 3], hsol[(size_t)id * 3 + 1], hsol[((size_t)id + npt) * 3 + 1]};
+        const C det = hh[0] * hh[3] - hh[1] * hh[2];
+        const C ih[4] = {hh[3] / det, -hh[1] / det, -hh[2] / det, hh[0] / det};
+        C zz[4];
+        zz[0] = ih[0] * e[0] + ih[2] * e[1];
+        zz[1] = ih[1] * e[0] + ih[3] * e[1];
+        zz[2] = ih[0] * e[2] + ih[2] * e[3];
+        zz[3] = ih[1] * e[2] + ih[3] * e[3];
+        for (int i = 0; i < 4; ++i) {
+            z[(size_t)id * 4 + i] = zz[i];
+            double rho = (1.0 / (omega * mu0)) * (zz[i].re * zz[i].re + zz[i].im * zz[i].im), phi = 0.0;
+            if (rho < 1.e-2) rho = 0.0;
+            else phi = std::atan(zz[i].im / zz[i].re) * (180. / PI);
+            rho_[(size_t)id * 4 + i] = rho; phi_[(size_t)id * 4 + i] = phi;
+        }
+    }
+    return 0;
+}
+
 }  // extern "C"

@@ -44,6 +44,7 @@ def lib():
         _LIB.oracle_get_in_pml.argtypes = [C.c_void_p, C.c_void_p]
         _LIB.oracle_set_in_pml.argtypes = [C.c_void_p, C.c_void_p]
         _LIB.oracle_effective_pml.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _LIB.oracle_node_solution.argtypes = [C.c_void_p, C.c_double] + [C.c_void_p] * 7
     return _LIB
 
 
@@ -145,3 +146,17 @@ class Oracle:
         n = nz.value
         return dict(a_t1=a_t1, irn=None if irn is None else irn[:n], jcn=None if jcn is None else jcn[:n],
                     a=None if a is None else a[:n], nz=n, rhs=rhs, seconds=secs.value, jac_builds=jb.value)
+
+    def node_solution(self, omega, sigma, x):
+        """solution.f90 post-processing of a solved system x[2*nne]: total E, H at the grid nodes, impedance,
+        apparent resistivity and phase (the north_star's end-to-end observable).  Returns dict(esol, hsol, z, rho, phi)."""
+        npt = self.model.npt
+        sigma = np.ascontiguousarray(sigma, np.complex128)
+        x = np.ascontiguousarray(x, np.complex128)
+        assert x.size == 2 * self.nne
+        esol = np.zeros((2 * npt, 3), np.complex128); hsol = np.zeros((2 * npt, 3), np.complex128)
+        z = np.zeros((npt, 4), np.complex128); rho = np.zeros((npt, 4)); phi = np.zeros((npt, 4))
+        rc = lib().oracle_node_solution(self._h, omega, _p(sigma), _p(x), _p(esol), _p(hsol), _p(z), _p(rho), _p(phi))
+        if rc:
+            raise RuntimeError(f"oracle_node_solution failed: {rc}")
+        return dict(esol=esol, hsol=hsol, z=z, rho=rho, phi=phi)

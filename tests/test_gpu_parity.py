@@ -248,3 +248,33 @@ def test_x_slab_handles_concatenate_to_the_full_assembly(mn, dirichlet):
     assert np.array_equal(np.concatenate([p[2] for p in parts]), a[:nz])
     assert np.array_equal(rhs_acc, rhs)
     full.close()
+
+
+@pytest.mark.parametrize("mn,dirichlet", [(8, 0), (8, 1), (20, 1), (27, 0)])
+def test_end_to_end_apparent_resistivity_and_phase(mn, dirichlet):
+    """north_star: 'End-to-end apparent resistivity and phase after the unchanged solve must agree to <= 1e-6 relative.'
+    Graft and oracle triplets (tap T2 = what ZMUMPS receives, and the double-precision tap T1) go through the same
+    stand-in sparse LU and the same solution.f90 post-processing (tests/e2e_util.py)."""
+    from e2e_util import e2e_model, rho_phi_diff, solve_upper_triplets
+    m = e2e_model(mn, dirichlet)
+    asm, o = host.Assembly(m), Oracle(m)
+    om, sg = m.omega(1), m.sigma_for(1)
+    ro = o.assemble(om, sg)
+    # T2
+    irn, jcn, a, rhs, nz = asm.global_vfem(1, om, sg, mode=abi.MODE_T2)
+    assert nz == ro["nz"] and np.array_equal(irn[:nz], ro["irn"]) and np.array_equal(jcn[:nz], ro["jcn"])
+    xg = solve_upper_triplets(asm.nne, irn[:nz], jcn[:nz], a[:nz], rhs)
+    xo = solve_upper_triplets(o.nne, ro["irn"], ro["jcn"], ro["a"], ro["rhs"])
+    sg_, so_ = o.node_solution(om, sg, xg), o.node_solution(om, sg, xo)
+    drho, dphi, same, n = rho_phi_diff(so_, sg_)
+    assert same and n > 100 and drho <= 1e-6 and dphi <= 1e-6 * 90.0, (drho, dphi, same, n)
+    # T1 (double values, upper triangle in delivery order) against the oracle's T1 (lower triangle of the full pattern)
+    irn1, jcn1, a1, rhs1, nz1 = asm.global_vfem(1, om, sg, mode=abi.MODE_T1)
+    ia, ja = o.pattern()
+    keep = ia >= ja
+    xg1 = solve_upper_triplets(asm.nne, irn1[:nz1], jcn1[:nz1], a1[:nz1], rhs1)
+    xo1 = solve_upper_triplets(o.nne, ja[keep], ia[keep], ro["a_t1"][keep], ro["rhs"])
+    drho1, dphi1, same1, n1 = rho_phi_diff(o.node_solution(om, sg, xo1), o.node_solution(om, sg, xg1))
+    assert same1 and drho1 <= 1e-6 and dphi1 <= 1e-6 * 90.0, (drho1, dphi1)
+    assert np.linalg.norm(xg1 - xo1) <= 1e-9 * np.linalg.norm(xo1)
+    asm.close()

@@ -158,3 +158,41 @@ def test_q17_stale_flags_between_frequencies():
     g1 = set(o.gne()[0])
     assert d.size > 0 and set(ia[d]) <= g1 and set(ja[d]) <= g1
     assert list(o.effective_pml(2)) == [0, 0, 0] and list(o.effective_pml(m.g_nz)) == [0, 0, 1]   # bottom element of column 2 sees the top flags
+
+
+def test_node_solution_recovers_the_layered_halfspace_response():
+    """Pin of the post-processing restatement (solution.f90): on a laterally uniform earth the oracle's own triplets,
+    solved by the stand-in LU, must give a 1-D response -- Zxy = -Zyx, Zxx = Zyy = 0 to solver accuracy, and the same
+    rho_a at every surface node of the inner zone -- and a 1e-13 perturbation of A must not move rho_a (the
+    conditioning claim tests/e2e_util.py makes for its models)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from e2e_util import solve_upper_triplets, rho_phi_diff
+    from movfem_b200 import mesh
+    from oracle.oracle import Oracle
+    m = mesh.build_model("halfspace", 8, 8, 8, 1000., 1000., 500., 2, 4, 2, dirichlet=1, gpml_sch=1, freqs=(10.0,))
+    air = m.sigma_re[:, 0] == 0.0
+    for k in (0, 3, 5):
+        m.sigma_re[air, k] = 1e-3
+    o = Oracle(m)
+    om, sg = m.omega(1), m.sigma_for(1)
+    r = o.assemble(om, sg)
+    x = solve_upper_triplets(o.nne, r["irn"], r["jcn"], r["a"], r["rhs"])
+    s = o.node_solution(om, sg, x)
+    nn = m.g_nx
+    z = s["z"].reshape(nn, nn, m.g_nz, 4)
+    ks = 2 + 4                                   # surface node plane: nextd + n_earth
+    zc = z[3:6, 3:6, ks, :]                      # inner zone
+    # z(1..4) = Zxx, Zxy(-like), Zyx, Zyy (solution.f90:461-464).  1-D earth on an x<->y symmetric mesh: the diagonal
+    # vanishes, Zxy(i,j) = -Zyx(j,i) (H at a node is a one-sided derivative taken in the first element that visits
+    # it, solution.f90:244-254, so the response is not identical from node to node), exactly antisymmetric at the centre
+    off = np.abs(zc[..., 1])
+    assert np.all(np.abs(zc[..., 0]) <= 1e-6 * off) and np.all(np.abs(zc[..., 3]) <= 1e-6 * off)
+    assert np.all(np.abs(zc[..., 1] + np.swapaxes(zc[..., 2], 0, 1)) <= 1e-9 * off)
+    assert abs(zc[1, 1, 1] + zc[1, 1, 2]) <= 1e-9 * abs(zc[1, 1, 1])
+    rho = s["rho"].reshape(nn, nn, m.g_nz, 4)[3:6, 3:6, ks, 1]
+    assert 50.0 < rho.min() and rho.max() < 400.0          # 100 Ohm m half-space under a poor conductor, 500 m cells at 10 Hz
+    rng = np.random.default_rng(0)
+    xp = solve_upper_triplets(o.nne, r["irn"], r["jcn"], r["a"] * (1 + 1e-13 * rng.standard_normal(r["a"].size)), r["rhs"])
+    drho, dphi, same, n = rho_phi_diff(s, o.node_solution(om, sg, xp))
+    assert same and drho <= 1e-7, (drho, dphi)
