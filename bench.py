@@ -23,6 +23,11 @@ import sys
 import threading
 import time
 
+# NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION and latches the level at its first call, which can
+# happen while torch.distributed is imported; stdout carries exactly one JSON line, so lower the level before that
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -133,9 +138,6 @@ def run_graft(args):
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 

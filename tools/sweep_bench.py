@@ -8,6 +8,7 @@ cold assembly, the later ones recompute only the GPML layers and the RHS (the de
 No data-path collective; with --gather the finished value arrays go to rank 0 with NCCL send/recv (what a
 centralised ZMUMPS would need).  Prints one JSON line on rank 0; time = max over ranks of the whole shard."""
 import argparse, json, os, sys
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION": os.environ["NCCL_DEBUG"] = "WARN"   # keep the banner off stdout
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from movfem_b200 import mesh, host, abi
