@@ -5,8 +5,8 @@
 
 Each rank owns a range of ie (contiguous rows), computes its +x halo itself (no data-path collective) and, with
 --gather, hands its value slice to rank 0 with NCCL send/recv.  Prints one JSON line on rank 0."""
-import argparse, json, os, sys
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION": os.environ["NCCL_DEBUG"] = "WARN"   # keep the banner off stdout, time, copy
+import argparse, json, os, sys, time, copy
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION": os.environ["NCCL_DEBUG"] = "WARN"   # keep the banner off stdout
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from movfem_b200 import mesh, host, abi
