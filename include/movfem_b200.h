@@ -40,6 +40,11 @@ extern "C" {
                               exact zeros stripped (global_assembly.f90:123-150)           */
 #define MOVFEM_MODE_T1  1  /* tap before ga_sort_sparse: same ordering and pattern
                               (structural upper triangle, nothing stripped), double values */
+#define MOVFEM_MODE_KEEP_PATTERN 0x100  /* OR-ed into the mode of movfem_assemble: the caller's irn/jcn still hold what
+                              the previous movfem_assemble on this handle delivered (the structural pattern is static
+                              across frequencies), so they are re-sent only if the zero strip changed the delivered set.
+                              Saves 8 of the 24 B/entry on the host link.  The reference reallocates irn/jcn every
+                              frequency (MoVFEM_3DMT.f90:78,119); hoist that allocation to use this.             */
 
 /*
  * Mesh / problem descriptor.  Every field is the reference module variable of the same

@@ -17,6 +17,7 @@ MOVFEM_E_UNSUPPORTED = -7
 
 MODE_T2 = 0
 MODE_T1 = 1
+MODE_KEEP_PATTERN = 0x100
 
 ERROR_NAMES = {
     MOVFEM_E_BADARG: "bad argument",

@@ -97,6 +97,8 @@ struct movfem_handle {
     // state
     bool km_valid;      // Ke/Me of the unstretched elements are cached
     bool compacted;     // last result lives in the *_c arrays
+    int64_t pattern_nz_host;   // nz of the pattern last copied into the caller's irn/jcn (-1: none); MOVFEM_MODE_KEEP_PATTERN
+    bool pattern_host_compacted;
     int64_t nz_last;
     int32_t mode_last;
     cudaEvent_t ev[EV_COUNT];
@@ -595,6 +597,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     CK(dmalloc(&h->d_blkcnt, (size_t)h->nblk_fin)); CK(dmalloc(&h->d_blkoff, (size_t)h->nblk_fin + 1));
     CK(dmalloc(&h->d_finbsum, (size_t)(h->nblk_fin + kScanTile - 1) / kScanTile + 1));
     h->km_valid = false;
+    h->pattern_nz_host = -1; h->pattern_host_compacted = false;
     return MOVFEM_OK;
 }
 
@@ -757,16 +760,21 @@ int movfem_device_result(const movfem_handle *hc, const int32_t **irn, const int
 }
 
 int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega, const double *g_sigma, int32_t *irn, int32_t *jcn,
-                    double *a, double *rhs, int64_t *nz_out, int32_t mode) {
+                    double *a, double *rhs, int64_t *nz_out, int32_t mode_flags) {
     if (!h || !g_sigma || !irn || !jcn || !a || !rhs || !nz_out) return MOVFEM_E_BADARG;
+    const int32_t mode = mode_flags & 0xff;
+    // static structural pattern already in the caller's arrays (and not a compacted one)?
+    const bool keep = (mode_flags & MOVFEM_MODE_KEEP_PATTERN) && h->pattern_nz_host == h->nzu && !h->pattern_host_compacted;
     CK(cudaSetDevice(h->device));
     const MeshDims &m = h->m;
     cudaStream_t st = h->stream;
     CK(cudaEventRecord(h->ev[EV_START], st));
     // IRN/JCN of the structural pattern never change: start their D2H now, on the copy stream, so that it overlaps
     // the H2D of g_sigma (PCIe is full duplex) and the kernels.  If rem_zeros strips entries (rare) they are re-sent.
-    CK(cudaMemcpyAsync(irn, h->d_irn, sizeof(int) * (size_t)h->nzu, cudaMemcpyDeviceToHost, h->copy_stream));
-    CK(cudaMemcpyAsync(jcn, h->d_jcn, sizeof(int) * (size_t)h->nzu, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (!keep) {
+        CK(cudaMemcpyAsync(irn, h->d_irn, sizeof(int) * (size_t)h->nzu, cudaMemcpyDeviceToHost, h->copy_stream));
+        CK(cudaMemcpyAsync(jcn, h->d_jcn, sizeof(int) * (size_t)h->nzu, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
     CK(cudaMemcpyAsync(h->d_sigma + (size_t)6 * h->node_lo, reinterpret_cast<const double2 *>(g_sigma) + (size_t)6 * h->node_lo,
                        sizeof(double2) * (size_t)6 * (h->node_hi - h->node_lo), cudaMemcpyHostToDevice, st));
     int rc = movfem_assemble_device(h, freq_index, omega, reinterpret_cast<const double *>(h->d_sigma), mode);
@@ -787,6 +795,7 @@ int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega, const do
         CK(cudaMemcpyAsync(irn, d_irn, sizeof(int) * (size_t)nz, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(jcn, d_jcn, sizeof(int) * (size_t)nz, cudaMemcpyDeviceToHost, st));
     }
+    h->pattern_nz_host = h->compacted ? nz : h->nzu; h->pattern_host_compacted = h->compacted;
     CK(cudaEventRecord(h->ev[EV_D2H], st));
     CK(cudaStreamSynchronize(st));
     *nz_out = nz;

@@ -197,6 +197,23 @@ def test_error_codes_replace_stops():
     asm.close()
 
 
+def test_keep_pattern_mode_skips_static_irn_jcn():
+    """MOVFEM_MODE_KEEP_PATTERN: irn/jcn of the previous call are left alone (same values as a full call), and a
+    first call with the flag still delivers them."""
+    m = _small(20, 0, 1)
+    asm = host.Assembly(m)
+    full = asm.global_vfem(1, m.omega(1), m.sigma_for(1), mode=abi.MODE_T2)
+    irn = np.full(asm.nz_upper, -7, np.int32); jcn = np.full(asm.nz_upper, -7, np.int32)
+    r1 = asm.global_vfem(1, m.omega(1), m.sigma_for(1), mode=abi.MODE_T2 | abi.MODE_KEEP_PATTERN, irn=irn, jcn=jcn)
+    assert r1[4] == full[4] and np.all(irn[: r1[4]] == -7) == (full[4] == asm.nz_upper)   # untouched iff nothing was stripped
+    asm2 = host.Assembly(m)
+    r2 = asm2.global_vfem(1, m.omega(1), m.sigma_for(1), mode=abi.MODE_T2 | abi.MODE_KEEP_PATTERN)
+    nz = full[4]
+    assert r2[4] == nz and np.array_equal(r2[0][:nz], full[0][:nz]) and np.array_equal(r2[1][:nz], full[1][:nz])
+    assert np.array_equal(r2[2][:nz], full[2][:nz]) and np.array_equal(r1[2][:nz], full[2][:nz])
+    asm.close(); asm2.close()
+
+
 def test_device_resident_api():
     import torch
     m = _small(20, 0, 0)
