@@ -138,7 +138,19 @@ def run_graft(args):
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries exactly one JSON line: whatever NCCL / c10d print while the communicator is built (the
+        # "NCCL version ..." banner) goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     dev = torch.device("cuda", local_rank)
 
     model = mesh.config(WORKLOAD)

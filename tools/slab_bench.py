@@ -18,7 +18,10 @@ ap.add_argument("--gather", action="store_true"); ap.add_argument("--config", ty
 args = ap.parse_args()
 rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
-if world > 1: dist.init_process_group("nccl", device_id=dev)
+if world > 1:
+    _fd = os.dup(1); os.dup2(2, 1)          # NCCL's banner goes to stderr, stdout carries the JSON line
+    dist.init_process_group("nccl", device_id=dev); dist.barrier(); torch.cuda.synchronize()
+    sys.stdout.flush(); os.dup2(_fd, 1); os.close(_fd)
 m = mesh.config(args.config, scale=args.scale)
 if world > 1:
     m = copy.copy(m); m.ie_lo, m.ie_hi = slab_partition(m.g_nx - 1, rank, world)

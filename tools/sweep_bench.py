@@ -21,9 +21,9 @@ args = ap.parse_args()
 rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 if world > 1:
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
-    dist.init_process_group("nccl", device_id=dev)
+    _fd = os.dup(1); os.dup2(2, 1)          # NCCL's banner goes to stderr, stdout carries the JSON line
+    dist.init_process_group("nccl", device_id=dev); dist.barrier(); torch.cuda.synchronize()
+    sys.stdout.flush(); os.dup2(_fd, 1); os.close(_fd)
 m = mesh.config(4, scale=args.scale)
 nf = len(m.freqs)
 mine = frequency_shard(nf, rank, world)
