@@ -55,7 +55,6 @@ struct movfem_handle {
     MeshDims m;
     PmlParams pml;
     int NP, ngp, num_sms;
-    double h_Ntab[kMaxGp * kMaxMn];   // N[g][l] packed with stride mn (kernel-parameter copy)
     int nne;                 // global number of unknowns
     int row_lo, nrows;       // rows owned by this handle (whole matrix unless a slab was requested)
     int node_lo, node_hi;    // node id range [lo, hi) touched by the slab's elements
@@ -538,8 +537,6 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
         build_tables(*d, m, T[0], S);
         CK(dmalloc(&h->d_tab, 1)); CK(dmalloc(&h->d_share, 1));
         CK(cudaMemcpy(h->d_tab, T.data(), sizeof(ElemTables), cudaMemcpyHostToDevice));
-        for (int g = 0; g < m.ngp; ++g)
-            for (int l = 0; l < m.mn; ++l) h->h_Ntab[g * m.mn + l] = T[0].N[g][l];
         CK(cudaMemcpy(h->d_share, &S, sizeof(ShareTables), cudaMemcpyHostToDevice));
         build_contract_tables(m, T[0], h->ct);
     }
