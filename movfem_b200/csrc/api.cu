@@ -74,6 +74,9 @@ struct movfem_handle {
     int64_t *d_cptr;         // transient (pattern build); replaced by the compressed d_cblk / d_off16
     int64_t *d_cblk;
     uint16_t *d_off16;
+    uint32_t *d_pure;        // bit per entry: only unstretched elements contribute (gathered K/M cacheable across a sweep)
+    double2 *d_kmg;          // the cache: gathered (K, M) per entry, allocated on the second frequency if memory allows
+    int kmg_state;           // 0 not allocated, 1 allocated / to be filled, 2 valid, -1 does not fit
     uint32_t *d_src;
     double2 *d_KM;
     double *d_be;
@@ -370,7 +373,7 @@ int run_elements(movfem_handle *h, ElemArgs &A, bool full) {
 void free_all(movfem_handle *h) {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_xp, h->d_yp, h->d_zp, h->d_mu, h->d_sigma, h->d_nodes, h->d_tab, h->d_share, h->d_gne, h->d_ownE,
-                    h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_cblk, h->d_off16, h->d_src, h->d_KM,
+                    h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_cblk, h->d_off16, h->d_pure, h->d_kmg, h->d_src, h->d_KM,
                     h->d_be, h->d_qt, h->d_kmrow, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum,
                     h->d_status, h->d_flags};
     for (void *p : ptrs)
@@ -459,6 +462,15 @@ int build_pattern(movfem_handle *h) {
         CK(dmalloc(&h->d_cblk, (size_t)nblk + 1));
         CK(dmalloc(&h->d_off16, (size_t)h->nzu));
         if (nblk > 0) compress_cptr_kernel<<<nblk, kFinThreads, 0, h->stream>>>(h->nzu, h->d_cptr, h->d_cblk, h->d_off16);
+        h->launches += 1;
+        CK(cudaGetLastError());
+    }
+    {
+        const int nblk = (int)((h->nzu + kFinThreads - 1) / kFinThreads);
+        CK(dmalloc(&h->d_pure, (size_t)(h->nzu + 31) / 32));
+        if (nblk > 0)
+            pure_mask_kernel<<<nblk, kFinThreads, 0, h->stream>>>(h->nzu, h->d_cblk, h->d_off16, h->d_src, h->NP, (int64_t)(h->n_plain + 31) / 32 * 32,
+                                                                  h->d_pure);
         h->launches += 1;
         CK(cudaGetLastError());
     }
@@ -681,8 +693,22 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
     h->km_valid = true;
     CK(cudaEventRecord(h->ev[EV_ELEM], st));
 
+    // a later frequency of a sweep (K/M of the unstretched elements cached): keep the gathered K/M of the entries only
+    // they touch as well -- allocated on the second frequency if it fits, filled by that call, streamed afterwards
+    int cache = 0;
+    if (!full) {
+        if (h->kmg_state == 0) {
+            size_t fr = 0, tot = 0;
+            CK(cudaMemGetInfo(&fr, &tot));
+            const size_t need = sizeof(double2) * (size_t)h->nzu;
+            if (!getenv("MOVFEM_NO_GATHER_CACHE") && fr > need + ((size_t)2 << 30) && cudaMalloc((void **)&h->d_kmg, need) == cudaSuccess) h->kmg_state = 1;
+            else { cudaGetLastError(); h->kmg_state = -1; }
+        }
+        if (h->kmg_state == 1) { cache = 1; h->kmg_state = 2; }
+        else if (h->kmg_state == 2) cache = 2;
+    } else if (h->kmg_state == 2) h->kmg_state = 1;   // cold assembly: the cache content is stale
     gather_finalize_kernel<<<h->nblk_fin, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cblk, h->d_off16, h->d_src, h->d_KM, h->d_a,
-                                                              h->d_blkcnt, mode == MOVFEM_MODE_T1 ? 1 : 0);
+                                                              h->d_blkcnt, mode == MOVFEM_MODE_T1 ? 1 : 0, cache, h->d_pure, h->d_kmg, h->d_flags);
     rhs_kernel<<<(h->nrows + 127) / 128, 128, 0, st>>>(h->nrows, h->d_rown, reinterpret_cast<const double4 *>(h->d_be), h->d_rhs);
     h->launches += 2;
     CK(cudaGetLastError());

@@ -32,46 +32,89 @@ compress_cptr_kernel(int64_t nzu, const int64_t *__restrict__ cptr, int64_t *__r
     if (i < nzu) off16[i] = (uint16_t)(cptr[i] - b0);
 }
 
+// pure[i/32] bit i%32: every contribution of entry i comes from an unstretched element (K/M row < pml_row0), i.e. the
+// gathered (K, M) of the entry is frequency independent and can be cached across a sweep
+__global__ void __launch_bounds__(kFinThreads)
+pure_mask_kernel(int64_t nzu, const int64_t *__restrict__ cblk, const uint16_t *__restrict__ off16, const uint32_t *__restrict__ src,
+                 int NP, int64_t pml_row0, uint32_t *__restrict__ pure) {
+    const int64_t i = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
+    bool p = false;
+    if (i < nzu) {
+        const int64_t c0 = cblk[blockIdx.x];
+        const int lo = off16[i];
+        const int hi = (threadIdx.x + 1 < kFinThreads && i + 1 < nzu) ? off16[i + 1] : (int)(cblk[blockIdx.x + 1] - c0);
+        p = true;
+        for (int c = lo; c < hi; ++c) {
+            const uint32_t s = src[c0 + c];
+            const int64_t row = (int64_t)((s >> 5) / (uint32_t)NP) * 32 + (s & 31);
+            if (row >= pml_row0) p = false;
+        }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, p);
+    if ((threadIdx.x & 31) == 0 && i < nzu) pure[i >> 5] = bal;
+}
+
 // mode 0 (T2): values rounded through float32, per-block count of surviving (non-zero) entries
 // mode 1 (T1): double values, nothing stripped
 // Phase 1: the block's <= 1024 contributions are fetched by all threads (independent random 16-byte reads, up to four
 // in flight per thread) into shared memory; phase 2: one thread per entry sums its contributions in ascending order.
+// cache: 0 none; 1 fill kmg[i] = gathered (K, M) of every entry; 2 use it for the pure entries (a later frequency of a
+// sweep: streaming 16-byte reads instead of the gather) unless the node kernel saw Re(sigma) change (flags[1]), in which
+// case the call refills it.
 __global__ void __launch_bounds__(kFinThreads)
 gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk, const uint16_t *__restrict__ off16,
                        const uint32_t *__restrict__ src, const double2 *__restrict__ KM, double2 *__restrict__ a,
-                       int *__restrict__ blk_nonzero, int mode) {
+                       int *__restrict__ blk_nonzero, int mode, int cache, const uint32_t *__restrict__ pure,
+                       double2 *__restrict__ kmg, const int *__restrict__ flags) {
     __shared__ double2 vals[4 * kFinThreads];
     __shared__ uint16_t offs[kFinThreads + 1];
     const int64_t i = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
     const int64_t c0 = cblk[blockIdx.x];
     const int n = (int)(cblk[blockIdx.x + 1] - c0);
-    if (i < nzu) offs[threadIdx.x] = off16[i];
-    uint32_t sidx[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int c = threadIdx.x + k * kFinThreads;
-        sidx[k] = c < n ? src[c0 + c] : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int c = threadIdx.x + k * kFinThreads;
-        if (c < n) vals[c] = KM[sidx[k]];
-    }
-    __syncthreads();
+    if (cache == 2 && flags[1] != 0) cache = 1;
     int nzflag = 0;
-    if (i < nzu) {
-        const int lo = offs[threadIdx.x];
-        const int hi = (threadIdx.x + 1 < kFinThreads && i + 1 < nzu) ? offs[threadIdx.x + 1] : n;
-        double k = 0.0, mm = 0.0;
-        for (int c = lo; c < hi; ++c) {
-            const double2 v = vals[c];
-            k = k + v.x;
-            mm = mm + v.y;
+    // later frequency of a sweep: a block whose entries are all pure streams them from the cache; a block with any
+    // entry that a GPML element touches runs the staged gather below (block-uniform decision)
+    bool pure_e = true;
+    if (cache == 2 && i < nzu) pure_e = (pure[i >> 5] >> (i & 31)) & 1u;
+    const bool stream = cache == 2 && __syncthreads_and(pure_e);
+    if (stream) {
+        if (i < nzu) {
+            const double2 v = kmg[i];
+            double re = v.x, im = w32 * v.y;
+            if (mode == 0) { re = f32r(re); im = f32r(im); }
+            a[i] = make_double2(re, im);
+            nzflag = !(re == 0.0 && im == 0.0);
         }
-        double re = k, im = w32 * mm;
-        if (mode == 0) { re = f32r(re); im = f32r(im); }
-        a[i] = make_double2(re, im);
-        nzflag = !(re == 0.0 && im == 0.0);
+    } else {
+        if (i < nzu) offs[threadIdx.x] = off16[i];
+        uint32_t sidx[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = threadIdx.x + k * kFinThreads;
+            sidx[k] = c < n ? src[c0 + c] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = threadIdx.x + k * kFinThreads;
+            if (c < n) vals[c] = KM[sidx[k]];
+        }
+        __syncthreads();
+        if (i < nzu) {
+            const int lo = offs[threadIdx.x];
+            const int hi = (threadIdx.x + 1 < kFinThreads && i + 1 < nzu) ? offs[threadIdx.x + 1] : n;
+            double k = 0.0, mm = 0.0;
+            for (int c = lo; c < hi; ++c) {
+                const double2 v = vals[c];
+                k = k + v.x;
+                mm = mm + v.y;
+            }
+            if (cache == 1) kmg[i] = make_double2(k, mm);
+            double re = k, im = w32 * mm;
+            if (mode == 0) { re = f32r(re); im = f32r(im); }
+            a[i] = make_double2(re, im);
+            nzflag = !(re == 0.0 && im == 0.0);
+        }
     }
     const int cnt = __syncthreads_count(nzflag);
     if (threadIdx.x == 0) blk_nonzero[blockIdx.x] = cnt;

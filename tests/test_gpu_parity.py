@@ -151,6 +151,33 @@ def test_config4_sweep_cached_equals_cold_and_oracle():
     asm.close()
 
 
+def test_sweep_gather_cache_is_bitwise_neutral(monkeypatch):
+    """From the third frequency of a sweep on, entries that only unstretched elements touch take their gathered (K, M)
+    from a cache instead of re-gathering; the delivered triplets must not change by a bit, also when Re(sigma) changes
+    in mid-sweep (the cache is refilled on the device) -- compared with a handle that has the cache disabled."""
+    m = mesh.config(4, scale=0.12)
+    a1 = host.Assembly(m)
+    monkeypatch.setenv("MOVFEM_NO_GATHER_CACHE", "1")
+    a0 = host.Assembly(m)
+    seq = [1, 2, 3, 4, 5, 6]
+    for n, ifreq in enumerate(seq):
+        om, sg = m.omega(ifreq), m.sigma_for(ifreq).copy()
+        if n >= 4:
+            sg[::7] *= 1.25                      # a different earth from the fifth call on: cached K/M must be refreshed
+        r1 = a1.global_vfem(ifreq, om, sg)
+        r0 = a0.global_vfem(ifreq, om, sg)
+        nz = r1[4]
+        assert nz == r0[4]
+        for k in range(3):
+            assert np.array_equal(r1[k][:nz], r0[k][:nz]), (ifreq, k)
+        assert np.array_equal(r1[3], r0[3])
+        if n in (2, 5):                          # and both equal a cold assembly of the same inputs
+            a1.reset_cache()
+            rc = a1.global_vfem(ifreq, om, sg)
+            assert rc[4] == nz and np.array_equal(rc[2][:nz], r0[2][:nz])
+    a1.close(); a0.close()
+
+
 def test_full_size_properties_config2():
     """BASELINE configs[1] at full size (48000 20-node elements), through size-independent properties:
     determinism (bit-identical reruns), T2 == float32 round trip of T1 minus exact zeros, sorted upper
