@@ -65,12 +65,13 @@ __global__ void __launch_bounds__(kFinThreads)
 gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk, const uint16_t *__restrict__ off16,
                        const uint32_t *__restrict__ src, const double2 *__restrict__ KM, double2 *__restrict__ a,
                        int *__restrict__ blk_nonzero, int mode, int cache, const uint32_t *__restrict__ pure,
-                       double2 *__restrict__ kmg, const int *__restrict__ flags) {
+                       double2 *__restrict__ kmg, const int *__restrict__ flags, const int *__restrict__ blk_list) {
     __shared__ double2 vals[4 * kFinThreads];
     __shared__ uint16_t offs[kFinThreads + 1];
-    const int64_t i = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
-    const int64_t c0 = cblk[blockIdx.x];
-    const int n = (int)(cblk[blockIdx.x + 1] - c0);
+    const int blk = blk_list ? blk_list[blockIdx.x] : (int)blockIdx.x;   // the structured fast path leaves only some blocks here
+    const int64_t i = (int64_t)blk * kFinThreads + threadIdx.x;
+    const int64_t c0 = cblk[blk];
+    const int n = (int)(cblk[blk + 1] - c0);
     if (cache == 2 && flags[1] != 0) cache = 1;
     int nzflag = 0;
     // later frequency of a sweep: a block whose entries are all pure streams them from the cache; a block with any
@@ -117,7 +118,7 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
         }
     }
     const int cnt = __syncthreads_count(nzflag);
-    if (threadIdx.x == 0) blk_nonzero[blockIdx.x] = cnt;
+    if (threadIdx.x == 0) blk_nonzero[blk] = cnt;
 }
 
 // order-preserving compaction of the entries whose value is not exactly (0,0)

@@ -151,6 +151,30 @@ def test_config4_sweep_cached_equals_cold_and_oracle():
     asm.close()
 
 
+@pytest.mark.parametrize("mn,dirichlet,n", [(8, 0, (9, 8, 5, 3)), (8, 1, (9, 8, 5, 3)), (20, 0, (7, 6, 3, 2)), (27, 1, (6, 6, 3, 2))])
+def test_structured_gather_path_is_bitwise_neutral(monkeypatch, mn, dirichlet, n):
+    """With MOVFEM_GATHER_TEMPLATE=1 cold assemblies gather the rows of verified interior elements through a
+    translation-invariant template (gather_tmpl.cuh); the delivered triplets must equal the indexed gather's bit for
+    bit, at both taps."""
+    m = mesh.build_model(f"tmpl_mn{mn}", n[0], n[1], mn, 1000., 1100., 900., 2, n[2], n[3], dirichlet=dirichlet, gpml_sch=1, freqs=(0.5,),
+                         sigma_fn=mesh._layered((1500., 1500., 500., 1500.)), topo_amp=50.0)
+    monkeypatch.setenv("MOVFEM_GATHER_TEMPLATE", "1")      # opt-in: measured not faster than the indexed gather on B200
+    a1 = host.Assembly(m)
+    monkeypatch.delenv("MOVFEM_GATHER_TEMPLATE")
+    a0 = host.Assembly(m)
+    for mode in (abi.MODE_T2, abi.MODE_T1):
+        a1.reset_cache(); a0.reset_cache()
+        r1 = a1.global_vfem(1, m.omega(1), m.sigma_for(1), mode=mode)
+        r0 = a0.global_vfem(1, m.omega(1), m.sigma_for(1), mode=mode)
+        assert r1[4] == r0[4]
+        nz = r1[4]
+        for k in range(3):
+            assert np.array_equal(r1[k][:nz], r0[k][:nz]), (mode, k)
+        assert np.array_equal(r1[3], r0[3])
+    assert a1.stats()["launches"] == a0.stats()["launches"] + 1      # the template kernel really ran
+    a1.close(); a0.close()
+
+
 def test_sweep_gather_cache_is_bitwise_neutral(monkeypatch):
     """From the third frequency of a sweep on, entries that only unstretched elements touch take their gathered (K, M)
     from a cache instead of re-gathering; the delivered triplets must not change by a bit, also when Re(sigma) changes
