@@ -100,6 +100,8 @@ struct movfem_handle {
     int64_t km_rows;
     int *d_blkcnt;
     int64_t *d_blkoff, *d_finbsum;
+    unsigned long long *d_total;   // delivered (non-zero) entries of the last T2 assembly
+    bool offsets_valid;            // d_blkoff holds the scan of the last assembly's block counts
     int nblk_fin;
     int *d_status, *d_flags;
     // pinned host scratch
@@ -383,7 +385,7 @@ void free_all(movfem_handle *h) {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_xp, h->d_yp, h->d_zp, h->d_mu, h->d_sigma, h->d_nodes, h->d_tab, h->d_share, h->d_gne, h->d_ownE,
                     h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_cblk, h->d_off16, h->d_pure, h->d_kmg, h->d_estart, h->d_conform, h->d_blkgen, h->d_tmpl, h->d_groups, h->d_blklist, h->d_blkfull, h->d_src, h->d_KM,
-                    h->d_be, h->d_qt, h->d_kmrow, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum,
+                    h->d_be, h->d_qt, h->d_kmrow, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum, h->d_total,
                     h->d_status, h->d_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -712,6 +714,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     h->nblk_fin = (int)((h->nzu + kFinThreads - 1) / kFinThreads);
     CK(dmalloc(&h->d_blkcnt, (size_t)h->nblk_fin)); CK(dmalloc(&h->d_blkoff, (size_t)h->nblk_fin + 1));
     CK(dmalloc(&h->d_finbsum, (size_t)(h->nblk_fin + kScanTile - 1) / kScanTile + 1));
+    CK(dmalloc(&h->d_total, 1));
     h->km_valid = false;
     h->pattern_nz_host = -1; h->pattern_host_compacted = false;
     return MOVFEM_OK;
@@ -815,12 +818,14 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
         else if (h->kmg_state == 2) cache = 2;
     } else if (h->kmg_state == 2) h->kmg_state = 1;   // cold assembly: the cache content is stale
     const int gmode = mode == MOVFEM_MODE_T1 ? 1 : 0;
-    if (cache == 0 && h->tmpl_ok) {
+    const bool use_tmpl = cache == 0 && h->tmpl_ok;
+    if (gmode == 0 && !use_tmpl) CK(cudaMemsetAsync(h->d_total, 0, sizeof(unsigned long long), st));
+    if (use_tmpl) {
         // cold assembly: conforming interior elements take the structured path, the indexed gather keeps the other blocks
         if (gmode == 0) CK(cudaMemcpyAsync(h->d_blkcnt, h->d_blkfull, sizeof(int) * (size_t)h->nblk_fin, cudaMemcpyDeviceToDevice, st));
         if (h->tmpl_nblk_generic > 0)
             gather_finalize_kernel<<<h->tmpl_nblk_generic, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cblk, h->d_off16, h->d_src, h->d_KM, h->d_a,
-                                                                               h->d_blkcnt, gmode, 0, h->d_pure, h->d_kmg, h->d_flags, h->d_blklist);
+                                                                               h->d_blkcnt, gmode, 0, h->d_pure, h->d_kmg, h->d_flags, h->d_blklist, nullptr);
         const int64_t items = (int64_t)h->tmpl_groups * ((h->tmpl_nq + 31) / 32);
         gather_template_kernel<<<(unsigned)((items + kTmplWarps - 1) / kTmplWarps), kTmplWarps * 32, 0, st>>>(
             h->tmpl_groups, h->d_groups, m, h->e_base, h->tmpl_nq, h->d_tmpl, h->d_estart, h->d_kmrow, h->NP, h->d_KM, h->d_a, h->d_blkgen, h->d_blkcnt,
@@ -828,22 +833,27 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
         h->launches += 1;
     } else
         gather_finalize_kernel<<<h->nblk_fin, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cblk, h->d_off16, h->d_src, h->d_KM, h->d_a,
-                                                                  h->d_blkcnt, gmode, cache, h->d_pure, h->d_kmg, h->d_flags, nullptr);
+                                                                  h->d_blkcnt, gmode, cache, h->d_pure, h->d_kmg, h->d_flags, nullptr, h->d_total);
     rhs_kernel<<<(h->nrows + 127) / 128, 128, 0, st>>>(h->nrows, h->d_rown, reinterpret_cast<const double4 *>(h->d_be), h->d_rhs);
     h->launches += 2;
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[EV_GATHER], st));
     h->compacted = false; h->nz_last = -1; h->mode_last = mode;
+    h->offsets_valid = false;
     if (mode == MOVFEM_MODE_T2) {
-        // non-zero counts per block -> offsets; compaction itself runs only if something was stripped
-        const int nb = (h->nblk_fin + kScanTile - 1) / kScanTile;
-        int64_t *d_bsum = h->d_finbsum;
-        scan_block_sums<<<nb, kScanThreads, 0, st>>>(h->d_blkcnt, h->nblk_fin, d_bsum);
-        scan_block_offsets<<<1, 1024, 0, st>>>(d_bsum, nb);
-        scan_finish<<<nb, kScanThreads, 0, st>>>(h->d_blkcnt, h->nblk_fin, d_bsum, h->d_blkoff);
-        h->launches += 3;
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h->h_count, h->d_blkoff + h->nblk_fin, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        // find_zeros: the total comes from one integer atomic per block; the per-block offsets (a 3-kernel scan) are only
+        // needed if something was stripped and are then computed in movfem_device_result
+        if (use_tmpl) {   // the structured path adjusts the block counters itself: take the total from their scan
+            const int nb = (h->nblk_fin + kScanTile - 1) / kScanTile;
+            scan_block_sums<<<nb, kScanThreads, 0, st>>>(h->d_blkcnt, h->nblk_fin, h->d_finbsum);
+            scan_block_offsets<<<1, 1024, 0, st>>>(h->d_finbsum, nb);
+            scan_finish<<<nb, kScanThreads, 0, st>>>(h->d_blkcnt, h->nblk_fin, h->d_finbsum, h->d_blkoff);
+            h->launches += 3;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(h->h_count, h->d_blkoff + h->nblk_fin, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            h->offsets_valid = true;
+        } else
+            CK(cudaMemcpyAsync(h->h_count, h->d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     }
     CK(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(h->ev[EV_FINAL], st));
@@ -869,6 +879,15 @@ int movfem_device_result(const movfem_handle *hc, const int32_t **irn, const int
         else {
             h->nz_last = *h->h_count;
             if (h->nz_last != h->nzu) {   // find_zeros > 0: rem_zeros (global_assembly.f90:134-150)
+                if (!h->offsets_valid) {
+                    const int nb = (h->nblk_fin + kScanTile - 1) / kScanTile;
+                    scan_block_sums<<<nb, kScanThreads, 0, h->stream>>>(h->d_blkcnt, h->nblk_fin, h->d_finbsum);
+                    scan_block_offsets<<<1, 1024, 0, h->stream>>>(h->d_finbsum, nb);
+                    scan_finish<<<nb, kScanThreads, 0, h->stream>>>(h->d_blkcnt, h->nblk_fin, h->d_finbsum, h->d_blkoff);
+                    h->launches += 3;
+                    CK(cudaGetLastError());
+                    h->offsets_valid = true;
+                }
                 if (!h->d_a_c) {
                     CK(dmalloc(&h->d_a_c, (size_t)h->nzu)); CK(dmalloc(&h->d_irn_c, (size_t)h->nzu)); CK(dmalloc(&h->d_jcn_c, (size_t)h->nzu));
                 }

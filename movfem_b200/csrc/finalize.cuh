@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(kFinThreads)
 gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk, const uint16_t *__restrict__ off16,
                        const uint32_t *__restrict__ src, const double2 *__restrict__ KM, double2 *__restrict__ a,
                        int *__restrict__ blk_nonzero, int mode, int cache, const uint32_t *__restrict__ pure,
-                       double2 *__restrict__ kmg, const int *__restrict__ flags, const int *__restrict__ blk_list) {
+                       double2 *__restrict__ kmg, const int *__restrict__ flags, const int *__restrict__ blk_list,
+                       unsigned long long *__restrict__ total_nonzero) {
     __shared__ double2 vals[4 * kFinThreads];
     __shared__ uint16_t offs[kFinThreads + 1];
     const int blk = blk_list ? blk_list[blockIdx.x] : (int)blockIdx.x;   // the structured fast path leaves only some blocks here
@@ -118,7 +119,10 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
         }
     }
     const int cnt = __syncthreads_count(nzflag);
-    if (threadIdx.x == 0) blk_nonzero[blk] = cnt;
+    if (threadIdx.x == 0) {
+        blk_nonzero[blk] = cnt;
+        if (total_nonzero && cnt) atomicAdd(total_nonzero, (unsigned long long)cnt);   // integer: order-independent
+    }
 }
 
 // order-preserving compaction of the entries whose value is not exactly (0,0)
