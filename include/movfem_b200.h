@@ -32,7 +32,7 @@ extern "C" {
 #define MOVFEM_E_SINGULAR_MODEL (-4)  /* problem.f90:260-271 'no sigma/mu inversion'       */
 #define MOVFEM_E_NOGPU          (-5)  /* no CUDA device: there is NO CPU fallback          */
 #define MOVFEM_E_CAPACITY       (-6)  /* caller array too small                            */
-#define MOVFEM_E_UNSUPPORTED    (-7)  /* e.g. Dirichlet boundary model 2/3   */
+#define MOVFEM_E_UNSUPPORTED    (-7)  /* configuration outside what the driver hard-codes  */
 
 /* assembly output modes */
 #define MOVFEM_MODE_T2  0  /* what ZMUMPS receives: upper triangle, row-major sorted, values
@@ -59,7 +59,7 @@ typedef struct movfem_desc {
     int32_t nextd;              /* geometry.f90 nextd: extension / GPML layers per side       */
     int32_t nzl_top;            /* g_nzl(g_nsf): element layers of the top extension          */
     int32_t dirichlet;          /* boundary_conds.f90:15  1 = Dirichlet, 0 = GPML             */
-    int32_t bd_inimod;          /* boundary model (PARAM.INP line 7); only 1 (zero) supported */
+    int32_t bd_inimod;          /* Dirichlet boundary model (PARAM.INP line 7): 1 zero, 2 homogeneous, 3 layered */
     int32_t gpml_sch;           /* 0 = Fang 1996, 1 = Zhou 2012 (boundary_conds.f90:100-108)  */
     int32_t sym;                /* global_assembly.f90:18; the driver hard-codes 1            */
     int32_t ndir;               /* problem.f90 ndir; the driver hard-codes 2                  */
@@ -72,6 +72,14 @@ typedef struct movfem_desc {
     /* element slab owned by this handle (multi-GPU slab sharding); 1-based,
        inclusive, in the reference's ie index.  0,0 = whole mesh.                            */
     int32_t ie_lo, ie_hi;
+    /* Dirichlet boundary models 2 / 3 (boundary_conds.f90:188-250,392-598, arguments of bd_setmodel,
+       MoVFEM_3DMT.f90:388): the primary field of a homogeneous / layered earth on the side faces          */
+    double  g_ztop;             /* geometry.f90:394  lowest point of the topography interface              */
+    double  bd_hsigma;          /* PARAM.INP: conductivity of the half-space (bd_inimod = 2)               */
+    int32_t bd_nl;              /* PARAM.INP: number of layers (bd_inimod = 3), 1..16                       */
+    int32_t bd_pad;
+    double  bd_lsigma[16];      /* conductivity of layers 1..nl                                            */
+    double  bd_ldz[16];         /* thickness of layers 1..nl-1, as handed to bd_setmodel                    */
 } movfem_desc;
 
 typedef struct movfem_handle movfem_handle;

@@ -40,6 +40,8 @@ class MovfemDesc(C.Structure):
         ("a0", C.c_double), ("b0", C.c_double), ("nn", C.c_double),
         ("g_xp", C.c_void_p), ("g_yp", C.c_void_p), ("g_zp", C.c_void_p), ("g_mu", C.c_void_p),
         ("ie_lo", C.c_int32), ("ie_hi", C.c_int32),
+        ("g_ztop", C.c_double), ("bd_hsigma", C.c_double), ("bd_nl", C.c_int32), ("bd_pad", C.c_int32),
+        ("bd_lsigma", C.c_double * 16), ("bd_ldz", C.c_double * 16),
     ]
 
 

@@ -18,6 +18,7 @@
 #include "../../include/movfem_b200.h"
 #include "common.cuh"
 #include "contract.cuh"
+#include "dirichlet.cuh"
 #include "element.cuh"
 #include "finalize.cuh"
 #include "gather_tmpl.cuh"
@@ -95,6 +96,9 @@ struct movfem_handle {
     double2 *d_a, *d_a_c, *d_rhs;
     int *d_list_plain, *d_list_pml;
     int n_plain, n_pml;
+    BdTables *d_bdtab;       // Dirichlet boundary models 2/3 (dirichlet.cuh): node-point derivatives, DOF -> (node, dir)
+    int *d_bdlist;           // stored elements on the side faces ie=1|nx, je=1|ny
+    int n_bdlist;
     int *d_kmrow;            // element (slab-local) -> row of the K/M store: plain list first, each list padded to 32
     std::vector<int> kmrow;
     int64_t km_rows;
@@ -385,7 +389,7 @@ void free_all(movfem_handle *h) {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_xp, h->d_yp, h->d_zp, h->d_mu, h->d_sigma, h->d_nodes, h->d_tab, h->d_share, h->d_gne, h->d_ownE,
                     h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_cblk, h->d_off16, h->d_pure, h->d_kmg, h->d_estart, h->d_conform, h->d_blkgen, h->d_tmpl, h->d_groups, h->d_blklist, h->d_blkfull, h->d_src, h->d_KM,
-                    h->d_be, h->d_qt, h->d_kmrow, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum, h->d_total,
+                    h->d_be, h->d_qt, h->d_bdtab, h->d_bdlist, h->d_kmrow, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum, h->d_total,
                     h->d_status, h->d_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -606,7 +610,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
         return MOVFEM_E_BADARG;
     if (d->g_nx < 2 || d->g_ny < 2 || d->g_nz < 2 || !d->g_xp || !d->g_yp || !d->g_zp || !d->g_mu) return MOVFEM_E_BADARG;
     if (d->ndir != 2 || d->pe_sch != 1 || d->sym != 1) return MOVFEM_E_UNSUPPORTED;   // the driver hard-codes these
-    if (d->dirichlet && d->bd_inimod != 1) return MOVFEM_E_UNSUPPORTED;
+    if (d->dirichlet && (d->bd_inimod < 1 || d->bd_inimod > 3 || (d->bd_inimod == 3 && (d->bd_nl < 1 || d->bd_nl > 16)))) return MOVFEM_E_BADARG;
     if ((d->ie_lo != 0 || d->ie_hi != 0) && !(d->ie_lo >= 1 && d->ie_lo <= d->ie_hi && d->ie_hi <= d->g_nx - 1)) return MOVFEM_E_BADARG;
     if (!d->dirichlet && (d->nextd < 1 || 2 * d->nextd > std::min(d->g_nx, std::min(d->g_ny, d->g_nz)) - 1)) return MOVFEM_E_BADARG;
     int ndev = 0;
@@ -696,6 +700,35 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
 
     int rc = build_pattern(h);
     if (rc) return rc;
+
+    // Dirichlet boundary models 2 / 3: tables and the list of side-face elements
+    if (m.dirichlet && d->bd_inimod >= 2) {
+        std::vector<BdTables> B(1);
+        std::memset(&B[0], 0, sizeof(BdTables));
+        Shape shape(d->mn);
+        int i1[27], j1[27], k1[27], en[54], ed[54];
+        node_offsets(d->mn, d->nord, i1, j1, k1);
+        edge_dir_table(d->me, en, ed);
+        for (int i = 0; i < d->mn; ++i)
+            for (int l = 0; l < d->mn; ++l)
+                for (int k = 0; k < 3; ++k) B[0].dNn[i][l][k] = shape.nf_dln_dxi(k + 1, l + 1, shape.nr[i][0], shape.nr[i][1], shape.nr[i][2]);
+        for (int e = 0; e < d->me; ++e) { B[0].enode[e] = en[e] - 1; B[0].edir[e] = ed[e] - 1; }
+        for (int l = 0; l < d->mn; ++l) {
+            B[0].node_off[l] = (i1[l] - 1) * m.nyz + (j1[l] - 1) * m.nnz + (k1[l] - 1);
+            B[0].node_i[l] = i1[l] - 1; B[0].node_j[l] = j1[l] - 1;
+        }
+        CK(dmalloc(&h->d_bdtab, 1));
+        CK(cudaMemcpy(h->d_bdtab, B.data(), sizeof(BdTables), cudaMemcpyHostToDevice));
+        std::vector<int> bl;
+        for (int e = h->e_base; e < h->e_end; ++e) {
+            int ie, je, ke;
+            elem_ijk(m, e, ie, je, ke);
+            if (ie == 1 || ie == m.nx || je == 1 || je == m.ny) bl.push_back(e);
+        }
+        h->n_bdlist = (int)bl.size();
+        CK(dmalloc(&h->d_bdlist, bl.size()));
+        if (!bl.empty()) CK(cudaMemcpy(h->d_bdlist, bl.data(), sizeof(int) * bl.size(), cudaMemcpyHostToDevice));
+    }
 
     // work / result arrays
     CK(dmalloc(&h->d_KM, (size_t)h->km_rows * h->NP));
@@ -801,6 +834,15 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
     else rc = run_elements<Geo54, Con54, Geo54p, Con54p>(h, A, full);
     if (rc) return rc;
     h->km_valid = true;
+    if (h->n_bdlist > 0) {   // non-zero Dirichlet values (boundary models 2/3) moved to the RHS: b_e(im) -= sum f_boundary * A_e(im,jm)
+        BdModelDev B;
+        bd_model_host(h->d, omega, B);
+        const int nt = h->n_bdlist * m.me;
+        dirichlet_rhs_kernel<<<(nt + 127) / 128, 128, 0, st>>>(h->n_bdlist, h->d_bdlist, m, B, h->d_bdtab, h->d_gne, h->d_kmrow, h->e_base, h->NP, h->d_KM,
+                                                             h->d_xp, h->d_yp, h->d_zp, h->d_be);
+        h->launches += 1;
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(h->ev[EV_ELEM], st));
 
     // a later frequency of a sweep (K/M of the unstretched elements cached): keep the gathered K/M of the entries only

@@ -12,7 +12,7 @@ module movfem_cuda
     use kind_param
     implicit none
     private
-    public :: movfem_cuda_init, movfem_cuda_assemble, movfem_cuda_finalize, movfem_nz_upper
+    public :: movfem_cuda_init, movfem_cuda_assemble, movfem_cuda_finalize, movfem_nz_upper, movfem_cuda_set_boundary_model
 
     ! struct movfem_desc of include/movfem_b200.h, field for field
     type, bind(C) :: movfem_desc
@@ -21,7 +21,15 @@ module movfem_cuda
         real(c_double)     :: a0, b0, nn
         type(c_ptr)        :: g_xp, g_yp, g_zp, g_mu
         integer(c_int32_t) :: ie_lo, ie_hi
+        real(c_double)     :: g_ztop, bd_hsigma
+        integer(c_int32_t) :: bd_nl, bd_pad
+        real(c_double)     :: bd_lsigma(16), bd_ldz(16)
     end type movfem_desc
+
+    ! Dirichlet boundary models 2/3: the arguments of bd_setmodel (MoVFEM_3DMT.f90:388) are locals of the input reader
+    ! and boundary_conds keeps them private, so the driver hands a copy to movfem_cuda_set_boundary_model right there.
+    real(c_double), save     :: bdm_hsigma = 0.d0, bdm_lsigma(16) = 0.d0, bdm_ldz(16) = 0.d0
+    integer(c_int32_t), save :: bdm_nl = 1
 
     type(c_ptr), save          :: handle = c_null_ptr
     integer(c_int64_t), save   :: movfem_nz_upper = 0     ! capacity irn/jcn/a need (<= nnze)
@@ -70,10 +78,20 @@ module movfem_cuda
 
 contains
 
+    ! call movfem_cuda_set_boundary_model(h_sigma, nl, l_sigma, l_dz)   next to   call bd_setmodel(h_sigma,nl,l_sigma,l_dz)
+    subroutine movfem_cuda_set_boundary_model(h_sigma, nl, l_sigma, l_dz)
+        real(kind=double), intent(in) :: h_sigma, l_sigma(nl), l_dz(nl-1)
+        integer, intent(in)           :: nl
+        if (nl > 16) call die('more than 16 boundary layers', -1)
+        bdm_hsigma = h_sigma; bdm_nl = nl
+        bdm_lsigma(1:nl) = l_sigma(1:nl)
+        if (nl > 1) bdm_ldz(1:nl-1) = l_dz(1:nl-1)
+    end subroutine movfem_cuda_set_boundary_model
+
     ! Called from ga_init (global_assembly.f90:26) in place of ga_cgne / ga_nzindx.  Fills the module
     ! variables the rest of the program consumes: nne, nnze (MoVFEM_3DMT.f90:72-78), gne (solution.f90:331-336).
     subroutine movfem_cuda_init()
-        use geometry, only: g_nx, g_ny, g_nz, g_nordx, nextd, g_nsf, g_nzl, g_xp, g_yp, g_zp, g_mu
+        use geometry, only: g_nx, g_ny, g_nz, g_nordx, nextd, g_nsf, g_nzl, g_xp, g_yp, g_zp, g_mu, g_ztop
         use n_fem, only: nf_mn
         use v_fem, only: vf_me
         use problem, only: ndir, pe_sch
@@ -90,6 +108,8 @@ contains
         d%a0 = a0; d%b0 = b0; d%nn = nn
         d%g_xp = c_loc(g_xp); d%g_yp = c_loc(g_yp); d%g_zp = c_loc(g_zp); d%g_mu = c_loc(g_mu)   ! arrays need TARGET
         d%ie_lo = 0; d%ie_hi = 0
+        d%g_ztop = g_ztop; d%bd_hsigma = bdm_hsigma; d%bd_nl = bdm_nl; d%bd_pad = 0
+        d%bd_lsigma = bdm_lsigma; d%bd_ldz = bdm_ldz
         rc = movfem_create(d, 0_c_int, handle)
         if (rc /= 0) call die('movfem_create', rc)
         rc = movfem_sizes(handle, nne_c, nnze_c, movfem_nz_upper)

@@ -58,6 +58,10 @@ class Model:
     sigma_im_mask: np.ndarray   # (npt, 6) bool: entries that carry i*f32(eps*omega)
     freqs: np.ndarray
     bd_inimod: int = 1
+    g_ztop: float = 0.0                      # geometry.f90:394: lowest point of the topography interface
+    bd_hsigma: float = 0.01                  # PARAM.INP: half-space conductivity (boundary model 2)
+    bd_lsigma: tuple = (0.01,)               # PARAM.INP: layer conductivities (boundary model 3)
+    bd_ldz: tuple = ()                       # layer thicknesses as handed to bd_setmodel (nl-1 values)
     ie_lo: int = 0
     ie_hi: int = 0
     _sigma_state: np.ndarray | None = field(default=None, repr=False)
@@ -91,6 +95,11 @@ class Model:
         d.g_zp = self.g_zp.ctypes.data_as(C.c_void_p)
         d.g_mu = self.g_mu.ctypes.data_as(C.c_void_p)
         d.ie_lo, d.ie_hi = self.ie_lo, self.ie_hi
+        d.g_ztop, d.bd_hsigma, d.bd_nl = self.g_ztop, self.bd_hsigma, len(self.bd_lsigma)
+        for i, v in enumerate(self.bd_lsigma):
+            d.bd_lsigma[i] = v
+        for i, v in enumerate(self.bd_ldz):
+            d.bd_ldz[i] = v
         return d
 
     def omega(self, ifreq: int) -> float:
@@ -188,7 +197,8 @@ def build_model(name, nx, ny, mn, dx, dy, dz, nextd, n_earth, n_air, *, dirichle
     mask[:, [0, 3, 5]] = True                                    # diagonals carry i*f32(eps*omega)
     g_mu = np.zeros((npt, 6))
     g_mu[:, [0, 3, 5]] = MU0
-    return Model(name=name, g_nx=nx + 1, g_ny=ny + 1, g_nz=nz + 1, mn=mn, nextd=nextd, nzl_top=nextd,
+    g_ztop = float(Z[:, :, ksurf].min())
+    return Model(name=name, g_nx=nx + 1, g_ny=ny + 1, g_nz=nz + 1, mn=mn, nextd=nextd, nzl_top=nextd, g_ztop=g_ztop,
                  dirichlet=dirichlet, gpml_sch=gpml_sch, a0=a0, b0=b0, nn=nn,
                  g_xp=np.ascontiguousarray(g_xp), g_yp=np.ascontiguousarray(g_yp), g_zp=g_zp, g_mu=g_mu,
                  sigma_re=sigma_re, sigma_im_mask=mask, freqs=np.asarray(freqs, float))

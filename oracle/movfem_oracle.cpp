@@ -31,6 +31,7 @@
 #include <time.h>
 #include <numeric>
 #include <vector>
+#include <complex>
 
 #include "../include/movfem_b200.h"
 #include "shape.h"
@@ -687,6 +688,131 @@ static void effective_pml(const Ctx &c, int ide, const int first_flags[3], int o
     get_pml(c, ie, je, ke, out);
 }
 
+// ---- Dirichlet boundary models 2 / 3: boundary_conds.f90:188-250 f_boundary, :392-430 bd_setmodel (+ bd_updatemodel,
+//      :48-50, called every frequency), :436-518 p_pfields (the module's own, NOT problem.f90's), :523-552
+//      wait_recursion, :557-598 ezl.  Units and sign conventions are the reference's (depths in km against layer
+//      coordinates <= 0, single-precision cmplx() constructors); they are restated, not repaired. ----
+struct BdModel {
+    int nl;
+    C psig[17];              // pe_psigma: (f32(sigma), f32(eps*omega)) per medium / layer
+    double pmu;              // pe_pmu(1)
+    double dl[16], zl[17];   // pe_dl, pe_zl
+    C cz[17], ez[17];        // wait_recursion
+};
+typedef std::complex<double> Z;
+static inline Z zc(C a) { return Z(a.re, a.im); }
+static inline C cz_(Z a) { return mk(a.real(), a.imag()); }
+static inline C csqrt_(C a) { return cz_(std::sqrt(zc(a))); }
+static inline C cexp_(C a) { return cz_(std::exp(zc(a))); }
+static const C CI = {0.0, 1.0};
+
+static void bd_wait_recursion(BdModel &B, double omega) {
+    const int nl = B.nl;
+    for (int l = 0; l < nl; ++l) { B.cz[l] = mk(0, 0); B.ez[l] = mk(0, 0); }
+    C alpha = (omega * B.pmu) * B.psig[nl - 1];
+    C gamma = csqrt_(CI * alpha);
+    B.cz[nl - 1] = 1.0 / gamma;
+    for (int l = nl - 1; l >= 1; --l) {
+        alpha = (omega * B.pmu) * B.psig[l - 1];
+        gamma = csqrt_(CI * alpha);
+        const C r = (1.0 + (-(gamma * B.cz[l]))) / (1.0 + gamma * B.cz[l]);
+        const C e2 = cexp_((-2.0 * gamma) * B.dl[l - 1]);
+        B.cz[l - 1] = (1.0 + (-(r * e2))) / (gamma * (1.0 + r * e2));
+    }
+    B.ez[0] = mk(1.0, 0.0);
+    for (int l = 1; l <= nl - 1; ++l) {
+        alpha = (omega * B.pmu) * B.psig[l - 1];
+        gamma = csqrt_(CI * alpha);
+        B.ez[l] = cexp_((-gamma) * B.dl[l - 1]) * (B.ez[l - 1] * B.cz[l] * (1.0 + B.cz[l - 1] * gamma)) / (B.cz[l - 1] * (1.0 + B.cz[l] * gamma));
+    }
+}
+
+static void bd_model(const Ctx &c, double omega, BdModel &B) {
+    const movfem_desc &d = c.d;
+    B.pmu = 4.0 * PI * 1.e-7;
+    const double im = (double)(float)(EPS0 * omega);       // bd_updatemodel: real(pe_psigma)+cmplx(0.d0,eps*omega)
+    if (d.bd_inimod == 2) {
+        B.nl = 2;
+        B.psig[0] = mk(0.0, im);                            // air
+        B.psig[1] = mk((double)(float)d.bd_hsigma, im);     // cmplx(h_sigma,omega*eps): single precision
+    } else {
+        B.nl = d.bd_nl;
+        for (int l = 0; l < B.nl; ++l) B.psig[l] = mk((double)(float)d.bd_lsigma[l], im);
+        for (int l = 0; l < B.nl - 1; ++l) B.dl[l] = d.bd_ldz[l];
+        B.zl[0] = 0.0;
+        for (int l = 1; l < B.nl; ++l) B.zl[l] = B.zl[l - 1] - B.dl[l - 1];
+        bd_wait_recursion(B, omega);
+    }
+}
+
+static C bd_ezl(const BdModel &B, int d, double z, double omega) {
+    C out = mk(0, 0);
+    const int nl = B.nl;
+    for (int l = 1; l <= nl - 1; ++l) {
+        if (z <= B.zl[l - 1] && z > B.zl[l]) {
+            const C alpha = (omega * B.pmu) * B.psig[l - 1];
+            const C gamma = csqrt_(CI * alpha);
+            const C r = (1.0 + (-(gamma * B.cz[l]))) / (1.0 + gamma * B.cz[l]);
+            const C e2 = cexp_((-2.0 * gamma) * (z - B.zl[l])), e1 = cexp_((-gamma) * (B.zl[l - 1] - z));
+            if (d == 0) out = (B.ez[l - 1] * 0.5) * (1.0 + 1.0 / (B.cz[l - 1] * gamma)) * (1.0 + (-(r * e2))) * e1;
+            else out = (-(B.ez[l - 1] * 0.5)) * (gamma + 1.0 / B.cz[l - 1]) * (1.0 + r * e2) * e1;
+        }
+    }
+    if (z <= B.zl[nl - 1]) {
+        const C alpha = (omega * B.pmu) * B.psig[nl - 1];
+        const C gamma = csqrt_(CI * alpha);
+        const C e1 = cexp_((-gamma) * (B.zl[nl - 1] - z));
+        out = d == 0 ? B.ez[nl - 1] * e1 : B.ez[nl - 1] * e1 / (-gamma);
+    }
+    return out;
+}
+
+// pe_ep(1,1) and pe_ep(2,2) of boundary_conds.f90's p_pfields at grid node `id` (1-based)
+static void bd_pfields(const Ctx &c, const BdModel &B, double omega, int id, C &ex1, C &ey2) {
+    const double bb0 = 1.e-9;
+    const double zn = c.d.g_zp[id - 1];
+    const double z = (c.d.g_ztop - zn) / 1000.0;
+    if (c.d.bd_inimod == 2) {
+        C fp;
+        if (zn > c.d.g_ztop) {
+            const C alpha = (omega * B.pmu) * B.psig[0];
+            const C sq = csqrt_(CI * alpha);
+            fp = (1.0 / sq) * (1.0 + (-(z * sq)));
+        } else {
+            const C alpha = (omega * B.pmu) * B.psig[1];
+            const C sq = csqrt_(CI * alpha);
+            fp = (1.0 / sq) * cexp_((-z) * sq);
+        }
+        ex1 = cmplx32(0.0, -2.0 * omega * bb0) * fp;
+        ey2 = cmplx32(0.0, 2.0 * omega * bb0) * fp;
+    } else {
+        if (zn > c.d.g_ztop) {
+            ex1 = cmplx32(0.0, 2.0 * omega * bb0) * (B.cz[0] + mk(-z, 0.0));
+            ey2 = cmplx32(0.0, -2.0 * omega * bb0) * (B.cz[0] + mk(-z, 0.0));
+        } else {
+            const C e = bd_ezl(B, 0, z, omega);
+            ex1 = cmplx32(0.0, 2.0 * omega * bb0) * B.cz[0] * e;
+            ey2 = cmplx32(0.0, -2.0 * omega * bb0) * B.cz[0] * e;
+        }
+    }
+}
+
+// f_boundary(bd, jm), boundary_conds.f90:188-250: value of the Dirichlet DOF jm lying on face bd
+static void f_boundary(Elem &E, const BdModel &B, int bd, int jm, C f[2]) {
+    const Ctx &c = *E.c;
+    f[0] = mk(0, 0); f[1] = mk(0, 0);
+    if (!c.d.dirichlet || c.d.bd_inimod == 1) return;
+    if (bd == 3 || bd == 6) return;
+    const int i = c.enode[jm - 1], d = c.edir[jm - 1];
+    nf_jacobian(E, c.shape.nr[i - 1][0], c.shape.nr[i - 1][1], c.shape.nr[i - 1][2]);
+    const double *dne = E.nf_j[d - 1];                     // nf_dr_dxi: row d of the Jacobian
+    C ex1, ey2;
+    bd_pfields(c, B, E.omega, E.nf_index[i - 1], ex1, ey2);
+    // f(1) = pe_ep(1,1)*dne(1)+pe_ep(2,1)*dne(2)+pe_ep(3,1)*dne(3) with pe_ep(2:3,1) = 0 ; f(2) likewise with pe_ep(2,2)
+    f[0] = ex1 * dne[0] + mk(0, 0) * dne[1] + mk(0, 0) * dne[2];
+    f[1] = mk(0, 0) * dne[0] + ey2 * dne[1] + mk(0, 0) * dne[2];
+}
+
 static void elem_setup(Elem &E, const Ctx &c, double omega, const C *g_sigma, int faithful) {
     E.c = &c; E.omega = omega; E.g_sigma = g_sigma; E.faithful = faithful; E.jac_builds = 0;
     E.jac_valid = false; E.status = 0;
@@ -721,7 +847,7 @@ int oracle_create(const movfem_desc *d, oracle_ctx **out) {
           (d->mn == 27 && d->me == 54 && d->nord == 3)))
         return MOVFEM_E_BADARG;
     if (d->ndir != 2 || d->pe_sch != 1 || d->sym != 1) return MOVFEM_E_UNSUPPORTED;
-    if (d->dirichlet && d->bd_inimod != 1) return MOVFEM_E_UNSUPPORTED;
+    if (d->dirichlet && (d->bd_inimod < 1 || d->bd_inimod > 3 || (d->bd_inimod == 3 && (d->bd_nl < 1 || d->bd_nl > 16)))) return MOVFEM_E_BADARG;
     Ctx *c = new Ctx(d->mn);
     c->d = *d;
     c->nx = d->g_nx - 1; c->ny = d->g_ny - 1; c->nz = d->g_nz - 1; c->ne = c->nx * c->ny * c->nz;
@@ -884,7 +1010,10 @@ int oracle_assemble(oracle_ctx *h, double omega, const double *g_sigma_, int fai
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
 
-    auto scatter = [&](const Elem &E, int ide, const C *Al /*me*me or null*/, const C *Bl) {
+    BdModel BD;
+    const bool bd_vals = c.d.dirichlet && c.d.bd_inimod >= 2;
+    if (bd_vals) bd_model(c, omega, BD);
+    auto scatter = [&](Elem &E, int ide, const C *Al /*me*me or null*/, const C *Bl, const C *Fb /*me*2 or null*/) {
         for (int im = 1; im <= me; ++im) {
             if (G(ide, im) < 0) continue;
             for (int jm = 1; jm <= me; ++jm) {
@@ -902,8 +1031,13 @@ int oracle_assemble(oracle_ctx *h, double omega, const double *g_sigma_, int fai
                 if (G(ide, jm) >= 0) continue;
                 // f_boundary == (0,0) for bd_inimod=1 (boundary_conds.f90:200-214); the reference
                 // still evaluates alocal(im,jm) here
-                const C al = Al ? mk(0, 0) : alocal(E, im, jm);
-                bda[0] = bda[0] + mk(0, 0) * al; bda[1] = bda[1] + mk(0, 0) * al;
+                C fbv[2] = {mk(0, 0), mk(0, 0)};
+                if (bd_vals) {
+                    if (Fb) { fbv[0] = Fb[2 * (jm - 1)]; fbv[1] = Fb[2 * (jm - 1) + 1]; }
+                    else f_boundary(E, BD, -G(ide, jm), jm, fbv);
+                }
+                const C al = Al ? Al[(im - 1) * me + jm - 1] : alocal(E, im, jm);
+                bda[0] = bda[0] + fbv[0] * al; bda[1] = bda[1] + fbv[1] * al;
             }
             C bl[2];
             if (Bl) { bl[0] = Bl[2 * (im - 1)]; bl[1] = Bl[2 * (im - 1) + 1]; }
@@ -923,13 +1057,13 @@ int oracle_assemble(oracle_ctx *h, double omega, const double *g_sigma_, int fai
             effective_pml(c, ide, first_flags, pml);
             elem_compute(*E, ide, pml);
             if (E->status) { status = E->status; break; }
-            scatter(*E, ide, nullptr, nullptr);
+            scatter(*E, ide, nullptr, nullptr, nullptr);
         }
         jb = E->jac_builds;
         delete E;
     } else {
         const int CH = 256;
-        std::vector<C> Al((size_t)CH * me * me), Bl((size_t)CH * me * 2);
+        std::vector<C> Al((size_t)CH * me * me), Bl((size_t)CH * me * 2), Fb((size_t)CH * me * 2);
         for (int base = ide_lo; base <= ide_hi && !status; base += CH) {
             const int n = std::min(CH, ide_hi - base + 1);
 #pragma omp parallel num_threads(nthreads)
@@ -950,18 +1084,21 @@ int oracle_assemble(oracle_ctx *h, double omega, const double *g_sigma_, int fai
                     for (int im = 1; im <= me; ++im) {
                         const bool vi = G(ide, im) >= 0;
                         for (int jm = 1; jm <= me; ++jm) {
-                            const bool need = vi && G(ide, jm) >= 0 && !(c.d.sym && G(ide, im) < G(ide, jm));
+                            const bool need = vi && ((G(ide, jm) >= 0 && !(c.d.sym && G(ide, im) < G(ide, jm))) || (bd_vals && G(ide, jm) < 0));
                             Al[((size_t)t * me + im - 1) * me + jm - 1] = need ? alocal(*E, im, jm) : mk(0, 0);
                         }
                         if (vi) blocal(*E, im, &Bl[((size_t)t * me + im - 1) * 2]);
                     }
+                    if (bd_vals)
+                        for (int jm = 1; jm <= me; ++jm)
+                            if (G(ide, jm) < 0) f_boundary(*E, BD, -G(ide, jm), jm, &Fb[((size_t)t * me + jm - 1) * 2]);
                 }
                 delete E;
             }
             if (status) break;
             Elem dummy;
             dummy.c = &c;
-            for (int t = 0; t < n; ++t) scatter(dummy, base + t, &Al[(size_t)t * me * me], &Bl[(size_t)t * me * 2]);
+            for (int t = 0; t < n; ++t) scatter(dummy, base + t, &Al[(size_t)t * me * me], &Bl[(size_t)t * me * 2], &Fb[(size_t)t * me * 2]);
         }
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);
@@ -1025,6 +1162,9 @@ int oracle_node_solution(const oracle_ctx *h, double omega, const double *g_sigm
     const int g = c.d.nord, npt = c.npt, nne = c.nne, ne = c.ne, me = c.me, mn = c.mn;
     auto G = [&](int ide, int im) -> int { return c.gne[(size_t)(im - 1) * ne + (ide - 1)]; };
     std::vector<char> valued_e((size_t)2 * npt, 0), valued_h((size_t)2 * npt, 0);
+    BdModel BD;
+    const bool bd_vals = c.d.dirichlet && c.d.bd_inimod >= 2;
+    if (bd_vals) bd_model(c, omega, BD);
     for (size_t i = 0; i < (size_t)6 * npt; ++i) { esol[i] = mk(0, 0); hsol[i] = mk(0, 0); }
     double as[3];
     for (int j = 1; j <= g; ++j) as[j - 1] = -1 + (double)(j - 1) * (2 / (double)(g - 1));   // gqg_nodes, geometry.f90:720-739
@@ -1049,7 +1189,8 @@ int oracle_node_solution(const oracle_ctx *h, double omega, const double *g_sigm
                                 C ef[3] = {mk(0, 0), mk(0, 0), mk(0, 0)};            // get_er
                                 for (int im = 1; im <= me; ++im) {
                                     C f = mk(0, 0);
-                                    if (G(ide, im) >= 0) f = x[(size_t)G(ide, im) - 1 + (size_t)(edir - 1) * nne];   // f_boundary == 0 (bd_inimod 1)
+                                    if (G(ide, im) >= 0) f = x[(size_t)G(ide, im) - 1 + (size_t)(edir - 1) * nne];
+                                    else if (bd_vals) { C fbv[2]; f_boundary(*E, BD, -G(ide, im), im, fbv); f = fbv[edir - 1]; }
                                     double ve[3];
                                     vf_elem_ve(*E, im, r, ve);
                                     ef[0] = ef[0] + f * ve[0]; ef[1] = ef[1] + f * ve[1]; ef[2] = ef[2] + f * ve[2];

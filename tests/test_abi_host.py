@@ -38,9 +38,9 @@ def test_desc_layout_matches_header():
         if not decl:
             continue
         names = decl.replace("const double *", "").replace("int32_t", "").replace("double", "").split(",")
-        fields += [n.strip().lstrip("*") for n in names]
+        fields += [re.sub(r"\[\d+\]", "", n).strip().lstrip("*") for n in names]
     assert fields == [f for f, _ in abi.MovfemDesc._fields_]
-    assert C.sizeof(abi.MovfemDesc) == 14 * 4 + 3 * 8 + 4 * 8 + 2 * 4
+    assert C.sizeof(abi.MovfemDesc) == 14 * 4 + 3 * 8 + 4 * 8 + 2 * 4 + 2 * 8 + 2 * 4 + 32 * 8
 
 
 def test_no_gpu_means_loud_failure_not_fallback():
@@ -58,7 +58,11 @@ def test_bad_descriptors_are_rejected_before_touching_cuda():
     h = C.c_void_p()
     d.me = 13
     assert host.lib().movfem_create(C.byref(d), 0, C.byref(h)) == abi.MOVFEM_E_BADARG
-    d = m.desc(); d.bd_inimod = 2; d.dirichlet = 1
+    d = m.desc(); d.bd_inimod = 4; d.dirichlet = 1
+    assert host.lib().movfem_create(C.byref(d), 0, C.byref(h)) == abi.MOVFEM_E_BADARG
+    d = m.desc(); d.bd_inimod = 3; d.dirichlet = 1; d.bd_nl = 17          # more layers than the descriptor holds
+    assert host.lib().movfem_create(C.byref(d), 0, C.byref(h)) == abi.MOVFEM_E_BADARG
+    d = m.desc(); d.ndir = 1
     assert host.lib().movfem_create(C.byref(d), 0, C.byref(h)) == abi.MOVFEM_E_UNSUPPORTED
     assert host.lib().movfem_create(None, 0, C.byref(h)) == abi.MOVFEM_E_BADARG
 

@@ -61,6 +61,29 @@ def test_parity_small(mn, dirichlet, sch):
     asm.close()
 
 
+@pytest.mark.parametrize("mn", [8, 20, 27])
+@pytest.mark.parametrize("inimod", [2, 3])
+def test_parity_dirichlet_boundary_models(mn, inimod):
+    """Dirichlet boundary models 2 (homogeneous earth) and 3 (layered earth, Wait recursion): the primary field on the
+    side faces is moved to the right-hand side through the Dirichlet columns of A_e (MoVFEM_3DMT.f90:252-261,
+    boundary_conds.f90:188-250,436-598).  The matrix is untouched; the RHS must match the oracle and differ from the
+    zero-boundary model's."""
+    m = _small(mn, 1, 1)
+    m.bd_inimod = inimod
+    m.bd_hsigma = 0.02
+    m.bd_lsigma, m.bd_ldz = (0.01, 0.1, 0.001), (1.0, 2.5)
+    asm, o = host.Assembly(m), Oracle(m)
+    for ifreq in (1, 2):
+        r = compare_assembly(asm, o, m, ifreq=ifreq)
+        _check(r)
+    m1 = _small(mn, 1, 1)
+    a1 = host.Assembly(m1)
+    r2 = asm.global_vfem(1, m.omega(1), m.sigma_for(1), mode=abi.MODE_T1)
+    r1 = a1.global_vfem(1, m1.omega(1), m1.sigma_for(1), mode=abi.MODE_T1)
+    assert np.array_equal(r1[2], r2[2]) and not np.allclose(r1[3], r2[3])
+    asm.close(); a1.close()
+
+
 def test_parity_chunked_scratch(monkeypatch):
     """The Q|P,T scratch between geometry_kernel and contract_kernel is processed in chunks when an element list
     does not fit it (config 5 sizes).  Force a 1 MiB scratch so a small mesh runs through many chunks, ragged last
@@ -318,13 +341,14 @@ def test_x_slab_handles_concatenate_to_the_full_assembly(mn, dirichlet):
     full.close()
 
 
-@pytest.mark.parametrize("mn,dirichlet", [(8, 0), (8, 1), (20, 1), (27, 0)])
-def test_end_to_end_apparent_resistivity_and_phase(mn, dirichlet):
+@pytest.mark.parametrize("mn,dirichlet,inimod", [(8, 0, 1), (8, 1, 1), (20, 1, 1), (27, 0, 1), (8, 1, 3), (20, 1, 2)])
+def test_end_to_end_apparent_resistivity_and_phase(mn, dirichlet, inimod):
     """north_star: 'End-to-end apparent resistivity and phase after the unchanged solve must agree to <= 1e-6 relative.'
     Graft and oracle triplets (tap T2 = what ZMUMPS receives, and the double-precision tap T1) go through the same
     stand-in sparse LU and the same solution.f90 post-processing (tests/e2e_util.py)."""
     from e2e_util import e2e_model, rho_phi_diff, solve_upper_triplets
     m = e2e_model(mn, dirichlet)
+    m.bd_inimod, m.bd_hsigma, m.bd_lsigma, m.bd_ldz = inimod, 0.01, (0.01, 0.1), (1.5,)
     asm, o = host.Assembly(m), Oracle(m)
     om, sg = m.omega(1), m.sigma_for(1)
     ro = o.assemble(om, sg)
