@@ -139,6 +139,11 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega,
                            const double *g_sigma_dev, int32_t mode);
 int movfem_device_result(const movfem_handle *h, const int32_t **irn, const int32_t **jcn,
                          const double **a, const double **rhs, int64_t *nz /* syncs */);
+/* CSR view of the last device result for a GPU sparse direct solver: the delivered triplets are the
+   upper triangle sorted by (row, col), i.e. CSR minus the row pointers; rowptr[0..nrows] (device, 0-based offsets
+   into irn/jcn/a, rows local to the handle) completes it: row r holds entries rowptr[r] .. rowptr[r+1]-1, its
+   column indices are jcn (1-based) and its values a.  Valid until the next assemble on the handle.           */
+int movfem_device_csr(const movfem_handle *h, const int64_t **rowptr, int32_t *nrows);
 
 /* Forget the cached K_e/M_e of the unstretched elements: the next assemble recomputes every
    element (what a single-frequency run does).  A sweep keeps them.            */

@@ -104,6 +104,7 @@ struct movfem_handle {
     int64_t km_rows;
     int *d_blkcnt;
     int64_t *d_blkoff, *d_finbsum;
+    int64_t *d_csr;                // row pointers of the last device result (movfem_device_csr), built on request
     unsigned long long *d_total;   // delivered (non-zero) entries of the last T2 assembly
     bool offsets_valid;            // d_blkoff holds the scan of the last assembly's block counts
     int nblk_fin;
@@ -389,7 +390,7 @@ void free_all(movfem_handle *h) {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_xp, h->d_yp, h->d_zp, h->d_mu, h->d_sigma, h->d_nodes, h->d_tab, h->d_share, h->d_gne, h->d_ownE,
                     h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_cblk, h->d_off16, h->d_pure, h->d_kmg, h->d_estart, h->d_conform, h->d_blkgen, h->d_tmpl, h->d_groups, h->d_blklist, h->d_blkfull, h->d_src, h->d_KM,
-                    h->d_be, h->d_qt, h->d_bdtab, h->d_bdlist, h->d_kmrow, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum, h->d_total,
+                    h->d_be, h->d_qt, h->d_bdtab, h->d_bdlist, h->d_kmrow, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum, h->d_total, h->d_csr,
                     h->d_status, h->d_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -960,6 +961,24 @@ int movfem_device_result(const movfem_handle *hc, const int32_t **irn, const int
     if (a) *a = reinterpret_cast<const double *>(h->compacted ? h->d_a_c : h->d_a);
     if (rhs) *rhs = reinterpret_cast<const double *>(h->d_rhs);
     if (nz) *nz = h->nz_last;
+    return MOVFEM_OK;
+}
+
+int movfem_device_csr(const movfem_handle *hc, const int64_t **rowptr, int32_t *nrows) {
+    movfem_handle *h = const_cast<movfem_handle *>(hc);
+    if (!h || !rowptr) return MOVFEM_E_BADARG;
+    const int32_t *d_irn, *d_jcn;
+    const double *d_a, *d_rhs;
+    int64_t nz = 0;
+    int rc = movfem_device_result(h, &d_irn, &d_jcn, &d_a, &d_rhs, &nz);
+    if (rc) return rc;
+    if (!h->d_csr) CK(dmalloc(&h->d_csr, (size_t)h->nrows + 1));
+    csr_rowptr_kernel<<<(h->nrows + 256) / 256, 256, 0, h->stream>>>(h->nrows, h->row_lo, nz, d_irn, h->d_csr);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    *rowptr = h->d_csr;
+    if (nrows) *nrows = h->nrows;
     return MOVFEM_OK;
 }
 

@@ -146,6 +146,19 @@ compact_kernel(int64_t nzu, const int64_t *__restrict__ blk_off, const int *__re
     }
 }
 
+// CSR row pointers of delivered (row-sorted, 1-based) triplets: rowptr[r] = first entry with irn >= row_lo + r + 1
+__global__ void csr_rowptr_kernel(int nrows, int row_lo, int64_t nz, const int *__restrict__ irn, int64_t *__restrict__ rowptr) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > nrows) return;
+    const int key = row_lo + r + 1;
+    int64_t lo = 0, hi = nz;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (irn[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    rowptr[r] = lo;
+}
+
 // b(gne + (d-1)*nne) += blocal(d): sum of the <= 4 sharing elements in ascending element order
 __global__ void rhs_kernel(int nrows, const int *__restrict__ rown, const double4 *__restrict__ be, double2 *__restrict__ rhs) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;   // row local to the handle's slab; rhs is [2][nrows]

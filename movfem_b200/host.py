@@ -61,6 +61,7 @@ def lib():
         L.movfem_assemble.argtypes = [vp, i32, dbl, vp, vp, vp, vp, vp, C.POINTER(i64), i32]
         L.movfem_assemble_device.argtypes = [vp, i32, dbl, vp, i32]
         L.movfem_device_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
+        L.movfem_device_csr.argtypes = [vp, C.POINTER(vp), C.POINTER(i32)]
         L.movfem_set_stream.argtypes = [vp, vp]
         L.movfem_get_stats.argtypes = [vp, C.POINTER(MovfemStats)]
         L.movfem_last_error.argtypes = [vp]
@@ -76,7 +77,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "movfem_create", "movfem_destroy", "movfem_sizes", "movfem_get_gne", "movfem_get_pattern", "movfem_assemble",
-    "movfem_assemble_device", "movfem_device_result", "movfem_set_stream", "movfem_get_stats", "movfem_last_error",
+    "movfem_assemble_device", "movfem_device_result", "movfem_device_csr", "movfem_set_stream", "movfem_get_stats", "movfem_last_error",
     "movfem_version", "movfem_debug_element", "movfem_reset_cache", "movfem_fp64_peak", "movfem_slab_rows",
 ]
 
@@ -174,6 +175,12 @@ class Assembly:
         nz = C.c_int64()
         self._check(lib().movfem_device_result(self._h, C.byref(irn), C.byref(jcn), C.byref(a), C.byref(rhs), C.byref(nz)))
         return irn.value, jcn.value, a.value, rhs.value, nz.value
+
+    def device_csr(self):
+        """(device pointer to rowptr[nrows+1], nrows): CSR row pointers of the last device result."""
+        rp, n = C.c_void_p(), C.c_int32()
+        self._check(lib().movfem_device_csr(self._h, C.byref(rp), C.byref(n)))
+        return rp.value, n.value
 
     def reset_cache(self):
         """Next call recomputes every element's K_e/M_e (cold single-frequency assembly)."""

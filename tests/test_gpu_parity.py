@@ -307,6 +307,12 @@ def test_device_resident_api():
     rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
     rc = rt.cudaMemcpy(buf.ctypes.data, p_a, nz * 16, 2)
     assert int(rc) == 0 and np.array_equal(buf, a[:nz])
+    # CSR hand-off: row pointers of the sorted upper-triangle triplets
+    p_rp, nrows = asm.device_csr()
+    rp = np.empty(nrows + 1, np.int64)
+    assert int(rt.cudaMemcpy(rp.ctypes.data, p_rp, rp.nbytes, 2)) == 0 and nrows == asm.nne
+    assert np.array_equal(rp, np.searchsorted(irn[:nz], np.arange(1, nrows + 2), side="left"))
+    assert rp[0] == 0 and rp[-1] == nz and np.all(jcn[rp[:-1]] == np.arange(1, nrows + 1))   # every row starts at its diagonal
     asm.close()
 
 
