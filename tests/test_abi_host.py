@@ -102,3 +102,20 @@ def test_update_sigma_reproduces_q12():
     w5 = np.float64(np.float32(mesh.EPS0 * m.omega(5)))
     assert np.all(flat5.imag[:n][flat5.imag[:n] != 0] == w5)
     assert np.all(flat5.imag[n:][flat5.imag[n:] != 0] == np.float64(np.float32(mesh.EPS0 * m.omega(1))))
+
+
+def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """bench.py --impl reference (the reference's CPU algorithm through the oracle port) runs without a GPU and prints
+    exactly one JSON line with the keys the driver reads."""
+    import json, subprocess, sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-elements", "40"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+              "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
