@@ -228,20 +228,11 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
     }
 
     // phase-B1 GEMM fragments (mma.m8n8k4: A row = lane/4, k = lane%4; B k = lane%4, n = lane/4; C row = lane/4, cols 2(lane%4)+{0,1})
-    constexpr int NW = CFG::THREADS / 32, MB = (NGP + 7) / 8, MH = MB > 1 ? 2 : 1, MBH = MB / MH, KB = (MN + 3) / 4, NB = (NCOLA + 7) / 8;
-    static_assert(MB % MH == 0 && NW % MH == 0, "a warp always owns the same half of the Gauss-point blocks");
+    constexpr int NW = CFG::THREADS / 32, MB = (NGP + 7) / 8, MH = 1, MBH = MB / MH, KB = (MN + 3) / 4, NB = (NCOLA + 7) / 8;
     const int lane = tid & 31;
-    const int b1_mh = (tid >> 5) % MH;
+    constexpr int b1_mh = 0;
     const double psig = f32r(A.omega * kEps0);   // pset_pmodel, problem.f90:250
-    double b1_a[MBH][KB];
     int b1_off[NB], b1_flag[NB];
-#pragma unroll
-    for (int mi = 0; mi < MBH; ++mi)
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-            const int g = 8 * (b1_mh * MBH + mi) + (lane >> 2), l = 4 * kb + (lane & 3);
-            b1_a[mi][kb] = (g < NGP && l < MN) ? T.N[g][l] : 0.0;
-        }
 #pragma unroll
     for (int nbk = 0; nbk < NB; ++nbk) {
         const int c = CLO + 8 * nbk + (lane >> 2);
@@ -304,6 +295,18 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         //      transform; one warp per (element, half of the Gauss-point blocks). ----
         if (A.phase_mask & 1) {
             const int wid = tid >> 5;
+            // A fragments (N, a constant of the element type) are re-read from L1 at the start of the phase instead of
+            // occupying registers through B2 and the RHS phase
+            double b1_a[MBH][KB];
+            if (wid < nb) {
+#pragma unroll
+                for (int mi = 0; mi < MBH; ++mi)
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb) {
+                        const int g = 8 * mi + (lane >> 2), l = 4 * kb + (lane & 3);
+                        b1_a[mi][kb] = (g < NGP && l < MN) ? T.N[g][l] : 0.0;
+                    }
+            }
             for (int task = wid; task < nb * MH; task += NW) {
                 const int s = task / MH;
                 const double *nd = s_nodes + s * CFG::NSTR;
