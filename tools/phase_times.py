@@ -1,4 +1,5 @@
-"""Per-phase timing of the element kernel (profiling aid): runs bench-like cold assemblies with MOVFEM_PHASE_MASK."""
+"""Per-phase timing of geometry_kernel (profiling aid): cold assemblies with MOVFEM_PHASE_MASK (bit 0: interpolation +
+Jacobian/tensor phases, bit 1: RHS phase); prints the geometry and contraction times of each mask."""
 import os, sys, subprocess, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 cfg = sys.argv[1] if len(sys.argv) > 1 else "2"
@@ -16,10 +17,10 @@ for it in range(6):
     asm.reset_cache(); asm.assemble_device(1, om, d.data_ptr(), abi.MODE_T2)
     try: asm.device_result()
     except Exception as e: pass
-    ts.append(asm.stats()["ms_element"])
-print(min(ts[2:]))
+    ts.append((asm.stats()["ms_geometry"], asm.stats()["ms_contract"]))
+print("geometry %.4f contraction %.4f" % min(ts[2:]))
 ''' % (ROOT, cfg, dirich)
-for mask, name in ((0, "A only (gather nodes)"), (1, "A+B"), (3, "A+B+C"), (7, "A+B+C+D"), (15, "all (with write-out)"), (14, "no B"), (6, "C+D only")):
+for mask, name in ((0, "node staging only"), (1, "staging + B1 + B2"), (2, "staging + RHS"), (3, "all")):
     env = dict(os.environ, MOVFEM_PHASE_MASK=str(mask))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     print(f"mask {mask:2d} {name:26s} {out.stdout.strip()} ms", out.stderr.strip()[-200:] if out.returncode else "")
