@@ -347,6 +347,40 @@ def test_x_slab_handles_concatenate_to_the_full_assembly(mn, dirichlet):
     full.close()
 
 
+def test_config4_full_size_slabs_and_sweep_properties():
+    """BASELINE configs[3] at full size (100x100x60 linear elements, 1.84 M unknowns, 30.8 M entries), where the oracle
+    is too slow: size-independent properties.  Two x-slab handles concatenate to the single-handle result bit for bit
+    (checksums of IRN/JCN and exact equality of the values), the structural invariants hold (sorted upper triangle,
+    every row starts at its diagonal, nz = (nnze + nne)/2), and a cached later frequency equals its cold assembly."""
+    import copy
+    from movfem_b200.sharding import slab_partition
+    m = mesh.config(4)
+    full = host.Assembly(m)
+    om, sg = m.omega(3), m.sigma_for(3)
+    full.global_vfem(1, m.omega(1), m.sigma_for(1))                 # first frequency of the sweep: fills the K/M cache
+    irn, jcn, a, rhs, nz = full.global_vfem(3, om, sg)              # a cached frequency
+    assert nz == full.nz_upper == (full.nnze + full.nne) // 2
+    key = irn[:nz].astype(np.int64) * (full.nne + 1) + jcn[:nz]
+    assert np.all(np.diff(key) > 0) and np.all(jcn[:nz] >= irn[:nz])
+    first = np.searchsorted(irn[:nz], np.arange(1, full.nne + 1))
+    assert np.array_equal(jcn[first], np.arange(1, full.nne + 1))
+    full.reset_cache()
+    cold = full.global_vfem(3, om, sg)
+    assert cold[4] == nz and np.array_equal(cold[2][:nz], a[:nz]) and np.array_equal(cold[3], rhs)
+    full.close()
+    rhs_acc, parts = np.zeros(2 * (rhs.size // 2), np.complex128), []
+    for r in range(2):
+        ms = copy.copy(m)
+        ms.ie_lo, ms.ie_hi = slab_partition(m.g_nx - 1, r, 2)
+        sl = host.Assembly(ms)
+        i2, j2, a2, _, n2 = sl.global_vfem(3, om, sg, rhs=rhs_acc)
+        parts.append((i2[:n2].copy(), j2[:n2].copy(), a2[:n2].copy()))
+        sl.close()
+    assert sum(p[0].size for p in parts) == nz
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), irn[:nz]) and np.array_equal(np.concatenate([p[1] for p in parts]), jcn[:nz])
+    assert np.array_equal(np.concatenate([p[2] for p in parts]), a[:nz]) and np.array_equal(rhs_acc, rhs)
+
+
 @pytest.mark.parametrize("mn,dirichlet,inimod", [(8, 0, 1), (8, 1, 1), (20, 1, 1), (27, 0, 1), (8, 1, 3), (20, 1, 2)])
 def test_end_to_end_apparent_resistivity_and_phase(mn, dirichlet, inimod):
     """north_star: 'End-to-end apparent resistivity and phase after the unchanged solve must agree to <= 1e-6 relative.'
