@@ -19,7 +19,8 @@
  * Quirks reproduced on purpose: Q1 float32 Gauss literals, Q2 single
  * precision cmplx(), Q3 real-valued f1/f2, Q4 +i*omega, Q5 8-node dN/dzeta typo, Q6 abs(det),
  * Q7 one-sided GPML, Q8 omega-dependent h, Q9 full structural pattern, Q10 float32 scratch +
- * unpermuted second pass in ga_sort_sparse, Q11 zero stripping, Q17 lagging GPML flags.
+ * unpermuted second pass in ga_sort_sparse, Q11 zero stripping, Q17 lagging GPML flags,
+ * Q18 the GPML stretch is stored in a REAL array (integration.f90:16), i.e. only Re(h) is used.
  */
 #include <algorithm>
 #include <cmath>
@@ -381,9 +382,13 @@ static void int_elem_params(Elem &E) {
                 g_rw[1] = g_rw[1] + c.shape.nf_ln(j + 1, r[0], r[1], r[2]) * E.nf_re[j][1];
                 g_rw[2] = g_rw[2] + c.shape.nf_ln(j + 1, r[0], r[1], r[2]) * E.nf_re[j][2];
             }
-            E.gpml[id][0] = gpml_h_axis(c, E.in_pml[0], g_rw[0], c.xa, c.xb, E.omega);
-            E.gpml[id][1] = gpml_h_axis(c, E.in_pml[1], g_rw[1], c.ya, c.yb, E.omega);
-            E.gpml[id][2] = gpml_h_axis(c, E.in_pml[2], g_rw[2], c.za, c.zb, E.omega);
+            // Q18: integration.f90:16 declares gpml REAL(kind=double), so `gpml(i,:)=gpml_h(g_rw(1:3))`
+            // (integration.f90:125) keeps only the real part of the complex stretch; f1/f2/f3 then read it back
+            // into a complex h with zero imaginary part (integration.f90:170,225,253).  Found by executing the
+            // reference source (tests/golden/f90exec.py); scheme 1 (Zhou) therefore has h = 1 exactly.
+            E.gpml[id][0] = mk(gpml_h_axis(c, E.in_pml[0], g_rw[0], c.xa, c.xb, E.omega).re, 0.0);
+            E.gpml[id][1] = mk(gpml_h_axis(c, E.in_pml[1], g_rw[1], c.ya, c.yb, E.omega).re, 0.0);
+            E.gpml[id][2] = mk(gpml_h_axis(c, E.in_pml[2], g_rw[2], c.za, c.zb, E.omega).re, 0.0);
         }
         C t_src[2][3];
         p_source(E, r, t_src);
