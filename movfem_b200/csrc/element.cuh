@@ -142,30 +142,20 @@ struct ElemCfg {
     static_assert(32 % EB == 0, "a batch of the contraction (32 lanes) is a whole number of geometry batches");
 };
 
-// gpml_h for one axis, boundary_conds.f90:94-123
+// gpml_h for one axis, boundary_conds.f90:94-123, AS STORED by the reference: integration.f90:16 declares the
+// per-Gauss-point stretch array `gpml` REAL(kind=double), so `gpml(i,:)=gpml_h(...)` (integration.f90:125) keeps
+// Re(h) only and f1/f2/f3 read it back with a zero imaginary part (found by executing the reference
+// source).  Scheme 0 (Fang): Re[hx0*cmplx(1,-bx/(omega*eps))] = hx0 = 1 + a0*rho^n; scheme 1 (Zhou):
+// Re[1 + cmplx(0,bx)] = 1.  The imaginary parts (the sin^2 profile, the Smith division) never reach the matrix.
 __device__ __forceinline__ double2 gpml_axis(const PmlParams &p, int flag, int axis, double r, double omega) {
-    if (flag == 0) return make_double2(1.0, 0.0);
+    if (flag == 0 || p.sch != 0) return make_double2(1.0, 0.0);
     const int s = flag < 0 ? 0 : 1;
-    const double dw = p.omegar[1] - p.omegar[0], ww_pml = sqrt(dw * dw);
-    const double d1 = omega - p.omegar[0], ww = sqrt(d1 * d1);
-    double a0 = p.a0, b0 = p.b0;
-    if (p.sch == 1) { a0 = 100.0 * (ww / ww_pml); b0 = (1.e6 - 1.e-2) * (ww / ww_pml) + 1.e-2; }
     const double dl = p.b[axis][s] - p.a[axis][s], rr_pml = sqrt(dl * dl);
     const double dr = r - p.a[axis][s], rr = sqrt(dr * dr);
     const double rho = rr / rr_pml;
     const double pw = (p.nn == 2.0) ? rho * rho : (p.nn == 1.0 ? rho : pow(rho, p.nn));
-    if (p.sch == 0) {
-        const double hx0 = 1.0 + a0 * pw;
-        const double sn = sin((kPi / 2.0) * rho);
-        const double bx = b0 * (sn * sn);
-        return make_double2(hx0 * 1.0, hx0 * f32r(-bx / (omega * kEps0)));
-    }
-    // Re[(b0*rho^n, 0) / cmplx32(a0, omega)], Smith's division as gfortran emits it
-    const double x = b0 * pw, br = f32r(a0), bi = f32r(omega);
-    double re;
-    if (fabs(br) < fabs(bi)) { const double ratio = br / bi, div = (br * ratio) + bi; re = ((x * ratio) + 0.0) / div; }
-    else { const double ratio = bi / br, div = (bi * ratio) + br; re = ((0.0 * ratio) + x) / div; }
-    return make_double2(1.0, f32r(re));
+    const double hx0 = 1.0 + p.a0 * pw;
+    return make_double2(hx0 * 1.0, 0.0);
 }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }

@@ -929,10 +929,31 @@ def _re_if_c(x):
     return x
 
 
+def _cdiv(a, b):
+    """complex division as gfortran emits it (-fcx-fortran-rules: Smith's algorithm, tree-complex.c
+    expand_complex_div_wide); numpy's own scalar division multiplies by a reciprocal and can differ in the last bit"""
+    single = not (isinstance(a, (_C8, _F8, complex)) or isinstance(b, (_C8, _F8, complex)))
+    ft, ct = (_F4, _C4) if single else (_F8, _C8)
+    ar, ai, br, bi = ft(a.real), ft(a.imag), ft(b.real), ft(b.imag)
+    if abs(br) < abs(bi):
+        ratio = br / bi
+        div = (br * ratio) + bi
+        tr = (ar * ratio) + ai
+        ti = (ai * ratio) - ar
+    else:
+        ratio = bi / br
+        div = (bi * ratio) + br
+        tr = (ai * ratio) + ar
+        ti = ai - (ar * ratio)
+    return ct(complex(tr / div, ti / div))
+
+
 def _div(a, b):
     if type(a) is int and type(b) is int:
         q = abs(a) // abs(b)
         return q if (a >= 0) == (b >= 0) else -q
+    if isinstance(b, _CPLX) and not isinstance(a, np.ndarray):
+        return _cdiv(a, b)
     if isinstance(a, np.ndarray) and isinstance(b, (np.ndarray, int)) and a.dtype.kind == "i" and \
             (type(b) is int or b.dtype.kind == "i"):
         return np.trunc(a / b).astype(np.int64)
@@ -965,6 +986,8 @@ def _pow(a, b):
         return _powi(a, b)
     if type(a) is int:
         a = type(b)(a) if not isinstance(b, np.ndarray) else a
+    if type(a) is _F8 and type(b) is _F8:
+        return _F8(math.pow(a, b))            # libm pow, as gfortran calls it
     return np.power(a, b)
 
 
@@ -1131,16 +1154,38 @@ def _unsupported(msg):
 
 
 _INTRINSICS = {
-    "abs": "_i_abs", "dabs": "_i_abs", "cabs": "_i_abs", "sqrt": "np.sqrt", "dsqrt": "np.sqrt", "csqrt": "np.sqrt",
-    "sin": "np.sin", "dsin": "np.sin", "cos": "np.cos", "dcos": "np.cos", "tan": "np.tan", "atan": "np.arctan",
-    "datan": "np.arctan", "atan2": "np.arctan2", "asin": "np.arcsin", "acos": "np.arccos", "exp": "np.exp", "dexp": "np.exp",
-    "cexp": "np.exp", "log": "np.log", "dlog": "np.log", "log10": "np.log10", "sinh": "np.sinh", "cosh": "np.cosh",
+    "abs": "_i_abs", "dabs": "_i_abs", "cabs": "_i_abs", "sqrt": "_i_sqrt", "dsqrt": "_i_sqrt", "csqrt": "np.sqrt",
+    "sin": "_i_sin", "dsin": "_i_sin", "cos": "_i_cos", "dcos": "_i_cos", "tan": "_i_tan", "atan": "_i_atan",
+    "datan": "_i_atan", "atan2": "_i_atan2", "asin": "np.arcsin", "acos": "np.arccos", "exp": "_i_exp", "dexp": "_i_exp",
+    "cexp": "np.exp", "log": "_i_log", "dlog": "_i_log", "log10": "_i_log10", "sinh": "np.sinh", "cosh": "np.cosh",
     "tanh": "np.tanh", "conjg": "np.conj", "aimag": "_i_aimag", "dimag": "_i_aimag", "real": "_i_real", "dble": "_i_dble",
     "cmplx": "_i_cmplx", "dcmplx": "_i_dcmplx", "int": "_i_int", "nint": "_i_nint", "mod": "_i_mod", "sign": "_i_sign",
     "min": "_i_min", "max": "_i_max", "dmin1": "_i_min", "dmax1": "_i_max", "maxval": "_i_maxval", "minval": "_i_minval",
     "sum": "_i_sum", "size": "_i_size", "allocated": "_i_allocated", "sizeof": "_i_sizeof", "matmul": "_i_matmul",
     "dot_product": "_i_dot_product", "transpose": "np.transpose", "floor": "_i_floor", "float": "_i_real",
 }
+
+
+def _libm(fmath, fnp):
+    def f(x, *rest):
+        t = type(x)
+        if t is _F8 and all(type(r) in (_F8, int) for r in rest):
+            return _F8(fmath(x, *rest))
+        if t is _F4 and not rest:
+            return _F4(fmath(float(x)))
+        return fnp(x, *rest)
+    return f
+
+
+_i_sqrt = _libm(math.sqrt, np.sqrt)
+_i_sin = _libm(math.sin, np.sin)
+_i_cos = _libm(math.cos, np.cos)
+_i_tan = _libm(math.tan, np.tan)
+_i_atan = _libm(math.atan, np.arctan)
+_i_atan2 = _libm(math.atan2, np.arctan2)
+_i_exp = _libm(math.exp, np.exp)
+_i_log = _libm(math.log, np.log)
+_i_log10 = _libm(math.log10, np.log10)
 
 
 def _i_dcmplx(x, y=None):
@@ -1165,10 +1210,10 @@ class ModNS:
 
 
 class Runtime:
-    def __init__(self, paths, skip_calls=()):
+    def __init__(self, paths, skip_calls=(), hookable=()):
         self.modules, self.ns = {}, {}
         self.skip_calls = set(skip_calls)
-        self.hooks = {}
+        self.hookable, self.hooks = set(hookable), {}
         self.consts = []
         self.env = dict(np=np, math=math, FArray=FArray, _FA=FArray, _zeros=_zeros, _bind=_bind, _seq=_seq, _wrap=_wrap,
                         _toi=_toi, _tor4=_tor4, _tor8=_tor8, _toc4=_toc4, _toc8=_toc8, _tol=_tol, _tos=_tos, _re_if_c=_re_if_c,
@@ -1309,6 +1354,11 @@ class Runtime:
 
     def mod(self, name):
         return self.ns[name]
+
+    def run_hook(self, name):
+        h = self.hooks.get(name)
+        if h is not None:
+            h()
 
 
 class Gen:
@@ -1596,8 +1646,8 @@ class Gen:
         if name in self.rt.skip_calls:
             self.emit("pass")
             return
-        if name in self.rt.hooks:
-            self.emit("_rt.hooks[%r]()" % name)      # test tap: runs just before the call
+        if name in self.rt.hookable:
+            self.emit("_rt.run_hook(%r)" % name)      # test tap: runs just before the call
         r = self.lookup(name)
         if r is None or r[0] != "proc":
             raise Unsupported("call of unknown subroutine %r" % name)

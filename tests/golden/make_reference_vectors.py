@@ -1,0 +1,97 @@
+"""Generates tests/golden/ref_*.npz: outputs of the REFERENCE ITSELF (MoVFEM_3DMT Fortran sources under
+/root/reference, executed by f90exec through ref_exec.ReferenceRun) on small synthetic meshes.
+
+These are the pins of the oracle and of the CUDA path: gne/nne/nnze, and per frequency of the reference's sequential
+frequency loop the delivered triplets (irn, jcn, a, nz after find_zeros/rem_zeros = tap T2), the right-hand side,
+the pre-sort triplets (tap T1) and, for a few elements, the per-element caches of integration.f90 and A_e / b_e.
+
+Run (needs /root/reference, takes ~15 min on 8 cores):   python tests/golden/make_reference_vectors.py [case ...]
+"""
+import multiprocessing as mp
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from movfem_b200 import mesh  # noqa: E402
+
+
+def _mesh(nx, ny, mn, nextd, n_earth, n_air, **kw):
+    kw.setdefault("freqs", (0.5, 2.0))
+    kw.setdefault("sigma_fn", mesh._layered((600., 600., 0., 900.)))
+    kw.setdefault("topo_amp", 40.0)
+    return mesh.build_model("ref", nx, ny, mn, 1000., 1100., 900., nextd, n_earth, n_air, **kw)
+
+
+def _mu(m, seed):
+    """a non-trivial permeability so that the curl part of the secondary source (problem.f90:362-420) is exercised"""
+    rng = np.random.default_rng(seed)
+    mur = 1.0 + 0.5 * rng.random(m.npt)
+    m.g_mu[:, [0, 3, 5]] = (mesh.MU0 * mur)[:, None]
+    m.g_mu[:, 1] = 0.05 * mesh.MU0 * rng.random(m.npt)
+    return m
+
+
+def _bd(m, inimod):
+    m.bd_inimod, m.bd_hsigma, m.bd_lsigma, m.bd_ldz = inimod, 0.02, (0.01, 0.1, 0.001), (1.0, 2.5)
+    return m
+
+
+# name -> (model factory, frequencies to run, elements to tap)
+CASES = {
+    # 8-node elements: 5x5x6 with nextd=2 (upper-side GPML only) and 4x3x4 with nextd=1 (both sides)
+    "ref_mn8_gpml_zhou": (lambda: _mesh(5, 5, 8, 2, 1, 1, dirichlet=0, gpml_sch=1), (1, 2), (1, 2, 75, 150)),
+    "ref_mn8_gpml_fang": (lambda: _mesh(4, 3, 8, 1, 1, 1, dirichlet=0, gpml_sch=0, a0=1.5, b0=0.7, nn=2.0), (1, 2), (1, 2, 24, 48)),
+    "ref_mn8_gpml_fang_n3": (lambda: _mu(_mesh(3, 4, 8, 1, 1, 1, dirichlet=0, gpml_sch=0, a0=2.0, b0=1.0, nn=2.5, aniso=True, seed=3), 11),
+                             (1,), (1, 2, 20)),
+    "ref_mn8_dirichlet": (lambda: _mesh(5, 5, 8, 2, 1, 1, dirichlet=1, gpml_sch=1), (1, 2), (1, 32, 150)),
+    "ref_mn8_dirichlet_model2": (lambda: _bd(_mesh(4, 3, 8, 1, 1, 1, dirichlet=1), 2), (1, 2), (1, 17)),
+    "ref_mn8_dirichlet_model3": (lambda: _bd(_mesh(4, 3, 8, 1, 1, 1, dirichlet=1), 3), (1, 2), (1, 17)),
+    # 20-node elements
+    "ref_mn20_gpml_fang": (lambda: _mesh(3, 3, 20, 1, 1, 1, dirichlet=0, gpml_sch=0), (1, 2), (1, 2, 20)),
+    "ref_mn20_dirichlet_model3": (lambda: _bd(_mesh(3, 3, 20, 1, 1, 0, dirichlet=1), 3), (1,), (1, 14)),
+    # 27-node elements
+    "ref_mn27_gpml_zhou_aniso": (lambda: _mu(_mesh(3, 3, 27, 1, 1, 1, dirichlet=0, gpml_sch=1, aniso=True, seed=20141), 7), (1, 2), (1, 2, 20)),
+    "ref_mn27_gpml_fang": (lambda: _mesh(3, 3, 27, 1, 1, 0, dirichlet=0, gpml_sch=0, a0=1.0, b0=1.0, nn=2.0), (1,), (2, 14)),
+    "ref_mn27_dirichlet": (lambda: _mesh(3, 3, 27, 1, 1, 0, dirichlet=1), (1,), (14,)),
+}
+
+
+def model_of(name):
+    return CASES[name][0]()
+
+
+def run_case(name):
+    import ref_exec
+    t0 = time.time()
+    factory, freqs, taps = CASES[name]
+    m = factory()
+    r = ref_exec.ReferenceRun(m)
+    out = dict(gne=r.gne, nne=r.nne, nnze=r.nnze, freqs=np.array(freqs), taps=np.array(taps))
+    for ii in freqs:
+        res = r.frequency(ii, tap_elements=taps if ii == freqs[0] else ())
+        for k in ("irn", "jcn", "a", "rhs", "ia_t1", "ja_t1", "a_t1"):
+            out["%s%d" % (k, ii)] = res[k]
+        out["find_zeros%d" % ii] = res["find_zeros"]
+        for ide, t in res.get("elements", {}).items():
+            for k, v in t.items():
+                out["el%d_%s" % (ide, k)] = v
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    return name, r.nne, r.nnze, int(out["a%d" % freqs[0]].size), time.time() - t0
+
+
+def main():
+    names = sys.argv[1:] or list(CASES)
+    with mp.Pool(min(len(names), os.cpu_count() or 1)) as pool:
+        for res in pool.imap_unordered(run_case, names):
+            print("%-28s nne %6d nnze %8d nz %8d  %.0f s" % res, flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -34,7 +34,8 @@ def available():
 class ReferenceRun:
     def __init__(self, model, src=SRC):
         self.model = m = model
-        self.rt = rt = fx.Runtime([os.path.join(src, f + ".f90") for f in FILES], skip_calls=("estimate_memory",))
+        self.rt = rt = fx.Runtime([os.path.join(src, f + ".f90") for f in FILES], skip_calls=("estimate_memory",),
+                                   hookable=("ga_sort_sparse", "local_vfem"))
         g = rt.mod("geometry")
         nord = m.nord
         # ---- what grid_3d leaves in module geometry (geometry.f90:79-84, 517-521) ----
