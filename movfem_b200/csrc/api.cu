@@ -672,13 +672,16 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     CK(cudaMemset(h->d_status, 0, sizeof(int))); CK(cudaMemset(h->d_flags, 0, 2 * sizeof(int)));
 
     // element lists: stretched = predecessor in loop order carries a GPML flag (Q17); element (1,1,1)
-    // always goes through the stretched kernel (its flags are a per-call input)
+    // always goes through the stretched kernel (its flags are a per-call input).  Scheme 1 (Zhou 2012) has no
+    // stretched elements at all: the reference stores Re(h) = Re[1 + i*bx] = 1 (integration.f90:16, Q18), and
+    // f1/f2/f3 evaluated with h = (1,0) are bit for bit the unstretched expressions, so every K_e, M_e is
+    // frequency independent and cached.
     {
         std::vector<int> plain, pmlv;
         plain.reserve(h->e_end - h->e_base);
         for (int e = h->e_base; e < h->e_end; ++e) {
             bool st = false;
-            if (!m.dirichlet) {
+            if (!m.dirichlet && d->gpml_sch != 1) {
                 if (e == 0) st = true;
                 else { int f[3]; effective_pml(m, h->pml, e, f); st = f[0] || f[1] || f[2]; }
             }

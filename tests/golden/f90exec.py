@@ -1158,7 +1158,7 @@ _INTRINSICS = {
     "sin": "_i_sin", "dsin": "_i_sin", "cos": "_i_cos", "dcos": "_i_cos", "tan": "_i_tan", "atan": "_i_atan",
     "datan": "_i_atan", "atan2": "_i_atan2", "asin": "np.arcsin", "acos": "np.arccos", "exp": "_i_exp", "dexp": "_i_exp",
     "cexp": "np.exp", "log": "_i_log", "dlog": "_i_log", "log10": "_i_log10", "sinh": "np.sinh", "cosh": "np.cosh",
-    "tanh": "np.tanh", "conjg": "np.conj", "aimag": "_i_aimag", "dimag": "_i_aimag", "real": "_i_real", "dble": "_i_dble",
+    "tanh": "np.tanh", "conjg": "np.conj", "aimag": "_i_aimag", "dimag": "_i_aimag", "real": "_i_real", "dble": "_i_dble", "dfloat": "_i_dble",
     "cmplx": "_i_cmplx", "dcmplx": "_i_dcmplx", "int": "_i_int", "nint": "_i_nint", "mod": "_i_mod", "sign": "_i_sign",
     "min": "_i_min", "max": "_i_max", "dmin1": "_i_min", "dmax1": "_i_max", "maxval": "_i_maxval", "minval": "_i_minval",
     "sum": "_i_sum", "size": "_i_size", "allocated": "_i_allocated", "sizeof": "_i_sizeof", "matmul": "_i_matmul",

@@ -63,8 +63,41 @@ CASES = {
 }
 
 
+def _poor_air(m):
+    """tests/e2e_util.py: a poor conductor instead of vacuum above the surface keeps the solve well conditioned"""
+    air = m.sigma_re[:, 0] == 0.0
+    for k in (0, 3, 5):
+        m.sigma_re[air, k] = 1e-3
+    return m
+
+
+# end-to-end cases: assembly -> sparse LU (SciPy SuperLU standing in for ZMUMPS) -> the reference's own
+# solution.f90 node_solution / z_rho_phi (executed): nodal E, H, impedance, apparent resistivity and phase
+SOLUTION_CASES = {
+    "refsol_mn8_dirichlet": lambda: _poor_air(_mesh(4, 3, 8, 1, 1, 1, dirichlet=1, freqs=(5.0,))),
+    "refsol_mn8_gpml_fang": lambda: _poor_air(_mesh(4, 4, 8, 1, 2, 1, dirichlet=0, gpml_sch=0, freqs=(5.0,))),
+    "refsol_mn20_gpml_fang": lambda: _poor_air(_mesh(3, 3, 20, 1, 1, 1, dirichlet=0, gpml_sch=0, freqs=(5.0,))),
+    "refsol_mn27_dirichlet_model3": lambda: _bd(_poor_air(_mesh(3, 3, 27, 1, 1, 0, dirichlet=1, freqs=(5.0,))), 3),
+}
+
+
 def model_of(name):
-    return CASES[name][0]()
+    return SOLUTION_CASES[name]() if name in SOLUTION_CASES else CASES[name][0]()
+
+
+def run_solution_case(name):
+    import ref_exec
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from e2e_util import solve_upper_triplets
+    t0 = time.time()
+    m = SOLUTION_CASES[name]()
+    r = ref_exec.ReferenceRun(m, with_solution=True)
+    res = r.frequency(1)
+    x = solve_upper_triplets(r.nne, res["irn"], res["jcn"], res["a"], res["rhs"])
+    sol = r.node_solution(x)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), nne=r.nne, nnze=r.nnze, irn=res["irn"], jcn=res["jcn"], a=res["a"],
+                        rhs=res["rhs"], x=x, **sol)
+    return name, r.nne, r.nnze, int(res["a"].size), time.time() - t0
 
 
 def run_case(name):
@@ -86,10 +119,14 @@ def run_case(name):
     return name, r.nne, r.nnze, int(out["a%d" % freqs[0]].size), time.time() - t0
 
 
+def _run(name):
+    return run_solution_case(name) if name in SOLUTION_CASES else run_case(name)
+
+
 def main():
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or (list(CASES) + list(SOLUTION_CASES))
     with mp.Pool(min(len(names), os.cpu_count() or 1)) as pool:
-        for res in pool.imap_unordered(run_case, names):
+        for res in pool.imap_unordered(_run, names):
             print("%-28s nne %6d nnze %8d nz %8d  %.0f s" % res, flush=True)
 
 

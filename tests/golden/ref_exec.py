@@ -32,9 +32,10 @@ def available():
 
 
 class ReferenceRun:
-    def __init__(self, model, src=SRC):
+    def __init__(self, model, src=SRC, with_solution=False):
         self.model = m = model
-        self.rt = rt = fx.Runtime([os.path.join(src, f + ".f90") for f in FILES], skip_calls=("estimate_memory",),
+        files = FILES + (["solution"] if with_solution else [])
+        self.rt = rt = fx.Runtime([os.path.join(src, f + ".f90") for f in files], skip_calls=("estimate_memory",),
                                    hookable=("ga_sort_sparse", "local_vfem"))
         g = rt.mod("geometry")
         nord = m.nord
@@ -57,6 +58,7 @@ class ReferenceRun:
         g.g_nf = int(m.freqs.size)
         g.g_ztop = np.float64(m.g_ztop)
         g.omega = np.float64(2.0) * g.pi * g.g_freq.a[0]                         # geometry.f90:73
+        rt.call("geometry", "gqg_nodes")                                        # asx, asy, asz (geometry.f90:715-740)
         bc = rt.mod("boundary_conds")
         bc.gpml_sch = int(m.gpml_sch)
         bc.a0, bc.b0, bc.nn = np.float64(m.a0), np.float64(m.b0), np.float64(m.nn)
@@ -125,4 +127,15 @@ class ReferenceRun:
             rt.call("global_assembly", "rem_zeros", n, irn, jcn, a, tia, tja, ta)
             irn, jcn, a = tia, tja, ta
         out.update(irn=irn.astype(np.int32), jcn=jcn.astype(np.int32), a=a, rhs=rhs, nz=int(a.size))
+        return out
+
+    def node_solution(self, x):
+        """solution.f90:18-69 node_solution + z_rho_phi on a solved system x[2*nne] (needs with_solution=True):
+        total E and H at the grid nodes, impedance tensor, apparent resistivity and phase."""
+        rt = self.rt
+        rt.call("solution", "node_solution", np.array(x, dtype=np.complex128))
+        sol = rt.mod("solution")
+        out = {k: getattr(sol, k).a.copy() for k in ("esol", "hsol", "z", "rho", "phi")}
+        for k in ("esol", "hsol", "z", "rho", "phi"):          # the main program's write_solution deallocates them
+            getattr(sol, k).a = None
         return out
