@@ -6,12 +6,18 @@
  * CHECKER and the timed CPU baseline.  It is never linked into, imported by or called from the
  * product (movfem_b200/): the product fails loudly when its CUDA library is missing.
  *
- * PARITY PIN STATUS: **parity unpinned** by reference runs -- the reference ships no tests, golden
- * vectors or sample outputs and no Fortran compiler exists in this image, so the
- * reference itself cannot be run (no oracle/_ref).  What pins this oracle instead: (i) the numeric element-matrix known answers of SURVEY App. B item 4
- * (obtained by executing a mechanical translation of the reference's own shape tables),
- * (ii) the exact nne / nnze counts of SURVEY section 6 (emulated c_gne12 / ga_nzindx),
- * (iii) mathematical invariants (App. B items 3 and 5).  See tests/test_oracle_pins.py.
+ * PARITY PIN STATUS: **pinned against outputs of the reference itself.**  The reference ships no tests or
+ * golden vectors and no Fortran compiler exists in this image (no oracle/_ref), but its own Fortran sources are
+ * EXECUTED by tests/golden/f90exec.py (a Fortran-subset executor with Fortran kind/assignment/array semantics;
+ * nothing is copied, the sources are read where they lie) through tests/golden/ref_exec.py: init_n_fem,
+ * init_v_fem, init_problem, init_integration, ga_init, bd_setmodel, global_vfem / local_vfem (MoVFEM_3DMT.f90:
+ * 167-263), find_zeros / rem_zeros, and solution.f90 node_solution.  tests/golden/ref_*.npz hold those outputs for
+ * 8/20/27-node elements, GPML Fang / Zhou, Dirichlet boundary models 1-3, two frequencies of the sequential loop;
+ * tests/test_reference_vectors.py checks this oracle against them: gne / nne / nnze / IRN / JCN identical, the
+ * delivered values (tap T2) and every per-element cache, A_e and b_e BIT FOR BIT equal, RHS bit for bit (<= 2e-16
+ * for boundary models 2/3, whose complex sqrt/exp come from different math libraries).  Additional pins:
+ * (i) the element-matrix known answers of SURVEY App. B item 4, (ii) the exact nne / nnze counts of SURVEY
+ * section 6, (iii) mathematical invariants (App. B items 3 and 5).  See tests/test_oracle_pins.py.
  *
  * Build: g++ -O1 -ffp-contract=off  (mirrors `gfortran -O` on x86-64: no FMA contraction, no
  * reassociation).  Every floating-point expression keeps the Fortran evaluation order.

@@ -123,3 +123,51 @@ def test_cuda_path_against_the_executed_reference(name):
         assert np.array_equal(irn[:nz], ref["irn%d" % ii]) and np.array_equal(jcn[:nz], ref["jcn%d" % ii])
         assert rel_err(a[:nz], ref["a%d" % ii]) <= TOL and rel_err(rhs, ref["rhs%d" % ii]) <= TOL
     asm.close()
+
+
+# ---- end to end: the reference's own solution.f90 post-processing, executed ------------------------
+
+SOL_CASES = sorted(mrv.SOLUTION_CASES)
+
+
+def _phase_diff(a, b):
+    d = np.abs(a - b)
+    return np.minimum(d, 180.0 - d)          # atan branch: +-90 degrees where Re z is a signed zero
+
+
+@pytest.mark.parametrize("name", SOL_CASES)
+def test_oracle_node_solution_reproduces_the_executed_reference(name):
+    """oracle.node_solution (restating solution.f90:18-69,207-256,304-505) against node_solution/z_rho_phi of the
+    reference executed on the same solved system x: total E, H at the nodes, impedance, rho_a, phase."""
+    ref = _load(name)
+    m = mrv.model_of(name)
+    o = Oracle(m)
+    res = o.assemble(m.omega(1), m.sigma_for(1), faithful=True)
+    assert np.array_equal(res["irn"], ref["irn"]) and np.array_equal(res["jcn"], ref["jcn"])
+    assert rel_err(res["a"], ref["a"]) <= TOL and rel_err(res["rhs"], ref["rhs"]) <= TOL
+    s = o.node_solution(m.omega(1), m.sigma_for(1), ref["x"])
+    for k in ("esol", "hsol", "z", "rho"):
+        assert rel_err(s[k], ref[k]) <= TOL, k
+    assert _phase_diff(s["phi"], ref["phi"]).max() <= 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SOL_CASES)
+def test_cuda_end_to_end_rho_phase_against_the_executed_reference(name):
+    """north_star: apparent resistivity and phase after the (unchanged) solve agree with the reference to <= 1e-6.
+    Graft triplets -> SuperLU (standing in for ZMUMPS) -> post-processing; compared with the reference's own
+    rho / phi obtained from the reference's triplets through the same solver."""
+    from movfem_b200 import host
+    from e2e_util import solve_upper_triplets
+    ref = _load(name)
+    m = mrv.model_of(name)
+    asm, o = host.Assembly(m), Oracle(m)
+    irn, jcn, a, rhs, nz = asm.global_vfem(1, m.omega(1), m.sigma_for(1))
+    assert nz == ref["a"].size and np.array_equal(irn[:nz], ref["irn"]) and np.array_equal(jcn[:nz], ref["jcn"])
+    x = solve_upper_triplets(asm.nne, irn[:nz], jcn[:nz], a[:nz], rhs)
+    s = o.node_solution(m.omega(1), m.sigma_for(1), x)
+    ok = (ref["rho"] >= 1e-2) & (s["rho"] >= 1e-2)
+    assert np.array_equal(ref["rho"] >= 1e-2, s["rho"] >= 1e-2)
+    assert (np.abs(s["rho"] - ref["rho"])[ok] / ref["rho"][ok]).max() <= 1e-6
+    assert _phase_diff(s["phi"], ref["phi"])[ok].max() <= 1e-6
+    asm.close()
