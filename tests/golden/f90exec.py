@@ -874,6 +874,21 @@ def _seq(arr, *idx):
     return FArray(flat[off:], flat[off:])
 
 
+def _lin(arr, *idx):
+    """element arr(idx...) addressed through the storage sequence WITHOUT bounds checks per dimension, as compiled
+    Fortran does (geometry.f90 update_sigma indexes g_sigma(6,npt) as g_sigma(i<=npt, j<=6)); -> (value, setter)"""
+    a = arr.a
+    flat = a.reshape(-1, order="F")
+    off, mult = 0, 1
+    for k, i in enumerate(idx):
+        off += (i - 1) * mult
+        mult *= a.shape[k]
+
+    def setter(v):
+        flat[off] = v
+    return flat[off], setter
+
+
 def _wrap(v):
     if isinstance(v, np.ndarray):
         return FArray(v)
@@ -1210,12 +1225,13 @@ class ModNS:
 
 
 class Runtime:
-    def __init__(self, paths, skip_calls=(), hookable=()):
+    def __init__(self, paths, skip_calls=(), hookable=(), linear=()):
         self.modules, self.ns = {}, {}
         self.skip_calls = set(skip_calls)
+        self.linear = set(linear)       # arrays addressed through their storage sequence (out-of-bounds subscripts)
         self.hookable, self.hooks = set(hookable), {}
         self.consts = []
-        self.env = dict(np=np, math=math, FArray=FArray, _FA=FArray, _zeros=_zeros, _bind=_bind, _seq=_seq, _wrap=_wrap,
+        self.env = dict(np=np, math=math, FArray=FArray, _FA=FArray, _zeros=_zeros, _bind=_bind, _seq=_seq, _wrap=_wrap, _lin=_lin,
                         _toi=_toi, _tor4=_tor4, _tor8=_tor8, _toc4=_toc4, _toc8=_toc8, _tol=_tol, _tos=_tos, _re_if_c=_re_if_c,
                         _div=_div, _pow=_pow, _ac=_ac, _frange=_frange, _after_loop=_after_loop, _assign_alloc=_assign_alloc,
                         _stop=_stop, _unsupported=_unsupported, _Z4=_F4(0), _Z8=_F8(0), _ZC4=_C4(0), _ZC8=_C8(0), _int=int,
@@ -1531,6 +1547,8 @@ class Gen:
             if not sym.rank:
                 raise Unsupported("subscripted scalar %r" % name)
             idx, element = self.subscript(sym, args)
+            if element and sym.name in self.rt.linear:
+                return "_lin(%s, %s)[0]" % (ref, ", ".join(self.expr(x) for x in args))
             st = self.storage(sym, element)
             if element and sym.type == "i":
                 return "_int(%s.%s[%s])" % (ref, st, idx)
@@ -1636,6 +1654,9 @@ class Gen:
                 raise Unsupported("assignment to %r" % (lhs[1],))
             idx, element = self.subscript(sym, lhs[2])
             val = self.expr(rhs)
+            if element and sym.name in self.rt.linear:
+                self.emit("_lin(%s, %s)[1](%s)" % (ref, ", ".join(self.expr(x) for x in lhs[2]), val))
+                return
             if sym.type in ("i", "r4", "r8"):
                 val = "_re_if_c(%s)" % val
             self.emit("%s.%s[%s] = %s" % (ref, self.storage(sym, element), idx, val))

@@ -253,3 +253,27 @@ def test_live_execution_of_the_reference_matches_the_oracle(mn, dirichlet, sch):
     res = o.assemble(m.omega(1), m.sigma_for(1), faithful=True)
     assert np.array_equal(ref["irn"], res["irn"]) and np.array_equal(ref["jcn"], res["jcn"])
     assert np.array_equal(ref["a"], res["a"]) and np.array_equal(ref["rhs"], res["rhs"])      # bit for bit
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/MoVFEM_3DMT/src"), reason="reference sources not present")
+def test_live_update_sigma_q12_matches_the_mesh_model():
+    """geometry.f90:144-153 update_sigma indexes g_sigma(6,npt) as g_sigma(i<=npt, j<=6): executed with
+    storage-sequence addressing, as compiled Fortran behaves, it must leave exactly what mesh.Model.sigma_for models --
+    the g_sigma every multi-frequency test and the frequency-sharded runs hand to the assembly."""
+    from movfem_b200 import mesh
+    src = "/root/reference/MoVFEM_3DMT/src/"
+    rt = fx.Runtime([src + "kind_param.f90", src + "geometry.f90"], linear=("g_sigma",))
+    m = mesh.build_model("q12", 3, 3, 20, 1000., 1100., 900., 1, 1, 1, freqs=(0.5, 2.0, 7.0), sigma_fn=mesh._layered((600., 600., 0., 900.)))
+    g = rt.mod("geometry")
+    g.g_npt = m.npt
+    g.g_freq.a = np.array(m.freqs)
+    g.g_sigma.a = np.asfortranarray(m.sigma_initial().T.copy())
+    for ii in (1, 2, 3):
+        rt.call("geometry", "update_omega", ii)
+        rt.call("geometry", "update_sigma")
+        assert g.omega == m.omega(ii)
+        assert np.array_equal(g.g_sigma.a.T, m.sigma_for(ii))
+    assert not np.array_equal(m.sigma_for(1), m.sigma_for(3))
+    # only the first npt+30 storage positions are ever refreshed: the tail keeps the first frequency's imaginary part
+    tail = g.g_sigma.a.T.reshape(-1)[m.npt + 30:]
+    assert np.all(tail.imag[tail.imag != 0] == np.float32(mesh.EPS0 * m.omega(1)))
