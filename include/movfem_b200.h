@@ -152,6 +152,28 @@ int movfem_reset_cache(movfem_handle *h);
 /* Measured FP64 FMA-loop throughput of the device in TFLOP/s (roofline denominator). */
 int movfem_fp64_peak(int device, double *tflops);
 
+/*
+ * Geomodel -> grid nodes: replaces geometry.f90:801-970 innermodel_gqg with min_dd_inner (:975-1031,
+ * a serial O(npt x model cells) nearest-neighbour search) and assign_model (:1037-1085).  Arguments are those of the
+ * reference call at geometry.f90:99 (after coord_transform) plus the mesh it reads from module geometry.
+ */
+typedef struct movfem_geomodel {
+    int32_t mx, my, mz;          /* read_input.f90 in_mx, in_my, in_mz: model grid                               */
+    int32_t isigma, imu;         /* number of conductivity / permeability tensor components given (1..9)         */
+    int32_t nzl_air;             /* g_nzl(g_nsf-1): element layers of the air below the top extension            */
+    int32_t ijsigma[9][2];       /* ijsigma(i,1:2): (row, col) of component i                                    */
+    int32_t ijmu[9][2];
+    const double *xm, *ym;       /* (mx), (my)                                                                   */
+    const double *zm;            /* (mx*my*mz), idd=(im-1)*my*mz+(jm-1)*mz+km                                    */
+    const double *sigma;         /* (isigma, mx*my*mz) column-major                                              */
+    const double *mu;            /* (imu, mx*my*mz) column-major, relative permeability                          */
+} movfem_geomodel;
+/* mesh: g_nx,g_ny,g_nz,nord,nextd,nzl_top,g_xp,g_yp,g_zp of the descriptor are read.  omega = 2*pi*g_freq(1)
+   (geometry.f90:73).  g_sigma (6,g_npt) complex128 and g_mu (6,g_npt) are written as innermodel_gqg leaves them.
+   ms_device (optional): device time of the kernels in milliseconds.                                             */
+int movfem_geo_innermodel(const movfem_desc *mesh, int32_t device, const movfem_geomodel *gm, double omega,
+                          double *g_sigma, double *g_mu, double *ms_device);
+
 /* stream the handle launches on (cudaStream_t as void*); set before assembling. */
 int movfem_set_stream(movfem_handle *h, void *cuda_stream);
 int movfem_get_stats(const movfem_handle *h, movfem_stats *out);

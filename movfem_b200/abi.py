@@ -52,3 +52,13 @@ class MovfemStats(C.Structure):
         ("ms_total", C.c_double), ("nz", C.c_int64), ("launches", C.c_int64),
         ("ms_geometry", C.c_double), ("ms_contract", C.c_double),
     ]
+
+
+class MovfemGeomodel(C.Structure):
+    """struct movfem_geomodel: arguments of geometry.f90 innermodel_gqg"""
+    _fields_ = [
+        ("mx", C.c_int32), ("my", C.c_int32), ("mz", C.c_int32),
+        ("isigma", C.c_int32), ("imu", C.c_int32), ("nzl_air", C.c_int32),
+        ("ijsigma", (C.c_int32 * 2) * 9), ("ijmu", (C.c_int32 * 2) * 9),
+        ("xm", C.c_void_p), ("ym", C.c_void_p), ("zm", C.c_void_p), ("sigma", C.c_void_p), ("mu", C.c_void_p),
+    ]

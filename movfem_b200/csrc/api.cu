@@ -23,6 +23,7 @@
 #include "finalize.cuh"
 #include "gather_tmpl.cuh"
 #include "pattern.cuh"
+#include "geo.cuh"
 #include "ref_element.h"
 
 using namespace movfem;
@@ -1075,6 +1076,71 @@ int movfem_fp64_peak(int device, double *tflops) {
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     *tflops = best;
     return cudaGetLastError() == cudaSuccess ? MOVFEM_OK : MOVFEM_E_CUDA;
+}
+
+// geomodel -> grid nodes: geometry.f90:801-1085 innermodel_gqg / min_dd_inner / assign_model
+int movfem_geo_innermodel(const movfem_desc *d, int32_t device, const movfem_geomodel *gm, double omega, double *g_sigma, double *g_mu,
+                          double *ms_device) {
+    if (!d || !gm || !g_sigma || !g_mu || !d->g_xp || !d->g_yp || !d->g_zp || !gm->xm || !gm->ym || !gm->zm || !gm->sigma || !gm->mu)
+        return MOVFEM_E_BADARG;
+    if (d->nord < 2 || d->nord > 3 || d->nextd < 1 || d->nzl_top < 1 || gm->nzl_air < 0 || gm->mx < 1 || gm->my < 1 || gm->mz < 1 ||
+        gm->isigma < 1 || gm->isigma > 9 || gm->imu < 0 || gm->imu > 9)
+        return MOVFEM_E_BADARG;
+    if (gm->imu == 0) return MOVFEM_E_UNSUPPORTED;     // the reference reads mu(1) of a zero-size array (geometry.f90:1066-1069)
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return MOVFEM_E_NOGPU;
+    GeoDims g;
+    g.o = d->nord - 1;
+    g.nnx = (d->g_nx - 1) * g.o + 1; g.nny = (d->g_ny - 1) * g.o + 1; g.nnz = (d->g_nz - 1) * g.o + 1;
+    const int top = (d->nzl_top + gm->nzl_air) * g.o;
+    // nodes of the inner elements ie=nextd+1..g_nx-nextd-1, je likewise, ke=nextd..g_nz-nzl_top-nzl_air-1 (geometry.f90:833-835)
+    g.x0 = d->nextd * g.o + 1; g.x1 = g.nnx - d->nextd * g.o;
+    g.y0 = d->nextd * g.o + 1; g.y1 = g.nny - d->nextd * g.o;
+    g.z0 = (d->nextd - 1) * g.o + 1; g.z1 = g.nnz - top;
+    g.ka = d->nextd * g.o; g.kb = g.nnz - top;
+    g.mx = gm->mx; g.my = gm->my; g.mz = gm->mz;
+    if (d->nextd + 1 > d->g_nx - d->nextd - 1 || d->nextd + 1 > d->g_ny - d->nextd - 1 ||
+        d->nextd > d->g_nz - d->nzl_top - gm->nzl_air - 1 || g.ka > g.kb)
+        return MOVFEM_E_UNSUPPORTED;                   // no inner element: the reference leaves -1 everywhere
+    const int64_t npt = (int64_t)g.nnx * g.nny * g.nnz;
+    const int64_t ncell64 = (int64_t)gm->mx * gm->my * gm->mz;
+    if (ncell64 > 0x7ffffff0) return MOVFEM_E_UNSUPPORTED;
+    const int ncell = (int)ncell64;
+    if (cudaSetDevice(device) != cudaSuccess) return MOVFEM_E_CUDA;
+    double *d_xp = nullptr, *d_yp = nullptr, *d_zp = nullptr, *d_xm = nullptr, *d_ym = nullptr, *d_zm = nullptr, *d_sig = nullptr, *d_mu = nullptr, *d_cm = nullptr, *d_gmu = nullptr;
+    double2 *d_cs = nullptr, *d_gs = nullptr;
+    int *d_cell = nullptr, *d_ij = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = MOVFEM_OK;
+    auto ok = [&](cudaError_t e) { if (e != cudaSuccess && rc == MOVFEM_OK) rc = MOVFEM_E_CUDA; return e == cudaSuccess; };
+    auto up = [&](double **p, const double *src, size_t n) { return ok(dmalloc(p, n)) && ok(cudaMemcpy(*p, src, sizeof(double) * n, cudaMemcpyHostToDevice)); };
+    int ij[36];
+    for (int i = 0; i < gm->isigma; ++i) { ij[i] = gm->ijsigma[i][0]; ij[gm->isigma + i] = gm->ijsigma[i][1]; }
+    for (int i = 0; i < gm->imu; ++i) { ij[18 + i] = gm->ijmu[i][0]; ij[18 + gm->imu + i] = gm->ijmu[i][1]; }
+    if (up(&d_xp, d->g_xp, g.nnx) && up(&d_yp, d->g_yp, g.nny) && up(&d_zp, d->g_zp, npt) && up(&d_xm, gm->xm, gm->mx) && up(&d_ym, gm->ym, gm->my) &&
+        up(&d_zm, gm->zm, ncell) && up(&d_sig, gm->sigma, (size_t)ncell * gm->isigma) && up(&d_mu, gm->mu, (size_t)ncell * gm->imu) &&
+        ok(dmalloc(&d_cs, (size_t)ncell * 6)) && ok(dmalloc(&d_cm, (size_t)ncell * 6)) && ok(dmalloc(&d_gs, (size_t)npt * 6)) &&
+        ok(dmalloc(&d_gmu, (size_t)npt * 6)) && ok(dmalloc(&d_cell, (size_t)npt)) && ok(dmalloc(&d_ij, 36)) &&
+        ok(cudaMemcpy(d_ij, ij, sizeof(ij), cudaMemcpyHostToDevice)) && ok(cudaEventCreate(&e0)) && ok(cudaEventCreate(&e1))) {
+        const double im32 = f32r(kEps0 * omega);
+        const int64_t nvis = (int64_t)(g.x1 - g.x0 + 1) * (g.y1 - g.y0 + 1) * (g.z1 - g.z0 + 1);
+        cudaEventRecord(e0);
+        geo_cell_tensors_kernel<<<(ncell + 127) / 128, 128>>>(ncell, gm->isigma, gm->imu, d_ij, d_ij + 18, d_sig, d_mu, im32, d_cs, d_cm);
+        geo_nearest_kernel<<<(unsigned)((nvis * 32 + 255) / 256), 256>>>(g, d_xp, d_yp, d_zp, d_xm, d_ym, d_zm, d_cell);
+        geo_fill_kernel<<<(unsigned)((npt + 255) / 256), 256>>>(g, d_cell, d_cs, d_cm, im32, d_gs, d_gmu);
+        const int64_t ncol = (int64_t)g.nnx * g.nny;
+        geo_negative_fill_kernel<<<(unsigned)((ncol * 12 + 127) / 128), 128>>>(ncol, g.nnz, d_gs, d_gmu);
+        cudaEventRecord(e1);
+        ok(cudaGetLastError());
+        ok(cudaMemcpy(g_sigma, d_gs, sizeof(double2) * (size_t)npt * 6, cudaMemcpyDeviceToHost));
+        ok(cudaMemcpy(g_mu, d_gmu, sizeof(double) * (size_t)npt * 6, cudaMemcpyDeviceToHost));
+        if (ms_device && rc == MOVFEM_OK) { float t = 0; cudaEventElapsedTime(&t, e0, e1); *ms_device = t; }
+    }
+    void *ptrs[] = {d_xp, d_yp, d_zp, d_xm, d_ym, d_zm, d_sig, d_mu, d_cm, d_gmu, d_cs, d_gs, d_cell, d_ij};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return rc;
 }
 
 int movfem_get_stats(const movfem_handle *h, movfem_stats *out) {

@@ -22,6 +22,7 @@ __host__ __device__ __forceinline__ double f32r(double x) { return (double)(floa
 
 constexpr double kPi = 3.1415926535897932384626433;   // geometry.f90:25
 constexpr double kEps0 = 8.854187817e-12;              // geometry.f90:25
+constexpr double kMu0 = 4.0 * kPi * 1.0e-7;            // geometry.f90:26  mu_0=4.d0*pi*1.d-7
 constexpr double kB0 = 1.e-9;                          // problem.f90:27
 
 // Per grid node, rebuilt every frequency by node_kernel (replaces the per-element recomputation

@@ -71,6 +71,7 @@ def lib():
         L.movfem_fp64_peak.argtypes = [C.c_int, C.POINTER(dbl)]
         L.movfem_debug_element.argtypes = [vp, i32, vp, vp, vp]
         L.movfem_debug_tables.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.movfem_geo_innermodel.argtypes = [C.POINTER(MovfemDesc), i32, C.POINTER(abi.MovfemGeomodel), dbl, vp, vp, C.POINTER(dbl)]
         _LIB = L
     return _LIB
 
@@ -79,6 +80,7 @@ EXPORTED_SYMBOLS = [
     "movfem_create", "movfem_destroy", "movfem_sizes", "movfem_get_gne", "movfem_get_pattern", "movfem_assemble",
     "movfem_assemble_device", "movfem_device_result", "movfem_device_csr", "movfem_set_stream", "movfem_get_stats", "movfem_last_error",
     "movfem_version", "movfem_debug_element", "movfem_reset_cache", "movfem_fp64_peak", "movfem_slab_rows",
+    "movfem_geo_innermodel",
 ]
 
 
@@ -93,6 +95,32 @@ def fp64_peak_tflops(device: int = 0) -> float:
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def innermodel_gqg(model, nzl_air, omega, xm, ym, zm, ijsigma, sigma, ijmu, mu, device: int = 0):
+    """geometry.f90 innermodel_gqg on the GPU: copies the input geomodel to the grid nodes.
+    model: mesh.Model (its g_nx.., nord, nextd, nzl_top, g_xp, g_yp, g_zp are read); xm(mx), ym(my), zm(mx*my*mz);
+    sigma (isigma, ncell) and mu (imu, ncell) as the Fortran arrays (column-major); ijsigma/ijmu (n, 2).
+    Returns g_sigma (npt, 6) complex128, g_mu (npt, 6) float64 and the device time in ms."""
+    xm, ym, zm = (np.ascontiguousarray(v, np.float64) for v in (xm, ym, zm))
+    sigma = np.asfortranarray(sigma, np.float64)
+    mu = np.asfortranarray(mu, np.float64)
+    gm = abi.MovfemGeomodel()
+    gm.mx, gm.my, gm.mz = xm.size, ym.size, zm.size // (xm.size * ym.size)
+    gm.isigma, gm.imu, gm.nzl_air = sigma.shape[0], mu.shape[0], nzl_air
+    for i, (r, c) in enumerate(np.asarray(ijsigma).reshape(-1, 2)):
+        gm.ijsigma[i][0], gm.ijsigma[i][1] = int(r), int(c)
+    for i, (r, c) in enumerate(np.asarray(ijmu).reshape(-1, 2)):
+        gm.ijmu[i][0], gm.ijmu[i][1] = int(r), int(c)
+    gm.xm, gm.ym, gm.zm, gm.sigma, gm.mu = _p(xm), _p(ym), _p(zm), _p(sigma), _p(mu)
+    d = model.desc()
+    g_sigma = np.zeros((model.npt, 6), np.complex128)
+    g_mu = np.zeros((model.npt, 6), np.float64)
+    ms = C.c_double(0)
+    rc = lib().movfem_geo_innermodel(C.byref(d), device, C.byref(gm), float(omega), _p(g_sigma), _p(g_mu), C.byref(ms))
+    if rc:
+        raise MovfemError(rc)
+    return g_sigma, g_mu, ms.value
 
 
 class Assembly:

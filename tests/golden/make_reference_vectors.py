@@ -81,6 +81,69 @@ SOLUTION_CASES = {
 }
 
 
+# geomodel -> grid nodes: geometry.f90 innermodel_gqg / min_dd_inner / assign_model executed
+def _geo_inputs(m, mx, my, mz, isigma, imu, seed, negative_offdiag=False, coincide=0):
+    rng = np.random.default_rng(seed)
+    xm = np.sort(rng.uniform(m.g_xp[0], m.g_xp[-1], mx))
+    ym = np.sort(rng.uniform(m.g_yp[0], m.g_yp[-1], my))
+    zm = rng.uniform(m.g_zp.min(), m.g_zp.max(), mx * my * mz)
+    nnz = (m.g_nz - 1) * (m.nord - 1) + 1
+    for c in range(coincide):               # model cells that coincide with grid nodes: the dd <= 1e-5 branch
+        ii, jj = mx // 2, (my // 2 + c) % my
+        i_node, j_node, k_node = m.g_xp.size // 2, (m.g_yp.size // 2 + c) % m.g_yp.size, nnz // 2
+        xm[ii], ym[jj] = m.g_xp[i_node], m.g_yp[j_node]
+        zm[(ii * my + jj) * mz + (c % mz)] = m.g_zp[(i_node * m.g_yp.size + j_node) * nnz + k_node]
+    comps = {1: [(1, 1)], 3: [(1, 1), (2, 2), (3, 3)], 6: [(1, 1), (1, 2), (1, 3), (2, 2), (2, 3), (3, 3)]}
+    ijs, iju = np.array(comps[isigma]), np.array(comps[imu])
+    sigma = rng.uniform(0.001, 1.0, (isigma, mx * my * mz))
+    if negative_offdiag and isigma == 6:
+        for i in (1, 2, 4):
+            sigma[i] *= rng.choice([-0.3, 0.3], mx * my * mz)      # negative entries trigger geometry.f90:947-962
+    mu = rng.uniform(1.0, 2.0, (imu, mx * my * mz))
+    return dict(xm=xm, ym=ym, zm=zm, ijsigma=ijs, ijmu=iju, sigma=sigma, mu=mu)
+
+
+GEO_CASES = {
+    # name -> (mesh factory, n_air, (mx, my, mz, isigma, imu, seed), kwargs)
+    "refgeo_mn8_iso": (lambda: _mesh(6, 5, 8, 2, 2, 1, freqs=(0.5,)), 1, (3, 4, 3, 1, 1, 1), dict(coincide=2)),
+    "refgeo_mn8_aniso_negative": (lambda: _mesh(5, 5, 8, 1, 3, 2, freqs=(2.0,)), 2, (4, 3, 5, 6, 3, 2), dict(negative_offdiag=True)),
+    "refgeo_mn20_aniso": (lambda: _mesh(4, 4, 20, 1, 2, 1, freqs=(0.5,)), 1, (3, 3, 4, 6, 6, 3), dict(coincide=1, negative_offdiag=True)),
+    "refgeo_mn27_diag": (lambda: _mesh(6, 5, 27, 2, 1, 1, freqs=(1.0,)), 1, (2, 3, 3, 3, 1, 4), dict()),
+}
+
+
+def geo_case(name):
+    factory, n_air, (mx, my, mz, isigma, imu, seed), kw = GEO_CASES[name]
+    m = factory()
+    return m, n_air, _geo_inputs(m, mx, my, mz, isigma, imu, seed, **kw)
+
+
+def run_geo_case(name):
+    import f90exec as fx
+    t0 = time.time()
+    m, n_air, inp = geo_case(name)
+    src = "/root/reference/MoVFEM_3DMT/src/"
+    rt = fx.Runtime([src + "kind_param.f90", src + "geometry.f90"])
+    g = rt.mod("geometry")
+    o = m.nord - 1
+    g.g_nx, g.g_ny, g.g_nz = m.g_nx, m.g_ny, m.g_nz
+    g.g_nordx = g.g_nordy = g.g_nordz = m.nord
+    g.g_nnx, g.g_nny, g.g_nnz = (m.g_nx - 1) * o + 1, (m.g_ny - 1) * o + 1, (m.g_nz - 1) * o + 1
+    g.g_nyz = g.g_nny * g.g_nnz
+    g.g_npt = g.g_nnx * g.g_nyz
+    g.nextd, g.g_nsf = m.nextd, 3
+    g.g_nzl.a = np.array([m.g_nz - 1 - 2 * m.nextd - n_air, n_air, m.nzl_top], dtype=np.int64)
+    g.g_xp.a, g.g_yp.a, g.g_zp.a = m.g_xp.copy(), m.g_yp.copy(), m.g_zp.copy()
+    g.omega = np.float64(m.omega(1))
+    mx, my = inp["xm"].size, inp["ym"].size
+    mz = inp["zm"].size // (mx * my)
+    rt.call("geometry", "innermodel_gqg", mx, my, mz, inp["xm"].copy(), inp["ym"].copy(), inp["zm"].copy(), inp["sigma"].shape[0],
+            inp["mu"].shape[0], np.asfortranarray(inp["ijsigma"].astype(np.int64)), np.asfortranarray(inp["ijmu"].astype(np.int64)),
+            np.asfortranarray(inp["sigma"]), np.asfortranarray(inp["mu"]))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), g_sigma=g.g_sigma.a.T.copy(), g_mu=g.g_mu.a.T.copy())
+    return name, int(g.g_npt), mx * my * mz, int((g.g_sigma.a.real < 0).sum()), time.time() - t0
+
+
 def model_of(name):
     return SOLUTION_CASES[name]() if name in SOLUTION_CASES else CASES[name][0]()
 
@@ -120,11 +183,13 @@ def run_case(name):
 
 
 def _run(name):
+    if name in GEO_CASES:
+        return run_geo_case(name)
     return run_solution_case(name) if name in SOLUTION_CASES else run_case(name)
 
 
 def main():
-    names = sys.argv[1:] or (list(CASES) + list(SOLUTION_CASES))
+    names = sys.argv[1:] or (list(CASES) + list(SOLUTION_CASES) + list(GEO_CASES))
     with mp.Pool(min(len(names), os.cpu_count() or 1)) as pool:
         for res in pool.imap_unordered(_run, names):
             print("%-28s nne %6d nnze %8d nz %8d  %.0f s" % res, flush=True)
