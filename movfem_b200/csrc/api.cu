@@ -1108,7 +1108,7 @@ int movfem_geo_innermodel(const movfem_desc *d, int32_t device, const movfem_geo
     const int ncell = (int)ncell64;
     if (cudaSetDevice(device) != cudaSuccess) return MOVFEM_E_CUDA;
     double *d_xp = nullptr, *d_yp = nullptr, *d_zp = nullptr, *d_xm = nullptr, *d_ym = nullptr, *d_zm = nullptr, *d_sig = nullptr, *d_mu = nullptr, *d_cm = nullptr, *d_gmu = nullptr;
-    double2 *d_cs = nullptr, *d_gs = nullptr;
+    double2 *d_cs = nullptr, *d_gs = nullptr, *d_cxy = nullptr;
     int *d_cell = nullptr, *d_ij = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int rc = MOVFEM_OK;
@@ -1119,14 +1119,15 @@ int movfem_geo_innermodel(const movfem_desc *d, int32_t device, const movfem_geo
     for (int i = 0; i < gm->imu; ++i) { ij[18 + i] = gm->ijmu[i][0]; ij[18 + gm->imu + i] = gm->ijmu[i][1]; }
     if (up(&d_xp, d->g_xp, g.nnx) && up(&d_yp, d->g_yp, g.nny) && up(&d_zp, d->g_zp, npt) && up(&d_xm, gm->xm, gm->mx) && up(&d_ym, gm->ym, gm->my) &&
         up(&d_zm, gm->zm, ncell) && up(&d_sig, gm->sigma, (size_t)ncell * gm->isigma) && up(&d_mu, gm->mu, (size_t)ncell * gm->imu) &&
-        ok(dmalloc(&d_cs, (size_t)ncell * 6)) && ok(dmalloc(&d_cm, (size_t)ncell * 6)) && ok(dmalloc(&d_gs, (size_t)npt * 6)) &&
+        ok(dmalloc(&d_cs, (size_t)ncell * 6)) && ok(dmalloc(&d_cxy, (size_t)ncell)) && ok(dmalloc(&d_cm, (size_t)ncell * 6)) && ok(dmalloc(&d_gs, (size_t)npt * 6)) &&
         ok(dmalloc(&d_gmu, (size_t)npt * 6)) && ok(dmalloc(&d_cell, (size_t)npt)) && ok(dmalloc(&d_ij, 36)) &&
         ok(cudaMemcpy(d_ij, ij, sizeof(ij), cudaMemcpyHostToDevice)) && ok(cudaEventCreate(&e0)) && ok(cudaEventCreate(&e1))) {
         const double im32 = f32r(kEps0 * omega);
         const int64_t nvis = (int64_t)(g.x1 - g.x0 + 1) * (g.y1 - g.y0 + 1) * (g.z1 - g.z0 + 1);
         cudaEventRecord(e0);
         geo_cell_tensors_kernel<<<(ncell + 127) / 128, 128>>>(ncell, gm->isigma, gm->imu, d_ij, d_ij + 18, d_sig, d_mu, im32, d_cs, d_cm);
-        geo_nearest_kernel<<<(unsigned)((nvis * 32 + 255) / 256), 256>>>(g, d_xp, d_yp, d_zp, d_xm, d_ym, d_zm, d_cell);
+        geo_cell_xy_kernel<<<(ncell + 127) / 128, 128>>>(ncell, gm->my, gm->mz, d_xm, d_ym, d_cxy);
+        geo_nearest_kernel<<<(unsigned)((nvis + 8 * kGeoNpw - 1) / (8 * kGeoNpw)), 256>>>(g, d_xp, d_yp, d_zp, d_cxy, d_zm, d_cell);
         geo_fill_kernel<<<(unsigned)((npt + 255) / 256), 256>>>(g, d_cell, d_cs, d_cm, im32, d_gs, d_gmu);
         const int64_t ncol = (int64_t)g.nnx * g.nny;
         geo_negative_fill_kernel<<<(unsigned)((ncol * 12 + 127) / 128), 128>>>(ncol, g.nnz, d_gs, d_gmu);
@@ -1136,7 +1137,7 @@ int movfem_geo_innermodel(const movfem_desc *d, int32_t device, const movfem_geo
         ok(cudaMemcpy(g_mu, d_gmu, sizeof(double) * (size_t)npt * 6, cudaMemcpyDeviceToHost));
         if (ms_device && rc == MOVFEM_OK) { float t = 0; cudaEventElapsedTime(&t, e0, e1); *ms_device = t; }
     }
-    void *ptrs[] = {d_xp, d_yp, d_zp, d_xm, d_ym, d_zm, d_sig, d_mu, d_cm, d_gmu, d_cs, d_gs, d_cell, d_ij};
+    void *ptrs[] = {d_xp, d_yp, d_zp, d_xm, d_ym, d_zm, d_sig, d_mu, d_cm, d_gmu, d_cs, d_gs, d_cxy, d_cell, d_ij};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);

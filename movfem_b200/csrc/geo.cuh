@@ -49,35 +49,75 @@ __global__ void geo_cell_tensors_kernel(int ncell, int isigma, int imu, const in
     }
 }
 
-// one warp per visited node: nearest model cell (min_dd_inner)
+// model cell centres as (x, y) pairs so that the search stages plain copies: cxy[c] = (xm(im), ym(jm)), c = (im*my+jm)*mz+km
+__global__ void geo_cell_xy_kernel(int ncell, int my, int mz, const double *__restrict__ xm, const double *__restrict__ ym, double2 *__restrict__ cxy) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const int myz = my * mz;
+    cxy[c] = make_double2(xm[c / myz], ym[(c % myz) / mz]);
+}
+
+// nearest model cell (min_dd_inner).  A block of 8 warps owns 8 x kGeoNpw visited nodes; the cells pass through shared
+// memory in tiles (24 B per cell, read by every warp), each lane keeps kGeoNpw running minima over the cells it
+// strides.  The reference compares dd = sqrt(d2); sqrt is monotone, so d2 < (d2 of the current best) is a necessary
+// condition for dd < ddmin and the IEEE sqrt is evaluated only then (and the comparison that decides is the
+// reference's own, on dd): the chosen cell is bit-exact, at 8 FP64 operations per (node, cell) pair.
+constexpr int kGeoNpw = 4, kGeoTile = 1024;
 __global__ void __launch_bounds__(256)
 geo_nearest_kernel(GeoDims g, const double *__restrict__ xp, const double *__restrict__ yp, const double *__restrict__ zp,
-                   const double *__restrict__ xm, const double *__restrict__ ym, const double *__restrict__ zm, int *__restrict__ cell) {
-    const int lane = threadIdx.x & 31;
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                   const double2 *__restrict__ cxy, const double *__restrict__ zm, int *__restrict__ cell) {
+    __shared__ double2 s_xy[kGeoTile];
+    __shared__ double s_z[kGeoTile];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nvx = g.x1 - g.x0 + 1, nvy = g.y1 - g.y0 + 1, nvz = g.z1 - g.z0 + 1;
-    if (w >= (int64_t)nvx * nvy * nvz) return;
-    const int kk = g.z0 + (int)(w % nvz), jj = g.y0 + (int)((w / nvz) % nvy), ii = g.x0 + (int)(w / ((int64_t)nvz * nvy));
-    const int64_t id = ((int64_t)(ii - 1) * g.nny + (jj - 1)) * g.nnz + (kk - 1);
-    const double x = xp[ii - 1], y = yp[jj - 1], z = zp[id];
-    const int ncell = g.mx * g.my * g.mz, myz = g.my * g.mz;
-    double best = 1.e20;          // ddmin=1.d20 (geometry.f90:995)
-    int best_i = -1, exact_i = 0x7fffffff;
-    for (int c = lane; c < ncell; c += 32) {
-        const int im = c / myz, jm = (c % myz) / g.mz;
-        const double dx = x - xm[im], dy = y - ym[jm], dz = z - zm[c];
-        const double dd = sqrt((dx * dx + dy * dy) + dz * dz);
-        if (dd <= 1.e-5) { if (c < exact_i) exact_i = c; }
-        else if (dd < best) { best = dd; best_i = c; }     // ascending c per lane: strict < keeps the earliest
+    const int64_t nvis = (int64_t)nvx * nvy * nvz;
+    const int64_t w0 = ((int64_t)blockIdx.x * 8 + warp) * kGeoNpw;
+    double x[kGeoNpw], y[kGeoNpw], z[kGeoNpw], best[kGeoNpw], best2[kGeoNpw];
+    int best_i[kGeoNpw], exact_i[kGeoNpw];
+    int64_t id[kGeoNpw];
+#pragma unroll
+    for (int n = 0; n < kGeoNpw; ++n) {
+        const int64_t w = min(w0 + n, nvis - 1);        // surplus slots repeat the last node (not stored)
+        const int kk = g.z0 + (int)(w % nvz), jj = g.y0 + (int)((w / nvz) % nvy), ii = g.x0 + (int)(w / ((int64_t)nvz * nvy));
+        id[n] = ((int64_t)(ii - 1) * g.nny + (jj - 1)) * g.nnz + (kk - 1);
+        x[n] = xp[ii - 1]; y[n] = yp[jj - 1]; z[n] = zp[id[n]];
+        best[n] = 1.e20; best2[n] = 1.e300;             // ddmin=1.d20 (geometry.f90:995)
+        best_i[n] = -1; exact_i[n] = 0x7fffffff;
+    }
+    const int ncell = g.mx * g.my * g.mz;
+    for (int t0 = 0; t0 < ncell; t0 += kGeoTile) {
+        const int tn = min(kGeoTile, ncell - t0);
+        __syncthreads();
+        for (int c = threadIdx.x; c < tn; c += 256) { s_xy[c] = cxy[t0 + c]; s_z[c] = zm[t0 + c]; }
+        __syncthreads();
+        for (int c = lane; c < tn; c += 32) {
+            const double2 xy = s_xy[c];
+            const double cz = s_z[c];
+#pragma unroll
+            for (int n = 0; n < kGeoNpw; ++n) {
+                const double dx = x[n] - xy.x, dy = y[n] - xy.y, dz = z[n] - cz;
+                const double d2 = (dx * dx + dy * dy) + dz * dz;
+                if (d2 < best2[n]) {                     // rare after the first few cells
+                    const double dd = sqrt(d2);
+                    if (dd <= 1.e-5) { if (t0 + c < exact_i[n]) exact_i[n] = t0 + c; }
+                    else if (dd < best[n]) { best[n] = dd; best2[n] = d2; best_i[n] = t0 + c; }   // ascending c per lane: strict < keeps the earliest
+                } else if (d2 <= 1.0000001e-10) {        // a cell within 1e-5 always takes the assignment (geometry.f90:1000-1003)
+                    if (sqrt(d2) <= 1.e-5 && t0 + c < exact_i[n]) exact_i[n] = t0 + c;
+                }
+            }
+        }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-        const int oi = __shfl_xor_sync(0xffffffffu, best_i, off), oe = __shfl_xor_sync(0xffffffffu, exact_i, off);
-        if (oi >= 0 && (best_i < 0 || ob < best || (ob == best && oi < best_i))) { best = ob; best_i = oi; }
-        exact_i = min(exact_i, oe);
+    for (int n = 0; n < kGeoNpw; ++n) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best[n], off);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i[n], off), oe = __shfl_xor_sync(0xffffffffu, exact_i[n], off);
+            if (oi >= 0 && (best_i[n] < 0 || ob < best[n] || (ob == best[n] && oi < best_i[n]))) { best[n] = ob; best_i[n] = oi; }
+            exact_i[n] = min(exact_i[n], oe);
+        }
+        if (lane == 0 && w0 + n < nvis) cell[id[n]] = exact_i[n] != 0x7fffffff ? exact_i[n] : best_i[n];
     }
-    if (lane == 0) cell[id] = exact_i != 0x7fffffff ? exact_i : best_i;
 }
 
 // one thread per node: visited nodes take their cell, extension nodes the clamped inner node's (the net effect of the
