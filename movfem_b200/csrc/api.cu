@@ -114,7 +114,8 @@ struct movfem_handle {
     int *h_status;      // [0] status [1..2] flags
     int64_t *h_count;   // total non-zeros
     // state
-    bool km_valid;      // Ke/Me of the unstretched elements are cached
+    bool km_valid;      // Ke/Me of all elements are cached
+    int km_first[3];    // GPML flags of element (1,1,1) they were formed with (Q17)
     bool compacted;     // last result lives in the *_c arrays
     int64_t pattern_nz_host;   // nz of the pattern last copied into the caller's irn/jcn (-1: none); MOVFEM_MODE_KEEP_PATTERN
     bool pattern_host_compacted;
@@ -382,8 +383,16 @@ int run_elements(movfem_handle *h, ElemArgs &A, bool full) {
         // refresh K/M only if the node kernel saw Re(sigma) change
         if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 0, 1))) return rc;
     }
-    // stretched (GPML) elements depend on omega through h: always recomputed
-    if ((rc = launch_elements<GQ, CQ, true>(h, A, h->d_list_pml, h->n_pml, (h->n_plain + 31) / 32 * 32, 0))) return rc;
+    // stretched (GPML, scheme 0) elements: the stored stretch is Re(h) = 1 + a0*rho^n (Q18), independent of omega, so
+    // their K_e, M_e are cached like the others; only element (1,1,1) can change, when its lagging flags do (Q17), and
+    // movfem_assemble_device then asks for a full pass
+    const int64_t row0 = (h->n_plain + 31) / 32 * 32;
+    if (full) {
+        if ((rc = launch_elements<GQ, CQ, true>(h, A, h->d_list_pml, h->n_pml, row0, 0))) return rc;
+    } else {
+        if ((rc = launch_elements<GQ, CQ, false>(h, A, h->d_list_pml, h->n_pml, row0, 0))) return rc;
+        if ((rc = launch_elements<GQ, CQ, true>(h, A, h->d_list_pml, h->n_pml, row0, 1))) return rc;
+    }
     return 0;
 }
 
@@ -582,8 +591,8 @@ int build_pattern(movfem_handle *h) {
         const int nblk = (int)((h->nzu + kFinThreads - 1) / kFinThreads);
         CK(dmalloc(&h->d_pure, (size_t)(h->nzu + 31) / 32));
         if (nblk > 0)
-            pure_mask_kernel<<<nblk, kFinThreads, 0, h->stream>>>(h->nzu, h->d_cblk, h->d_off16, h->d_src, h->NP, (int64_t)(h->n_plain + 31) / 32 * 32,
-                                                                  h->d_pure);
+            // every K/M row is frequency independent (Q18), so every entry's gathered (K, M) can be cached across a sweep
+            pure_mask_kernel<<<nblk, kFinThreads, 0, h->stream>>>(h->nzu, h->d_cblk, h->d_off16, h->d_src, h->NP, h->km_rows, h->d_pure);
         h->launches += 1;
         CK(cudaGetLastError());
     }
@@ -754,6 +763,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     CK(dmalloc(&h->d_finbsum, (size_t)(h->nblk_fin + kScanTile - 1) / kScanTile + 1));
     CK(dmalloc(&h->d_total, 1));
     h->km_valid = false;
+    h->km_first[0] = h->km_first[1] = h->km_first[2] = 0;
     h->pattern_nz_host = -1; h->pattern_host_compacted = false;
     return MOVFEM_OK;
 }
@@ -817,6 +827,10 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
     if (!m.dirichlet) {
         if (freq_index == 1) h->pml.first[0] = h->pml.first[1] = h->pml.first[2] = 0;
         else get_pml(h->pml, m.nx, m.ny, m.nz, h->pml.first);
+        // the cached K_e, M_e of element (1,1,1) were formed with the flags of an earlier call: recompute when they differ
+        if (h->n_pml > 0 && (h->pml.first[0] != h->km_first[0] || h->pml.first[1] != h->km_first[1] || h->pml.first[2] != h->km_first[2]))
+            h->km_valid = false;
+        for (int k = 0; k < 3; ++k) h->km_first[k] = h->pml.first[k];
     }
     CK(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), st));
     CK(cudaEventRecord(h->ev[EV_H2D], st));

@@ -175,8 +175,9 @@ __host__ __device__ __forceinline__ constexpr int sym3(int r, int c) {
 // index of (r,c), r <= c, in a packed upper-triangular 9x9 stored row-major
 __host__ __device__ __forceinline__ constexpr int up9(int r, int c) { return r * 9 - r * (r - 1) / 2 + (c - r); }
 
-// DO_QT = false: RHS-only variant for the unstretched elements of a later frequency of a sweep (their K_e, M_e are
-// cached): only the source columns are interpolated and Q, T are neither formed nor written.
+// DO_QT = false: RHS-only variant for a later frequency of a sweep (K_e, M_e are cached -- of the stretched elements
+// too, because the stored stretch Re(h) does not depend on omega, Q18): only the source columns are interpolated and
+// Q|P, T are neither formed nor written; the RHS of a stretched element still carries h1*h2*h3.
 template <class CFG, bool DO_QT>
 __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemArgs A) {
     constexpr int MN = CFG::MN, ME = CFG::ME, MEP = CFG::MEP, EB = CFG::EB, NGP = CFG::NGP;
@@ -184,7 +185,6 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
     constexpr bool PML = CFG::PML;
     constexpr int GR = 0;                                   // R overwrites the record's first 12 columns
     constexpr int CLO = DO_QT ? 0 : 12, CHI = DO_QT ? CFG::NCOL : 24, NCOLA = CHI - CLO;   // active columns
-    static_assert(DO_QT || !PML, "stretched elements are always recomputed in full");
     if (A.skip_unless_changed && A.flags[1] == 0) return;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -415,11 +415,14 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                 }
                 // GPML stretch (boundary_conds.f90:84-186) with the LAGGING flags (Q17)
                 double2 hhh = make_double2(1.0, 0.0);
+                double2 h1 = hhh, h2 = hhh, h3 = hhh;
                 if (PML) {
-                    const double2 h1 = gpml_axis(A.pml, s_el[s * 4 + 1], 0, xg[0], A.omega);
-                    const double2 h2 = gpml_axis(A.pml, s_el[s * 4 + 2], 1, xg[1], A.omega);
-                    const double2 h3 = gpml_axis(A.pml, s_el[s * 4 + 3], 2, xg[2], A.omega);
+                    h1 = gpml_axis(A.pml, s_el[s * 4 + 1], 0, xg[0], A.omega);
+                    h2 = gpml_axis(A.pml, s_el[s * 4 + 2], 1, xg[1], A.omega);
+                    h3 = gpml_axis(A.pml, s_el[s * 4 + 3], 2, xg[2], A.omega);
                     hhh = cmul(cmul(h1, h2), h3);
+                }
+                if (PML && DO_QT) {
                     // Re G_ij, G_ij = h1h2h3/(h_i h_j): the factor of the half-curl pair with derivative axes i,j
                     double Gr[6];
                     Gr[0] = cdivf(cmul(h2, h3), h1).x; Gr[3] = cdivf(cmul(h1, h3), h2).x; Gr[5] = cdivf(cmul(h1, h2), h3).x;

@@ -410,3 +410,22 @@ def test_end_to_end_apparent_resistivity_and_phase(mn, dirichlet, inimod):
     assert same1 and drho1 <= 1e-6 and dphi1 <= 1e-6 * 90.0, (drho1, dphi1)
     assert np.linalg.norm(xg1 - xo1) <= 1e-9 * np.linalg.norm(xo1)
     asm.close()
+
+
+@pytest.mark.parametrize("mn", [8, 20, 27])
+def test_fang_sweep_keeps_the_stretched_elements_cached(mn):
+    """GPML scheme 0 over four frequencies of the sequential loop.  The reference stores Re(h) = 1 + a0*rho^n (Q18), which
+    does not depend on omega, so K_e/M_e of the stretched elements are cached like the others: frequency 1 is a cold
+    pass, frequency 2 recomputes once because element (1,1,1) now sees the flags of the last element (Q17), later
+    frequencies form only the right-hand sides -- and every frequency must match the oracle's sequential run."""
+    m = mesh.build_model(f"fang_sweep_mn{mn}", 6, 5, mn, 1000., 1100., 900., 2, 2, 1, dirichlet=0, gpml_sch=0, a0=1.5, b0=0.8, nn=2.0,
+                         freqs=(0.5, 3.0, 7.0, 20.0), sigma_fn=mesh._layered((1500., 1500., 500., 1500.)), topo_amp=50.0)
+    asm, o = host.Assembly(m), Oracle(m)
+    contract_ms = []
+    for ifreq in (1, 2, 3, 4):
+        asm.global_vfem(ifreq, m.omega(ifreq), m.sigma_for(ifreq), mode=abi.MODE_T1)
+        contract_ms.append(asm.stats()["ms_contract"])
+        _check(compare_assembly(asm, o, m, ifreq=ifreq), allow_noise_pattern=True)
+    assert contract_ms[0] > 0 and contract_ms[1] > 0          # cold pass; flags of element (1,1,1) changed
+    assert contract_ms[2] == 0 and contract_ms[3] == 0        # nothing contracted: K_e, M_e cached for every element
+    asm.close()
