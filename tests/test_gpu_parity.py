@@ -429,5 +429,4 @@ def test_fang_sweep_keeps_the_stretched_elements_cached(mn):
     cold = fresh.global_vfem(4, m.omega(4), m.sigma_for(4), mode=abi.MODE_T1)
     for x, y in zip(cached[:4], cold[:4]):
         assert np.array_equal(x, y)
-    assert fresh.stats()["ms_contract"] > 3 * asm.stats()["ms_contract"]     # cached: the contraction kernels return at once
     asm.close(); fresh.close()
