@@ -17,10 +17,13 @@
 
 namespace movfem {
 
-constexpr int kFinThreads = 256;
+#ifndef MOVFEM_FIN_THREADS
+#define MOVFEM_FIN_THREADS 128      // entries per gather block.  Measured on config 2 (tools/ab_gather_block.sh): 64: 0.400 ms, 128: 0.334, 256: 0.342, 512: 0.361
+#endif
+constexpr int kFinThreads = MOVFEM_FIN_THREADS;
 
 // Contribution index, compressed once per mesh: per block of kFinThreads entries the 64-bit position of its first
-// contribution (cblk) and per entry a 16-bit offset from it (an entry has <= 4 contributions, so a block has <= 1024).
+// contribution (cblk) and per entry a 16-bit offset from it (an entry has <= 4 contributions, so a block has <= 4*kFinThreads).
 __global__ void __launch_bounds__(kFinThreads)
 compress_cptr_kernel(int64_t nzu, const int64_t *__restrict__ cptr, int64_t *__restrict__ cblk, uint16_t *__restrict__ off16) {
     const int64_t i = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
@@ -56,7 +59,7 @@ pure_mask_kernel(int64_t nzu, const int64_t *__restrict__ cblk, const uint16_t *
 
 // mode 0 (T2): values rounded through float32, per-block count of surviving (non-zero) entries
 // mode 1 (T1): double values, nothing stripped
-// Phase 1: the block's <= 1024 contributions are fetched by all threads (independent random 16-byte reads, up to four
+// Phase 1: the block's <= 4*kFinThreads contributions are fetched by all threads (independent random 16-byte reads, up to four
 // in flight per thread) into shared memory; phase 2: one thread per entry sums its contributions in ascending order.
 // cache: 0 none; 1 fill kmg[i] = gathered (K, M) of every entry; 2 use it for the pure entries (a later frequency of a
 // sweep: streaming 16-byte reads instead of the gather) unless the node kernel saw Re(sigma) change (flags[1]), in which

@@ -153,10 +153,10 @@ gather_template_kernel(int ngroups, const int2 *__restrict__ groups, MeshDims m,
             const int64_t s2 = __shfl_sync(0xffffffffu, s, e2);
             if (e2 < grp.y && qq + u < nq) {
                 const int64_t i = s2 + q0 + qq + u;
-                if (!blk_generic[i >> 8]) {
+                if (!blk_generic[i / kFinThreads]) {
                     const double2 val = tile[warp][e2][u];
                     a[i] = val;
-                    if (mode == 0 && val.x == 0.0 && val.y == 0.0) atomicSub(&blk_nonzero[i >> 8], 1);
+                    if (mode == 0 && val.x == 0.0 && val.y == 0.0) atomicSub(&blk_nonzero[i / kFinThreads], 1);
                 }
             }
         }

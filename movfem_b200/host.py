@@ -25,7 +25,7 @@ from . import abi
 from .abi import MovfemDesc, MovfemStats
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libmovfem_b200.so")
+_SO = os.environ.get("MOVFEM_B200_LIB") or os.path.join(_HERE, "libmovfem_b200.so")   # override: A/B builds of the same ABI
 _LIB = None
 
 

@@ -144,8 +144,6 @@ def tokenize(s):
         k = m.lastgroup
         if k != "ws":
             toks.append((k, m.group()))
-    # "(/" directly after a name or ")" is a call/subscript followed by a division only in "a(/" -- which is an
-    # array constructor argument; the ambiguous case "x/(/..." does not occur.  But "(/" must not swallow "(" + "/="
     return toks
 
 
@@ -451,7 +449,7 @@ def _split_top(s, sep=","):
         elif ch == ")":
             depth -= 1
             cur.append(ch)
-        elif ch == sep and depth == 0 and not (sep == "," and False):
+        elif ch == sep and depth == 0:
             parts.append("".join(cur).strip())
             cur = []
         else:

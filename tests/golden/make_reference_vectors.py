@@ -55,6 +55,7 @@ CASES = {
     "ref_mn8_dirichlet_model3": (lambda: _bd(_mesh(4, 3, 8, 1, 1, 1, dirichlet=1), 3), (1, 2), (1, 17)),
     # 20-node elements
     "ref_mn20_gpml_fang": (lambda: _mesh(3, 3, 20, 1, 1, 1, dirichlet=0, gpml_sch=0), (1, 2), (1, 2, 20)),
+    "ref_mn20_gpml_fang_nextd2": (lambda: _mesh(5, 5, 20, 2, 1, 1, dirichlet=0, gpml_sch=0, a0=2.0, b0=1.0, nn=2.0, freqs=(1.0,)), (1,), (1, 2, 150)),
     "ref_mn20_dirichlet_model3": (lambda: _bd(_mesh(3, 3, 20, 1, 1, 0, dirichlet=1), 3), (1,), (1, 14)),
     # 27-node elements
     "ref_mn27_gpml_zhou_aniso": (lambda: _mu(_mesh(3, 3, 27, 1, 1, 1, dirichlet=0, gpml_sch=1, aniso=True, seed=20141), 7), (1, 2), (1, 2, 20)),

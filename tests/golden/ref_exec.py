@@ -95,7 +95,6 @@ class ReferenceRun:
         rt.hooks["ga_sort_sparse"] = before_sort
         if tap_elements:
             integ = rt.mod("integration")
-            prob = rt.mod("problem")
             count = [0]
             me = m.me
 
