@@ -163,3 +163,86 @@ contains
         stop
     end subroutine die
 end module movfem_cuda
+
+! Geomodel -> grid nodes (SURVEY 8f rank 4): drop-in for `call innermodel_gqg(mx,my,mz,xm,ym,zm,isigma,imu,ijsigma,ijmu,
+! sigma,mu)` at geometry.f90:99.  A separate module that does NOT use geometry (geometry.f90 itself calls it), so the
+! mesh arrives as arguments: the caller allocates g_sigma(6,g_npt), g_mu(6,g_npt) exactly as innermodel_gqg does
+! (geometry.f90:824) and passes its module variables.
+!
+!   ! geometry.f90:99, was: call innermodel_gqg(mx,my,mz,xm,ym,zm,isigma, imu, ijsigma,ijmu, sigma,mu)
+!   allocate(g_sigma(6,g_npt), g_mu(6,g_npt))
+!   call movfem_cuda_innermodel(g_nx,g_ny,g_nz,g_nordx,nextd,g_nzl(g_nsf),g_nzl(g_nsf-1),g_xp,g_yp,g_zp,omega, &
+!                               mx,my,mz,xm,ym,zm,isigma,imu,ijsigma,ijmu,sigma,mu,g_sigma,g_mu)
+module movfem_cuda_geo
+    use, intrinsic :: iso_c_binding
+    use kind_param
+    implicit none
+    private
+    public :: movfem_cuda_innermodel
+
+    type, bind(C) :: movfem_desc_geo        ! struct movfem_desc of include/movfem_b200.h, field for field
+        integer(c_int32_t) :: g_nx, g_ny, g_nz, nord, mn, me, nextd, nzl_top
+        integer(c_int32_t) :: dirichlet, bd_inimod, gpml_sch, sym, ndir, pe_sch
+        real(c_double)     :: a0, b0, nn
+        type(c_ptr)        :: g_xp, g_yp, g_zp, g_mu
+        integer(c_int32_t) :: ie_lo, ie_hi
+        real(c_double)     :: g_ztop, bd_hsigma
+        integer(c_int32_t) :: bd_nl, bd_pad
+        real(c_double)     :: bd_lsigma(16), bd_ldz(16)
+    end type movfem_desc_geo
+
+    type, bind(C) :: movfem_geomodel        ! struct movfem_geomodel
+        integer(c_int32_t) :: mx, my, mz, isigma, imu, nzl_air
+        integer(c_int32_t) :: ijsigma(2,9), ijmu(2,9)      ! C [9][2]: (row, col) of component i in column i
+        type(c_ptr)        :: xm, ym, zm, sigma, mu
+    end type movfem_geomodel
+
+    interface
+        integer(c_int) function movfem_geo_innermodel(mesh, device, gm, omega, g_sigma, g_mu, ms_device) &
+                bind(C, name='movfem_geo_innermodel')
+            import :: c_int, c_int32_t, c_double, c_double_complex, c_ptr, movfem_desc_geo, movfem_geomodel
+            type(movfem_desc_geo), intent(in) :: mesh
+            integer(c_int32_t), value :: device
+            type(movfem_geomodel), intent(in) :: gm
+            real(c_double), value :: omega
+            complex(c_double_complex), intent(out) :: g_sigma(6,*)
+            real(c_double), intent(out) :: g_mu(6,*)
+            type(c_ptr), value :: ms_device
+        end function
+    end interface
+
+    contains
+
+    subroutine movfem_cuda_innermodel(g_nx,g_ny,g_nz,nord,nextd,nzl_top,nzl_air,g_xp,g_yp,g_zp,omega, &
+                                      mx,my,mz,xm,ym,zm,isigma,imu,ijsigma,ijmu,sigma,mu,g_sigma,g_mu)
+        integer, intent(in) :: g_nx,g_ny,g_nz,nord,nextd,nzl_top,nzl_air,mx,my,mz,isigma,imu
+        integer, intent(in) :: ijsigma(isigma,2), ijmu(imu,2)
+        real(kind=double), intent(in), target :: g_xp(*), g_yp(*), g_zp(*), xm(mx), ym(my), zm(*), sigma(isigma,*), mu(imu,*)
+        real(kind=double), intent(in) :: omega
+        complex(kind=double), intent(out) :: g_sigma(6,*)
+        real(kind=double), intent(out) :: g_mu(6,*)
+        type(movfem_desc_geo) :: d
+        type(movfem_geomodel) :: gm
+        integer :: i
+        integer(c_int) :: rc
+        d%g_nx = g_nx; d%g_ny = g_ny; d%g_nz = g_nz; d%nord = nord; d%nextd = nextd; d%nzl_top = nzl_top
+        d%mn = 0; d%me = 0; d%dirichlet = 0; d%bd_inimod = 1; d%gpml_sch = 0; d%sym = 1; d%ndir = 2; d%pe_sch = 1
+        d%a0 = 0.d0; d%b0 = 0.d0; d%nn = 0.d0; d%ie_lo = 0; d%ie_hi = 0; d%g_ztop = 0.d0; d%bd_hsigma = 0.d0; d%bd_nl = 1; d%bd_pad = 0
+        d%bd_lsigma = 0.d0; d%bd_ldz = 0.d0
+        d%g_xp = c_loc(g_xp); d%g_yp = c_loc(g_yp); d%g_zp = c_loc(g_zp); d%g_mu = c_null_ptr
+        gm%mx = mx; gm%my = my; gm%mz = mz; gm%isigma = isigma; gm%imu = imu; gm%nzl_air = nzl_air
+        gm%ijsigma = 0; gm%ijmu = 0
+        do i = 1, isigma
+            gm%ijsigma(1,i) = ijsigma(i,1); gm%ijsigma(2,i) = ijsigma(i,2)
+        end do
+        do i = 1, imu
+            gm%ijmu(1,i) = ijmu(i,1); gm%ijmu(2,i) = ijmu(i,2)
+        end do
+        gm%xm = c_loc(xm); gm%ym = c_loc(ym); gm%zm = c_loc(zm); gm%sigma = c_loc(sigma); gm%mu = c_loc(mu)
+        rc = movfem_geo_innermodel(d, 0_c_int32_t, gm, omega, g_sigma, g_mu, c_null_ptr)
+        if (rc /= 0) then
+            print *, 'movfem_geo_innermodel failed with code ', rc
+            stop
+        end if
+    end subroutine movfem_cuda_innermodel
+end module movfem_cuda_geo
