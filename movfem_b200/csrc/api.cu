@@ -374,7 +374,7 @@ int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist,
 template <class GP, class CP, class GQ, class CQ>
 int run_elements(movfem_handle *h, ElemArgs &A, bool full) {
     int rc;
-    // unstretched elements: K_e, M_e are frequency independent (SURVEY Q8) -> computed on the first
+    // unstretched elements: K_e, M_e are frequency independent -> computed on the first
     // frequency and whenever Re(sigma) changed; their RHS is rebuilt every frequency
     if (full) {
         if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 0, 0))) return rc;

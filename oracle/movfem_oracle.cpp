@@ -24,7 +24,7 @@
  *
  * Quirks reproduced on purpose: Q1 float32 Gauss literals, Q2 single
  * precision cmplx(), Q3 real-valued f1/f2, Q4 +i*omega, Q5 8-node dN/dzeta typo, Q6 abs(det),
- * Q7 one-sided GPML, Q8 omega-dependent h, Q9 full structural pattern, Q10 float32 scratch +
+ * Q7 one-sided GPML, Q8 omega-dependent gpml_h (its omega-dependent part is imaginary and dropped by Q18), Q9 full structural pattern, Q10 float32 scratch +
  * unpermuted second pass in ga_sort_sparse, Q11 zero stripping, Q17 lagging GPML flags,
  * Q18 the GPML stretch is stored in a REAL array (integration.f90:16), i.e. only Re(h) is used.
  */
