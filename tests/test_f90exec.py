@@ -277,3 +277,27 @@ def test_live_update_sigma_q12_matches_the_mesh_model():
     # only the first npt+30 storage positions are ever refreshed: the tail keeps the first frequency's imaginary part
     tail = g.g_sigma.a.T.reshape(-1)[m.npt + 30:]
     assert np.all(tail.imag[tail.imag != 0] == np.float32(mesh.EPS0 * m.omega(1)))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/MoVFEM_3DMT/src"), reason="reference sources not present")
+def test_live_extension_reproduces_the_config1_grid_lines():
+    """geometry.f90:223-343 `extension` executed with the shipped example's parameters (100 km x 100 km inner zone,
+    dx = dy = 1990 m, dz = 2000 m, sigma_bg = 0.01 S/m, f = 0.1 Hz): nextd = 4, 59 x 59 grid lines, extension cells
+    1.3*i*dx -- the shape mesh.config(1) (BASELINE configs[0]) is built from.  The reference centres the lines on the
+    extended *input* range, the stand-in on the lines themselves: equal up to a translation."""
+    from movfem_b200 import mesh
+    src = "/root/reference/MoVFEM_3DMT/src/"
+    rt = fx.Runtime([src + "kind_param.f90", src + "geometry.f90"])
+    g = rt.mod("geometry")
+    g.g_nf = 1
+    g.g_freq.a = np.array([0.1])
+    g.xmin, g.xmax, g.ymin, g.ymax = np.float64(0.0), np.float64(1.0e5), np.float64(0.0), np.float64(1.0e5)
+    g.zmin, g.zmax = np.float64(-50000.0), np.float64(20000.0)
+    nsf, nsp = 4, np.array([4, 4, 4, 4], dtype=np.int64)
+    xto, yto, zto = (np.zeros((nsf, 8), order="F") for _ in range(3))
+    rt.call("geometry", "extension", 0.01, 1990.0, 1990.0, 2000.0, nsf, nsp, xto, yto, zto)
+    m = mesh.config(1)
+    assert (g.nextd, g.g_nx, g.g_ny) == (m.nextd, m.g_nx, m.g_ny) == (4, 59, 59)
+    np.testing.assert_allclose(np.diff(g.x.a), np.diff(m.g_xp), rtol=1e-12)
+    np.testing.assert_allclose(np.diff(g.y.a), np.diff(m.g_yp), rtol=1e-12)
+    np.testing.assert_allclose(g.dmz.a, 1.3 * 2000.0 * np.arange(1, 5), rtol=1e-15)       # z extension: 26 km per side
