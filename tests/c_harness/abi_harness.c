@@ -84,6 +84,9 @@ int main(int argc, char **argv)
         printf("get_gne %d gne(1,1) %d\n", rc, (int)gne[0]);
         rc = movfem_assemble(h, 1, 6.283185307179586 * 0.1, sigma, irn, jcn, a, rhs, &nz, MOVFEM_MODE_T2);
         printf("assemble %d nz %ld\n", rc, (long)nz);
+        /* 2x2x2 bricks, all faces Dirichlet: the six edges at the centre node are the unknowns; 18 upper-triangle entries
+           (the CPU oracle's figures for this mesh) */
+        if (rc == MOVFEM_OK && (nne != 6 || nzu != 18 || nz != 18)) { printf("unexpected sizes\n"); rc = 1; }
         if (rc != MOVFEM_OK) printf("error %s\n", movfem_last_error(h));
         for (i = 0; i + 1 < (int)nz; ++i)   /* delivered order: row-major, upper triangle, 1-based */
             if (irn[i] > irn[i + 1] || (irn[i] == irn[i + 1] && jcn[i] >= jcn[i + 1]) || jcn[i] < irn[i] || irn[i] < 1) {
