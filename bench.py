@@ -93,6 +93,32 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def phase_roofs(model, nne, nz_upper, phases_ms, fp64_peak, hbm_peak):
+    """Both roofline fractions for every phase of a step, from the ALGORITHMIC work of each phase:
+    flops = the B^T D B count (contraction only; Jacobian/basis/RHS flops are deliberately not counted), bytes = the
+    data a phase must read and write once.  Every element is taken as unstretched (the GPML layers move 51 instead of
+    12 scratch components, so their share is understated).  Pure function of its arguments (tests/test_abi_host.py)."""
+    me, ngp = model.me, (8 if model.me == 12 else 27)
+    npairs = me * (me + 1) // 2
+    node_in = 152 if model.nord == 2 else 1216              # new grid nodes per element x (z 8 + sigma 96 + mu 48) B
+    scratch = 12 * ngp * 8                                  # Q (6) | T (6) per Gauss point
+    work = {
+        "node": (0, model.npt * (152 + 208)),               # read z, sigma, mu; write one node record
+        "geometry": (0, model.ne * (node_in + scratch + me * 32)),          # nodes in, Q|T scratch and b_e out
+        "contract": (FLOPS_PER_ELEMENT[me] * model.ne, model.ne * (scratch + npairs * 16)),   # scratch in, K_e/M_e out
+        "gather": (0, nz_upper * BYTES_PER_NNZ_UPDATE + nne * 64),           # K, M in, A out; RHS rows out (2 columns)
+    }
+    out = {}
+    for name, (flops, nbytes) in work.items():
+        ms = phases_ms.get("ms_" + name)
+        if not ms or ms <= 0:
+            continue
+        tf, gbs = flops / (ms * 1e-3) * 1e-12, nbytes / (ms * 1e-3) * 1e-9
+        out[name] = {"ms": ms, "tflops": tf if flops else None, "frac_fp64": tf / fp64_peak if flops and fp64_peak else None,
+                     "gbs": gbs, "frac_hbm": gbs / hbm_peak if hbm_peak else None}
+    return out
+
+
 def all_cores_port(o, model, omega, sigma, n_sample, lo):
     """Informational: the same arithmetic with the Jacobian memoised per Gauss point and the element matrices computed
     by all host threads (OpenMP; scattered serially in element order, same bits).  NOT the reference's structure -- the
@@ -297,6 +323,10 @@ def run_graft(args):
                              "unit": "GB/s", "frac": ga_bytes / (ms_ga * 1e-3) * 1e-9 / hbm_peak, "traffic": NCU_TRAFFIC_BYTES["gather_finalize_kernel"],
                              "peak_source": f"MEASURED_PEAKS.json ({hbm_src})", "bytes_per_nnz": BYTES_PER_NNZ_UPDATE, "ms_kernel": ms_ga},
         }
+        try:    # informational table; never allowed to cost the line
+            line["phase_roofs"] = phase_roofs(model, asm.nne, asm.nz_upper, line["phases_ms"], fp64_peak, hbm_peak)
+        except Exception as exc:   # pragma: no cover
+            line["phase_roofs"] = {"error": repr(exc)}
         if world == 1 and not args.no_cpu_baseline:
             from oracle.oracle import Oracle
             o = Oracle(model)

@@ -119,3 +119,21 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_bench_phase_roofs_uses_the_survey_figures():
+    """bench.py's per-phase roofline table (both fractions for every phase) is a pure function: check it on
+    round-1's measured phase times -- the contraction must reproduce the headline FP64 fraction."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    m = mesh.config(2)
+    ph = {"ms_node": 0.0436, "ms_geometry": 0.2878, "ms_contract": 0.4337, "ms_gather": 0.3344}
+    r = b.phase_roofs(m, 600220, 24676330, ph, 34.87, 6556.5)
+    assert set(r) == {"node", "geometry", "contract", "gather"}
+    assert abs(r["contract"]["tflops"] - 250776 * 48000 / 0.4337e-3 * 1e-12) < 1e-9
+    assert 0.79 < r["contract"]["frac_fp64"] < 0.80
+    assert abs(r["gather"]["gbs"] - (24676330 * 32 + 600220 * 64) / 0.3344e-3 * 1e-9) < 1e-6
+    assert r["node"]["frac_fp64"] is None and 0 < r["node"]["frac_hbm"] < 1
+    assert b.phase_roofs(m, 1, 1, {}, 34.87, 6556.5) == {}
