@@ -184,6 +184,10 @@ class Assembly:
         jcn = np.empty(self.nz_upper, np.int32) if jcn is None else jcn
         a = np.empty(self.nz_upper, np.complex128) if a is None else a
         rhs = np.empty(2 * self.nne, np.complex128) if rhs is None else rhs
+        # the library writes through raw pointers: refuse anything that is not the Fortran caller's array types
+        for name, arr, dt in (("irn", irn, np.int32), ("jcn", jcn, np.int32), ("a", a, np.complex128), ("rhs", rhs, np.complex128)):
+            if not isinstance(arr, np.ndarray) or arr.dtype != dt or not arr.flags.c_contiguous or not arr.flags.writeable:
+                raise MovfemError(abi.MOVFEM_E_BADARG, f"{name} must be a writable contiguous numpy array of {np.dtype(dt).name}")
         if min(irn.size, jcn.size, a.size) < self.nz_upper or rhs.size < 2 * self.nne:
             raise MovfemError(abi.MOVFEM_E_CAPACITY)
         nz = C.c_int64(0)

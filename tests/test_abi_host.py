@@ -137,3 +137,25 @@ def test_bench_phase_roofs_uses_the_survey_figures():
     assert abs(r["gather"]["gbs"] - (24676330 * 32 + 600220 * 64) / 0.3344e-3 * 1e-9) < 1e-6
     assert r["node"]["frac_fp64"] is None and 0 < r["node"]["frac_hbm"] < 1
     assert b.phase_roofs(m, 1, 1, {}, 34.87, 6556.5) == {}
+
+
+def test_global_vfem_refuses_arrays_that_are_not_the_callers_fortran_types():
+    """host.Assembly.global_vfem hands raw pointers to the library: wrong dtype, strided or read-only arrays and short
+    arrays are rejected in Python, before any pointer crosses the ABI (no handle, no GPU needed to see that)."""
+    m = mesh.config(1, scale=0.2)
+    asm = host.Assembly.__new__(host.Assembly)          # no movfem_create: only the argument checks run
+    asm.model, asm.nne, asm.nz_upper, asm._h = m, 10, 20, None
+    sg = m.sigma_for(1)
+    good = dict(irn=np.zeros(20, np.int32), jcn=np.zeros(20, np.int32), a=np.zeros(20, np.complex128), rhs=np.zeros(20, np.complex128))
+    ro = np.zeros(20, np.int32); ro.flags.writeable = False
+    for key, bad in (("irn", np.zeros(20, np.int64)), ("jcn", np.zeros(40, np.int32)[::2]), ("a", np.zeros(40, np.float64)),
+                     ("rhs", np.zeros(20, np.complex64)), ("irn", ro), ("a", [0j] * 20)):
+        with pytest.raises(host.MovfemError) as ei:
+            asm.global_vfem(1, 1.0, sg, **{**good, key: bad})
+        assert ei.value.code == abi.MOVFEM_E_BADARG, key
+    with pytest.raises(host.MovfemError) as ei:
+        asm.global_vfem(1, 1.0, sg, **{**good, "rhs": np.zeros(19, np.complex128)})
+    assert ei.value.code == abi.MOVFEM_E_CAPACITY
+    with pytest.raises(host.MovfemError) as ei:
+        asm.global_vfem(1, 1.0, sg[:-1], **good)
+    assert ei.value.code == abi.MOVFEM_E_BADARG
