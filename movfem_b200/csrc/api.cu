@@ -39,12 +39,27 @@ using Geo36p = ElemCfg<20, 36, 36, 27, 8, 256, 2, true>;
 using Geo54  = ElemCfg<27, 54, 60, 27, 4, 128, 3, false>;
 using Geo54p = ElemCfg<27, 54, 60, 27, 4, 128, 2, true>;
 // contract_kernel:          ME MEP NGP PML   W STAGES    (W consumer warps + 1 producer warp; ring of STAGES class blocks)
-using Con12  = ContractCfg<12, 12, 8, false, 6, 6, 2>;
-using Con12p = ContractCfg<12, 12, 8, true, 6, 3, 2>;
-using Con36  = ContractCfg<36, 36, 27, false, 15, 5>;
-using Con36p = ContractCfg<36, 36, 27, true, 12, 2>;
-using Con54  = ContractCfg<54, 60, 27, false, 15, 4>;
-using Con54p = ContractCfg<54, 60, 27, true, 15, 2>;
+// The warp counts can be overridden at build time for A/B libraries (make OUT=... EXTRA=-DMOVFEM_CON12_W=7, loaded through
+// MOVFEM_B200_LIB): tools/micro/tile_bench.cu shows the loop losing 7-25 % when the consumer warps do not divide evenly
+// over the four SMSPs, which the 6 + 1 warps of the me = 12 configurations may be paying.
+#ifndef MOVFEM_CON12_W
+#define MOVFEM_CON12_W 6
+#endif
+#ifndef MOVFEM_CON36_W
+#define MOVFEM_CON36_W 15
+#endif
+#ifndef MOVFEM_CON36P_W
+#define MOVFEM_CON36P_W 12
+#endif
+#ifndef MOVFEM_CON54_W
+#define MOVFEM_CON54_W 15
+#endif
+using Con12  = ContractCfg<12, 12, 8, false, MOVFEM_CON12_W, 6, 2>;
+using Con12p = ContractCfg<12, 12, 8, true, MOVFEM_CON12_W, 3, 2>;
+using Con36  = ContractCfg<36, 36, 27, false, MOVFEM_CON36_W, 5>;
+using Con36p = ContractCfg<36, 36, 27, true, MOVFEM_CON36P_W, 2>;
+using Con54  = ContractCfg<54, 60, 27, false, MOVFEM_CON54_W, 4>;
+using Con54p = ContractCfg<54, 60, 27, true, MOVFEM_CON54_W, 2>;
 
 constexpr size_t kScratchCap = (size_t)512 << 20;   // Q|P,T scratch: larger lists are processed in chunks
 
