@@ -28,6 +28,10 @@
 
 namespace movfem {
 
+#ifndef MOVFEM_KM_ST
+#define MOVFEM_KM_ST 0          // A/B builds: 1 = K_e/M_e leave with streaming stores (they are read much later, by the gather)
+#endif
+
 constexpr int kMaxTiles = 120;   // me=54: 15 groups of 4 slots
 
 // Constants of the element type (one resident table per device, see api.cu: const_table_acquire)
@@ -209,7 +213,11 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(Contr
                             const int sj = 4 * tj + j, jm = c_ct.slot_dof[sj];
                             if (im >= 0 && jm >= 0 && sj <= si) {
                                 const int hi = im > jm ? im : jm, lo = im > jm ? jm : im;
+#if MOVFEM_KM_ST == 1
+                                __stcs(KMo + (hi * (hi + 1) / 2 + lo) * 32, make_double2(accK[i * 4 + j], accM[i * 4 + j]));   // A/B: streaming store
+#else
                                 KMo[(hi * (hi + 1) / 2 + lo) * 32] = make_double2(accK[i * 4 + j], accM[i * 4 + j]);
+#endif
                             }
                         }
                     }

@@ -22,6 +22,34 @@ namespace movfem {
 #endif
 constexpr int kFinThreads = MOVFEM_FIN_THREADS;
 
+// Cache-policy experiments for A/B builds (make OUT=... EXTRA=-DMOVFEM_GATHER_LD=2; defaults generate the code measured in
+// round 1).  The K/M store is read once per assembly in scattered 16-byte pieces and A is written once: neither profits
+// from an L1 line, and evict-first keeps them from displacing the contribution index in L2.
+#ifndef MOVFEM_GATHER_LD
+#define MOVFEM_GATHER_LD 0      // 0 plain load; 1 __ldcs (streaming, evict-first); 2 ld.global.nc.L1::no_allocate
+#endif
+#ifndef MOVFEM_GATHER_ST
+#define MOVFEM_GATHER_ST 0      // 0 plain store; 1 __stcs (streaming)
+#endif
+__device__ __forceinline__ double2 ld_km(const double2 *p) {
+#if MOVFEM_GATHER_LD == 1
+    return __ldcs(p);
+#elif MOVFEM_GATHER_LD == 2
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+__device__ __forceinline__ void st_a(double2 *p, double2 v) {
+#if MOVFEM_GATHER_ST == 1
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // Contribution index, compressed once per mesh: per block of kFinThreads entries the 64-bit position of its first
 // contribution (cblk) and per entry a 16-bit offset from it (an entry has <= 4 contributions, so a block has <= 4*kFinThreads).
 __global__ void __launch_bounds__(kFinThreads)
@@ -88,7 +116,7 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
             const double2 v = kmg[i];
             double re = v.x, im = w32 * v.y;
             if (mode == 0) { re = f32r(re); im = f32r(im); }
-            a[i] = make_double2(re, im);
+            st_a(a + i, make_double2(re, im));
             nzflag = !(re == 0.0 && im == 0.0);
         }
     } else {
@@ -102,7 +130,7 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = threadIdx.x + k * kFinThreads;
-            if (c < n) vals[c] = KM[sidx[k]];
+            if (c < n) vals[c] = ld_km(KM + sidx[k]);
         }
         __syncthreads();
         if (i < nzu) {
@@ -117,7 +145,7 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
             if (cache == 1) kmg[i] = make_double2(k, mm);
             double re = k, im = w32 * mm;
             if (mode == 0) { re = f32r(re); im = f32r(im); }
-            a[i] = make_double2(re, im);
+            st_a(a + i, make_double2(re, im));
             nzflag = !(re == 0.0 && im == 0.0);
         }
     }

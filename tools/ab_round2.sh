@@ -1,0 +1,55 @@
+#!/bin/bash
+# Round-2 A/B sweep: every experiment DESIGN.md section 7 lists that needs no new kernel code.  All variants compute the
+# same bits as the default library (warp counts, cache policies and chunk sizes do not change any summation order).
+#   tools/ab_round2.sh build        here, no GPU: builds ab/lib_<variant>.so (about 20 s each)
+#   gpurun --timeout 900 -- 'tools/ab_round2.sh run'      on the B200: bench.py (config 2) per variant, then the env-var runs
+# Results: gpurun_out/ab2_<variant>.json (bench lines) and the one-line summaries on stdout.
+set -e
+cd "$(dirname "$0")/.."
+variants=(
+  "base:"
+  "c12w7:-DMOVFEM_CON12_W=7"            # me=12: 7 consumers + producer = 8 warps per CTA (even over the SMSPs)
+  "c12w3:-DMOVFEM_CON12_W=3"            # me=12: 3 + 1 = 4 warps per CTA
+  "c36w11:-DMOVFEM_CON36_W=11"          # me=36: 11 + 1 = 12 warps
+  "c36pw11:-DMOVFEM_CON36P_W=11"        # me=36 GPML: 11 + 1 = 12 warps (today 12 + 1 = 13)
+  "c36pw15:-DMOVFEM_CON36P_W=15"        # me=36 GPML: 15 + 1 = 16 warps
+  "gld1:-DMOVFEM_GATHER_LD=1"           # gather: __ldcs on the K/M reads
+  "gld2:-DMOVFEM_GATHER_LD=2"           # gather: ld.global.nc.L1::no_allocate
+  "gst1:-DMOVFEM_GATHER_ST=1"           # gather: streaming stores of A
+  "kmst1:-DMOVFEM_KM_ST=1"              # contraction: streaming stores of K_e/M_e
+  "hints:-DMOVFEM_GATHER_LD=2 -DMOVFEM_GATHER_ST=1 -DMOVFEM_KM_ST=1"
+)
+if [ "$1" = build ]; then
+  mkdir -p ab
+  for v in "${variants[@]}"; do
+    name=${v%%:*}; flags=${v#*:}
+    [ "$name" = base ] && continue
+    make -s -C movfem_b200/csrc OUT=$PWD/ab/lib_$name.so EXTRA="$flags" -B 2>&1 | grep -iE "error" || true
+    ls -la ab/lib_$name.so
+  done
+  exit 0
+fi
+mkdir -p gpurun_out
+summary() { python -c "
+import json,sys; b=json.load(open(sys.argv[1])); print(sys.argv[2], 'ms/step', round(b['ms_per_step'],4), {k: round(x,4) for k,x in b['phases_ms'].items()})" "$1" "$2" || true; }
+for v in "${variants[@]}"; do
+  name=${v%%:*}
+  if [ "$name" = base ]; then unset MOVFEM_B200_LIB; else export MOVFEM_B200_LIB=$PWD/ab/lib_$name.so; [ -f "$MOVFEM_B200_LIB" ] || continue; fi
+  timeout 150 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab2_$name.json 2> gpurun_out/ab2_$name.err || true
+  summary gpurun_out/ab2_$name.json $name
+done
+unset MOVFEM_B200_LIB
+# env-var experiments on the default library: scratch chunks small enough to stay in the 126 MB L2 between geometry_kernel
+# and contract_kernel (config 2 writes 124 MB of Q|T for the unstretched list), and the structured gather
+for mb in 24 48 96; do
+  MOVFEM_SCRATCH_MB=$mb timeout 150 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab2_scratch$mb.json 2> gpurun_out/ab2_scratch$mb.err || true
+  summary gpurun_out/ab2_scratch$mb.json scratch${mb}MB
+done
+MOVFEM_GATHER_TEMPLATE=1 timeout 150 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab2_tmpl.json 2> gpurun_out/ab2_tmpl.err || true
+summary gpurun_out/ab2_tmpl.json gather_template
+# the me=12 variants matter on the linear meshes: config 4 sweep (cold first frequency + cached ones)
+for name in base c12w7 c12w3; do
+  if [ "$name" = base ]; then unset MOVFEM_B200_LIB; else export MOVFEM_B200_LIB=$PWD/ab/lib_$name.so; [ -f "$MOVFEM_B200_LIB" ] || continue; fi
+  timeout 200 python tools/sweep_bench.py > gpurun_out/ab2_sweep_$name.json 2> gpurun_out/ab2_sweep_$name.err || true
+  echo "sweep $name: $(tail -c 500 gpurun_out/ab2_sweep_$name.json)"
+done
