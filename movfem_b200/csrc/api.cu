@@ -56,7 +56,10 @@ using Geo54p = ElemCfg<27, 54, 60, 27, 4, 128, 2, true>;
 #endif
 using Con12  = ContractCfg<12, 12, 8, false, MOVFEM_CON12_W, 6, 2>;
 using Con12p = ContractCfg<12, 12, 8, true, MOVFEM_CON12_W, 3, 2>;
-using Con36  = ContractCfg<36, 36, 27, false, MOVFEM_CON36_W, 5>;
+#ifndef MOVFEM_CON36_STAGES
+#define MOVFEM_CON36_STAGES 5
+#endif
+using Con36  = ContractCfg<36, 36, 27, false, MOVFEM_CON36_W, MOVFEM_CON36_STAGES>;
 using Con36p = ContractCfg<36, 36, 27, true, MOVFEM_CON36P_W, 2>;
 using Con54  = ContractCfg<54, 60, 27, false, MOVFEM_CON54_W, 4>;
 using Con54p = ContractCfg<54, 60, 27, true, MOVFEM_CON54_W, 2>;

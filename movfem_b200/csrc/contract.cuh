@@ -32,6 +32,11 @@ namespace movfem {
 #define MOVFEM_KM_ST 0          // A/B builds: 1 = K_e/M_e leave with streaming stores (they are read much later, by the gather)
 #endif
 
+#ifndef MOVFEM_CON_UNROLL
+#define MOVFEM_CON_UNROLL 3      // unroll of the Gauss-point loop (A/B builds: 1, 9)
+#endif
+constexpr int kConUnroll = MOVFEM_CON_UNROLL;
+
 constexpr int kMaxTiles = 120;   // me=54: 15 groups of 4 slots
 
 // Constants of the element type (one resident table per device, see api.cu: const_table_acquire)
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(Contr
                 if (!PML) {
                     const double *Y1 = s_tab + k1I * MEP + 4 * ti, *Y2 = s_tab + k2I * MEP + 4 * ti, *Y3 = s_tab + 3 * MEP + 4 * ti;
                     const double *X1 = s_tab + k1J * MEP + 4 * tj, *X2 = s_tab + k2J * MEP + 4 * tj, *X3 = s_tab + 3 * MEP + 4 * tj;
-#pragma unroll 3
+#pragma unroll kConUnroll
                     for (int g = 0; g < NGP; ++g) {
                         const int o = g * 4 * MEP;
                         const double q00 = S[(0 * NGP + g) * 32], q01 = S[(1 * NGP + g) * 32], q10 = S[(2 * NGP + g) * 32],
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(Contr
                     for (int i = 0; i < 16; ++i) accK[i] *= tau;
                 } else {
                     const double *Y = s_tab + 4 * ti, *X = s_tab + 4 * tj;
-#pragma unroll 3
+#pragma unroll kConUnroll
                     for (int g = 0; g < NGP; ++g) {
                         const int o = g * 4 * MEP;
                         double P[9];

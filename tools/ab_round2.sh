@@ -18,6 +18,10 @@ variants=(
   "gst1:-DMOVFEM_GATHER_ST=1"           # gather: streaming stores of A
   "kmst1:-DMOVFEM_KM_ST=1"              # contraction: streaming stores of K_e/M_e
   "hints:-DMOVFEM_GATHER_LD=2 -DMOVFEM_GATHER_ST=1 -DMOVFEM_KM_ST=1"
+  "u1:-DMOVFEM_CON_UNROLL=1"            # contraction: Gauss-point loop not unrolled (today 3)
+  "u9:-DMOVFEM_CON_UNROLL=9"            # ... unrolled by 9
+  "st4:-DMOVFEM_CON36_STAGES=4"         # me=36: ring of 4 class blocks (today 5)
+  "st6:-DMOVFEM_CON36_STAGES=6"         # ... 6 (fits: 6 x 34.5 kB + 31 kB table)
 )
 if [ "$1" = build ]; then
   mkdir -p ab
