@@ -304,6 +304,26 @@ void build_contract_tables(const MeshDims &m, const ElemTables &T, ContractTable
                 }
     }
     C.cls_begin[6] = (short)nt_out;
+#if MOVFEM_TALL_TILES
+    {   // tall tiles: per class and column group, the row groups of the class's row direction in pairs (+ a single leftover)
+        int ntt = 0;
+        for (int c = 0; c < 6; ++c) {
+            C.tall_begin[c] = (short)ntt;
+            for (int tj = 0; tj < nt; ++tj) {
+                if (T.slot_dir[4 * tj] != cls_dJ(c)) continue;
+                int rows[kMaxSlots / 4], nr = 0;
+                for (int ti = tj; ti < nt; ++ti)
+                    if (T.slot_dir[4 * ti] == cls_dI(c)) rows[nr++] = ti;
+                for (int r = 0; r < nr; r += 2) {
+                    const int rg = (r + 1 < nr && rows[r + 1] == rows[r] + 1) ? 2 : 1;
+                    C.tall_ti[ntt] = (unsigned char)rows[r]; C.tall_tj[ntt] = (unsigned char)tj; C.tall_rg[ntt] = (unsigned char)rg; ++ntt;
+                    if (rg == 1 && r + 1 < nr) --r;   // not adjacent (cannot happen: the groups of a direction are contiguous)
+                }
+            }
+        }
+        C.tall_begin[6] = (short)ntt;
+    }
+#endif
     // scratch components a class streams: plain Q[r0|r1(dI)][m0|m1(dJ)] (components 0-5, sym3 order) and T[dI][dJ]
     // (6-11); GPML P[(u,dI)][(v,dJ)] (0-44, up9 order) and T (45-50)
     for (int c = 0; c < 6; ++c) {

@@ -37,6 +37,10 @@ namespace movfem {
 #endif
 constexpr int kConUnroll = MOVFEM_CON_UNROLL;
 
+#ifndef MOVFEM_TALL_TILES
+#define MOVFEM_TALL_TILES 0     // A/B builds: 1 = 8x4 tiles for the unstretched 20/27-node elements (see tall_tile below)
+#endif
+
 constexpr int kMaxTiles = 120;   // me=54: 15 groups of 4 slots
 
 // Constants of the element type (one resident table per device, see api.cu: const_table_acquire)
@@ -46,6 +50,11 @@ struct ContractTables {
     unsigned char tile_ti[kMaxTiles], tile_tj[kMaxTiles];   // tiles sorted by class
     short cls_begin[8];                  // first tile of class c (c = 0..5), cls_begin[6] = number of tiles
     unsigned char comp[2][6][10];        // [pml][class][k]: scratch component streamed to stage block k
+#if MOVFEM_TALL_TILES
+    // tall tiles: (first row group, column group, number of row groups 1|2), sorted by class; rows of one direction only
+    unsigned char tall_ti[kMaxTiles], tall_tj[kMaxTiles], tall_rg[kMaxTiles];
+    short tall_begin[8];
+#endif
 };
 __constant__ ContractTables c_ct;
 
@@ -80,6 +89,67 @@ struct ContractCfg {
     static constexpr size_t SMEM = sizeof(double) * ((size_t)STAGES * STAGE_D + TAB_D) + sizeof(uint64_t) * 2 * STAGES;
     static constexpr int NT = MEP / 4, NTILES = NT * (NT + 1) / 2, NP = ME * (ME + 1) / 2;
 };
+
+#if MOVFEM_TALL_TILES
+// A/B variant (not the default; measured in isolation by tools/micro/tile_bench.cu: +17 % pair updates per cycle).  A warp
+// takes RG = 2 row groups of ONE direction against one column group: the column operands and b1/b2/bw are formed once for
+// 8 rows, 116 instead of 2 x 68 FP64 instructions and 18 instead of 24 broadcast LDS.128 per Gauss point.  Every pair is
+// accumulated by the same dfma chain in the same Gauss-point order as in the 4x4 path, so the results are bit-identical.
+template <int RG, int MEP, int NGP>
+__device__ __forceinline__ void tall_tile(const double *__restrict__ S, const double *__restrict__ s_tab, int ti, int tj, int k1I, int k2I,
+                                          int k1J, int k2J, double tau, double2 *__restrict__ KMo, bool live) {
+    double accK[RG * 16], accM[RG * 16];
+#pragma unroll
+    for (int i = 0; i < RG * 16; ++i) { accK[i] = 0.0; accM[i] = 0.0; }
+    const double *Y1 = s_tab + k1I * MEP + 4 * ti, *Y2 = s_tab + k2I * MEP + 4 * ti, *Y3 = s_tab + 3 * MEP + 4 * ti;
+    const double *X1 = s_tab + k1J * MEP + 4 * tj, *X2 = s_tab + k2J * MEP + 4 * tj, *X3 = s_tab + 3 * MEP + 4 * tj;
+#pragma unroll kConUnroll
+    for (int g = 0; g < NGP; ++g) {
+        const int o = g * 4 * MEP;
+        const double q00 = S[(0 * NGP + g) * 32], q01 = S[(1 * NGP + g) * 32], q10 = S[(2 * NGP + g) * 32],
+                     q11 = S[(3 * NGP + g) * 32], tt = S[(4 * NGP + g) * 32];
+        double b1[4], b2[4], bw[4], xa[4], xb[4], xc[4];
+        ld4(xa, X1 + o); ld4(xb, X2 + o); ld4(xc, X3 + o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            b1[j] = dfma(q00, xa[j], -(q01 * xb[j]));
+            b2[j] = dfma(q10, xa[j], -(q11 * xb[j]));
+            bw[j] = xc[j] * tt;
+        }
+#pragma unroll
+        for (int rg = 0; rg < RG; ++rg) {
+            double ya[4], yb[4], yc[4];
+            ld4(ya, Y1 + o + 4 * rg); ld4(yb, Y2 + o + 4 * rg); ld4(yc, Y3 + o + 4 * rg);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double y1 = ya[i], y2 = yb[i], y3 = yc[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int a = (rg * 4 + i) * 4 + j;
+                    accK[a] = dfma(y1, b1[j], dfma(-y2, b2[j], accK[a]));
+                    accM[a] = dfma(y3, bw[j], accM[a]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RG * 16; ++i) accK[i] *= tau;
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < RG * 4; ++i) {
+            const int si = 4 * ti + i, im = c_ct.slot_dof[si];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int sj = 4 * tj + j, jm = c_ct.slot_dof[sj];
+                if (im >= 0 && jm >= 0 && sj <= si) {
+                    const int hi = im > jm ? im : jm, lo = im > jm ? jm : im;
+                    KMo[(hi * (hi + 1) / 2 + lo) * 32] = make_double2(accK[i * 4 + j], accM[i * 4 + j]);
+                }
+            }
+        }
+    }
+}
+#endif
 
 template <class CFG>
 __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(ContractArgs A) {
@@ -125,6 +195,36 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(Contr
         return;
     }
 
+#if MOVFEM_TALL_TILES
+    if constexpr (!PML && MEP > 12) {
+        // ---- consumers, tall-tile variant: same item walk, the tile stream is the tall list ----
+        const int ntt = c_ct.tall_begin[6];
+        const int tpos0 = (n0 / 6) * ntt + c_ct.tall_begin[n0 % 6];
+#pragma unroll 1
+        for (int n = n0; n < n1; ++n) {
+            const int b = n / 6, c = n - b * 6, k = n - n0;
+            const bool live = b * 32 + lane < A.nlist;
+            double2 *KMo = A.KM + (size_t)b * NP * 32 + lane;
+            const int slot = k % STAGES, round = k / STAGES;
+            mbar_wait(&full[slot], (unsigned)(round & 1));
+            const double *S = s_stage + (size_t)slot * STAGE_D + lane;
+            const int dI = cls_dI(c), dJ = cls_dJ(c);
+            const int t_lo = c_ct.tall_begin[c], t_hi = c_ct.tall_begin[c + 1];
+            const int k1I = dI == 2 ? 1 : 2, k2I = dI == 0 ? 1 : 0, k1J = dJ == 2 ? 1 : 2, k2J = dJ == 0 ? 1 : 0;
+            const double tau = ((dI == 1) != (dJ == 1)) ? -1.0 : 1.0;
+            const int first = (b * ntt + t_lo - tpos0) % W;
+#pragma unroll 1
+            for (int t = t_lo + ((warp - first + W) % W); t < t_hi; t += W) {
+                const int ti = c_ct.tall_ti[t], tj = c_ct.tall_tj[t];
+                if (c_ct.tall_rg[t] == 2) tall_tile<2, MEP, NGP>(S, s_tab, ti, tj, k1I, k2I, k1J, k2J, tau, KMo, live);
+                else tall_tile<1, MEP, NGP>(S, s_tab, ti, tj, k1I, k2I, k1J, k2J, tau, KMo, live);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+        }
+        return;
+    }
+#endif
     // ---- consumers ----
     const int pos0 = (n0 / 6) * CFG::NTILES + c_ct.cls_begin[n0 % 6];   // stream position of the CTA's first tile
     {

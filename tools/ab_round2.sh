@@ -21,6 +21,8 @@ variants=(
   "u1:-DMOVFEM_CON_UNROLL=1"            # contraction: Gauss-point loop not unrolled (today 3)
   "u9:-DMOVFEM_CON_UNROLL=9"            # ... unrolled by 9
   "st4:-DMOVFEM_CON36_STAGES=4"         # me=36: ring of 4 class blocks (today 5)
+  "tall7:-DMOVFEM_TALL_TILES=1 -DMOVFEM_CON36_W=7 -DMOVFEM_CON54_W=7"     # 8x4 contraction tiles, 7 consumers + producer = 8 warps, 236 regs, no spills
+  "tall11:-DMOVFEM_TALL_TILES=1 -DMOVFEM_CON36_W=11 -DMOVFEM_CON54_W=11"  # ... 12 warps, 168 regs (the per-SMSP limit at 3 warps), 376 B of spills
   "st3:-DMOVFEM_CON36_STAGES=3"         # ... 3 (6 would need 238 kB > 227 kB)
 )
 if [ "$1" = build ]; then
@@ -39,6 +41,8 @@ import json,sys; b=json.load(open(sys.argv[1])); print(sys.argv[2], 'ms/step', r
 for v in "${variants[@]}"; do
   name=${v%%:*}
   if [ "$name" = base ]; then unset MOVFEM_B200_LIB; else export MOVFEM_B200_LIB=$PWD/ab/lib_$name.so; [ -f "$MOVFEM_B200_LIB" ] || continue; fi
+  timeout 120 python tools/ab_hash.py > gpurun_out/ab2_hash_$name.txt 2> gpurun_out/ab2_hash_$name.err || true
+  if [ "$name" != base ] && ! cmp -s gpurun_out/ab2_hash_base.txt gpurun_out/ab2_hash_$name.txt; then echo "$name: RESULTS DIFFER FROM THE DEFAULT LIBRARY"; fi
   timeout 150 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab2_$name.json 2> gpurun_out/ab2_$name.err || true
   summary gpurun_out/ab2_$name.json $name
 done
