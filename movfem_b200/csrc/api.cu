@@ -314,10 +314,11 @@ void build_contract_tables(const MeshDims &m, const ElemTables &T, ContractTable
                 int rows[kMaxSlots / 4], nr = 0;
                 for (int ti = tj; ti < nt; ++ti)
                     if (T.slot_dir[4 * ti] == cls_dI(c)) rows[nr++] = ti;
-                for (int r = 0; r < nr; r += 2) {
-                    const int rg = (r + 1 < nr && rows[r + 1] == rows[r] + 1) ? 2 : 1;
+                for (int r = 0; r < nr;) {   // runs of up to MOVFEM_TALL_RG adjacent row groups (the groups of a direction are contiguous)
+                    int rg = 1;
+                    while (rg < MOVFEM_TALL_RG && r + rg < nr && rows[r + rg] == rows[r] + rg) ++rg;
                     C.tall_ti[ntt] = (unsigned char)rows[r]; C.tall_tj[ntt] = (unsigned char)tj; C.tall_rg[ntt] = (unsigned char)rg; ++ntt;
-                    if (rg == 1 && r + 1 < nr) --r;   // not adjacent (cannot happen: the groups of a direction are contiguous)
+                    r += rg;
                 }
             }
         }

@@ -40,6 +40,9 @@ constexpr int kConUnroll = MOVFEM_CON_UNROLL;
 #ifndef MOVFEM_TALL_TILES
 #define MOVFEM_TALL_TILES 0     // A/B builds: 1 = 8x4 tiles for the unstretched 20/27-node elements (see tall_tile below)
 #endif
+#ifndef MOVFEM_TALL_RG
+#define MOVFEM_TALL_RG 2        // row groups per tall tile: 2 (8x4) or 3 (12x4: 192 accumulator registers)
+#endif
 
 constexpr int kMaxTiles = 120;   // me=54: 15 groups of 4 slots
 
@@ -242,7 +245,12 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(Contr
 #pragma unroll 1
             for (int t = t_lo + ((warp - first + W) % W); t < t_hi; t += W) {
                 const int ti = c_ct.tall_ti[t], tj = c_ct.tall_tj[t];
-                if (c_ct.tall_rg[t] == 2) tall_tile<2, MEP, NGP>(S, s_tab, ti, tj, k1I, k2I, k1J, k2J, tau, KMo, live);
+                const int rg = c_ct.tall_rg[t];
+#if MOVFEM_TALL_RG >= 3
+                if (rg == 3) tall_tile<3, MEP, NGP>(S, s_tab, ti, tj, k1I, k2I, k1J, k2J, tau, KMo, live);
+                else
+#endif
+                if (rg == 2) tall_tile<2, MEP, NGP>(S, s_tab, ti, tj, k1I, k2I, k1J, k2J, tau, KMo, live);
                 else tall_tile<1, MEP, NGP>(S, s_tab, ti, tj, k1I, k2I, k1J, k2J, tau, KMo, live);
             }
             __syncwarp();

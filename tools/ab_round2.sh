@@ -24,6 +24,7 @@ variants=(
   "tall7:-DMOVFEM_TALL_TILES=1 -DMOVFEM_CON36_W=7 -DMOVFEM_CON54_W=7"     # 8x4 contraction tiles, 7 consumers + producer = 8 warps, 236 regs, no spills
   "tall11:-DMOVFEM_TALL_TILES=1 -DMOVFEM_CON36_W=11 -DMOVFEM_CON54_W=11"  # ... 12 warps, 168 regs (the per-SMSP limit at 3 warps), 376 B of spills
   "tallfold:-DMOVFEM_TALL_TILES=2 -DMOVFEM_CON36_W=8 -DMOVFEM_CON54_W=8"  # 8x4 tiles, producer folded into consumer warp 0: 8 even warps, 236 regs, no spills
+  "tall3fold:-DMOVFEM_TALL_TILES=2 -DMOVFEM_TALL_RG=3 -DMOVFEM_CON_UNROLL=1 -DMOVFEM_CON36_W=8 -DMOVFEM_CON54_W=8"  # 12x4 tiles: 254 regs, no spills only with the g loop not unrolled
   "st3:-DMOVFEM_CON36_STAGES=3"         # ... 3 (6 would need 238 kB > 227 kB)
 )
 if [ "$1" = build ]; then
