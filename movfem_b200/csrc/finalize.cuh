@@ -26,7 +26,7 @@ constexpr int kFinThreads = MOVFEM_FIN_THREADS;
 // round 1).  The K/M store is read once per assembly in scattered 16-byte pieces and A is written once: neither profits
 // from an L1 line, and evict-first keeps them from displacing the contribution index in L2.
 #ifndef MOVFEM_GATHER_LD
-#define MOVFEM_GATHER_LD 0      // 0 plain load; 1 __ldcs (streaming, evict-first); 2 ld.global.nc.L1::no_allocate
+#define MOVFEM_GATHER_LD 0      // 0 plain load; 1 __ldcs (streaming, evict-first); 2 ld.global.nc.L1::no_allocate; 3 cp.async.cg straight into shared memory
 #endif
 #ifndef MOVFEM_GATHER_ST
 #define MOVFEM_GATHER_ST 0      // 0 plain store; 1 __stcs (streaming)
@@ -130,8 +130,19 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = threadIdx.x + k * kFinThreads;
+#if MOVFEM_GATHER_LD == 3
+            if (c < n) {   // LDGSTS: global -> shared without the register round trip, L1 bypassed (.cg)
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&vals[c]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(KM + sidx[k]) : "memory");
+            }
+#else
             if (c < n) vals[c] = ld_km(KM + sidx[k]);
+#endif
         }
+#if MOVFEM_GATHER_LD == 3
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
         __syncthreads();
         if (i < nzu) {
             const int lo = offs[threadIdx.x];

@@ -15,6 +15,7 @@ variants=(
   "c36pw15:-DMOVFEM_CON36P_W=15"        # me=36 GPML: 15 + 1 = 16 warps
   "gld1:-DMOVFEM_GATHER_LD=1"           # gather: __ldcs on the K/M reads
   "gld2:-DMOVFEM_GATHER_LD=2"           # gather: ld.global.nc.L1::no_allocate
+  "gld3:-DMOVFEM_GATHER_LD=3"           # gather: cp.async.cg 16-byte copies global -> shared (no register round trip, no L1)
   "gst1:-DMOVFEM_GATHER_ST=1"           # gather: streaming stores of A
   "kmst1:-DMOVFEM_KM_ST=1"              # contraction: streaming stores of K_e/M_e
   "hints:-DMOVFEM_GATHER_LD=2 -DMOVFEM_GATHER_ST=1 -DMOVFEM_KM_ST=1"
