@@ -347,6 +347,9 @@ int const_table_acquire(movfem_handle *h) {
     if (g_ct_owner[h->device] == h->m.me) return 0;
     CK(cudaDeviceSynchronize());   // no kernel of another element type may still be reading c_ct
     CK(cudaMemcpyToSymbol(c_ct, &h->ct, sizeof(ContractTables)));
+#if MOVFEM_TAB_GLOBAL
+    CK(cudaMemcpyToSymbol(g_ct_at, h->ct.at, sizeof(h->ct.at)));
+#endif
     g_ct_owner[h->device] = h->m.me;
     return 0;
 }

@@ -60,6 +60,12 @@ struct ContractTables {
 #endif
 };
 __constant__ ContractTables c_ct;
+#ifndef MOVFEM_TAB_GLOBAL
+#define MOVFEM_TAB_GLOBAL 0     // A/B builds: 1 = the CTA's shared-memory operand table is filled from a global-memory copy.
+#endif                          // ncu (r01): the fill from the constant bank (lane-distinct LDC, serialised) takes 4 % of the warp samples
+#if MOVFEM_TAB_GLOBAL
+__device__ double g_ct_at[kMaxGp * 4 * kMaxSlots];
+#endif
 
 // class c <-> (dI, dJ), dI >= dJ
 __host__ __device__ __forceinline__ constexpr int cls_dI(int c) { return c == 0 ? 0 : (c <= 2 ? 1 : 2); }
@@ -172,7 +178,11 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(Contr
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int nbatch = (A.nlist + 31) / 32;
+#if MOVFEM_TAB_GLOBAL
+    for (int i = threadIdx.x; i < CFG::TAB_D; i += CFG::THREADS) s_tab[i] = g_ct_at[i];
+#else
     for (int i = threadIdx.x; i < CFG::TAB_D; i += CFG::THREADS) s_tab[i] = c_ct.at[i];
+#endif
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], W); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
