@@ -91,6 +91,9 @@ __global__ void node_kernel(int n0, int npt, double omega, const double *__restr
 // ------------------------------------------------------------------------------------------
 // element kernel
 // ------------------------------------------------------------------------------------------
+#ifndef MOVFEM_GEO_PREFETCH
+#define MOVFEM_GEO_PREFETCH 0   // A/B builds: 1 = L2 prefetch of the next batch's node records during phase B2.  ncu (r01): 19 % of
+#endif                          // geometry_kernel's warp samples sit in the wait for the node-record bulk copies (phase A)
 struct ElemArgs {
     MeshDims m;
     PmlParams pml;
@@ -276,6 +279,11 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         mbar_wait(s_bar, node_phase);
         node_phase ^= 1;
         __syncthreads();
+#if MOVFEM_GEO_PREFETCH
+        // A/B variant: resolve the NEXT batch's node ids already here (s_rbase / s_rxy have no reader during B1) so that
+        // phase B2 can start pulling its records into L2 one phase before the bulk copies are issued
+        if (batch + (int)gridDim.x < nbatch) prepare_request(batch + gridDim.x);
+#endif
 
         // ---- phase B1: interpolate node data to the Gauss points (p_intmodels problem.f90:139-142 and the N_l-weighted
         //      part of p_source problem.f90:424-457): per element the small GEMM  out[g][c] = sum_l N[g][l] V[l][c]
@@ -339,7 +347,18 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         __syncthreads();
 
         // ---- phase B2: one thread per (Gauss point, element): J, G, GPML, source -> Q|P, T (scratch), R (in place) ----
+#if MOVFEM_GEO_PREFETCH
+        if (batch + (int)gridDim.x < nbatch) {
+            const int nbn = min(EB, A.nlist - (batch + (int)gridDim.x) * EB);
+            for (int i = tid; i < nbn * MN; i += CFG::THREADS) {
+                const char *rec = reinterpret_cast<const char *>(A.nodes + (s_rbase[i / MN] + s_noff[(i % MN) * 3]));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rec));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 128));   // a 208-byte record spans two or three 128-byte lines
+            }
+        }
+#else
         if (batch + (int)gridDim.x < nbatch) prepare_request(batch + gridDim.x);
+#endif
         if (A.phase_mask & 1) {
             const int has_dmu = A.flags[0];
             const double w32 = f32r(A.omega);            // cmplx(0.d0,-omega), problem.f90:112
