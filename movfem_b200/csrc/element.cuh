@@ -91,6 +91,9 @@ __global__ void node_kernel(int n0, int npt, double omega, const double *__restr
 // ------------------------------------------------------------------------------------------
 // element kernel
 // ------------------------------------------------------------------------------------------
+#ifndef MOVFEM_RHS_PER_SLOT
+#define MOVFEM_RHS_PER_SLOT 0   // A/B builds: 1 = RHS phase with one thread per (element, slot) instead of per group of four slots
+#endif
 #ifndef MOVFEM_GEO_PREFETCH
 #define MOVFEM_GEO_PREFETCH 0   // A/B builds: 1 = L2 prefetch of the next batch's node records during phase B2.  ncu (r01): 19 % of
 #endif                          // geometry_kernel's warp samples sit in the wait for the node-record bulk copies (phase A)
@@ -549,6 +552,30 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
 
         // ---- RHS: one thread per (element, group of four slots of one direction): blocal / f3,
         //      integration.f90:96-104,258-263.  R[d] is loaded once per Gauss point for the four slots. ----
+#if MOVFEM_RHS_PER_SLOT
+        // A/B variant: one thread per (element, slot) -- EB*MEP tasks keep every warp busy (the default below has EB*MEP/4
+        // tasks: 72 of 256 threads for the 20-node element, and ncu shows 29 % of the kernel's samples stalled at barriers).
+        // Each (slot, polarisation) sum runs over the Gauss points in the same order: bit-identical.
+        if (A.phase_mask & 2) {
+            for (int i = tid; i < nb * MEP; i += CFG::THREADS) {
+                const int cs = i / MEP, sl = i % MEP;
+                const int cdof = s_slot[sl];
+                if (cdof < 0) continue;
+                const int cd = s_sdir[sl];
+                double bacc[4] = {0.0, 0.0, 0.0, 0.0};
+                const double *R0 = s_geo + cs * GEO + GR + cd * 4, *ph = s_phi + sl;
+#pragma unroll
+                for (int g = 0; g < NGP; ++g) {
+                    const double phi = ph[g * MEP];
+                    const double2 r01 = *reinterpret_cast<const double2 *>(R0 + g * EB * GEO), r23 = *reinterpret_cast<const double2 *>(R0 + g * EB * GEO + 2);
+                    bacc[0] = dfma(phi, r01.x, bacc[0]); bacc[1] = dfma(phi, r01.y, bacc[1]);
+                    bacc[2] = dfma(phi, r23.x, bacc[2]); bacc[3] = dfma(phi, r23.y, bacc[3]);
+                }
+                const int64_t e = s_el[cs * 4];
+                reinterpret_cast<double4 *>(A.be)[(e - A.e_base) * ME + cdof] = make_double4(bacc[0], bacc[1], bacc[2], bacc[3]);
+            }
+        }
+#else
         if (A.phase_mask & 2) {
             constexpr int NQ = MEP / 4;
             for (int i = tid; i < nb * NQ; i += CFG::THREADS) {
@@ -579,6 +606,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                 }
             }
         }
+#endif
     }
 }
 
