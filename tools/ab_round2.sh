@@ -13,6 +13,7 @@ variants=(
   "c36w11:-DMOVFEM_CON36_W=11"          # me=36: 11 + 1 = 12 warps
   "c36pw11:-DMOVFEM_CON36P_W=11"        # me=36 GPML: 11 + 1 = 12 warps (today 12 + 1 = 13)
   "c36pw15:-DMOVFEM_CON36P_W=15"        # me=36 GPML: 15 + 1 = 16 warps
+  "c36pw8:-DMOVFEM_CON36P_W=8"          # me=36 GPML: 8 + 1 warps (an item has 6 or 9 tiles and the ring only 2 stages: idle warps run ahead into the barrier)
   "gld1:-DMOVFEM_GATHER_LD=1"           # gather: __ldcs on the K/M reads
   "gld2:-DMOVFEM_GATHER_LD=2"           # gather: ld.global.nc.L1::no_allocate
   "gld3:-DMOVFEM_GATHER_LD=3"           # gather: cp.async.cg 16-byte copies global -> shared (no register round trip, no L1)
