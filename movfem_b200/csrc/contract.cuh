@@ -40,6 +40,9 @@ constexpr int kConUnroll = MOVFEM_CON_UNROLL;
 #ifndef MOVFEM_TALL_TILES
 #define MOVFEM_TALL_TILES 0     // A/B builds: 1 = 8x4 tiles for the unstretched 20/27-node elements (see tall_tile below)
 #endif
+#ifndef MOVFEM_FOLD_PRODUCER
+#define MOVFEM_FOLD_PRODUCER 0  // A/B builds: 1 = no producer warp in any contraction kernel (lane 0 of consumer warp 0 issues the bulk
+#endif                          // copies), so W can be a multiple of four with every warp a consumer (16 x 128 registers fill the file)
 #ifndef MOVFEM_TALL_RG
 #define MOVFEM_TALL_RG 2        // row groups per tall tile: 2 (8x4) or 3 (12x4: 192 accumulator registers)
 #endif
@@ -96,7 +99,7 @@ struct ContractCfg {
     // MOVFEM_TALL_TILES == 2 (A/B): the tall-tile kernels have no producer warp -- lane 0 of consumer warp 0 issues the bulk
     // copies -- so that 8 warps x 32 threads can use the full 255 registers (the register file is per SMSP: a ninth warp
     // would cap every thread at 168)
-    static constexpr bool FOLD = (MOVFEM_TALL_TILES == 2) && !PML_ && MEP_ > 12;
+    static constexpr bool FOLD = ((MOVFEM_TALL_TILES == 2) && !PML_ && MEP_ > 12) || (MOVFEM_FOLD_PRODUCER != 0);
     static constexpr int THREADS = (W + (FOLD ? 0 : 1)) * 32;
     static constexpr int TAB_D = NGP * 4 * MEP;      // constant operand table, broadcast-read from shared memory
     static constexpr size_t SMEM = sizeof(double) * ((size_t)STAGES * STAGE_D + TAB_D) + sizeof(uint64_t) * 2 * STAGES;
@@ -212,34 +215,35 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(Contr
         return;
     }
 
+    // folded producer (CFG::FOLD): item k2 of this CTA into its ring slot; same protocol as the producer warp above
+    auto issue = [&](int k2) {
+        const int n2 = n0 + k2;
+        if (n2 >= n1) return;
+        const int b2 = n2 / 6, c2 = n2 - b2 * 6;
+        const double *src = A.qt + (size_t)b2 * NCMP * CB;
+        const int slot2 = k2 % STAGES, round2 = k2 / STAGES;
+        if (round2 > 0) mbar_wait(&empty[slot2], (unsigned)((round2 - 1) & 1));
+        mbar_expect_tx(&full[slot2], (unsigned)(STAGE_D * sizeof(double)));
+        double *dst = s_stage + (size_t)slot2 * STAGE_D;
+#pragma unroll 1
+        for (int q = 0; q < NC; ++q)
+            bulk_g2s(dst + q * CB, src + (size_t)c_ct.comp[PML ? 1 : 0][c2][q] * CB, (unsigned)(CB * sizeof(double)), &full[slot2]);
+    };
+    // prefetch distance: STAGES-2 where the ring allows (the slot asked for at item k was released at item k-2 by every
+    // warp, so the issuing lane practically never waits while its own tiles are pending), else 1
+    constexpr int PFD = STAGES > 2 ? STAGES - 2 : 1;
+    if (CFG::FOLD && warp == 0 && lane == 0)
+        for (int k2 = 0; k2 < PFD; ++k2) issue(k2);
 #if MOVFEM_TALL_TILES
     if constexpr (!PML && MEP > 12) {
         // ---- consumers, tall-tile variant: same item walk, the tile stream is the tall list ----
         const int ntt = c_ct.tall_begin[6];
         const int tpos0 = (n0 / 6) * ntt + c_ct.tall_begin[n0 % 6];
-        // folded producer (CFG::FOLD): item k2 of this CTA into its ring slot; same protocol as the producer warp above
-        auto issue = [&](int k2) {
-            const int n2 = n0 + k2;
-            if (n2 >= n1) return;
-            const int b2 = n2 / 6, c2 = n2 - b2 * 6;
-            const double *src = A.qt + (size_t)b2 * NCMP * CB;
-            const int slot2 = k2 % STAGES, round2 = k2 / STAGES;
-            if (round2 > 0) mbar_wait(&empty[slot2], (unsigned)((round2 - 1) & 1));
-            mbar_expect_tx(&full[slot2], (unsigned)(STAGE_D * sizeof(double)));
-            double *dst = s_stage + (size_t)slot2 * STAGE_D;
-#pragma unroll 1
-            for (int q = 0; q < NC; ++q)
-                bulk_g2s(dst + q * CB, src + (size_t)c_ct.comp[0][c2][q] * CB, (unsigned)(CB * sizeof(double)), &full[slot2]);
-        };
-        // prefetch distance STAGES-2: the slot asked for at item k was released at item k-2 by every warp, so the issuing
-        // lane practically never waits while its own tiles are pending
-        if (CFG::FOLD && warp == 0 && lane == 0)
-            for (int k2 = 0; k2 < STAGES - 2; ++k2) issue(k2);
 #pragma unroll 1
         for (int n = n0; n < n1; ++n) {
             const int b = n / 6, c = n - b * 6, k = n - n0;
             if (CFG::FOLD && warp == 0) {
-                if (lane == 0) issue(k + STAGES - 2);
+                if (lane == 0) issue(k + PFD);
                 __syncwarp();
             }
             const bool live = b * 32 + lane < A.nlist;
@@ -275,6 +279,10 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(Contr
 #pragma unroll 1
         for (int n = n0; n < n1; ++n) {
             const int b = n / 6, c = n - b * 6, k = n - n0;
+            if (CFG::FOLD && warp == 0) {
+                if (lane == 0) issue(k + PFD);
+                __syncwarp();
+            }
             const bool live = b * 32 + lane < A.nlist;
             double2 *KMo = A.KM + (size_t)b * NP * 32 + lane;
             const int slot = k % STAGES, round = k / STAGES;

@@ -31,6 +31,8 @@ variants=(
   "tall11:-DMOVFEM_TALL_TILES=1 -DMOVFEM_CON36_W=11 -DMOVFEM_CON54_W=11"  # ... 12 warps, 168 regs (the per-SMSP limit at 3 warps), 376 B of spills
   "tallfold:-DMOVFEM_TALL_TILES=2 -DMOVFEM_CON36_W=8 -DMOVFEM_CON54_W=8"  # 8x4 tiles, producer folded into consumer warp 0: 8 even warps, 236 regs, no spills
   "tall3fold:-DMOVFEM_TALL_TILES=2 -DMOVFEM_TALL_RG=3 -DMOVFEM_CON_UNROLL=1 -DMOVFEM_CON36_W=8 -DMOVFEM_CON54_W=8"  # 12x4 tiles: 254 regs, no spills only with the g loop not unrolled
+  "fold16:-DMOVFEM_FOLD_PRODUCER=1 -DMOVFEM_CON12_W=8 -DMOVFEM_CON36_W=16 -DMOVFEM_CON36P_W=12 -DMOVFEM_CON54_W=16"   # 4x4 tiles, no producer warp: 16 (8, 12) consumer warps, all SMSPs even; 128 regs with ~150 B of spills
+  "fold12:-DMOVFEM_FOLD_PRODUCER=1 -DMOVFEM_CON12_W=4 -DMOVFEM_CON36_W=12 -DMOVFEM_CON36P_W=8 -DMOVFEM_CON54_W=12"    # ... 12 (4, 8) consumer warps, up to 168 regs
   "st3:-DMOVFEM_CON36_STAGES=3"         # ... 3 (6 would need 238 kB > 227 kB)
 )
 if [ "$1" = build ]; then
