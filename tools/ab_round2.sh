@@ -35,6 +35,12 @@ variants=(
   "fold12:-DMOVFEM_FOLD_PRODUCER=1 -DMOVFEM_CON12_W=4 -DMOVFEM_CON36_W=12 -DMOVFEM_CON36P_W=8 -DMOVFEM_CON54_W=12"    # ... 12 (4, 8) consumer warps, up to 168 regs
   "st3:-DMOVFEM_CON36_STAGES=3"         # ... 3 (6 would need 238 kB > 227 kB)
 )
+# ONLY="name1 name2 ..." restricts build/run to those variants (base always runs)
+if [ -n "$ONLY" ]; then
+  keep=("base:")
+  for v in "${variants[@]}"; do for o in $ONLY; do [ "${v%%:*}" = "$o" ] && keep+=("$v"); done; done
+  variants=("${keep[@]}")
+fi
 if [ "$1" = build ]; then
   mkdir -p ab
   for v in "${variants[@]}"; do
