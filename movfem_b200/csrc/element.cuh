@@ -94,6 +94,9 @@ __global__ void node_kernel(int n0, int npt, double omega, const double *__restr
 #ifndef MOVFEM_RHS_PER_SLOT
 #define MOVFEM_RHS_PER_SLOT 0   // A/B builds: 1 = RHS phase with one thread per (element, slot) instead of per group of four slots
 #endif
+#ifndef MOVFEM_GEO_EARLY_REQ
+#define MOVFEM_GEO_EARLY_REQ 0  // A/B builds: 1 = phase B2 reads z and the x/y lines from a small copy made during B1, so the staged node
+#endif                          // records are dead after B1 and the next batch's bulk copies are issued one phase earlier (B2 + RHS to land)
 #ifndef MOVFEM_GEO_PREFETCH
 #define MOVFEM_GEO_PREFETCH 0   // A/B builds: 1 = L2 prefetch of the next batch's node records during phase B2.  ncu (r01): 19 % of
 #endif                          // geometry_kernel's warp samples sit in the wait for the node-record bulk copies (phase A)
@@ -143,7 +146,9 @@ struct ElemCfg {
     static constexpr size_t ATAB_D = (size_t)NGP * MEP + (size_t)MN * 4 * NGPP, GEO_D = (size_t)EB * NGP * GEO;
     static constexpr int NSTR = MN * NDW + 2;              // per-element stride of the node records (+16 B: bank shift)
     static constexpr size_t NODES_D = (size_t)EB * NSTR;
-    static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + NODES_D + EB + 1) + sizeof(int) * (EB * 4 + 2 * MEP + 2 * EB + 3 * MN);
+    static constexpr int ZXY = MN + 6;                      // MOVFEM_GEO_EARLY_REQ: per element z of every node, 3 x lines, 3 y lines
+    static constexpr size_t ZXY_D = MOVFEM_GEO_EARLY_REQ ? (size_t)((EB * ZXY + 1) & ~1) : 0;
+    static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + NODES_D + ZXY_D + EB + 1) + sizeof(int) * (EB * 4 + 2 * MEP + 2 * EB + 3 * MN);
     static_assert((ATAB_D % 2) == 0 && (GEO_D % 2) == 0, "16-byte alignment of the smem regions");
     static_assert(32 % EB == 0, "a batch of the contraction (32 lanes) is a whole number of geometry batches");
 };
@@ -198,7 +203,10 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
     double *s_dN = s_phi + NGP * MEP;                              // [MN][4][NGPP]: dN/dxi (0..2), N (3); Gauss point fastest
     double *s_geo = s_phi + CFG::ATAB_D;                              // [NGP][EB][GEO]
     double *s_nodes = s_geo + CFG::GEO_D;                             // [EB][MN][NDW]
-    int64_t *s_rbase = reinterpret_cast<int64_t *>(s_nodes + CFG::NODES_D);   // [EB] base node id of the batch being prefetched
+#if MOVFEM_GEO_EARLY_REQ
+    double *s_zxy = s_nodes + CFG::NODES_D;                           // [EB][MN + 6]
+#endif
+    int64_t *s_rbase = reinterpret_cast<int64_t *>(s_nodes + CFG::NODES_D + CFG::ZXY_D);   // [EB] base node id of the batch being prefetched
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_rbase + EB);     // mbarrier of the node-record bulk copies
     int *s_el = reinterpret_cast<int *>(s_bar + 1);                   // [EB][4]: element id, GPML flags
     int *s_slot = s_el + EB * 4;                                      // [MEP] slot -> local DOF (0-based) or -1
@@ -282,10 +290,31 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         mbar_wait(s_bar, node_phase);
         node_phase ^= 1;
         __syncthreads();
-#if MOVFEM_GEO_PREFETCH
-        // A/B variant: resolve the NEXT batch's node ids already here (s_rbase / s_rxy have no reader during B1) so that
-        // phase B2 can start pulling its records into L2 one phase before the bulk copies are issued
+#if MOVFEM_GEO_PREFETCH || MOVFEM_GEO_EARLY_REQ
+        // A/B variants: resolve the NEXT batch's node ids already here (s_rbase / s_rxy have no reader during B1) so that
+        // phase B2 can start pulling its records into L2 (PREFETCH) or issue the bulk copies themselves (EARLY_REQ)
         if (batch + (int)gridDim.x < nbatch) prepare_request(batch + gridDim.x);
+#endif
+#if MOVFEM_GEO_EARLY_REQ
+        {   // what B2 needs from the staged records: z of every node and the 2 or 3 distinct x / y values
+            constexpr int NORDc = MN == 8 ? 2 : 3;
+            for (int i = tid; i < nb * CFG::ZXY; i += CFG::THREADS) {
+                const int cs = i / CFG::ZXY, j = i % CFG::ZXY;
+                const double *nd = s_nodes + cs * CFG::NSTR;
+                double v = 0.0;
+                if (j < MN) v = nd[j * NDW];
+                else {
+                    const int q = j - MN;            // 0..2: xs[q], 3..5: ys[q-3]  (same sources as phase B2 below)
+                    if (q == 0) v = nd[2 * NDW + NREC];
+                    else if (q == NORDc - 1) v = nd[NREC];
+                    else if (q == 1 && NORDc == 3) v = nd[9 * NDW + NREC];
+                    else if (q == 3) v = nd[NREC + 1];
+                    else if (q == 3 + NORDc - 1) v = nd[NDW + NREC + 1];
+                    else if (q == 4 && NORDc == 3) v = nd[8 * NDW + NREC + 1];
+                }
+                s_zxy[cs * CFG::ZXY + j] = v;
+            }
+        }
 #endif
 
         // ---- phase B1: interpolate node data to the Gauss points (p_intmodels problem.f90:139-142 and the N_l-weighted
@@ -350,7 +379,9 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         __syncthreads();
 
         // ---- phase B2: one thread per (Gauss point, element): J, G, GPML, source -> Q|P, T (scratch), R (in place) ----
-#if MOVFEM_GEO_PREFETCH
+#if MOVFEM_GEO_EARLY_REQ
+        if (batch + (int)gridDim.x < nbatch) request_nodes(batch + gridDim.x);   // s_nodes is dead: lands during B2 + RHS
+#elif MOVFEM_GEO_PREFETCH
         if (batch + (int)gridDim.x < nbatch) {
             const int nbn = min(EB, A.nlist - (batch + (int)gridDim.x) * EB);
             for (int i = tid; i < nbn * MN; i += CFG::THREADS) {
@@ -377,12 +408,22 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                 // tensor-product lines (2 or 3 distinct values per element): loaded once, selected per node at compile time
                 constexpr int NORD = MN == 8 ? 2 : 3;
                 double xs[3], ys[3];
+#if MOVFEM_GEO_EARLY_REQ
+                const double *zx = s_zxy + s * CFG::ZXY;
+                xs[0] = zx[MN]; xs[NORD - 1] = zx[MN + NORD - 1]; ys[0] = zx[MN + 3]; ys[NORD - 1] = zx[MN + 3 + NORD - 1];
+                if (NORD == 3) { xs[1] = zx[MN + 1]; ys[1] = zx[MN + 4]; }
+#else
                 xs[0] = nd[2 * NDW + NREC]; xs[NORD - 1] = nd[NREC]; ys[0] = nd[NREC + 1]; ys[NORD - 1] = nd[NDW + NREC + 1];
                 if (NORD == 3) { xs[1] = nd[9 * NDW + NREC]; ys[1] = nd[8 * NDW + NREC + 1]; }
+#endif
                 double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, xg[3] = {0, 0, 0};
 #pragma unroll
                 for (int l = 0; l < MN; ++l) {
+#if MOVFEM_GEO_EARLY_REQ
+                    const double x = xs[kNodeI27[l] * (NORD - 1) / 2], y = ys[kNodeJ27[l] * (NORD - 1) / 2], z = zx[l];
+#else
                     const double x = xs[kNodeI27[l] * (NORD - 1) / 2], y = ys[kNodeJ27[l] * (NORD - 1) / 2], z = nd[l * NDW];
+#endif
 #pragma unroll
                     for (int mm = 0; mm < 3; ++mm) {
                         const double dn = s_dN[(l * 4 + mm) * NGPP + g];
@@ -548,7 +589,9 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         }
         __syncthreads();
 
+#if !MOVFEM_GEO_EARLY_REQ
         if (batch + (int)gridDim.x < nbatch) request_nodes(batch + gridDim.x);   // lands during the RHS phase / next wait
+#endif
 
         // ---- RHS: one thread per (element, group of four slots of one direction): blocal / f3,
         //      integration.f90:96-104,258-263.  R[d] is loaded once per Gauss point for the four slots. ----

@@ -21,6 +21,8 @@ variants=(
   "kmst1:-DMOVFEM_KM_ST=1"              # contraction: streaming stores of K_e/M_e
   "hints:-DMOVFEM_GATHER_LD=2 -DMOVFEM_GATHER_ST=1 -DMOVFEM_KM_ST=1"
   "geopf:-DMOVFEM_GEO_PREFETCH=1"       # geometry: L2 prefetch of the next batch's node records one phase before the bulk copies (19 % of the samples wait for them)
+  "geoearly:-DMOVFEM_GEO_EARLY_REQ=1"   # geometry: next batch's bulk copies issued after B1 instead of after B2 (B2 reads a small z/x/y copy)
+  "geoearly2:-DMOVFEM_GEO_EARLY_REQ=1 -DMOVFEM_RHS_PER_SLOT=1"
   "rhsslot:-DMOVFEM_RHS_PER_SLOT=1"     # geometry: RHS phase with EB*MEP tasks instead of EB*MEP/4 (72 of 256 threads busy today)
   "geoall:-DMOVFEM_RHS_PER_SLOT=1 -DMOVFEM_GEO_PREFETCH=1"
   "tabg:-DMOVFEM_TAB_GLOBAL=1"          # contraction: operand table filled from global memory instead of lane-distinct constant loads (4 % of the samples)
