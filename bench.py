@@ -323,6 +323,10 @@ def run_graft(args):
                              "unit": "GB/s", "frac": ga_bytes / (ms_ga * 1e-3) * 1e-9 / hbm_peak, "traffic": NCU_TRAFFIC_BYTES["gather_finalize_kernel"],
                              "peak_source": f"MEASURED_PEAKS.json ({hbm_src})", "bytes_per_nnz": BYTES_PER_NNZ_UPDATE, "ms_kernel": ms_ga},
         }
+        try:    # which library produced the numbers (A/B builds announce their switches in the version string)
+            line["config"]["library"] = host.lib().movfem_version().decode()
+        except Exception:   # pragma: no cover
+            pass
         try:    # informational table; never allowed to cost the line
             line["phase_roofs"] = phase_roofs(model, asm.nne, asm.nz_upper, line["phases_ms"], fp64_peak, hbm_peak)
         except Exception as exc:   # pragma: no cover

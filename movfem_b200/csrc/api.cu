@@ -651,7 +651,22 @@ int build_pattern(movfem_handle *h) {
 
 extern "C" {
 
+// A/B libraries (tools/ab_round2.sh) announce themselves: any build-time switch away from its default shows in the version string
+#define MOVFEM_STR2(x) #x
+#define MOVFEM_STR(x) MOVFEM_STR2(x)
+#if MOVFEM_TALL_TILES || MOVFEM_FOLD_PRODUCER || MOVFEM_TAB_GLOBAL || MOVFEM_KM_ST || MOVFEM_GATHER_LD || MOVFEM_GATHER_ST || MOVFEM_GEO_PREFETCH || \
+    MOVFEM_GEO_EARLY_REQ || MOVFEM_RHS_PER_SLOT || MOVFEM_CON_UNROLL != 3 || MOVFEM_CON12_W != 6 || MOVFEM_CON36_W != 15 || MOVFEM_CON36P_W != 12 || \
+    MOVFEM_CON54_W != 15 || MOVFEM_CON36_STAGES != 5 || MOVFEM_FIN_THREADS != 128
+const char *movfem_version(void) {
+    return "movfem_b200 0.1.0 (sm_100a) A/B build: tall=" MOVFEM_STR(MOVFEM_TALL_TILES) "x" MOVFEM_STR(MOVFEM_TALL_RG) " fold=" MOVFEM_STR(MOVFEM_FOLD_PRODUCER)
+           " tabg=" MOVFEM_STR(MOVFEM_TAB_GLOBAL) " kmst=" MOVFEM_STR(MOVFEM_KM_ST) " gld=" MOVFEM_STR(MOVFEM_GATHER_LD) " gst=" MOVFEM_STR(MOVFEM_GATHER_ST)
+           " geopf=" MOVFEM_STR(MOVFEM_GEO_PREFETCH) " geoearly=" MOVFEM_STR(MOVFEM_GEO_EARLY_REQ) " rhsslot=" MOVFEM_STR(MOVFEM_RHS_PER_SLOT)
+           " unroll=" MOVFEM_STR(MOVFEM_CON_UNROLL) " w12=" MOVFEM_STR(MOVFEM_CON12_W) " w36=" MOVFEM_STR(MOVFEM_CON36_W) " w36p=" MOVFEM_STR(MOVFEM_CON36P_W)
+           " w54=" MOVFEM_STR(MOVFEM_CON54_W) " st36=" MOVFEM_STR(MOVFEM_CON36_STAGES) " fin=" MOVFEM_STR(MOVFEM_FIN_THREADS);
+}
+#else
 const char *movfem_version(void) { return "movfem_b200 0.1.0 (sm_100a)"; }
+#endif
 
 const char *movfem_last_error(const movfem_handle *h) { return h ? h->err : "null handle"; }
 

@@ -25,6 +25,8 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/movfem_b200.h but not exported"
     assert set(host.EXPORTED_SYMBOLS) <= set(names)
     assert b"sm_100a" in host.lib().movfem_version()
+    if not os.environ.get("MOVFEM_B200_LIB"):     # the in-tree library is the default configuration, never an A/B variant
+        assert b"A/B" not in host.lib().movfem_version()
 
 
 def test_desc_layout_matches_header():
