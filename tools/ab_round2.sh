@@ -73,7 +73,14 @@ for mb in 24 48 96; do
 done
 MOVFEM_GATHER_TEMPLATE=1 timeout 150 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab2_tmpl.json 2> gpurun_out/ab2_tmpl.err || true
 summary gpurun_out/ab2_tmpl.json gather_template
-# the me=12 variants matter on the linear meshes: config 4 sweep (cold first frequency + cached ones)
+# the me=12 variants matter on the linear meshes: config 5 at half scale (cold single-frequency assembly, GPML Fang) ...
+for name in base c12w7 c12w3 fold16 fold12 geoearly geoearly2 rhsslot tabg gld3 hints; do
+  if [ "$name" = base ]; then unset MOVFEM_B200_LIB; else export MOVFEM_B200_LIB=$PWD/ab/lib_$name.so; [ -f "$MOVFEM_B200_LIB" ] || continue; fi
+  timeout 200 python tools/slab_bench.py --scale 0.5 --steps 3 > gpurun_out/ab2_slab_$name.json 2> gpurun_out/ab2_slab_$name.err || true
+  echo "config5 x0.5 $name: $(python -c "
+import json,sys; b=json.load(open(sys.argv[1])); s=b.get('stats_rank0',{}); print(round(b['ms_per_assembly_max_over_ranks'],3),'ms', {k: round(s[k],3) for k in ('ms_node','ms_geometry','ms_contract','ms_gather') if k in s})" gpurun_out/ab2_slab_$name.json 2>/dev/null)"
+done
+# ... and the config 4 sweep (cold first frequency + cached ones)
 for name in base c12w7 c12w3; do
   if [ "$name" = base ]; then unset MOVFEM_B200_LIB; else export MOVFEM_B200_LIB=$PWD/ab/lib_$name.so; [ -f "$MOVFEM_B200_LIB" ] || continue; fi
   timeout 200 python tools/sweep_bench.py > gpurun_out/ab2_sweep_$name.json 2> gpurun_out/ab2_sweep_$name.err || true
