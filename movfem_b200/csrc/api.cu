@@ -670,6 +670,29 @@ const char *movfem_version(void) { return "movfem_b200 0.1.0 (sm_100a)"; }
 
 const char *movfem_last_error(const movfem_handle *h) { return h ? h->err : "null handle"; }
 
+// Experiment (MOVFEM_L2_PERSIST_MB=<n>, off by default): keep the Q|P,T scratch resident in L2 between geometry_kernel and
+// contract_kernel with an access-policy window on the launching stream (use together with MOVFEM_SCRATCH_MB <= n so that a
+// chunk fits the persisting carve-out).  ncu (r01): 10.6 % / 17 % of the contraction's warp samples wait for ring data.
+static int apply_l2_window(movfem_handle *h) {
+    const char *mb = getenv("MOVFEM_L2_PERSIST_MB");
+    if (!mb || !h->d_qt) return 0;
+    const size_t want = (size_t)std::max(1, atoi(mb)) << 20;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    const size_t carve = std::min(want, (size_t)prop.persistingL2CacheMaxSize);
+    if (carve == 0) return 0;
+    CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = h->d_qt;
+    attr.accessPolicyWindow.num_bytes = std::min(h->qt_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)std::max<size_t>(attr.accessPolicyWindow.num_bytes, 1));
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CK(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return 0;
+}
+
 int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     if (!d || !out) return MOVFEM_E_BADARG;
     *out = nullptr;
@@ -812,6 +835,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
         h->qt_bytes = std::max(std::min(need, cap), (size_t)51 * cb);
         CK(cudaMalloc((void **)&h->d_qt, h->qt_bytes));
         CK(cudaMemset(h->d_qt, 0, h->qt_bytes));   // lanes past the end of a ragged last batch read zeros, not NaNs
+        if (int rc_l2 = apply_l2_window(h)) return rc_l2;
     }
     CK(dmalloc(&h->d_a, (size_t)h->nzu));   // the compacted copies (a_c, irn_c, jcn_c) are allocated on first use
     CK(dmalloc(&h->d_rhs, (size_t)2 * std::max(h->nrows, 1)));
@@ -869,7 +893,7 @@ int movfem_set_stream(movfem_handle *h, void *cuda_stream) {
     CK(cudaStreamSynchronize(h->stream));
     if (h->own_stream) { CK(cudaStreamDestroy(h->stream)); h->own_stream = false; }
     h->stream = (cudaStream_t)cuda_stream;
-    return MOVFEM_OK;
+    return apply_l2_window(h);
 }
 
 int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, const double *g_sigma_dev, int32_t mode) {

@@ -71,6 +71,10 @@ for mb in 24 48 96; do
   MOVFEM_SCRATCH_MB=$mb timeout 150 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab2_scratch$mb.json 2> gpurun_out/ab2_scratch$mb.err || true
   summary gpurun_out/ab2_scratch$mb.json scratch${mb}MB
 done
+for cfg in "48:64" "32:48" "64:96"; do   # scratch chunk : persisting-L2 carve-out (MB): the chunk stays in L2 between the two kernels
+  MOVFEM_SCRATCH_MB=${cfg%%:*} MOVFEM_L2_PERSIST_MB=${cfg#*:} timeout 150 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab2_l2p_${cfg%%:*}.json 2> gpurun_out/ab2_l2p_${cfg%%:*}.err || true
+  summary gpurun_out/ab2_l2p_${cfg%%:*}.json scratch${cfg%%:*}MB+persist${cfg#*:}MB
+done
 MOVFEM_GATHER_TEMPLATE=1 timeout 150 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab2_tmpl.json 2> gpurun_out/ab2_tmpl.err || true
 summary gpurun_out/ab2_tmpl.json gather_template
 # the me=12 variants matter on the linear meshes: config 5 at half scale (cold single-frequency assembly, GPML Fang) ...
