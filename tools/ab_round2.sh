@@ -4,6 +4,9 @@
 #   tools/ab_round2.sh build        here, no GPU: builds ab/lib_<variant>.so (about 20 s each)
 #   gpurun --timeout 900 -- 'tools/ab_round2.sh run'      on the B200: bench.py (config 2) per variant, then the env-var runs
 # Results: gpurun_out/ab2_<variant>.json (bench lines) and the one-line summaries on stdout.
+# ab/ is git-ignored but travels with every gpurun snapshot (about 5 MB per library): build only what the call needs
+# (ONLY="...") and remove ab/ afterwards.  A full run is roughly 30 variants x (hash 10 s + bench 30 s) + the sweeps: split it
+# over two or three calls with ONLY.
 set -e
 cd "$(dirname "$0")/.."
 variants=(
