@@ -68,6 +68,7 @@ for v in "${variants[@]}"; do
   summary gpurun_out/ab2_$name.json $name
 done
 unset MOVFEM_B200_LIB
+[ -n "$SKIP_ENV" ] && exit 0      # SKIP_ENV=1: library variants only
 # env-var experiments on the default library: scratch chunks small enough to stay in the 126 MB L2 between geometry_kernel
 # and contract_kernel (config 2 writes 124 MB of Q|T for the unstretched list), and the structured gather
 for mb in 24 48 96; do
