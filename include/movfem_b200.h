@@ -91,6 +91,8 @@ typedef struct movfem_stats {
     int64_t launches;     /* kernels launched by the call                       */
     double ms_geometry;   /* part of ms_element: geometry_kernel launches        */
     double ms_contract;   /* part of ms_element: contract_kernel launches        */
+    double ms_exact;      /* part of ms_element: exact_kernel launches (reference-order re-evaluation of residue pairs) */
+    int64_t nflagged;     /* (element, pair)s re-evaluated in the reference's operation order                          */
 } movfem_stats;
 
 /* Create: uploads the mesh once, builds gne + pattern ON THE DEVICE

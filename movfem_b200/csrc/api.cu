@@ -20,8 +20,8 @@
 #include "contract.cuh"
 #include "dirichlet.cuh"
 #include "element.cuh"
+#include "exact.cuh"
 #include "finalize.cuh"
-#include "gather_tmpl.cuh"
 #include "pattern.cuh"
 #include "geo.cuh"
 #include "ref_element.h"
@@ -95,14 +95,18 @@ struct movfem_handle {
     int64_t *d_cptr;         // transient (pattern build); replaced by the compressed d_cblk / d_off16
     int64_t *d_cblk;
     uint16_t *d_off16;
-    // structured fast path of the gather (gather_tmpl.cuh): template of an interior element's rows, verified per element
-    int64_t *d_estart;       // first entry of each owned element's rows (+ sentinel)
-    uint8_t *d_conform, *d_blkgen;
-    TmplEntry *d_tmpl;
-    int2 *d_groups;
-    int *d_blklist, *d_blkfull;   // generic block list; entry count of every block (initial value of the non-zero counters)
-    int tmpl_nq, tmpl_groups, tmpl_nblk_generic;
-    bool tmpl_ok;
+    // reference-order re-evaluation of the round-off-residue pairs (exact.cuh)
+    double2 *d_escale;       // [km_rows] element scales (K, M) from geometry_kernel
+    uint32_t *d_pairflags;   // [km_rows][flagW] pairs to re-evaluate
+    uint32_t *d_batchany;    // [km_rows/32] rows with flagged pairs
+    unsigned long long *d_nflag;   // [0] flagged (element, pair)s of the last cold pass, [1] entries in doubt of the last gather
+    unsigned long long *h_nflag;   // pinned copy
+    int flagW;
+    bool flags_dirty;        // pairflags / batchany hold bits
+    int64_t nflag_last;
+    double w32_last, omega_last;
+    int cache_last;
+    bool have_result;
     uint32_t *d_pure;        // bit per entry: only unstretched elements contribute (gathered K/M cacheable across a sweep)
     double2 *d_kmg;          // the cache: gathered (K, M) per entry, allocated on the second frequency if memory allows
     int kmg_state;           // 0 not allocated, 1 allocated / to be filled, 2 valid, -1 does not fit
@@ -392,6 +396,7 @@ int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist,
     for (int64_t cb = 0; cb < nbatch_all; cb += chunk_b) {
         const int off = (int)(cb * 32), n = (int)std::min<int64_t>(nlist - off, chunk_b * 32);
         A.list = d_list + off; A.nlist = n; A.qt = DO_QT ? h->d_qt : nullptr;
+        A.escale = DO_QT ? h->d_escale + km_row0 + off : nullptr;
         const int ngb = (n + GEO::EB - 1) / GEO::EB;
         if (kernel_event(h, 0, true)) return MOVFEM_E_CUDA;
         gk<<<std::max(1, std::min(ngb, std::max(1, g_per_sm) * h->num_sms)), GEO::THREADS, GEO::SMEM, h->stream>>>(A);
@@ -402,6 +407,9 @@ int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist,
             ContractArgs C;
             C.qt = h->d_qt; C.nlist = n; C.KM = h->d_KM + (size_t)(km_row0 + off) * h->NP; C.flags = h->d_flags;
             C.skip_unless_changed = skip_unless_changed;
+            C.escale = getenv("MOVFEM_TEST_NO_L1") ? nullptr : h->d_escale + km_row0 + off;   // test hook: no element-level flags
+            C.pairflags = h->d_pairflags + (size_t)(km_row0 + off) * h->flagW;
+            C.batchany = h->d_batchany + (km_row0 + off) / 32; C.nflag = h->d_nflag; C.W = h->flagW;
             const int ncb = (n + 31) / 32;
             if (kernel_event(h, 1, true)) return MOVFEM_E_CUDA;
             ck<<<std::max(1, std::min(ncb * 6, std::max(1, c_per_sm) * h->num_sms)), CON::THREADS, CON::SMEM, h->stream>>>(C);
@@ -441,115 +449,19 @@ int run_elements(movfem_handle *h, ElemArgs &A, bool full) {
 void free_all(movfem_handle *h) {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_xp, h->d_yp, h->d_zp, h->d_mu, h->d_sigma, h->d_nodes, h->d_tab, h->d_share, h->d_gne, h->d_ownE,
-                    h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_cblk, h->d_off16, h->d_pure, h->d_kmg, h->d_estart, h->d_conform, h->d_blkgen, h->d_tmpl, h->d_groups, h->d_blklist, h->d_blkfull, h->d_src, h->d_KM,
+                    h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_cblk, h->d_off16, h->d_pure, h->d_kmg, h->d_escale, h->d_pairflags, h->d_batchany, h->d_nflag, h->d_src, h->d_KM,
                     h->d_be, h->d_qt, h->d_bdtab, h->d_bdlist, h->d_kmrow, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum, h->d_total, h->d_csr,
                     h->d_status, h->d_flags};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_count) cudaFreeHost(h->h_count);
+    if (h->h_nflag) cudaFreeHost(h->h_nflag);
     for (int i = 0; i < EV_COUNT; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
-}
-
-// Structured fast path of the gather: extract the template from one interior element, verify every candidate element
-// against it on the device, group the conforming elements by column and mark the entry blocks left to the indexed gather.
-// Any failure to find a usable template just leaves tmpl_ok = false (the indexed gather then handles every block).
-int build_gather_template(movfem_handle *h, const int64_t *d_base, const int64_t *d_rowptr) {
-    const MeshDims &m = h->m;
-    h->tmpl_ok = false;
-    // Opt-in (MOVFEM_GATHER_TEMPLATE=1): measured on B200 the structured path is bit-identical but not faster than the
-    // indexed gather (config 2: 284 us + 68 us for the non-conforming blocks against 320 us; it trades LSU wavefronts
-    // for instructions), so it is off by default and costs nothing at create time.
-    if (!getenv("MOVFEM_GATHER_TEMPLATE") || m.nx < 4 || m.ny < 4 || m.nz < 4 || h->nzu == 0) return 0;
-    const int n_own = h->e_own_end - h->e_base;
-    // reference element: (ie, 2, 2) with ie the second layer the handle owns
-    const int ie0 = h->e_base / (m.ny * m.nz) + 1, ie_ref = std::max(ie0, 2);
-    const int e_ref = (ie_ref - 1) * m.ny * m.nz + m.nz + 1;
-    if (ie_ref >= m.nx || e_ref + m.ny * m.nz + m.nz + 1 >= h->e_end || e_ref >= h->e_own_end) return 0;
-    int64_t rb[2];
-    CK(cudaMemcpy(rb, d_base + e_ref, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost));
-    const int nrows_t = (int)(rb[1] - rb[0]);
-    if (nrows_t <= 0 || nrows_t > 64) return 0;
-    std::vector<int64_t> rp(nrows_t + 1);
-    CK(cudaMemcpy(rp.data(), d_rowptr + (rb[0] - h->row_lo), sizeof(int64_t) * (nrows_t + 1), cudaMemcpyDeviceToHost));
-    const int NQ = (int)(rp[nrows_t] - rp[0]);
-    std::vector<int> rowlen(nrows_t);
-    for (int r = 0; r < nrows_t; ++r) rowlen[r] = (int)(rp[r + 1] - rp[r]);
-    std::vector<int64_t> cp(NQ + 1);
-    CK(cudaMemcpy(cp.data(), h->d_cptr + rp[0], sizeof(int64_t) * (NQ + 1), cudaMemcpyDeviceToHost));
-    std::vector<uint32_t> sr((size_t)(cp[NQ] - cp[0]));
-    CK(cudaMemcpy(sr.data(), h->d_src + cp[0], sizeof(uint32_t) * sr.size(), cudaMemcpyDeviceToHost));
-    const int eo[8] = {0, 1, m.nz, m.nz + 1, m.ny * m.nz, m.ny * m.nz + 1, m.ny * m.nz + m.nz, m.ny * m.nz + m.nz + 1};
-    std::vector<TmplEntry> tm(NQ);
-    for (int q = 0; q < NQ; ++q) {
-        const int nc = (int)(cp[q + 1] - cp[q]);
-        if (nc < 1 || nc > 4) return 0;
-        for (int k = 0; k < 4; ++k) tm[q].c[k] = (uint16_t)kTmplNone;
-        for (int k = 0; k < nc; ++k) {
-            const uint32_t s = sr[(size_t)(cp[q] - cp[0]) + k];
-            const int kr = (int)((s >> 5) / (uint32_t)h->NP) * 32 + (int)(s & 31), p = (int)((s >> 5) % (uint32_t)h->NP);
-            int off = -1;
-            for (int o = 0; o < 8; ++o)
-                if (h->kmrow[e_ref + eo[o] - h->e_base] == kr) off = o;
-            if (off < 0 || p > 0x7ff) return 0;
-            tm[q].c[k] = (uint16_t)((off << 11) | p);
-        }
-    }
-    int *d_rowlen = nullptr;
-    CK(dmalloc(&d_rowlen, (size_t)nrows_t));
-    CK(cudaMemcpy(d_rowlen, rowlen.data(), sizeof(int) * nrows_t, cudaMemcpyHostToDevice));
-    CK(dmalloc(&h->d_tmpl, (size_t)NQ));
-    CK(cudaMemcpy(h->d_tmpl, tm.data(), sizeof(TmplEntry) * NQ, cudaMemcpyHostToDevice));
-    CK(dmalloc(&h->d_estart, (size_t)n_own + 1));
-    CK(dmalloc(&h->d_conform, (size_t)n_own));
-    elem_entry_start_kernel<<<(n_own + 256) / 256, 256, 0, h->stream>>>(n_own, h->e_base, d_base, h->row_lo, d_rowptr, h->d_estart);
-    template_verify_kernel<<<(n_own + 127) / 128, 128, 0, h->stream>>>(m, n_own, h->e_base, h->e_end, d_base, h->row_lo, d_rowptr, h->d_cptr, h->d_src,
-                                                                      h->d_kmrow, h->NP, nrows_t, d_rowlen, NQ, h->d_tmpl, h->d_conform);
-    const int nblk = (int)((h->nzu + kFinThreads - 1) / kFinThreads);
-    CK(dmalloc(&h->d_blkgen, (size_t)nblk));
-    template_block_kernel<<<(nblk + 255) / 256, 256, 0, h->stream>>>(h->nzu, nblk, h->e_base, n_own, h->d_irn, 0, h->d_ownE, h->d_estart, h->d_conform,
-                                                                    h->d_blkgen);
-    h->launches += 3;
-    CK(cudaGetLastError());
-    std::vector<uint8_t> conf(n_own), gen(nblk);
-    CK(cudaMemcpyAsync(conf.data(), h->d_conform, n_own, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(gen.data(), h->d_blkgen, nblk, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    CK(cudaFree(d_rowlen));
-    // groups: runs of consecutive conforming elements inside one (ie, je) column, at most 32 long
-    std::vector<int2> groups;
-    for (int col = 0; col < n_own / m.nz; ++col) {
-        int k = 0;
-        while (k < m.nz) {
-            const int i = col * m.nz + k;
-            if (!conf[i]) { ++k; continue; }
-            int n = 1;
-            while (k + n < m.nz && n < 32 && conf[i + n]) ++n;
-            groups.push_back(make_int2(h->e_base + i, n));
-            k += n;
-        }
-    }
-    std::vector<int> blklist;
-    for (int b = 0; b < nblk; ++b)
-        if (gen[b]) blklist.push_back(b);
-    if (groups.empty()) return 0;
-    CK(dmalloc(&h->d_groups, groups.size()));
-    CK(cudaMemcpy(h->d_groups, groups.data(), sizeof(int2) * groups.size(), cudaMemcpyHostToDevice));
-    CK(dmalloc(&h->d_blklist, blklist.size()));
-    if (!blklist.empty()) CK(cudaMemcpy(h->d_blklist, blklist.data(), sizeof(int) * blklist.size(), cudaMemcpyHostToDevice));
-    {
-        std::vector<int> full(nblk, kFinThreads);
-        full[nblk - 1] = (int)(h->nzu - (int64_t)(nblk - 1) * kFinThreads);
-        CK(dmalloc(&h->d_blkfull, (size_t)nblk));
-        CK(cudaMemcpy(h->d_blkfull, full.data(), sizeof(int) * nblk, cudaMemcpyHostToDevice));
-    }
-    h->tmpl_nq = NQ; h->tmpl_groups = (int)groups.size(); h->tmpl_nblk_generic = (int)blklist.size();
-    h->tmpl_ok = true;
-    return 0;
 }
 
 int build_pattern(movfem_handle *h) {
@@ -639,7 +551,6 @@ int build_pattern(movfem_handle *h) {
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(h->stream));
-    rc = build_gather_template(h, d_base, d_rowptr);
     CK(cudaFree(h->d_cptr));
     h->d_cptr = nullptr;
     CK(cudaFree(d_base));
@@ -704,6 +615,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     if (d->dirichlet && (d->bd_inimod < 1 || d->bd_inimod > 3 || (d->bd_inimod == 3 && (d->bd_nl < 1 || d->bd_nl > 16)))) return MOVFEM_E_BADARG;
     if ((d->ie_lo != 0 || d->ie_hi != 0) && !(d->ie_lo >= 1 && d->ie_lo <= d->ie_hi && d->ie_hi <= d->g_nx - 1)) return MOVFEM_E_BADARG;
     if (!d->dirichlet && (d->nextd < 1 || 2 * d->nextd > std::min(d->g_nx, std::min(d->g_ny, d->g_nz)) - 1)) return MOVFEM_E_BADARG;
+    if (!d->dirichlet && (d->nzl_top < 1 || d->nzl_top > d->g_nz - 1)) return MOVFEM_E_BADARG;   // init_gpml reads g_zp(last - nzl_top*(nord-1))
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return MOVFEM_E_NOGPU;
 
@@ -735,6 +647,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     for (int i = 0; i < EV_COUNT; ++i) CK(cudaEventCreate(&h->ev[i]));
     CK(cudaMallocHost((void **)&h->h_status, 4 * sizeof(int)));
     CK(cudaMallocHost((void **)&h->h_count, sizeof(int64_t)));
+    h->h_status[0] = 0; *h->h_count = 0;
 
     // mesh upload (once per run)
     CK(dmalloc(&h->d_xp, (size_t)m.nnx)); CK(dmalloc(&h->d_yp, (size_t)m.nny));
@@ -826,6 +739,16 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
 
     // work / result arrays
     CK(dmalloc(&h->d_KM, (size_t)h->km_rows * h->NP));
+    h->flagW = (h->NP + 31) / 32;
+    CK(dmalloc(&h->d_escale, (size_t)h->km_rows)); CK(dmalloc(&h->d_pairflags, (size_t)h->km_rows * h->flagW));
+    CK(dmalloc(&h->d_batchany, (size_t)h->km_rows / 32 + 1)); CK(dmalloc(&h->d_nflag, 2));
+    CK(cudaMemset(h->d_escale, 0, sizeof(double2) * (size_t)h->km_rows));
+    CK(cudaMemset(h->d_pairflags, 0, sizeof(uint32_t) * (size_t)h->km_rows * h->flagW));
+    CK(cudaMemset(h->d_batchany, 0, sizeof(uint32_t) * ((size_t)h->km_rows / 32 + 1)));
+    CK(cudaMemset(h->d_nflag, 0, 2 * sizeof(unsigned long long)));
+    CK(cudaMallocHost((void **)&h->h_nflag, 2 * sizeof(unsigned long long)));
+    h->h_nflag[0] = h->h_nflag[1] = 0;
+    h->flags_dirty = false; h->nflag_last = 0; h->have_result = false;
     CK(dmalloc(&h->d_be, (size_t)(h->e_end - h->e_base) * m.me * 4));
     {   // Q|P,T scratch: whole 32-element batches of the larger of the two lists, capped (launch_elements chunks)
         const size_t cb = sizeof(double) * (size_t)m.ngp * 32;
@@ -896,6 +819,52 @@ int movfem_set_stream(movfem_handle *h, void *cuda_stream) {
     return apply_l2_window(h);
 }
 
+// exact_kernel over both element lists (exact.cuh): re-evaluates the flagged pairs in the reference's operation order
+static int launch_exact(movfem_handle *h, double omega) {
+    const MeshDims &m = h->m;
+    ExactArgs X;
+    X.m = m; X.pml = h->pml; X.omega = omega; X.T = h->d_tab; X.nodes = h->d_nodes; X.xp = h->d_xp; X.yp = h->d_yp;
+    X.batchany = h->d_batchany; X.pairflags = h->d_pairflags; X.W = h->flagW; X.NP = h->NP; X.gne = h->d_gne; X.KM = h->d_KM;
+    auto run = [&](auto kern, size_t smem) -> int {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int pass = 0; pass < 2; ++pass) {
+            X.list = pass ? h->d_list_pml : h->d_list_plain;
+            X.nlist = pass ? h->n_pml : h->n_plain;
+            X.row0 = pass ? (int64_t)(h->n_plain + 31) / 32 * 32 : 0;
+            X.stretched = pass;
+            if (X.nlist <= 0) continue;
+            const int nb = (X.nlist + 31) / 32;
+            if (kernel_event(h, 2, true)) return MOVFEM_E_CUDA;
+            kern<<<std::min(nb, 2 * h->num_sms), 256, smem, h->stream>>>(X);
+            h->launches += 1;
+            CK(cudaGetLastError());
+            if (kernel_event(h, 2, false)) return MOVFEM_E_CUDA;
+        }
+        return 0;
+    };
+    if (m.me == 12) return run(exact_kernel<8, 12, 8>, ExactCfg<8, 12, 8>::SMEM);
+    if (m.me == 36) return run(exact_kernel<20, 36, 27>, ExactCfg<20, 36, 27>::SMEM);
+    return run(exact_kernel<27, 54, 27>, ExactCfg<27, 54, 27>::SMEM);
+}
+
+// gather + RHS + the counters' way back to the host
+static int launch_gather(movfem_handle *h, double omega, int32_t mode, int cache) {
+    cudaStream_t st = h->stream;
+    const int gmode = mode == MOVFEM_MODE_T1 ? 1 : 0;
+    if (gmode == 0) CK(cudaMemsetAsync(h->d_total, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(h->d_nflag + 1, 0, sizeof(unsigned long long), st));
+    double dk = -1.0, dm = -1.0;
+    if (const char *t = getenv("MOVFEM_TEST_DOUBT_ABS")) sscanf(t, "%lf,%lf", &dk, &dm);   // test hook (tests/test_gpu_parity.py)
+    gather_finalize_kernel<<<h->nblk_fin, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cblk, h->d_off16, h->d_src, h->d_KM, h->d_a,
+                                                              h->d_blkcnt, gmode, cache, h->d_pure, h->d_kmg, h->d_flags, nullptr, h->d_total,
+                                                              h->NP, h->flagW, h->d_pairflags, h->d_batchany, h->d_nflag + 1, dk, dm);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    if (mode == MOVFEM_MODE_T2) CK(cudaMemcpyAsync(h->h_count, h->d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h->h_nflag, h->d_nflag, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
 int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, const double *g_sigma_dev, int32_t mode) {
     if (!h || !g_sigma_dev || freq_index < 1 || (mode != MOVFEM_MODE_T1 && mode != MOVFEM_MODE_T2)) return MOVFEM_E_BADARG;
     CK(cudaSetDevice(h->device));
@@ -903,17 +872,28 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
     cudaStream_t st = h->stream;
     h->launches = 0;
     h->kev_kind.clear();
+    h->have_result = false;
     // Q17: element (1,1,1) sees the SAVEd in_pml: zeros on the first assembled frequency, the flags
     // of the last element afterwards
     if (!m.dirichlet) {
         if (freq_index == 1) h->pml.first[0] = h->pml.first[1] = h->pml.first[2] = 0;
         else get_pml(h->pml, m.nx, m.ny, m.nz, h->pml.first);
         // the cached K_e, M_e of element (1,1,1) were formed with the flags of an earlier call: recompute when they differ
-        if (h->n_pml > 0 && (h->pml.first[0] != h->km_first[0] || h->pml.first[1] != h->km_first[1] || h->pml.first[2] != h->km_first[2]))
+        if (h->n_pml > 0 && h->e_base == 0 &&
+            (h->pml.first[0] != h->km_first[0] || h->pml.first[1] != h->km_first[1] || h->pml.first[2] != h->km_first[2]))
             h->km_valid = false;
         for (int k = 0; k < 3; ++k) h->km_first[k] = h->pml.first[k];
     }
+    const bool full = !h->km_valid;
     CK(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), st));
+    if (full) {   // a cold pass re-derives the tiny-pair flags
+        if (h->flags_dirty) {
+            CK(cudaMemsetAsync(h->d_pairflags, 0, sizeof(uint32_t) * (size_t)h->km_rows * h->flagW, st));
+            CK(cudaMemsetAsync(h->d_batchany, 0, sizeof(uint32_t) * (size_t)(h->km_rows / 32 + 1), st));
+            h->flags_dirty = false;
+        }
+        CK(cudaMemsetAsync(h->d_nflag, 0, 2 * sizeof(unsigned long long), st));
+    }
     CK(cudaEventRecord(h->ev[EV_H2D], st));
     node_kernel<<<(h->node_hi - h->node_lo + 127) / 128, 128, 0, st>>>(h->node_lo, h->node_hi, omega, h->d_zp, h->d_mu, reinterpret_cast<const double2 *>(g_sigma_dev),
                                                     h->d_nodes, h->d_status, h->d_flags, h->km_valid ? 1 : 0);
@@ -923,12 +903,11 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
 
     ElemArgs A;
     A.m = m; A.pml = h->pml; A.omega = omega; A.T = h->d_tab; A.nodes = h->d_nodes; A.xp = h->d_xp; A.yp = h->d_yp;
-    A.list = nullptr; A.nlist = 0; A.e_base = h->e_base; A.qt = nullptr; A.be = h->d_be; A.status = h->d_status; A.flags = h->d_flags;
+    A.list = nullptr; A.nlist = 0; A.e_base = h->e_base; A.qt = nullptr; A.be = h->d_be; A.escale = nullptr; A.status = h->d_status; A.flags = h->d_flags;
     A.skip_unless_changed = 0;
     A.phase_mask = 3;
     if (const char *pm = getenv("MOVFEM_PHASE_MASK")) A.phase_mask = atoi(pm);   // profiling aid only
     int rc;
-    const bool full = !h->km_valid;
     if (m.me == 12) rc = run_elements<Geo12, Con12, Geo12p, Con12p>(h, A, full);
     else if (m.me == 36) rc = run_elements<Geo36, Con36, Geo36p, Con36p>(h, A, full);
     else rc = run_elements<Geo54, Con54, Geo54p, Con54p>(h, A, full);
@@ -943,12 +922,19 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
         h->launches += 1;
         CK(cudaGetLastError());
     }
+    // round-off-residue pairs in the reference's operation order (exact.cuh).  On a cold pass the flags are not known on the
+    // host yet, so the kernel is launched and finds nothing to do on meshes without such pairs; a cached frequency knows.
+    h->w32_last = f32r(omega);
+    if (!getenv("MOVFEM_NO_EXACT") && (full || h->nflag_last > 0 || h->flags_dirty)) {
+        if ((rc = launch_exact(h, omega))) return rc;
+    }
     CK(cudaEventRecord(h->ev[EV_ELEM], st));
 
-    // a later frequency of a sweep (K/M of the unstretched elements cached): keep the gathered K/M of the entries only
-    // they touch as well -- allocated on the second frequency if it fits, filled by that call, streamed afterwards
+    // a later frequency of a sweep (K/M of every element cached): keep the gathered K/M of the entries as well -- allocated
+    // on the second frequency if it fits, filled by that call, streamed afterwards.  Not on meshes with re-evaluated pairs
+    // (their imaginary parts carry w32 inside the Gauss-point sum and change with the frequency).
     int cache = 0;
-    if (!full) {
+    if (!full && h->nflag_last == 0 && !h->flags_dirty) {
         if (h->kmg_state == 0) {
             size_t fr = 0, tot = 0;
             CK(cudaMemGetInfo(&fr, &tot));
@@ -959,46 +945,17 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
         if (h->kmg_state == 1) { cache = 1; h->kmg_state = 2; }
         else if (h->kmg_state == 2) cache = 2;
     } else if (h->kmg_state == 2) h->kmg_state = 1;   // cold assembly: the cache content is stale
-    const int gmode = mode == MOVFEM_MODE_T1 ? 1 : 0;
-    const bool use_tmpl = cache == 0 && h->tmpl_ok;
-    if (gmode == 0 && !use_tmpl) CK(cudaMemsetAsync(h->d_total, 0, sizeof(unsigned long long), st));
-    if (use_tmpl) {
-        // cold assembly: conforming interior elements take the structured path, the indexed gather keeps the other blocks
-        if (gmode == 0) CK(cudaMemcpyAsync(h->d_blkcnt, h->d_blkfull, sizeof(int) * (size_t)h->nblk_fin, cudaMemcpyDeviceToDevice, st));
-        if (h->tmpl_nblk_generic > 0)
-            gather_finalize_kernel<<<h->tmpl_nblk_generic, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cblk, h->d_off16, h->d_src, h->d_KM, h->d_a,
-                                                                               h->d_blkcnt, gmode, 0, h->d_pure, h->d_kmg, h->d_flags, h->d_blklist, nullptr);
-        const int64_t items = (int64_t)h->tmpl_groups * ((h->tmpl_nq + 31) / 32);
-        gather_template_kernel<<<(unsigned)((items + kTmplWarps - 1) / kTmplWarps), kTmplWarps * 32, 0, st>>>(
-            h->tmpl_groups, h->d_groups, m, h->e_base, h->tmpl_nq, h->d_tmpl, h->d_estart, h->d_kmrow, h->NP, h->d_KM, h->d_a, h->d_blkgen, h->d_blkcnt,
-            f32r(omega), gmode);
-        h->launches += 1;
-    } else
-        gather_finalize_kernel<<<h->nblk_fin, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cblk, h->d_off16, h->d_src, h->d_KM, h->d_a,
-                                                                  h->d_blkcnt, gmode, cache, h->d_pure, h->d_kmg, h->d_flags, nullptr, h->d_total);
+    h->cache_last = cache; h->omega_last = omega;
+    if ((rc = launch_gather(h, omega, mode, cache))) return rc;
     rhs_kernel<<<(h->nrows + 127) / 128, 128, 0, st>>>(h->nrows, h->d_rown, reinterpret_cast<const double4 *>(h->d_be), h->d_rhs);
-    h->launches += 2;
+    h->launches += 1;
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[EV_GATHER], st));
     h->compacted = false; h->nz_last = -1; h->mode_last = mode;
     h->offsets_valid = false;
-    if (mode == MOVFEM_MODE_T2) {
-        // find_zeros: the total comes from one integer atomic per block; the per-block offsets (a 3-kernel scan) are only
-        // needed if something was stripped and are then computed in movfem_device_result
-        if (use_tmpl) {   // the structured path adjusts the block counters itself: take the total from their scan
-            const int nb = (h->nblk_fin + kScanTile - 1) / kScanTile;
-            scan_block_sums<<<nb, kScanThreads, 0, st>>>(h->d_blkcnt, h->nblk_fin, h->d_finbsum);
-            scan_block_offsets<<<1, 1024, 0, st>>>(h->d_finbsum, nb);
-            scan_finish<<<nb, kScanThreads, 0, st>>>(h->d_blkcnt, h->nblk_fin, h->d_finbsum, h->d_blkoff);
-            h->launches += 3;
-            CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(h->h_count, h->d_blkoff + h->nblk_fin, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-            h->offsets_valid = true;
-        } else
-            CK(cudaMemcpyAsync(h->h_count, h->d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    }
     CK(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(h->ev[EV_FINAL], st));
+    h->have_result = true;
     return MOVFEM_OK;
 }
 
@@ -1006,7 +963,7 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
 int movfem_device_result(const movfem_handle *hc, const int32_t **irn, const int32_t **jcn, const double **a,
                          const double **rhs, int64_t *nz) {
     movfem_handle *h = const_cast<movfem_handle *>(hc);
-    if (!h) return MOVFEM_E_BADARG;
+    if (!h || !h->have_result) return MOVFEM_E_BADARG;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     if (h->h_status[0] != 0) {
@@ -1017,6 +974,17 @@ int movfem_device_result(const movfem_handle *hc, const int32_t **irn, const int
         return s == -3 ? MOVFEM_E_SINGULAR_JAC : MOVFEM_E_SINGULAR_MODEL;
     }
     if (h->nz_last < 0) {
+        // entries whose zero test is in doubt because they cancel across elements: their contributions were flagged by the
+        // gather; re-evaluate them in the reference's order and gather again (bounded: every pass only adds flags)
+        for (int pass = 0; pass < 4 && h->h_nflag[1] > 0 && !getenv("MOVFEM_NO_EXACT"); ++pass) {
+            h->flags_dirty = true;
+            int rc = launch_exact(h, h->omega_last);
+            if (rc) return rc;
+            if ((rc = launch_gather(h, h->omega_last, h->mode_last, 0))) return rc;
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        h->nflag_last = (int64_t)h->h_nflag[0];
+        if (h->nflag_last > 0 || h->h_nflag[1] > 0) h->flags_dirty = true;
         if (h->mode_last == MOVFEM_MODE_T1) h->nz_last = h->nzu;
         else {
             h->nz_last = *h->h_count;
@@ -1048,11 +1016,12 @@ int movfem_device_result(const movfem_handle *hc, const int32_t **irn, const int
         h->stats.ms_node = ms(EV_H2D, EV_NODE); h->stats.ms_element = ms(EV_NODE, EV_ELEM);
         h->stats.ms_gather = ms(EV_ELEM, EV_GATHER); h->stats.ms_finalize = ms(EV_GATHER, EV_FINAL);
         h->stats.ms_total = ms(EV_H2D, EV_FINAL); h->stats.nz = h->nz_last; h->stats.launches = h->launches;
-        h->stats.ms_geometry = h->stats.ms_contract = 0;
+        h->stats.ms_geometry = h->stats.ms_contract = h->stats.ms_exact = 0;
+        h->stats.nflagged = h->nflag_last;
         for (size_t k = 0; k < h->kev_kind.size(); ++k) {
             float t = 0;
             cudaEventElapsedTime(&t, h->kev[2 * k], h->kev[2 * k + 1]);
-            (h->kev_kind[k] ? h->stats.ms_contract : h->stats.ms_geometry) += t;
+            (h->kev_kind[k] == 2 ? h->stats.ms_exact : (h->kev_kind[k] ? h->stats.ms_contract : h->stats.ms_geometry)) += t;
         }
     }
     if (irn) *irn = h->compacted ? h->d_irn_c : h->d_irn;
@@ -1255,7 +1224,15 @@ int movfem_debug_element(movfem_handle *h, int32_t ide, double *Ke, double *Me, 
     const int kr = h->kmrow[e];
     CK(cudaMemcpy2D(km.data(), sizeof(double2), h->d_KM + ((size_t)(kr >> 5) * h->NP << 5) + (kr & 31), 32 * sizeof(double2), sizeof(double2), h->NP,
                     cudaMemcpyDeviceToHost));
-    for (int p = 0; p < h->NP; ++p) { if (Ke) Ke[p] = km[p].x; if (Me) Me[p] = km[p].y; }
+    for (int p = 0; p < h->NP; ++p) {
+        double kx = km[p].x, mx = km[p].y;
+        if (std::fabs(kx) < kExactBelow && std::fabs(mx) < kExactBelow) {   // re-evaluated pair (exact.cuh): K_e, and w32*M_e summed the reference's way
+            kx *= kExactUnscale;
+            mx = h->w32_last != 0.0 ? mx * kExactUnscale / h->w32_last : 0.0;
+        }
+        if (Ke) Ke[p] = kx;
+        if (Me) Me[p] = mx;
+    }
     if (be) CK(cudaMemcpy(be, h->d_be + e * h->m.me * 4, sizeof(double) * h->m.me * 4, cudaMemcpyDeviceToHost));
     return MOVFEM_OK;
 }

@@ -80,7 +80,15 @@ struct ContractArgs {
     double2 *KM;          // K/M store at this launch's first row: [batch][NP][32 lanes]
     const int *flags;     // flags[1]: Re sigma changed (cache refresh launches)
     int skip_unless_changed;
+    // tiny-pair flags (exact.cuh): a pair whose K_e and M_e are both below kTinyRel of the element's scale is a round-off
+    // residue of a mathematically zero entry; the reference's residue decides what rem_zeros strips, so it is re-evaluated
+    const double2 *escale;          // [list position] (K scale, M scale) from geometry_kernel
+    uint32_t *pairflags;            // [row][W] at this launch's first row
+    uint32_t *batchany;             // [row0/32 + batch]
+    unsigned long long *nflag;      // number of flagged (element, pair)s
+    int W;
 };
+constexpr double kTinyRelC = 1e-9, kFlagAbsC = 0x1p-400;
 
 // four consecutive doubles (16-byte aligned) as two 128-bit loads
 __device__ __forceinline__ void ld4(double (&v)[4], const double *p) {
@@ -294,8 +302,8 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(Contr
             //   d=0: (dphi_2, -dphi_1)   d=1: -(dphi_2, -dphi_0)   d=2: (dphi_1, -dphi_0)
             const int k1I = dI == 2 ? 1 : 2, k2I = dI == 0 ? 1 : 0, k1J = dJ == 2 ? 1 : 2, k2J = dJ == 0 ? 1 : 0;
             const double tau = ((dI == 1) != (dJ == 1)) ? -1.0 : 1.0;
-#pragma unroll 1
             const int first = (b * CFG::NTILES + t_lo - pos0) % W;   // warp that owns the class's first tile
+#pragma unroll 1
             for (int t = t_lo + ((warp - first + W) % W); t < t_hi; t += W) {
                 const int ti = c_ct.tile_ti[t], tj = c_ct.tile_tj[t];
                 double accK[16], accM[16];
@@ -362,6 +370,11 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(Contr
                 }
                 // write-out: packed lower triangle by LOCAL DOF index, 32 elements interleaved -> 512-byte coalesced stores
                 if (live) {
+                    int nfl = 0;
+                    // tiny-pair test against the element's scale (re-read per tile: nothing extra lives across the Gauss-point loop)
+                    const double2 sc = A.escale ? __ldg(A.escale + b * 32 + lane) : make_double2(-1.0, -1.0);
+                    const double thrK = kTinyRelC * sc.x, thrM = kTinyRelC * sc.y;
+                    uint32_t *pfl = A.pairflags + (size_t)(b * 32 + lane) * A.W;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int si = 4 * ti + i, im = c_ct.slot_dof[si];
@@ -370,14 +383,18 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(Contr
                             const int sj = 4 * tj + j, jm = c_ct.slot_dof[sj];
                             if (im >= 0 && jm >= 0 && sj <= si) {
                                 const int hi = im > jm ? im : jm, lo = im > jm ? jm : im;
-#if MOVFEM_KM_ST == 1
-                                __stcs(KMo + (hi * (hi + 1) / 2 + lo) * 32, make_double2(accK[i * 4 + j], accM[i * 4 + j]));   // A/B: streaming store
-#else
-                                KMo[(hi * (hi + 1) / 2 + lo) * 32] = make_double2(accK[i * 4 + j], accM[i * 4 + j]);
-#endif
+                                const int p = hi * (hi + 1) / 2 + lo;
+                                const double kv = accK[i * 4 + j], mv = accM[i * 4 + j];
+                                KMo[p * 32] = make_double2(kv, mv);
+                                const double ak = fabs(kv), am = fabs(mv);
+                                if ((ak <= thrK && am <= thrM) || (ak < kFlagAbsC && am < kFlagAbsC)) {
+                                    atomicOr(pfl + (p >> 5), 1u << (p & 31));
+                                    ++nfl;
+                                }
                             }
                         }
                     }
+                    if (nfl) { atomicOr(A.batchany + b, 1u << lane); atomicAdd(A.nflag, (unsigned long long)nfl); }
                 }
             }
             __syncwarp();

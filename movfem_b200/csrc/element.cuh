@@ -112,6 +112,8 @@ struct ElemArgs {
     int e_base;           // first element stored in KM / be (slab handles keep only their slab + halo)
     double *qt;           // scratch [nbatch32][NCMP][NGP][32]: Q|P and T per (element, Gauss point), see contract.cuh
     double *be;           // [ne][ME][4]  (re,im) x 2 polarisations
+    double2 *escale;      // [list position]: (ngp * max_g tr Q|P, ngp * max_g tr T): the element's K / M magnitude, the scale the
+                          // contraction's tiny-pair test (exact.cuh) is relative to
     int *status;
     const int *flags;     // flags[0] any dmu, flags[1] Re sigma changed
     int skip_unless_changed;   // launch is a cache refresh: exit unless flags[1]
@@ -148,7 +150,7 @@ struct ElemCfg {
     static constexpr size_t NODES_D = (size_t)EB * NSTR;
     static constexpr int ZXY = MN + 6;                      // MOVFEM_GEO_EARLY_REQ: per element z of every node, 3 x lines, 3 y lines
     static constexpr size_t ZXY_D = MOVFEM_GEO_EARLY_REQ ? (size_t)((EB * ZXY + 1) & ~1) : 0;
-    static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + NODES_D + ZXY_D + EB + 1) + sizeof(int) * (EB * 4 + 2 * MEP + 2 * EB + 3 * MN);
+    static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + NODES_D + ZXY_D + EB + 1 + 2 * EB) + sizeof(int) * (EB * 4 + 2 * MEP + 2 * EB + 3 * MN);
     static_assert((ATAB_D % 2) == 0 && (GEO_D % 2) == 0, "16-byte alignment of the smem regions");
     static_assert(32 % EB == 0, "a batch of the contraction (32 lanes) is a whole number of geometry batches");
 };
@@ -208,7 +210,8 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
 #endif
     int64_t *s_rbase = reinterpret_cast<int64_t *>(s_nodes + CFG::NODES_D + CFG::ZXY_D);   // [EB] base node id of the batch being prefetched
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_rbase + EB);     // mbarrier of the node-record bulk copies
-    int *s_el = reinterpret_cast<int *>(s_bar + 1);                   // [EB][4]: element id, GPML flags
+    unsigned long long *s_scale = reinterpret_cast<unsigned long long *>(s_bar + 1);   // [EB][2]: max_g tr Q|P, max_g tr T (bit patterns of >= 0 doubles)
+    int *s_el = reinterpret_cast<int *>(s_scale + 2 * EB);            // [EB][4]: element id, GPML flags
     int *s_slot = s_el + EB * 4;                                      // [MEP] slot -> local DOF (0-based) or -1
     int *s_sdir = s_slot + MEP;                                       // [MEP] slot -> direction (0-based)
     int *s_rxy = s_sdir + MEP;                                        // [EB][2] x / y line index of the prefetched elements' base node
@@ -283,6 +286,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
             int f[3] = {0, 0, 0};
             if (PML && e >= 0) effective_pml(m, A.pml, e, f);
             s_el[tid * 4 + 1] = f[0]; s_el[tid * 4 + 2] = f[1]; s_el[tid * 4 + 3] = f[2];
+            s_scale[tid * 2] = 0ull; s_scale[tid * 2 + 1] = 0ull;
         }
 
         // ---- phase A: the node records of this batch were requested with bulk copies while the previous batch was in
@@ -476,6 +480,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                         pc2[0] += vc[5] * dn[1] - vc[4] * dn[2]; pc2[1] += vc[3] * dn[2] - vc[5] * dn[0]; pc2[2] += vc[4] * dn[0] - vc[3] * dn[1];
                     }
                 }
+                double trq = 0.0, trt = 0.0;   // traces of Q|P and T at this Gauss point (magnitude of the element's K / M)
                 // GPML stretch (boundary_conds.f90:84-186) with the LAGGING flags (Q17)
                 double2 hhh = make_double2(1.0, 0.0);
                 double2 h1 = hhh, h2 = hhh, h3 = hhh;
@@ -532,7 +537,9 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
 #pragma unroll
                         for (int row = 0; row <= col; ++row) {
                             const int u = row / 3, d2 = row % 3;
-                            qo[up9(row, col) * QS] = dfma(G[0][u], E[0][d2], dfma(G[1][u], E[1][d2], G[2][u] * E[2][d2]));
+                            const double pv = dfma(G[0][u], E[0][d2], dfma(G[1][u], E[1][d2], G[2][u] * E[2][d2]));
+                            qo[up9(row, col) * QS] = pv;
+                            if (row == col) trq += fabs(pv);
                         }
                     }
                 } else if (DO_QT) {
@@ -548,8 +555,11 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
 #pragma unroll
                     for (int a = 0; a < 3; ++a)
 #pragma unroll
-                        for (int b = a; b < 3; ++b)
-                            qo[(q6++) * QS] = f * dfma(Jm[a][0], J[b][0], dfma(Jm[a][1], J[b][1], Jm[a][2] * J[b][2]));
+                        for (int b = a; b < 3; ++b) {
+                            const double qv = f * dfma(Jm[a][0], J[b][0], dfma(Jm[a][1], J[b][1], Jm[a][2] * J[b][2]));
+                            qo[(q6++) * QS] = qv;
+                            if (a == b) trq += fabs(qv);
+                        }
                 }
                 // T = G^T S G with the mass tensor S = w Re[h1h2h3 sigma_g] (integration.f90:228-236, Q3)
                 if (DO_QT) {
@@ -565,8 +575,14 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
 #pragma unroll
                     for (int a = 0; a < 3; ++a)
 #pragma unroll
-                        for (int b = a; b < 3; ++b)
-                            qo[((PML ? 45 : 6) + q6++) * QS] = dfma(G[0][a], SG[0][b], dfma(G[1][a], SG[1][b], G[2][a] * SG[2][b]));
+                        for (int b = a; b < 3; ++b) {
+                            const double tv = dfma(G[0][a], SG[0][b], dfma(G[1][a], SG[1][b], G[2][a] * SG[2][b]));
+                            qo[((PML ? 45 : 6) + q6++) * QS] = tv;
+                            if (a == b) trt += fabs(tv);
+                        }
+                    // element scales for the tiny-pair test of the contraction: max over the Gauss points, order independent
+                    atomicMax(&s_scale[s * 2], (unsigned long long)__double_as_longlong(trq));
+                    atomicMax(&s_scale[s * 2 + 1], (unsigned long long)__double_as_longlong(trt));
                 }
                 // R[d][pol] = G[:,d] . (w h1h2h3 src_pol);  src = (dmpf + pcrl) * cmplx32(0,-omega)  (problem.f90:112)
                 {
@@ -588,6 +604,8 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
             }
         }
         __syncthreads();
+        if (DO_QT && A.escale && tid < nb)
+            A.escale[first + tid] = make_double2(NGP * __longlong_as_double((long long)s_scale[tid * 2]), NGP * __longlong_as_double((long long)s_scale[tid * 2 + 1]));
 
 #if !MOVFEM_GEO_EARLY_REQ
         if (batch + (int)gridDim.x < nbatch) request_nodes(batch + gridDim.x);   // lands during the RHS phase / next wait

@@ -1,0 +1,316 @@
+// movfem_b200/csrc/exact.cuh -- reference-order re-evaluation of the element-matrix entries that decide the
+// delivered sparsity pattern (SURVEY Q11, section 7 "exact-zero set").
+//
+// find_zeros / rem_zeros (global_assembly.f90:123-150, caller MoVFEM_3DMT.f90:85-97) strip the entries whose
+// float32-rounded value is exactly (0,0).  For the 20-node element 36 of the 666 pairs of a brick-like element are
+// mathematically zero (symmetry of the quadrature), and the reference delivers their ROUND-OFF RESIDUE: on BASELINE
+// config 2 1.71 M of 24.7 M entries are such residues (<= 5e-16 of the matrix scale) and 254 of them happen to cancel
+// to exactly zero and are stripped.  Which ones is a property of the reference's operation order -- alocal
+// (integration.f90:76-86) summing wgt*(f1 + i*w32*f2) over the Gauss points, f1 the 36-term expansion
+// (integration.f90:154-209), f2 the 9-term one (integration.f90:211-238), on top of nf_jacobian / nf_inv_jac
+// (n_fem.f90:355-388), mix_grad_ln / vf_elem_curl / vf_elem_ve (v_fem.f90:38-60,470-484) and p_intmodels
+// (problem.f90:139-142) -- so the tensor formulation of contract.cuh cannot reproduce it.
+//
+// This kernel therefore re-evaluates exactly those pairs the way the reference does: IEEE double, no FMA (the library is
+// built -fmad=false), the reference's association and term order, alocal(im,jm) with im the local DOF of the LARGER global
+// id (MoVFEM_3DMT.f90:241-250 evaluates gne(im) >= gne(jm) only).  Which pairs: contract_kernel flags every pair whose
+// K_e and M_e are both below 1e-9 of the element's scale (the residues sit 7 orders below that, the smallest genuine
+// entries 4 orders above), and gather_finalize_kernel flags the contributions of any entry that cancels ACROSS elements
+// (none on the BASELINE meshes).  The re-evaluated values replace the pair's slot of the K/M store, scaled by 2^-600
+// (exact) so that the gather recognises them by magnitude: K_e(ref) = sum_g wgt*f1 and the imaginary part
+// sum_g wgt*(w32*f2) with the float32 omega INSIDE the Gauss-point sum, as the reference rounds it -- hence the kernel
+// runs every frequency on meshes that have flagged pairs.  Linear (8-node) and Lagrangian (27-node) bricks have no such
+// pairs and pay one flag test per pair.
+#pragma once
+#include "common.cuh"
+#include "element.cuh"
+
+namespace movfem {
+
+constexpr double kExactScale = 0x1p-600, kExactUnscale = 0x1p+600, kExactBelow = 0x1p-500, kFlagAbs = 0x1p-400;
+constexpr double kTinyRel = 1e-9;
+
+struct ExactArgs {
+    MeshDims m;
+    PmlParams pml;
+    double omega;
+    const ElemTables *T;
+    const NodeRec *nodes;
+    const double *xp, *yp;
+    const int *list;               // element ids of this list, in K/M row order
+    int nlist;
+    int64_t row0;                  // K/M row of list position 0
+    const uint32_t *batchany;      // [km_rows/32]: bit l = row 32*b+l has flagged pairs
+    const uint32_t *pairflags;     // [km_rows][W]: bit p = packed pair p of the row is to be re-evaluated
+    int W, NP;
+    const int *gne;                // gne(ne,me): [im][e]
+    double2 *KM;                   // whole K/M store: [row/32][NP][32]
+    int stretched;                 // this list goes through the GPML form of f1/f2 with h != 1 (scheme 0 layers)
+};
+
+// per (element, Gauss point) cache, the module variables of integration.f90:16-17 restated: nf_ji, wgt, mf1, Re mf2, gpml
+struct ExactGp {
+    double ji[3][3], wgt, m1[6], m2[6], h[3], hf[3];   // hf: h1*h3/h2, h1*h2/h3, h2*h3/h1 (integration.f90:171-188)
+};
+
+template <int MN, int ME, int NGP>
+struct ExactCfg {
+    static constexpr int EB = 8, THREADS = 256;
+    static constexpr int NDD = 13;                       // staged per node: z, mu^-1 (6), Re sigma (6)
+    static constexpr size_t SMEM = sizeof(ExactGp) * EB * NGP + sizeof(double) * (EB * MN * NDD + EB * 6) + sizeof(int) * (EB * 8 + 4);
+};
+
+template <int MN, int ME, int NGP>
+__global__ void __launch_bounds__(256, 2) exact_kernel(ExactArgs A) {
+    using CFG = ExactCfg<MN, ME, NGP>;
+    constexpr int EB = CFG::EB, NDD = CFG::NDD, NORD = MN == 8 ? 2 : 3;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ExactGp *s_gp = reinterpret_cast<ExactGp *>(smem_raw);                    // [EB][NGP]
+    double *s_nd = reinterpret_cast<double *>(s_gp + EB * NGP);               // [EB][MN][NDD]
+    double *s_xy = s_nd + EB * MN * NDD;                                      // [EB][6]: xs[3], ys[3]
+    int *s_el = reinterpret_cast<int *>(s_xy + EB * 6);                       // [EB][8]: element, row, flags[3], npairs, prefix
+    int *s_n = s_el + EB * 8;
+
+    const ElemTables &T = *A.T;
+    const MeshDims &m = A.m;
+    const int tid = threadIdx.x;
+    const bool gpml_form = !m.dirichlet;   // integration.f90:169,224: the GPML form of f1/f2 is taken whenever dirichlet is false
+    const double w32 = f32r(A.omega);
+    const int nbatch = (A.nlist + 31) / 32;
+
+    for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
+        const int64_t brow = A.row0 + (int64_t)b * 32;
+        const uint32_t any = A.batchany[brow >> 5];
+        if (any == 0) continue;
+        for (uint32_t rest = any; rest;) {
+            __syncthreads();   // previous group consumed
+            if (tid == 0) {
+                int n = 0;
+                uint32_t r = rest;
+                while (r && n < EB) {
+                    const int l = __ffs(r) - 1;
+                    r &= r - 1;
+                    if (b * 32 + l < A.nlist) {
+                        s_el[n * 8] = A.list[b * 32 + l];
+                        s_el[n * 8 + 1] = l;
+                        ++n;
+                    }
+                }
+                s_n[0] = n;
+            }
+            {   // every thread advances `rest` the same way
+                int cnt = 0;
+                while (rest && cnt < EB) { rest &= rest - 1; ++cnt; }
+            }
+            __syncthreads();
+            const int n = s_n[0];
+            if (n == 0) continue;
+            // ---- phase 0: stage the node data of the group's elements; flags; pair counts ----
+            if (tid < n) {
+                const int e = s_el[tid * 8];
+                int f[3] = {0, 0, 0};
+                if (A.stretched) effective_pml(m, A.pml, e, f);
+                s_el[tid * 8 + 2] = f[0]; s_el[tid * 8 + 3] = f[1]; s_el[tid * 8 + 4] = f[2];
+                const uint32_t *fl = A.pairflags + (brow + s_el[tid * 8 + 1]) * A.W;
+                int c = 0;
+                for (int w = 0; w < A.W; ++w) c += __popc(fl[w]);
+                s_el[tid * 8 + 5] = c;
+            }
+            for (int i = tid; i < n * MN; i += CFG::THREADS) {
+                const int s = i / MN, l = i % MN;
+                int ie, je, ke;
+                elem_ijk(m, s_el[s * 8], ie, je, ke);
+                const int g1 = m.nord - 1;
+                const int64_t id0 = (int64_t)(ie - 1) * g1 * m.nyz + (int64_t)(je - 1) * g1 * m.nnz + (ke - 1) * g1;
+                const NodeRec &nr = A.nodes[id0 + T.node_off[l]];
+                double *d = s_nd + (s * MN + l) * NDD;
+                d[0] = nr.z;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { d[1 + k] = nr.inmu[k]; d[7 + k] = nr.sre[k]; }
+                if (l < 3) {
+                    s_xy[s * 6 + l] = l < NORD ? A.xp[(ie - 1) * g1 + l] : 0.0;
+                    s_xy[s * 6 + 3 + l] = l < NORD ? A.yp[(je - 1) * g1 + l] : 0.0;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int acc = 0;
+                for (int s = 0; s < n; ++s) { s_el[s * 8 + 6] = acc; acc += s_el[s * 8 + 5]; }
+                s_n[1] = acc;
+            }
+            // ---- phase 1: one thread per (Gauss point, element): int_elem_params, integration.f90:60-74,108-137 ----
+            for (int i = tid; i < n * NGP; i += CFG::THREADS) {
+                const int g = i / n, s = i % n;
+                const double *nd = s_nd + s * MN * NDD;
+                ExactGp &P = s_gp[s * NGP + g];
+                // nf_jacobian, n_fem.f90:359-366
+                double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, xg[3] = {0, 0, 0};
+                for (int l = 0; l < MN; ++l) {
+                    const double x = s_xy[s * 6 + T.node_i[l]], y = s_xy[s * 6 + 3 + T.node_j[l]], z = nd[l * NDD];
+#pragma unroll
+                    for (int mm = 0; mm < 3; ++mm) {
+                        const double dn = T.dN[g][l][mm];
+                        J[mm][0] = J[mm][0] + dn * x; J[mm][1] = J[mm][1] + dn * y; J[mm][2] = J[mm][2] + dn * z;
+                    }
+                    const double ln = T.N[g][l];   // g_rw, integration.f90:120-124
+                    xg[0] = xg[0] + ln * x; xg[1] = xg[1] + ln * y; xg[2] = xg[2] + ln * z;
+                }
+                // nf_det n_fem.f90:393-394, wgt integration.f90:71, nf_inv_jac n_fem.f90:378-386 (Q6: / dabs(det))
+                const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) + J[0][1] * (J[1][2] * J[2][0] - J[1][0] * J[2][2]) +
+                                   J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+                P.wgt = det * T.rw[g][3];
+                const double ad = fabs(det);
+                P.ji[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / ad;
+                P.ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / ad;
+                P.ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / ad;
+                P.ji[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / ad;
+                P.ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / ad;
+                P.ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / ad;
+                P.ji[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / ad;
+                P.ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / ad;
+                P.ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / ad;
+                // p_intmodels, problem.f90:139-142 (accumulating into zeroed mf1 / mf2; only Re mf2 reaches f2, Q3)
+                double m1[6] = {0, 0, 0, 0, 0, 0}, m2[6] = {0, 0, 0, 0, 0, 0};
+                for (int l = 0; l < MN; ++l) {
+                    const double ln = T.N[g][l];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) { m1[k] = m1[k] + ln * nd[l * NDD + 1 + k]; m2[k] = m2[k] + ln * nd[l * NDD + 7 + k]; }
+                }
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { P.m1[k] = m1[k]; P.m2[k] = m2[k]; }
+                // gpml(i,:) = Re gpml_h (integration.f90:16,125, Q18) with the lagging flags (Q17)
+                double h1 = 1.0, h2 = 1.0, h3 = 1.0;
+                if (A.stretched) {
+                    h1 = gpml_axis(A.pml, s_el[s * 8 + 2], 0, xg[0], A.omega).x;
+                    h2 = gpml_axis(A.pml, s_el[s * 8 + 3], 1, xg[1], A.omega).x;
+                    h3 = gpml_axis(A.pml, s_el[s * 8 + 4], 2, xg[2], A.omega).x;
+                }
+                P.h[0] = h1; P.h[1] = h2; P.h[2] = h3;
+                P.hf[0] = (h1 * h3) / h2; P.hf[1] = (h1 * h2) / h3; P.hf[2] = (h2 * h3) / h1;
+            }
+            __syncthreads();
+            // ---- phase 2: one thread per flagged (element, pair): alocal, integration.f90:76-86 ----
+            const int total = s_n[1];
+            for (int item = tid; item < total; item += CFG::THREADS) {
+                int s = 0;
+                while (s + 1 < n && s_el[(s + 1) * 8 + 6] <= item) ++s;
+                int rank = item - s_el[s * 8 + 6];
+                const int e = s_el[s * 8], lane = s_el[s * 8 + 1];
+                const uint32_t *fl = A.pairflags + (brow + lane) * A.W;
+                int p = -1;
+                for (int w = 0; w < A.W; ++w) {
+                    const uint32_t word = fl[w];
+                    const int c = __popc(word);
+                    if (rank < c) { p = w * 32 + (int)__fns(word, 0, rank + 1); break; }
+                    rank -= c;
+                }
+                if (p < 0 || p >= A.NP) continue;
+                int hi = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+                while (hi * (hi + 1) / 2 > p) --hi;
+                while ((hi + 1) * (hi + 2) / 2 <= p) ++hi;
+                const int lo = p - hi * (hi + 1) / 2;
+                const int gh = A.gne[(size_t)hi * m.ne + e], gl = A.gne[(size_t)lo * m.ne + e];
+                if (gh <= 0 || gl <= 0) continue;          // Dirichlet DOF: the pair never reaches the matrix
+                const int im = gh >= gl ? hi : lo, jm = gh >= gl ? lo : hi;
+                const int di = T.edir[im], dj = T.edir[jm];
+                double are = 0.0, aim = 0.0;
+                for (int g = 0; g < NGP; ++g) {
+                    const ExactGp &P = s_gp[s * NGP + g];
+                    // mix_grad_ln v_fem.f90:478-483, grad_xi :515-518, vf_elem_curl :55-59, vf_elem_ve :41-43
+                    double a1[3], a2[3], b1[3], b2[3], va[3], vb[3];
+                    {
+                        double dn[3], v[3];
+#pragma unroll
+                        for (int mm = 0; mm < 3; ++mm) {
+                            double sacc = 0.0;
+#pragma unroll
+                            for (int nn = 0; nn < 3; ++nn) sacc = sacc + P.ji[mm][nn] * T.dphi[g][im][nn];
+                            dn[mm] = sacc; v[mm] = P.ji[mm][di];
+                        }
+                        a1[0] = dn[1] * v[2]; a2[0] = dn[2] * v[1];
+                        a1[1] = dn[2] * v[0]; a2[1] = dn[0] * v[2];
+                        a1[2] = dn[0] * v[1]; a2[2] = dn[1] * v[0];
+                        const double ph = T.phi[g][im];
+#pragma unroll
+                        for (int mm = 0; mm < 3; ++mm) va[mm] = ph * v[mm];
+                    }
+                    {
+                        double dn[3], v[3];
+#pragma unroll
+                        for (int mm = 0; mm < 3; ++mm) {
+                            double sacc = 0.0;
+#pragma unroll
+                            for (int nn = 0; nn < 3; ++nn) sacc = sacc + P.ji[mm][nn] * T.dphi[g][jm][nn];
+                            dn[mm] = sacc; v[mm] = P.ji[mm][dj];
+                        }
+                        b1[0] = dn[1] * v[2]; b2[0] = dn[2] * v[1];
+                        b1[1] = dn[2] * v[0]; b2[1] = dn[0] * v[2];
+                        b1[2] = dn[0] * v[1]; b2[2] = dn[1] * v[0];
+                        const double ph = T.phi[g][jm];
+#pragma unroll
+                        for (int mm = 0; mm < 3; ++mm) vb[mm] = ph * v[mm];
+                    }
+                    const double *mu = P.m1, *sg = P.m2;
+                    double v1, v2;
+                    // f1, integration.f90:171-207: A(p,s) = cv1 of im, B(q,t) = cv2 of jm; a term whose factors contain an exact
+                    // zero adds +-0 and is skipped (the sum is unchanged)
+#define MOVFEM_T(sign, hfac, mk, aa, bb)                                            \
+    if (mu[mk] != 0.0) { const double t_ = (((hfac) * mu[mk]) * (aa)) * (bb); r = (sign) > 0 ? r + t_ : r - t_; }
+#define MOVFEM_U(sign, mk, aa, bb)                                                  \
+    if (mu[mk] != 0.0) { const double t_ = (mu[mk] * (aa)) * (bb); r = (sign) > 0 ? r + t_ : r - t_; }
+                    if (gpml_form) {
+                        const double h1 = P.h[0], h2 = P.h[1], h3 = P.h[2], f13_2 = P.hf[0], f12_3 = P.hf[1], f23_1 = P.hf[2];
+                        double r = 0.0;
+                        MOVFEM_T(+1, f13_2, 0, a1[0], b1[0]) MOVFEM_T(-1, h1, 0, a2[0], b1[0]) MOVFEM_T(-1, h1, 0, a1[0], b2[0]) MOVFEM_T(+1, f12_3, 0, a2[0], b2[0])
+                        MOVFEM_T(+1, h1, 1, a1[0], b1[1]) MOVFEM_T(-1, f12_3, 1, a2[0], b1[1]) MOVFEM_T(-1, h3, 1, a1[0], b2[1]) MOVFEM_T(+1, h2, 1, a2[0], b2[1])
+                        MOVFEM_T(+1, h3, 2, a1[0], b1[2]) MOVFEM_T(-1, h2, 2, a2[0], b1[2]) MOVFEM_T(-1, f13_2, 2, a1[0], b2[2]) MOVFEM_T(+1, h1, 2, a2[0], b2[2])
+                        MOVFEM_T(+1, h1, 1, a1[1], b1[0]) MOVFEM_T(-1, h3, 1, a2[1], b1[0]) MOVFEM_T(-1, f12_3, 1, a1[1], b2[0]) MOVFEM_T(+1, h2, 1, a2[1], b2[0])
+                        MOVFEM_T(+1, f12_3, 3, a1[1], b1[1]) MOVFEM_T(-1, h2, 3, a2[1], b1[1]) MOVFEM_T(-1, h2, 3, a1[1], b2[1]) MOVFEM_T(+1, f23_1, 3, a2[1], b2[1])
+                        MOVFEM_T(+1, h2, 4, a1[1], b1[2]) MOVFEM_T(-1, f23_1, 4, a2[1], b1[2]) MOVFEM_T(-1, h1, 4, a1[1], b2[2]) MOVFEM_T(+1, h3, 4, a2[1], b2[2])
+                        MOVFEM_T(+1, h3, 2, a1[2], b1[0]) MOVFEM_T(-1, f13_2, 2, a2[2], b1[0]) MOVFEM_T(-1, h2, 2, a1[2], b2[0]) MOVFEM_T(+1, h1, 2, a2[2], b2[0])
+                        MOVFEM_T(+1, h2, 4, a1[2], b1[1]) MOVFEM_T(-1, h1, 4, a2[2], b1[1]) MOVFEM_T(-1, f23_1, 4, a1[2], b2[1]) MOVFEM_T(+1, h3, 4, a2[2], b2[1])
+                        MOVFEM_T(+1, f23_1, 5, a1[2], b1[2]) MOVFEM_T(-1, h3, 5, a2[2], b1[2]) MOVFEM_T(-1, h3, 5, a1[2], b2[2]) MOVFEM_T(+1, f13_2, 5, a2[2], b2[2])
+                        v1 = r;
+                        // f2, integration.f90:228-232: h1*h2*h3*cv2(q)*m(k)*cv1(p), nine terms summed left to right
+                        const double hhh = (h1 * h2) * h3;
+                        double q = 0.0;
+#define MOVFEM_M(mk, bq, ap) if (sg[mk] != 0.0) q = q + ((hhh * vb[bq]) * sg[mk]) * va[ap];
+                        MOVFEM_M(0, 0, 0) MOVFEM_M(1, 1, 0) MOVFEM_M(2, 2, 0) MOVFEM_M(1, 0, 1) MOVFEM_M(3, 1, 1) MOVFEM_M(4, 2, 1)
+                        MOVFEM_M(2, 0, 2) MOVFEM_M(4, 1, 2) MOVFEM_M(5, 2, 2)
+#undef MOVFEM_M
+                        v2 = q;
+                    } else {
+                        double r = 0.0;
+                        MOVFEM_U(+1, 0, a1[0], b1[0]) MOVFEM_U(-1, 0, a2[0], b1[0]) MOVFEM_U(-1, 0, a1[0], b2[0]) MOVFEM_U(+1, 0, a2[0], b2[0])
+                        MOVFEM_U(+1, 1, a1[0], b1[1]) MOVFEM_U(-1, 1, a2[0], b1[1]) MOVFEM_U(-1, 1, a1[0], b2[1]) MOVFEM_U(+1, 1, a2[0], b2[1])
+                        MOVFEM_U(+1, 2, a1[0], b1[2]) MOVFEM_U(-1, 2, a2[0], b1[2]) MOVFEM_U(-1, 2, a1[0], b2[2]) MOVFEM_U(+1, 2, a2[0], b2[2])
+                        MOVFEM_U(+1, 1, a1[1], b1[0]) MOVFEM_U(-1, 1, a2[1], b1[0]) MOVFEM_U(-1, 1, a1[1], b2[0]) MOVFEM_U(+1, 1, a2[1], b2[0])
+                        MOVFEM_U(+1, 3, a1[1], b1[1]) MOVFEM_U(-1, 3, a2[1], b1[1]) MOVFEM_U(-1, 3, a1[1], b2[1]) MOVFEM_U(+1, 3, a2[1], b2[1])
+                        MOVFEM_U(+1, 4, a1[1], b1[2]) MOVFEM_U(-1, 4, a2[1], b1[2]) MOVFEM_U(-1, 4, a1[1], b2[2]) MOVFEM_U(+1, 4, a2[1], b2[2])
+                        MOVFEM_U(+1, 2, a1[2], b1[0]) MOVFEM_U(-1, 2, a2[2], b1[0]) MOVFEM_U(-1, 2, a1[2], b2[0]) MOVFEM_U(+1, 2, a2[2], b2[0])
+                        MOVFEM_U(+1, 4, a1[2], b1[1]) MOVFEM_U(-1, 4, a2[2], b1[1]) MOVFEM_U(-1, 4, a1[2], b2[1]) MOVFEM_U(+1, 4, a2[2], b2[1])
+                        MOVFEM_U(+1, 5, a1[2], b1[2]) MOVFEM_U(-1, 5, a2[2], b1[2]) MOVFEM_U(-1, 5, a1[2], b2[2]) MOVFEM_U(+1, 5, a2[2], b2[2])
+                        v1 = r;
+                        // f2 Dirichlet form, integration.f90:234-236: three parenthesised rows
+                        double rows[3];
+#pragma unroll
+                        for (int pp = 0; pp < 3; ++pp) {
+                            const int k0 = sym3(0, pp), k1 = sym3(1, pp), k2 = sym3(2, pp);
+                            rows[pp] = ((vb[0] * sg[k0]) * va[pp] + (vb[1] * sg[k1]) * va[pp]) + (vb[2] * sg[k2]) * va[pp];
+                        }
+                        v2 = (rows[0] + rows[1]) + rows[2];
+                    }
+#undef MOVFEM_T
+#undef MOVFEM_U
+                    // alocal, integration.f90:84: a = a + wgt*(f1 + cmplx(0,omega)*f2), cmplx() single precision (Q2)
+                    are = are + P.wgt * v1;
+                    aim = aim + P.wgt * (w32 * v2);
+                }
+                const int64_t row = brow + lane;
+                A.KM[(((row >> 5) * A.NP + p) << 5) + (row & 31)] = make_double2(are * kExactScale, aim * kExactScale);
+            }
+        }
+    }
+}
+
+}  // namespace movfem

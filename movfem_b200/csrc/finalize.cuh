@@ -97,7 +97,9 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
                        const uint32_t *__restrict__ src, const double2 *__restrict__ KM, double2 *__restrict__ a,
                        int *__restrict__ blk_nonzero, int mode, int cache, const uint32_t *__restrict__ pure,
                        double2 *__restrict__ kmg, const int *__restrict__ flags, const int *__restrict__ blk_list,
-                       unsigned long long *__restrict__ total_nonzero) {
+                       unsigned long long *__restrict__ total_nonzero, int NP, int W, uint32_t *__restrict__ pairflags,
+                       uint32_t *__restrict__ batchany, unsigned long long *__restrict__ n_doubt,
+                       double doubt_abs_k, double doubt_abs_m /* test hook: doubt every entry below these sizes; < 0 = off */) {
     __shared__ double2 vals[4 * kFinThreads];
     __shared__ uint16_t offs[kFinThreads + 1];
     const int blk = blk_list ? blk_list[blockIdx.x] : (int)blockIdx.x;   // the structured fast path leaves only some blocks here
@@ -147,14 +149,38 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
         if (i < nzu) {
             const int lo = offs[threadIdx.x];
             const int hi = (threadIdx.x + 1 < kFinThreads && i + 1 < nzu) ? offs[threadIdx.x + 1] : n;
-            double k = 0.0, mm = 0.0;
+            // Contributions re-evaluated in the reference's operation order (exact.cuh) are recognised by magnitude (both parts
+            // scaled by 2^-600); they carry K_e and the imaginary part with w32 already inside.  An entry made of such
+            // contributions only is summed exactly as the reference's a(idd)=a(idd)+aij does, so its (0,0) test agrees.
+            double k = 0.0, mm = 0.0, kx = 0.0, mx = 0.0, ak = 0.0, am = 0.0;
+            int ninexact = 0;
             for (int c = lo; c < hi; ++c) {
                 const double2 v = vals[c];
-                k = k + v.x;
-                mm = mm + v.y;
+                if (fabs(v.x) < 0x1p-500 && fabs(v.y) < 0x1p-500) {
+                    kx = kx + v.x * 0x1p+600;
+                    mx = mx + v.y * 0x1p+600;
+                } else {
+                    k = k + v.x; mm = mm + v.y;
+                    ak += fabs(v.x); am += fabs(v.y);
+                    ++ninexact;
+                }
+            }
+            // cancellation ACROSS elements down to round-off: the entry's zero test is in doubt -> flag its contributions for
+            // re-evaluation; the host re-runs exact_kernel and this gather (none on the BASELINE meshes)
+            if (ninexact && pairflags && ((fabs(k) <= 1e-9 * ak && fabs(mm) <= 1e-9 * am) || (fabs(k) <= doubt_abs_k && fabs(mm) <= doubt_abs_m))) {
+                for (int c = lo; c < hi; ++c) {
+                    const double2 v = vals[c];
+                    if (fabs(v.x) < 0x1p-500 && fabs(v.y) < 0x1p-500) continue;
+                    const uint32_t sx = src[c0 + c];
+                    const int64_t row = (int64_t)((sx >> 5) / (uint32_t)NP) * 32 + (sx & 31);
+                    const int pr = (int)((sx >> 5) % (uint32_t)NP);
+                    atomicOr(pairflags + row * W + (pr >> 5), 1u << (pr & 31));
+                    atomicOr(batchany + (row >> 5), 1u << (row & 31));
+                }
+                atomicAdd(n_doubt, 1ull);
             }
             if (cache == 1) kmg[i] = make_double2(k, mm);
-            double re = k, im = w32 * mm;
+            double re = k + kx, im = w32 * mm + mx;
             if (mode == 0) { re = f32r(re); im = f32r(im); }
             st_a(a + i, make_double2(re, im));
             nzflag = !(re == 0.0 && im == 0.0);

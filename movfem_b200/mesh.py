@@ -248,6 +248,13 @@ def config(n: int, *, scale: float = 1.0, dirichlet: int | None = None) -> Model
     raise ValueError(n)
 
 
+def config5_submesh() -> Model:
+    """The parity mesh of BASELINE configs[4]: 40x40x20 linear elements with the FULL topography amplitude
+    (300 m on every interface, tapering to 0 at the bottom / top planes), nextd = 4, GPML Fang, f = 1 Hz."""
+    return build_model("config5_submesh_40x40x20", 40, 40, 8, 250., 250., 250., 4, 9, 3, dirichlet=0, gpml_sch=0,
+                       a0=1., b0=1., nn=2., freqs=(1.0,), sigma_fn=_layered(), topo_amp=300.0)
+
+
 def brick_single_element(mn: int, hx=2000.0, hy=1500.0, hz=1000.0, top_shift=None) -> Model:
     """One element whose nodes are ``nf_nr(l,:)*(hx,hy,hz)/2`` (SURVEY App. B item 4 pins).
     ``top_shift`` raises the four top corner nodes 5..8 of an 8-node element (Q5 pin)."""

@@ -81,6 +81,7 @@ for cfg in "48:64" "32:48" "64:96"; do   # scratch chunk : persisting-L2 carve-o
 done
 MOVFEM_GATHER_TEMPLATE=1 timeout 150 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab2_tmpl.json 2> gpurun_out/ab2_tmpl.err || true
 summary gpurun_out/ab2_tmpl.json gather_template
+[ -n "$SKIP_LINEAR" ] && exit 0   # SKIP_LINEAR=1: no config-5 / config-4 runs
 # the me=12 variants matter on the linear meshes: config 5 at half scale (cold single-frequency assembly, GPML Fang) ...
 for name in base c12w7 c12w3 fold16 fold12 geoearly geoearly2 rhsslot tabg gld3 hints; do
   if [ "$name" = base ]; then unset MOVFEM_B200_LIB; else export MOVFEM_B200_LIB=$PWD/ab/lib_$name.so; [ -f "$MOVFEM_B200_LIB" ] || continue; fi
