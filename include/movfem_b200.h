@@ -93,6 +93,7 @@ typedef struct movfem_stats {
     double ms_contract;   /* part of ms_element: contract_kernel launches        */
     double ms_exact;      /* part of ms_element: exact_kernel launches (reference-order re-evaluation of residue pairs) */
     int64_t nflagged;     /* (element, pair)s re-evaluated in the reference's operation order                          */
+    double ms_fused;      /* part of ms_element: fused12_kernel (linear elements: geometry + contraction + RHS in one)  */
 } movfem_stats;
 
 /* Create: uploads the mesh once, builds gne + pattern ON THE DEVICE

@@ -50,7 +50,7 @@ class MovfemStats(C.Structure):
         ("ms_h2d", C.c_double), ("ms_node", C.c_double), ("ms_element", C.c_double),
         ("ms_gather", C.c_double), ("ms_finalize", C.c_double), ("ms_d2h", C.c_double),
         ("ms_total", C.c_double), ("nz", C.c_int64), ("launches", C.c_int64),
-        ("ms_geometry", C.c_double), ("ms_contract", C.c_double), ("ms_exact", C.c_double), ("nflagged", C.c_int64),
+        ("ms_geometry", C.c_double), ("ms_contract", C.c_double), ("ms_exact", C.c_double), ("nflagged", C.c_int64), ("ms_fused", C.c_double),
     ]
 
 

@@ -5,6 +5,7 @@
 // gather / A = K + i*w32*M / float32 round trip / zero strip -> RHS, and copies the triplets into
 // the caller's (Fortran-owned) arrays.  There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
+#include <omp.h>
 
 #include <algorithm>
 #include <cmath>
@@ -22,6 +23,7 @@
 #include "element.cuh"
 #include "exact.cuh"
 #include "finalize.cuh"
+#include "fused12.cuh"
 #include "pattern.cuh"
 #include "geo.cuh"
 #include "ref_element.h"
@@ -39,30 +41,14 @@ using Geo36p = ElemCfg<20, 36, 36, 27, 8, 256, 2, true>;
 using Geo54  = ElemCfg<27, 54, 60, 27, 4, 128, 3, false>;
 using Geo54p = ElemCfg<27, 54, 60, 27, 4, 128, 2, true>;
 // contract_kernel:          ME MEP NGP PML   W STAGES    (W consumer warps + 1 producer warp; ring of STAGES class blocks)
-// The warp counts can be overridden at build time for A/B libraries (make OUT=... EXTRA=-DMOVFEM_CON12_W=7, loaded through
-// MOVFEM_B200_LIB): tools/micro/tile_bench.cu shows the loop losing 7-25 % when the consumer warps do not divide evenly
-// over the four SMSPs, which the 6 + 1 warps of the me = 12 configurations may be paying.
-#ifndef MOVFEM_CON12_W
-#define MOVFEM_CON12_W 6
-#endif
-#ifndef MOVFEM_CON36_W
-#define MOVFEM_CON36_W 15
-#endif
-#ifndef MOVFEM_CON36P_W
-#define MOVFEM_CON36P_W 12
-#endif
-#ifndef MOVFEM_CON54_W
-#define MOVFEM_CON54_W 15
-#endif
-using Con12  = ContractCfg<12, 12, 8, false, MOVFEM_CON12_W, 6, 2>;
-using Con12p = ContractCfg<12, 12, 8, true, MOVFEM_CON12_W, 3, 2>;
-#ifndef MOVFEM_CON36_STAGES
-#define MOVFEM_CON36_STAGES 5
-#endif
-using Con36  = ContractCfg<36, 36, 27, false, MOVFEM_CON36_W, MOVFEM_CON36_STAGES>;
-using Con36p = ContractCfg<36, 36, 27, true, MOVFEM_CON36P_W, 2>;
-using Con54  = ContractCfg<54, 60, 27, false, MOVFEM_CON54_W, 4>;
-using Con54p = ContractCfg<54, 60, 27, true, MOVFEM_CON54_W, 2>;
+// Warp counts and ring depths measured on B200 (profiles/r02_ab_results.md): 11+1 / 8+1 / 15+1 (GPML) warps, rings of 3 or 4
+// stages and a folded producer are all slower than these.
+using Con12  = ContractCfg<12, 12, 8, false, 6, 6, 2>;
+using Con12p = ContractCfg<12, 12, 8, true, 6, 3, 2>;
+using Con36  = ContractCfg<36, 36, 27, false, 15, 5>;
+using Con36p = ContractCfg<36, 36, 27, true, 12, 2>;
+using Con54  = ContractCfg<54, 60, 27, false, 15, 4>;
+using Con54p = ContractCfg<54, 60, 27, true, 15, 2>;
 
 constexpr size_t kScratchCap = (size_t)512 << 20;   // Q|P,T scratch: larger lists are processed in chunks
 
@@ -134,13 +120,19 @@ struct movfem_handle {
     int *d_status, *d_flags;
     // pinned host scratch
     int *h_status;      // [0] status [1..2] flags
-    int64_t *h_count;   // total non-zeros
+    int64_t *h_count;   // [0] total non-zeros, [1..2] signature of the stripped set
     // state
     bool km_valid;      // Ke/Me of all elements are cached
     int km_first[3];    // GPML flags of element (1,1,1) they were formed with (Q17)
     bool compacted;     // last result lives in the *_c arrays
     int64_t pattern_nz_host;   // nz of the pattern last copied into the caller's irn/jcn (-1: none); MOVFEM_MODE_KEEP_PATTERN
-    bool pattern_host_compacted;
+    int64_t pattern_sig_host[2];   // ... and the signature of its stripped set
+    const void *pattern_ptr_host[2];   // ... and where it went
+    bool last_compacted;       // the previous T2 result had stripped entries: no speculative copy of the structural pattern
+    // host link (movfem_assemble): pinned staging ring + narrowed values
+    char *stage[3];
+    cudaEvent_t stage_ev[3];
+    float2 *d_a32;
     int64_t nz_last;
     int32_t mode_last;
     cudaEvent_t ev[EV_COUNT];
@@ -308,27 +300,6 @@ void build_contract_tables(const MeshDims &m, const ElemTables &T, ContractTable
                 }
     }
     C.cls_begin[6] = (short)nt_out;
-#if MOVFEM_TALL_TILES
-    {   // tall tiles: per class and column group, the row groups of the class's row direction in pairs (+ a single leftover)
-        int ntt = 0;
-        for (int c = 0; c < 6; ++c) {
-            C.tall_begin[c] = (short)ntt;
-            for (int tj = 0; tj < nt; ++tj) {
-                if (T.slot_dir[4 * tj] != cls_dJ(c)) continue;
-                int rows[kMaxSlots / 4], nr = 0;
-                for (int ti = tj; ti < nt; ++ti)
-                    if (T.slot_dir[4 * ti] == cls_dI(c)) rows[nr++] = ti;
-                for (int r = 0; r < nr;) {   // runs of up to MOVFEM_TALL_RG adjacent row groups (the groups of a direction are contiguous)
-                    int rg = 1;
-                    while (rg < MOVFEM_TALL_RG && r + rg < nr && rows[r + rg] == rows[r] + rg) ++rg;
-                    C.tall_ti[ntt] = (unsigned char)rows[r]; C.tall_tj[ntt] = (unsigned char)tj; C.tall_rg[ntt] = (unsigned char)rg; ++ntt;
-                    r += rg;
-                }
-            }
-        }
-        C.tall_begin[6] = (short)ntt;
-    }
-#endif
     // scratch components a class streams: plain Q[r0|r1(dI)][m0|m1(dJ)] (components 0-5, sym3 order) and T[dI][dJ]
     // (6-11); GPML P[(u,dI)][(v,dJ)] (0-44, up9 order) and T (45-50)
     for (int c = 0; c < 6; ++c) {
@@ -351,9 +322,7 @@ int const_table_acquire(movfem_handle *h) {
     if (g_ct_owner[h->device] == h->m.me) return 0;
     CK(cudaDeviceSynchronize());   // no kernel of another element type may still be reading c_ct
     CK(cudaMemcpyToSymbol(c_ct, &h->ct, sizeof(ContractTables)));
-#if MOVFEM_TAB_GLOBAL
     CK(cudaMemcpyToSymbol(g_ct_at, h->ct.at, sizeof(h->ct.at)));
-#endif
     g_ct_owner[h->device] = h->m.me;
     return 0;
 }
@@ -421,17 +390,46 @@ int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist,
     return 0;
 }
 
+// the linear-element path in one kernel (fused12.cuh): geometry, contraction and element RHS of the unstretched list
+template <bool DO_KM>
+int launch_fused12(movfem_handle *h, const ElemArgs &A, int skip_unless_changed) {
+    if (h->n_plain <= 0) return 0;
+    int rc = const_table_acquire(h);
+    if (rc) return rc;
+    auto kern = fused12_kernel<DO_KM>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fused12Cfg::SMEM));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Fused12Cfg::THREADS, Fused12Cfg::SMEM));
+    Fused12Args F;
+    F.m = A.m; F.omega = A.omega; F.T = A.T; F.nodes = A.nodes; F.xp = A.xp; F.yp = A.yp;
+    F.list = h->d_list_plain; F.nlist = h->n_plain; F.e_base = h->e_base; F.KM = h->d_KM; F.be = h->d_be;
+    F.status = h->d_status; F.flags = h->d_flags; F.pairflags = h->d_pairflags; F.batchany = h->d_batchany; F.nflag = h->d_nflag; F.W = h->flagW;
+    F.no_l1 = getenv("MOVFEM_TEST_NO_L1") ? 1 : 0;
+    F.skip_unless_changed = skip_unless_changed;
+    const int nb = (h->n_plain + 31) / 32;
+    if (kernel_event(h, 3, true)) return MOVFEM_E_CUDA;
+    kern<<<std::min(nb, std::max(1, per_sm) * h->num_sms), Fused12Cfg::THREADS, Fused12Cfg::SMEM, h->stream>>>(F);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    if (kernel_event(h, 3, false)) return MOVFEM_E_CUDA;
+    return 0;
+}
+
 template <class GP, class CP, class GQ, class CQ>
 int run_elements(movfem_handle *h, ElemArgs &A, bool full) {
     int rc;
+    const bool fused = GP::ME == 12 && !getenv("MOVFEM_NO_FUSED12");
     // unstretched elements: K_e, M_e are frequency independent -> computed on the first
     // frequency and whenever Re(sigma) changed; their RHS is rebuilt every frequency
     if (full) {
-        if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 0, 0))) return rc;
+        if (fused) { if ((rc = launch_fused12<true>(h, A, 0))) return rc; }
+        else if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 0, 0))) return rc;
     } else {
-        if ((rc = launch_elements<GP, CP, false>(h, A, h->d_list_plain, h->n_plain, 0, 0))) return rc;
+        if (fused) { if ((rc = launch_fused12<false>(h, A, 0))) return rc; }
+        else if ((rc = launch_elements<GP, CP, false>(h, A, h->d_list_plain, h->n_plain, 0, 0))) return rc;
         // refresh K/M only if the node kernel saw Re(sigma) change
-        if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 0, 1))) return rc;
+        if (fused) { if ((rc = launch_fused12<true>(h, A, 1))) return rc; }
+        else if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 0, 1))) return rc;
     }
     // stretched (GPML, scheme 0) elements: the stored stretch is Re(h) = 1 + a0*rho^n (Q18), independent of omega, so
     // their K_e, M_e are cached like the others; only element (1,1,1) can change, when its lagging flags do (Q17), and
@@ -457,6 +455,8 @@ void free_all(movfem_handle *h) {
     if (h->h_status) cudaFreeHost(h->h_status);
     if (h->h_count) cudaFreeHost(h->h_count);
     if (h->h_nflag) cudaFreeHost(h->h_nflag);
+    for (int i = 0; i < 3; ++i) { if (h->stage[i]) cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
+    if (h->d_a32) cudaFree(h->d_a32);
     for (int i = 0; i < EV_COUNT; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     for (cudaEvent_t e : h->kev) cudaEventDestroy(e);
@@ -562,47 +562,9 @@ int build_pattern(movfem_handle *h) {
 
 extern "C" {
 
-// A/B libraries (tools/ab_round2.sh) announce themselves: any build-time switch away from its default shows in the version string
-#define MOVFEM_STR2(x) #x
-#define MOVFEM_STR(x) MOVFEM_STR2(x)
-#if MOVFEM_TALL_TILES || MOVFEM_FOLD_PRODUCER || MOVFEM_TAB_GLOBAL || MOVFEM_KM_ST || MOVFEM_GATHER_LD || MOVFEM_GATHER_ST || MOVFEM_GEO_PREFETCH || \
-    MOVFEM_GEO_EARLY_REQ || MOVFEM_RHS_PER_SLOT || MOVFEM_CON_UNROLL != 3 || MOVFEM_CON12_W != 6 || MOVFEM_CON36_W != 15 || MOVFEM_CON36P_W != 12 || \
-    MOVFEM_CON54_W != 15 || MOVFEM_CON36_STAGES != 5 || MOVFEM_FIN_THREADS != 128
-const char *movfem_version(void) {
-    return "movfem_b200 0.1.0 (sm_100a) A/B build: tall=" MOVFEM_STR(MOVFEM_TALL_TILES) "x" MOVFEM_STR(MOVFEM_TALL_RG) " fold=" MOVFEM_STR(MOVFEM_FOLD_PRODUCER)
-           " tabg=" MOVFEM_STR(MOVFEM_TAB_GLOBAL) " kmst=" MOVFEM_STR(MOVFEM_KM_ST) " gld=" MOVFEM_STR(MOVFEM_GATHER_LD) " gst=" MOVFEM_STR(MOVFEM_GATHER_ST)
-           " geopf=" MOVFEM_STR(MOVFEM_GEO_PREFETCH) " geoearly=" MOVFEM_STR(MOVFEM_GEO_EARLY_REQ) " rhsslot=" MOVFEM_STR(MOVFEM_RHS_PER_SLOT)
-           " unroll=" MOVFEM_STR(MOVFEM_CON_UNROLL) " w12=" MOVFEM_STR(MOVFEM_CON12_W) " w36=" MOVFEM_STR(MOVFEM_CON36_W) " w36p=" MOVFEM_STR(MOVFEM_CON36P_W)
-           " w54=" MOVFEM_STR(MOVFEM_CON54_W) " st36=" MOVFEM_STR(MOVFEM_CON36_STAGES) " fin=" MOVFEM_STR(MOVFEM_FIN_THREADS);
-}
-#else
-const char *movfem_version(void) { return "movfem_b200 0.1.0 (sm_100a)"; }
-#endif
+const char *movfem_version(void) { return "movfem_b200 0.2.0 (sm_100a)"; }
 
 const char *movfem_last_error(const movfem_handle *h) { return h ? h->err : "null handle"; }
-
-// Experiment (MOVFEM_L2_PERSIST_MB=<n>, off by default): keep the Q|P,T scratch resident in L2 between geometry_kernel and
-// contract_kernel with an access-policy window on the launching stream (use together with MOVFEM_SCRATCH_MB <= n so that a
-// chunk fits the persisting carve-out).  ncu (r01): 10.6 % / 17 % of the contraction's warp samples wait for ring data.
-static int apply_l2_window(movfem_handle *h) {
-    const char *mb = getenv("MOVFEM_L2_PERSIST_MB");
-    if (!mb || !h->d_qt) return 0;
-    const size_t want = (size_t)std::max(1, atoi(mb)) << 20;
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, h->device));
-    const size_t carve = std::min(want, (size_t)prop.persistingL2CacheMaxSize);
-    if (carve == 0) return 0;
-    CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
-    cudaStreamAttrValue attr;
-    std::memset(&attr, 0, sizeof(attr));
-    attr.accessPolicyWindow.base_ptr = h->d_qt;
-    attr.accessPolicyWindow.num_bytes = std::min(h->qt_bytes, (size_t)prop.accessPolicyMaxWindowSize);
-    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)std::max<size_t>(attr.accessPolicyWindow.num_bytes, 1));
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    CK(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-    return 0;
-}
 
 int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     if (!d || !out) return MOVFEM_E_BADARG;
@@ -646,8 +608,8 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < EV_COUNT; ++i) CK(cudaEventCreate(&h->ev[i]));
     CK(cudaMallocHost((void **)&h->h_status, 4 * sizeof(int)));
-    CK(cudaMallocHost((void **)&h->h_count, sizeof(int64_t)));
-    h->h_status[0] = 0; *h->h_count = 0;
+    CK(cudaMallocHost((void **)&h->h_count, 3 * sizeof(int64_t)));
+    h->h_status[0] = 0; h->h_count[0] = h->h_count[1] = h->h_count[2] = 0;
 
     // mesh upload (once per run)
     CK(dmalloc(&h->d_xp, (size_t)m.nnx)); CK(dmalloc(&h->d_yp, (size_t)m.nny));
@@ -671,8 +633,8 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     }
     init_pml(*d, m, h->pml);
 
-    CK(dmalloc(&h->d_status, 1)); CK(dmalloc(&h->d_flags, 2));
-    CK(cudaMemset(h->d_status, 0, sizeof(int))); CK(cudaMemset(h->d_flags, 0, 2 * sizeof(int)));
+    CK(dmalloc(&h->d_status, 1)); CK(dmalloc(&h->d_flags, 4));
+    CK(cudaMemset(h->d_status, 0, sizeof(int))); CK(cudaMemset(h->d_flags, 0, 4 * sizeof(int)));
 
     // element lists: stretched = predecessor in loop order carries a GPML flag (Q17); element (1,1,1)
     // always goes through the stretched kernel (its flags are a per-call input).  Scheme 1 (Zhou 2012) has no
@@ -758,17 +720,16 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
         h->qt_bytes = std::max(std::min(need, cap), (size_t)51 * cb);
         CK(cudaMalloc((void **)&h->d_qt, h->qt_bytes));
         CK(cudaMemset(h->d_qt, 0, h->qt_bytes));   // lanes past the end of a ragged last batch read zeros, not NaNs
-        if (int rc_l2 = apply_l2_window(h)) return rc_l2;
     }
     CK(dmalloc(&h->d_a, (size_t)h->nzu));   // the compacted copies (a_c, irn_c, jcn_c) are allocated on first use
     CK(dmalloc(&h->d_rhs, (size_t)2 * std::max(h->nrows, 1)));
     h->nblk_fin = (int)((h->nzu + kFinThreads - 1) / kFinThreads);
     CK(dmalloc(&h->d_blkcnt, (size_t)h->nblk_fin)); CK(dmalloc(&h->d_blkoff, (size_t)h->nblk_fin + 1));
     CK(dmalloc(&h->d_finbsum, (size_t)(h->nblk_fin + kScanTile - 1) / kScanTile + 1));
-    CK(dmalloc(&h->d_total, 1));
+    CK(dmalloc(&h->d_total, 3));
     h->km_valid = false;
     h->km_first[0] = h->km_first[1] = h->km_first[2] = 0;
-    h->pattern_nz_host = -1; h->pattern_host_compacted = false;
+    h->pattern_nz_host = -1; h->last_compacted = false;
     return MOVFEM_OK;
 }
 
@@ -816,7 +777,7 @@ int movfem_set_stream(movfem_handle *h, void *cuda_stream) {
     CK(cudaStreamSynchronize(h->stream));
     if (h->own_stream) { CK(cudaStreamDestroy(h->stream)); h->own_stream = false; }
     h->stream = (cudaStream_t)cuda_stream;
-    return apply_l2_window(h);
+    return MOVFEM_OK;
 }
 
 // exact_kernel over both element lists (exact.cuh): re-evaluates the flagged pairs in the reference's operation order
@@ -825,8 +786,8 @@ static int launch_exact(movfem_handle *h, double omega) {
     ExactArgs X;
     X.m = m; X.pml = h->pml; X.omega = omega; X.T = h->d_tab; X.nodes = h->d_nodes; X.xp = h->d_xp; X.yp = h->d_yp;
     X.batchany = h->d_batchany; X.pairflags = h->d_pairflags; X.W = h->flagW; X.NP = h->NP; X.gne = h->d_gne; X.KM = h->d_KM;
-    auto run = [&](auto kern, size_t smem) -> int {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto run = [&](auto kern, size_t smem, size_t smem_h) -> int {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + smem_h)));
         for (int pass = 0; pass < 2; ++pass) {
             X.list = pass ? h->d_list_pml : h->d_list_plain;
             X.nlist = pass ? h->n_pml : h->n_plain;
@@ -835,23 +796,23 @@ static int launch_exact(movfem_handle *h, double omega) {
             if (X.nlist <= 0) continue;
             const int nb = (X.nlist + 31) / 32;
             if (kernel_event(h, 2, true)) return MOVFEM_E_CUDA;
-            kern<<<std::min(nb, 2 * h->num_sms), 256, smem, h->stream>>>(X);
+            kern<<<std::min(nb, 2 * h->num_sms), 256, smem + (pass ? smem_h : 0), h->stream>>>(X);
             h->launches += 1;
             CK(cudaGetLastError());
             if (kernel_event(h, 2, false)) return MOVFEM_E_CUDA;
         }
         return 0;
     };
-    if (m.me == 12) return run(exact_kernel<8, 12, 8>, ExactCfg<8, 12, 8>::SMEM);
-    if (m.me == 36) return run(exact_kernel<20, 36, 27>, ExactCfg<20, 36, 27>::SMEM);
-    return run(exact_kernel<27, 54, 27>, ExactCfg<27, 54, 27>::SMEM);
+    if (m.me == 12) return run(exact_kernel<8, 12, 8>, ExactCfg<8, 12, 8>::SMEM, ExactCfg<8, 12, 8>::SMEM_H);
+    if (m.me == 36) return run(exact_kernel<20, 36, 27>, ExactCfg<20, 36, 27>::SMEM, ExactCfg<20, 36, 27>::SMEM_H);
+    return run(exact_kernel<27, 54, 27>, ExactCfg<27, 54, 27>::SMEM, ExactCfg<27, 54, 27>::SMEM_H);
 }
 
 // gather + RHS + the counters' way back to the host
 static int launch_gather(movfem_handle *h, double omega, int32_t mode, int cache) {
     cudaStream_t st = h->stream;
     const int gmode = mode == MOVFEM_MODE_T1 ? 1 : 0;
-    if (gmode == 0) CK(cudaMemsetAsync(h->d_total, 0, sizeof(unsigned long long), st));
+    if (gmode == 0) CK(cudaMemsetAsync(h->d_total, 0, 3 * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(h->d_nflag + 1, 0, sizeof(unsigned long long), st));
     double dk = -1.0, dm = -1.0;
     if (const char *t = getenv("MOVFEM_TEST_DOUBT_ABS")) sscanf(t, "%lf,%lf", &dk, &dm);   // test hook (tests/test_gpu_parity.py)
@@ -860,7 +821,7 @@ static int launch_gather(movfem_handle *h, double omega, int32_t mode, int cache
                                                               h->NP, h->flagW, h->d_pairflags, h->d_batchany, h->d_nflag + 1, dk, dm);
     h->launches += 1;
     CK(cudaGetLastError());
-    if (mode == MOVFEM_MODE_T2) CK(cudaMemcpyAsync(h->h_count, h->d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (mode == MOVFEM_MODE_T2) CK(cudaMemcpyAsync(h->h_count, h->d_total, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h->h_nflag, h->d_nflag, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     return 0;
 }
@@ -885,7 +846,7 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
         for (int k = 0; k < 3; ++k) h->km_first[k] = h->pml.first[k];
     }
     const bool full = !h->km_valid;
-    CK(cudaMemsetAsync(h->d_flags, 0, 2 * sizeof(int), st));
+    CK(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int), st));
     if (full) {   // a cold pass re-derives the tiny-pair flags
         if (h->flags_dirty) {
             CK(cudaMemsetAsync(h->d_pairflags, 0, sizeof(uint32_t) * (size_t)h->km_rows * h->flagW, st));
@@ -987,7 +948,7 @@ int movfem_device_result(const movfem_handle *hc, const int32_t **irn, const int
         if (h->nflag_last > 0 || h->h_nflag[1] > 0) h->flags_dirty = true;
         if (h->mode_last == MOVFEM_MODE_T1) h->nz_last = h->nzu;
         else {
-            h->nz_last = *h->h_count;
+            h->nz_last = h->h_count[0];
             if (h->nz_last != h->nzu) {   // find_zeros > 0: rem_zeros (global_assembly.f90:134-150)
                 if (!h->offsets_valid) {
                     const int nb = (h->nblk_fin + kScanTile - 1) / kScanTile;
@@ -1016,12 +977,13 @@ int movfem_device_result(const movfem_handle *hc, const int32_t **irn, const int
         h->stats.ms_node = ms(EV_H2D, EV_NODE); h->stats.ms_element = ms(EV_NODE, EV_ELEM);
         h->stats.ms_gather = ms(EV_ELEM, EV_GATHER); h->stats.ms_finalize = ms(EV_GATHER, EV_FINAL);
         h->stats.ms_total = ms(EV_H2D, EV_FINAL); h->stats.nz = h->nz_last; h->stats.launches = h->launches;
-        h->stats.ms_geometry = h->stats.ms_contract = h->stats.ms_exact = 0;
+        h->stats.ms_geometry = h->stats.ms_contract = h->stats.ms_exact = h->stats.ms_fused = 0;
         h->stats.nflagged = h->nflag_last;
         for (size_t k = 0; k < h->kev_kind.size(); ++k) {
             float t = 0;
             cudaEventElapsedTime(&t, h->kev[2 * k], h->kev[2 * k + 1]);
-            (h->kev_kind[k] == 2 ? h->stats.ms_exact : (h->kev_kind[k] ? h->stats.ms_contract : h->stats.ms_geometry)) += t;
+            const int kind = h->kev_kind[k];   // 0 geometry, 1 contraction, 2 exact, 3 fused linear-element kernel
+            (kind == 3 ? h->stats.ms_fused : kind == 2 ? h->stats.ms_exact : kind == 1 ? h->stats.ms_contract : h->stats.ms_geometry) += t;
         }
     }
     if (irn) *irn = h->compacted ? h->d_irn_c : h->d_irn;
@@ -1050,19 +1012,86 @@ int movfem_device_csr(const movfem_handle *hc, const int64_t **rowptr, int32_t *
     return MOVFEM_OK;
 }
 
+// ---- the host link of movfem_assemble ------------------------------------------------------------------------------------
+// The caller's arrays are Fortran `allocate`d, i.e. pageable: a plain cudaMemcpyAsync into them is a synchronous, driver-staged
+// copy at a fraction of the link rate.  Everything that leaves for pageable memory therefore goes through a ring of three pinned
+// 32 MiB buffers: the copy of chunk c+1 is in flight while the host threads move chunk c to its destination.  The T2 values are
+// float32-exact (global_assembly.f90:157), so they cross the link as complex64 (8 instead of 16 B per entry) and are widened by
+// the same threads -- bit-identical to copying the complex128 values.
+constexpr size_t kStageBytes = (size_t)32 << 20;
+
+static bool host_is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static int host_threads() {
+    static int n = 0;
+    if (n == 0) {
+        const char *e = getenv("MOVFEM_HOST_THREADS");
+        n = e ? std::max(1, atoi(e)) : std::max(1, std::min(16, omp_get_num_procs()));
+    }
+    return n;
+}
+
+// kind 0: n bytes as they are; kind 1: n float2 -> n complex128
+static int pipe_d2h(movfem_handle *h, void *dst, const void *src_dev, size_t n, int kind) {
+    if (n == 0) return 0;
+    for (int i = 0; i < 3; ++i)
+        if (!h->stage[i]) { CK(cudaMallocHost((void **)&h->stage[i], kStageBytes)); CK(cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming)); }
+    const size_t isz = kind ? sizeof(float2) : 1, per = kStageBytes / isz, nchunks = (n + per - 1) / per;
+    const char *src = static_cast<const char *>(src_dev);
+    auto issue = [&](size_t c) -> cudaError_t {
+        const size_t cnt = std::min(per, n - c * per);
+        cudaError_t e = cudaMemcpyAsync(h->stage[c % 3], src + c * per * isz, cnt * isz, cudaMemcpyDeviceToHost, h->stream);
+        return e != cudaSuccess ? e : cudaEventRecord(h->stage_ev[c % 3], h->stream);
+    };
+    CK(issue(0));
+    const int nt = host_threads();
+    for (size_t c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) CK(issue(c + 1));
+        CK(cudaEventSynchronize(h->stage_ev[c % 3]));
+        const size_t cnt = std::min(per, n - c * per);
+        if (kind) {
+            const float2 *s2 = reinterpret_cast<const float2 *>(h->stage[c % 3]);
+            double2 *d2 = static_cast<double2 *>(dst) + c * per;
+#pragma omp parallel for num_threads(nt) schedule(static)
+            for (int64_t i = 0; i < (int64_t)cnt; ++i) d2[i] = make_double2((double)s2[i].x, (double)s2[i].y);
+        } else {
+            char *d1 = static_cast<char *>(dst) + c * per;
+            const char *s1 = h->stage[c % 3];
+            const int64_t nsl = (int64_t)((cnt + ((size_t)1 << 20) - 1) >> 20);
+#pragma omp parallel for num_threads(nt) schedule(static)
+            for (int64_t k = 0; k < nsl; ++k) {
+                const size_t o = (size_t)k << 20;
+                std::memcpy(d1 + o, s1 + o, std::min((size_t)1 << 20, cnt - o));
+            }
+        }
+    }
+    return 0;
+}
+
+// pinned destination: one asynchronous copy; pageable: the staging ring
+static int deliver(movfem_handle *h, void *dst, const void *src_dev, size_t bytes, bool pinned) {
+    if (pinned) { CK(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, h->stream)); return 0; }
+    return pipe_d2h(h, dst, src_dev, bytes, 0);
+}
+
 int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega, const double *g_sigma, int32_t *irn, int32_t *jcn,
                     double *a, double *rhs, int64_t *nz_out, int32_t mode_flags) {
     if (!h || !g_sigma || !irn || !jcn || !a || !rhs || !nz_out) return MOVFEM_E_BADARG;
     const int32_t mode = mode_flags & 0xff;
-    // static structural pattern already in the caller's arrays (and not a compacted one)?
-    const bool keep = (mode_flags & MOVFEM_MODE_KEEP_PATTERN) && h->pattern_nz_host == h->nzu && !h->pattern_host_compacted;
     CK(cudaSetDevice(h->device));
-    const MeshDims &m = h->m;
     cudaStream_t st = h->stream;
+    const bool want_keep = (mode_flags & MOVFEM_MODE_KEEP_PATTERN) != 0;
+    const bool pin_irn = host_is_pinned(irn), pin_jcn = host_is_pinned(jcn), pin_a = host_is_pinned(a), pin_rhs = host_is_pinned(rhs);
     CK(cudaEventRecord(h->ev[EV_START], st));
-    // IRN/JCN of the structural pattern never change: start their D2H now, on the copy stream, so that it overlaps
-    // the H2D of g_sigma (PCIe is full duplex) and the kernels.  If rem_zeros strips entries (rare) they are re-sent.
-    if (!keep) {
+    // IRN/JCN of the structural pattern never change: when the caller wants them every call (no KEEP_PATTERN), its arrays are
+    // pinned and the last result had nothing stripped, their D2H starts now, on the copy stream, and overlaps the H2D of
+    // g_sigma (PCIe is full duplex) and the kernels.  If rem_zeros then strips entries, the compacted pattern is sent instead.
+    const bool spec = !want_keep && pin_irn && pin_jcn && !h->last_compacted;
+    if (spec) {
         CK(cudaMemcpyAsync(irn, h->d_irn, sizeof(int) * (size_t)h->nzu, cudaMemcpyDeviceToHost, h->copy_stream));
         CK(cudaMemcpyAsync(jcn, h->d_jcn, sizeof(int) * (size_t)h->nzu, cudaMemcpyDeviceToHost, h->copy_stream));
     }
@@ -1075,18 +1104,33 @@ int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega, const do
     int64_t nz = 0;
     rc = movfem_device_result(h, &d_irn, &d_jcn, &d_a, &d_rhs, &nz);
     if (rc) { cudaStreamSynchronize(h->copy_stream); return rc; }
-    CK(cudaMemcpyAsync(a, d_a, sizeof(double2) * (size_t)nz, cudaMemcpyDeviceToHost, st));
+    // values: into pinned memory one asynchronous copy at the link rate; into pageable memory complex64 over the link and
+    // widening by the host threads that have to touch the destination anyway (T2 values are float32-exact).  Measured on
+    // config 5 (1.63 G entries): widening into PINNED memory is slower than the plain 16 B/entry copy (0.67 s vs 0.47 s)
+    if (mode == MOVFEM_MODE_T2 && !pin_a && !getenv("MOVFEM_NO_C64")) {
+        if (!h->d_a32) CK(dmalloc(&h->d_a32, (size_t)h->nzu));
+        if (nz > 0) narrow_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, st>>>(nz, reinterpret_cast<const double2 *>(d_a), h->d_a32);
+        h->launches += 1;
+        CK(cudaGetLastError());
+        if ((rc = pipe_d2h(h, a, h->d_a32, (size_t)nz, 1))) return rc;
+    } else if ((rc = deliver(h, a, d_a, sizeof(double2) * (size_t)nz, pin_a))) return rc;
     // RHS: the caller's array is rhs(ndir*nne), column d at offset (d-1)*nne (global_assembly.f90:70-74); a slab handle
     // fills only its own rows, so several handles can complete one array
     for (int dd = 0; dd < 2; ++dd)
-        CK(cudaMemcpyAsync(rhs + 2 * ((size_t)dd * h->nne + h->row_lo), d_rhs + 2 * (size_t)dd * h->nrows, sizeof(double2) * (size_t)h->nrows,
-                           cudaMemcpyDeviceToHost, st));
+        if ((rc = deliver(h, rhs + 2 * ((size_t)dd * h->nne + h->row_lo), d_rhs + 2 * (size_t)dd * h->nrows, sizeof(double2) * (size_t)h->nrows, pin_rhs))) return rc;
     CK(cudaStreamSynchronize(h->copy_stream));
-    if (h->compacted) {   // find_zeros > 0: the delivered pattern is the compacted one
-        CK(cudaMemcpyAsync(irn, d_irn, sizeof(int) * (size_t)nz, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(jcn, d_jcn, sizeof(int) * (size_t)nz, cudaMemcpyDeviceToHost, st));
+    // pattern: already on its way (speculative copy, nothing stripped), still in the caller's arrays (KEEP_PATTERN and the
+    // same delivered set -- same nz and same signature of the stripped entries -- in the same arrays), or sent now
+    const int64_t sig0 = h->compacted ? h->h_count[1] : 0, sig1 = h->compacted ? h->h_count[2] : 0;
+    const bool same = h->pattern_nz_host == nz && h->pattern_sig_host[0] == sig0 && h->pattern_sig_host[1] == sig1 &&
+                      h->pattern_ptr_host[0] == irn && h->pattern_ptr_host[1] == jcn;
+    if (!(spec && !h->compacted) && !(want_keep && same)) {
+        if ((rc = deliver(h, irn, d_irn, sizeof(int) * (size_t)nz, pin_irn))) return rc;
+        if ((rc = deliver(h, jcn, d_jcn, sizeof(int) * (size_t)nz, pin_jcn))) return rc;
     }
-    h->pattern_nz_host = h->compacted ? nz : h->nzu; h->pattern_host_compacted = h->compacted;
+    h->pattern_nz_host = nz; h->pattern_sig_host[0] = sig0; h->pattern_sig_host[1] = sig1;
+    h->pattern_ptr_host[0] = irn; h->pattern_ptr_host[1] = jcn;
+    if (mode == MOVFEM_MODE_T2) h->last_compacted = h->compacted;
     CK(cudaEventRecord(h->ev[EV_D2H], st));
     CK(cudaStreamSynchronize(st));
     *nz_out = nz;

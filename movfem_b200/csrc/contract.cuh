@@ -28,24 +28,7 @@
 
 namespace movfem {
 
-#ifndef MOVFEM_KM_ST
-#define MOVFEM_KM_ST 0          // A/B builds: 1 = K_e/M_e leave with streaming stores (they are read much later, by the gather)
-#endif
-
-#ifndef MOVFEM_CON_UNROLL
-#define MOVFEM_CON_UNROLL 3      // unroll of the Gauss-point loop (A/B builds: 1, 9)
-#endif
-constexpr int kConUnroll = MOVFEM_CON_UNROLL;
-
-#ifndef MOVFEM_TALL_TILES
-#define MOVFEM_TALL_TILES 0     // A/B builds: 1 = 8x4 tiles for the unstretched 20/27-node elements (see tall_tile below)
-#endif
-#ifndef MOVFEM_FOLD_PRODUCER
-#define MOVFEM_FOLD_PRODUCER 0  // A/B builds: 1 = no producer warp in any contraction kernel (lane 0 of consumer warp 0 issues the bulk
-#endif                          // copies), so W can be a multiple of four with every warp a consumer (16 x 128 registers fill the file)
-#ifndef MOVFEM_TALL_RG
-#define MOVFEM_TALL_RG 2        // row groups per tall tile: 2 (8x4) or 3 (12x4: 192 accumulator registers)
-#endif
+constexpr int kConUnroll = 3;   // unroll of the Gauss-point loop (1: -10 %, 9: +1.5 % and twice the code; profiles/r02_ab_results.md)
 
 constexpr int kMaxTiles = 120;   // me=54: 15 groups of 4 slots
 
@@ -56,19 +39,11 @@ struct ContractTables {
     unsigned char tile_ti[kMaxTiles], tile_tj[kMaxTiles];   // tiles sorted by class
     short cls_begin[8];                  // first tile of class c (c = 0..5), cls_begin[6] = number of tiles
     unsigned char comp[2][6][10];        // [pml][class][k]: scratch component streamed to stage block k
-#if MOVFEM_TALL_TILES
-    // tall tiles: (first row group, column group, number of row groups 1|2), sorted by class; rows of one direction only
-    unsigned char tall_ti[kMaxTiles], tall_tj[kMaxTiles], tall_rg[kMaxTiles];
-    short tall_begin[8];
-#endif
 };
 __constant__ ContractTables c_ct;
-#ifndef MOVFEM_TAB_GLOBAL
-#define MOVFEM_TAB_GLOBAL 0     // A/B builds: 1 = the CTA's shared-memory operand table is filled from a global-memory copy.
-#endif                          // ncu (r01): the fill from the constant bank (lane-distinct LDC, serialised) takes 4 % of the warp samples
-#if MOVFEM_TAB_GLOBAL
+// The CTAs fill their shared-memory operand table from this global copy of c_ct.at: the fill from the constant bank is a
+// lane-distinct LDC (serialised), 4 % of contract_kernel's warp samples in round 1; measured -3 % on the kernel.
 __device__ double g_ct_at[kMaxGp * 4 * kMaxSlots];
-#endif
 
 // class c <-> (dI, dJ), dI >= dJ
 __host__ __device__ __forceinline__ constexpr int cls_dI(int c) { return c == 0 ? 0 : (c <= 2 ? 1 : 2); }
@@ -104,76 +79,11 @@ struct ContractCfg {
     static constexpr int NCMP = PML ? 51 : 12;       // scratch components per (element, Gauss point): P(45)|Q(6), T(6)
     static constexpr int CB = NGP * 32;              // doubles per component block
     static constexpr int STAGE_D = NC * CB;
-    // MOVFEM_TALL_TILES == 2 (A/B): the tall-tile kernels have no producer warp -- lane 0 of consumer warp 0 issues the bulk
-    // copies -- so that 8 warps x 32 threads can use the full 255 registers (the register file is per SMSP: a ninth warp
-    // would cap every thread at 168)
-    static constexpr bool FOLD = ((MOVFEM_TALL_TILES == 2) && !PML_ && MEP_ > 12) || (MOVFEM_FOLD_PRODUCER != 0);
-    static constexpr int THREADS = (W + (FOLD ? 0 : 1)) * 32;
+    static constexpr int THREADS = (W + 1) * 32;     // W consumer warps + the producer warp
     static constexpr int TAB_D = NGP * 4 * MEP;      // constant operand table, broadcast-read from shared memory
     static constexpr size_t SMEM = sizeof(double) * ((size_t)STAGES * STAGE_D + TAB_D) + sizeof(uint64_t) * 2 * STAGES;
     static constexpr int NT = MEP / 4, NTILES = NT * (NT + 1) / 2, NP = ME * (ME + 1) / 2;
 };
-
-#if MOVFEM_TALL_TILES
-// A/B variant (not the default; measured in isolation by tools/micro/tile_bench.cu: +17 % pair updates per cycle).  A warp
-// takes RG = 2 row groups of ONE direction against one column group: the column operands and b1/b2/bw are formed once for
-// 8 rows, 116 instead of 2 x 68 FP64 instructions and 18 instead of 24 broadcast LDS.128 per Gauss point.  Every pair is
-// accumulated by the same dfma chain in the same Gauss-point order as in the 4x4 path, so the results are bit-identical.
-template <int RG, int MEP, int NGP>
-__device__ __forceinline__ void tall_tile(const double *__restrict__ S, const double *__restrict__ s_tab, int ti, int tj, int k1I, int k2I,
-                                          int k1J, int k2J, double tau, double2 *__restrict__ KMo, bool live) {
-    double accK[RG * 16], accM[RG * 16];
-#pragma unroll
-    for (int i = 0; i < RG * 16; ++i) { accK[i] = 0.0; accM[i] = 0.0; }
-    const double *Y1 = s_tab + k1I * MEP + 4 * ti, *Y2 = s_tab + k2I * MEP + 4 * ti, *Y3 = s_tab + 3 * MEP + 4 * ti;
-    const double *X1 = s_tab + k1J * MEP + 4 * tj, *X2 = s_tab + k2J * MEP + 4 * tj, *X3 = s_tab + 3 * MEP + 4 * tj;
-#pragma unroll kConUnroll
-    for (int g = 0; g < NGP; ++g) {
-        const int o = g * 4 * MEP;
-        const double q00 = S[(0 * NGP + g) * 32], q01 = S[(1 * NGP + g) * 32], q10 = S[(2 * NGP + g) * 32],
-                     q11 = S[(3 * NGP + g) * 32], tt = S[(4 * NGP + g) * 32];
-        double b1[4], b2[4], bw[4], xa[4], xb[4], xc[4];
-        ld4(xa, X1 + o); ld4(xb, X2 + o); ld4(xc, X3 + o);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            b1[j] = dfma(q00, xa[j], -(q01 * xb[j]));
-            b2[j] = dfma(q10, xa[j], -(q11 * xb[j]));
-            bw[j] = xc[j] * tt;
-        }
-#pragma unroll
-        for (int rg = 0; rg < RG; ++rg) {
-            double ya[4], yb[4], yc[4];
-            ld4(ya, Y1 + o + 4 * rg); ld4(yb, Y2 + o + 4 * rg); ld4(yc, Y3 + o + 4 * rg);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double y1 = ya[i], y2 = yb[i], y3 = yc[i];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int a = (rg * 4 + i) * 4 + j;
-                    accK[a] = dfma(y1, b1[j], dfma(-y2, b2[j], accK[a]));
-                    accM[a] = dfma(y3, bw[j], accM[a]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < RG * 16; ++i) accK[i] *= tau;
-    if (live) {
-#pragma unroll
-        for (int i = 0; i < RG * 4; ++i) {
-            const int si = 4 * ti + i, im = c_ct.slot_dof[si];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int sj = 4 * tj + j, jm = c_ct.slot_dof[sj];
-                if (im >= 0 && jm >= 0 && sj <= si) {
-                    const int hi = im > jm ? im : jm, lo = im > jm ? jm : im;
-                    KMo[(hi * (hi + 1) / 2 + lo) * 32] = make_double2(accK[i * 4 + j], accM[i * 4 + j]);
-                }
-            }
-        }
-    }
-}
-#endif
 
 template <class CFG>
 __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(ContractArgs A) {
@@ -189,11 +99,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(Contr
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int nbatch = (A.nlist + 31) / 32;
-#if MOVFEM_TAB_GLOBAL
     for (int i = threadIdx.x; i < CFG::TAB_D; i += CFG::THREADS) s_tab[i] = g_ct_at[i];
-#else
-    for (int i = threadIdx.x; i < CFG::TAB_D; i += CFG::THREADS) s_tab[i] = c_ct.at[i];
-#endif
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], W); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -223,74 +129,12 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(Contr
         return;
     }
 
-    // folded producer (CFG::FOLD): item k2 of this CTA into its ring slot; same protocol as the producer warp above
-    auto issue = [&](int k2) {
-        const int n2 = n0 + k2;
-        if (n2 >= n1) return;
-        const int b2 = n2 / 6, c2 = n2 - b2 * 6;
-        const double *src = A.qt + (size_t)b2 * NCMP * CB;
-        const int slot2 = k2 % STAGES, round2 = k2 / STAGES;
-        if (round2 > 0) mbar_wait(&empty[slot2], (unsigned)((round2 - 1) & 1));
-        mbar_expect_tx(&full[slot2], (unsigned)(STAGE_D * sizeof(double)));
-        double *dst = s_stage + (size_t)slot2 * STAGE_D;
-#pragma unroll 1
-        for (int q = 0; q < NC; ++q)
-            bulk_g2s(dst + q * CB, src + (size_t)c_ct.comp[PML ? 1 : 0][c2][q] * CB, (unsigned)(CB * sizeof(double)), &full[slot2]);
-    };
-    // prefetch distance: STAGES-2 where the ring allows (the slot asked for at item k was released at item k-2 by every
-    // warp, so the issuing lane practically never waits while its own tiles are pending), else 1
-    constexpr int PFD = STAGES > 2 ? STAGES - 2 : 1;
-    if (CFG::FOLD && warp == 0 && lane == 0)
-        for (int k2 = 0; k2 < PFD; ++k2) issue(k2);
-#if MOVFEM_TALL_TILES
-    if constexpr (!PML && MEP > 12) {
-        // ---- consumers, tall-tile variant: same item walk, the tile stream is the tall list ----
-        const int ntt = c_ct.tall_begin[6];
-        const int tpos0 = (n0 / 6) * ntt + c_ct.tall_begin[n0 % 6];
-#pragma unroll 1
-        for (int n = n0; n < n1; ++n) {
-            const int b = n / 6, c = n - b * 6, k = n - n0;
-            if (CFG::FOLD && warp == 0) {
-                if (lane == 0) issue(k + PFD);
-                __syncwarp();
-            }
-            const bool live = b * 32 + lane < A.nlist;
-            double2 *KMo = A.KM + (size_t)b * NP * 32 + lane;
-            const int slot = k % STAGES, round = k / STAGES;
-            mbar_wait(&full[slot], (unsigned)(round & 1));
-            const double *S = s_stage + (size_t)slot * STAGE_D + lane;
-            const int dI = cls_dI(c), dJ = cls_dJ(c);
-            const int t_lo = c_ct.tall_begin[c], t_hi = c_ct.tall_begin[c + 1];
-            const int k1I = dI == 2 ? 1 : 2, k2I = dI == 0 ? 1 : 0, k1J = dJ == 2 ? 1 : 2, k2J = dJ == 0 ? 1 : 0;
-            const double tau = ((dI == 1) != (dJ == 1)) ? -1.0 : 1.0;
-            const int first = (b * ntt + t_lo - tpos0) % W;
-#pragma unroll 1
-            for (int t = t_lo + ((warp - first + W) % W); t < t_hi; t += W) {
-                const int ti = c_ct.tall_ti[t], tj = c_ct.tall_tj[t];
-                const int rg = c_ct.tall_rg[t];
-#if MOVFEM_TALL_RG >= 3
-                if (rg == 3) tall_tile<3, MEP, NGP>(S, s_tab, ti, tj, k1I, k2I, k1J, k2J, tau, KMo, live);
-                else
-#endif
-                if (rg == 2) tall_tile<2, MEP, NGP>(S, s_tab, ti, tj, k1I, k2I, k1J, k2J, tau, KMo, live);
-                else tall_tile<1, MEP, NGP>(S, s_tab, ti, tj, k1I, k2I, k1J, k2J, tau, KMo, live);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[slot]);
-        }
-        return;
-    }
-#endif
     // ---- consumers ----
     const int pos0 = (n0 / 6) * CFG::NTILES + c_ct.cls_begin[n0 % 6];   // stream position of the CTA's first tile
     {
 #pragma unroll 1
         for (int n = n0; n < n1; ++n) {
             const int b = n / 6, c = n - b * 6, k = n - n0;
-            if (CFG::FOLD && warp == 0) {
-                if (lane == 0) issue(k + PFD);
-                __syncwarp();
-            }
             const bool live = b * 32 + lane < A.nlist;
             double2 *KMo = A.KM + (size_t)b * NP * 32 + lane;
             const int slot = k % STAGES, round = k / STAGES;

@@ -38,7 +38,7 @@ namespace movfem {
 // ------------------------------------------------------------------------------------------
 __global__ void node_kernel(int n0, int npt, double omega, const double *__restrict__ zp, const double *__restrict__ mu,
                             const double2 *__restrict__ sigma, NodeRec *__restrict__ out, int *__restrict__ status,
-                            int *__restrict__ flags /* [0]: any dmu != 0, [1]: Re sigma changed */, int check_re) {
+                            int *__restrict__ flags /* [0]: any dmu != 0, [1]: Re sigma changed, [2]: any off-diagonal sigma */, int check_re) {
     const int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;   // [n0, npt): the node planes this handle's slab touches
     if (i >= npt) return;
     double a[6];
@@ -85,21 +85,13 @@ __global__ void node_kernel(int n0, int npt, double omega, const double *__restr
     for (int k = 0; k < 6; ++k) anyd |= (d[k] != 0.0);
     if (anyd) flags[0] = 1;
     if (changed) flags[1] = 1;
+    if (s[1].x != 0.0 || s[1].y != 0.0 || s[2].x != 0.0 || s[2].y != 0.0 || s[4].x != 0.0 || s[4].y != 0.0) flags[2] = 1;
     out[i] = r;
 }
 
 // ------------------------------------------------------------------------------------------
 // element kernel
 // ------------------------------------------------------------------------------------------
-#ifndef MOVFEM_RHS_PER_SLOT
-#define MOVFEM_RHS_PER_SLOT 0   // A/B builds: 1 = RHS phase with one thread per (element, slot) instead of per group of four slots
-#endif
-#ifndef MOVFEM_GEO_EARLY_REQ
-#define MOVFEM_GEO_EARLY_REQ 0  // A/B builds: 1 = phase B2 reads z and the x/y lines from a small copy made during B1, so the staged node
-#endif                          // records are dead after B1 and the next batch's bulk copies are issued one phase earlier (B2 + RHS to land)
-#ifndef MOVFEM_GEO_PREFETCH
-#define MOVFEM_GEO_PREFETCH 0   // A/B builds: 1 = L2 prefetch of the next batch's node records during phase B2.  ncu (r01): 19 % of
-#endif                          // geometry_kernel's warp samples sit in the wait for the node-record bulk copies (phase A)
 struct ElemArgs {
     MeshDims m;
     PmlParams pml;
@@ -148,8 +140,7 @@ struct ElemCfg {
     static constexpr size_t ATAB_D = (size_t)NGP * MEP + (size_t)MN * 4 * NGPP, GEO_D = (size_t)EB * NGP * GEO;
     static constexpr int NSTR = MN * NDW + 2;              // per-element stride of the node records (+16 B: bank shift)
     static constexpr size_t NODES_D = (size_t)EB * NSTR;
-    static constexpr int ZXY = MN + 6;                      // MOVFEM_GEO_EARLY_REQ: per element z of every node, 3 x lines, 3 y lines
-    static constexpr size_t ZXY_D = MOVFEM_GEO_EARLY_REQ ? (size_t)((EB * ZXY + 1) & ~1) : 0;
+    static constexpr size_t ZXY_D = 0;
     static constexpr size_t SMEM = sizeof(double) * (ATAB_D + GEO_D + NODES_D + ZXY_D + EB + 1 + 2 * EB) + sizeof(int) * (EB * 4 + 2 * MEP + 2 * EB + 3 * MN);
     static_assert((ATAB_D % 2) == 0 && (GEO_D % 2) == 0, "16-byte alignment of the smem regions");
     static_assert(32 % EB == 0, "a batch of the contraction (32 lanes) is a whole number of geometry batches");
@@ -205,9 +196,6 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
     double *s_dN = s_phi + NGP * MEP;                              // [MN][4][NGPP]: dN/dxi (0..2), N (3); Gauss point fastest
     double *s_geo = s_phi + CFG::ATAB_D;                              // [NGP][EB][GEO]
     double *s_nodes = s_geo + CFG::GEO_D;                             // [EB][MN][NDW]
-#if MOVFEM_GEO_EARLY_REQ
-    double *s_zxy = s_nodes + CFG::NODES_D;                           // [EB][MN + 6]
-#endif
     int64_t *s_rbase = reinterpret_cast<int64_t *>(s_nodes + CFG::NODES_D + CFG::ZXY_D);   // [EB] base node id of the batch being prefetched
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_rbase + EB);     // mbarrier of the node-record bulk copies
     unsigned long long *s_scale = reinterpret_cast<unsigned long long *>(s_bar + 1);   // [EB][2]: max_g tr Q|P, max_g tr T (bit patterns of >= 0 doubles)
@@ -294,32 +282,6 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         mbar_wait(s_bar, node_phase);
         node_phase ^= 1;
         __syncthreads();
-#if MOVFEM_GEO_PREFETCH || MOVFEM_GEO_EARLY_REQ
-        // A/B variants: resolve the NEXT batch's node ids already here (s_rbase / s_rxy have no reader during B1) so that
-        // phase B2 can start pulling its records into L2 (PREFETCH) or issue the bulk copies themselves (EARLY_REQ)
-        if (batch + (int)gridDim.x < nbatch) prepare_request(batch + gridDim.x);
-#endif
-#if MOVFEM_GEO_EARLY_REQ
-        {   // what B2 needs from the staged records: z of every node and the 2 or 3 distinct x / y values
-            constexpr int NORDc = MN == 8 ? 2 : 3;
-            for (int i = tid; i < nb * CFG::ZXY; i += CFG::THREADS) {
-                const int cs = i / CFG::ZXY, j = i % CFG::ZXY;
-                const double *nd = s_nodes + cs * CFG::NSTR;
-                double v = 0.0;
-                if (j < MN) v = nd[j * NDW];
-                else {
-                    const int q = j - MN;            // 0..2: xs[q], 3..5: ys[q-3]  (same sources as phase B2 below)
-                    if (q == 0) v = nd[2 * NDW + NREC];
-                    else if (q == NORDc - 1) v = nd[NREC];
-                    else if (q == 1 && NORDc == 3) v = nd[9 * NDW + NREC];
-                    else if (q == 3) v = nd[NREC + 1];
-                    else if (q == 3 + NORDc - 1) v = nd[NDW + NREC + 1];
-                    else if (q == 4 && NORDc == 3) v = nd[8 * NDW + NREC + 1];
-                }
-                s_zxy[cs * CFG::ZXY + j] = v;
-            }
-        }
-#endif
 
         // ---- phase B1: interpolate node data to the Gauss points (p_intmodels problem.f90:139-142 and the N_l-weighted
         //      part of p_source problem.f90:424-457): per element the small GEMM  out[g][c] = sum_l N[g][l] V[l][c]
@@ -383,20 +345,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         __syncthreads();
 
         // ---- phase B2: one thread per (Gauss point, element): J, G, GPML, source -> Q|P, T (scratch), R (in place) ----
-#if MOVFEM_GEO_EARLY_REQ
-        if (batch + (int)gridDim.x < nbatch) request_nodes(batch + gridDim.x);   // s_nodes is dead: lands during B2 + RHS
-#elif MOVFEM_GEO_PREFETCH
-        if (batch + (int)gridDim.x < nbatch) {
-            const int nbn = min(EB, A.nlist - (batch + (int)gridDim.x) * EB);
-            for (int i = tid; i < nbn * MN; i += CFG::THREADS) {
-                const char *rec = reinterpret_cast<const char *>(A.nodes + (s_rbase[i / MN] + s_noff[(i % MN) * 3]));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(rec));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 128));   // a 208-byte record spans two or three 128-byte lines
-            }
-        }
-#else
         if (batch + (int)gridDim.x < nbatch) prepare_request(batch + gridDim.x);
-#endif
         if (A.phase_mask & 1) {
             const int has_dmu = A.flags[0];
             const double w32 = f32r(A.omega);            // cmplx(0.d0,-omega), problem.f90:112
@@ -412,22 +361,12 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                 // tensor-product lines (2 or 3 distinct values per element): loaded once, selected per node at compile time
                 constexpr int NORD = MN == 8 ? 2 : 3;
                 double xs[3], ys[3];
-#if MOVFEM_GEO_EARLY_REQ
-                const double *zx = s_zxy + s * CFG::ZXY;
-                xs[0] = zx[MN]; xs[NORD - 1] = zx[MN + NORD - 1]; ys[0] = zx[MN + 3]; ys[NORD - 1] = zx[MN + 3 + NORD - 1];
-                if (NORD == 3) { xs[1] = zx[MN + 1]; ys[1] = zx[MN + 4]; }
-#else
                 xs[0] = nd[2 * NDW + NREC]; xs[NORD - 1] = nd[NREC]; ys[0] = nd[NREC + 1]; ys[NORD - 1] = nd[NDW + NREC + 1];
                 if (NORD == 3) { xs[1] = nd[9 * NDW + NREC]; ys[1] = nd[8 * NDW + NREC + 1]; }
-#endif
                 double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, xg[3] = {0, 0, 0};
 #pragma unroll
                 for (int l = 0; l < MN; ++l) {
-#if MOVFEM_GEO_EARLY_REQ
-                    const double x = xs[kNodeI27[l] * (NORD - 1) / 2], y = ys[kNodeJ27[l] * (NORD - 1) / 2], z = zx[l];
-#else
                     const double x = xs[kNodeI27[l] * (NORD - 1) / 2], y = ys[kNodeJ27[l] * (NORD - 1) / 2], z = nd[l * NDW];
-#endif
 #pragma unroll
                     for (int mm = 0; mm < 3; ++mm) {
                         const double dn = s_dN[(l * 4 + mm) * NGPP + g];
@@ -607,16 +546,11 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
         if (DO_QT && A.escale && tid < nb)
             A.escale[first + tid] = make_double2(NGP * __longlong_as_double((long long)s_scale[tid * 2]), NGP * __longlong_as_double((long long)s_scale[tid * 2 + 1]));
 
-#if !MOVFEM_GEO_EARLY_REQ
         if (batch + (int)gridDim.x < nbatch) request_nodes(batch + gridDim.x);   // lands during the RHS phase / next wait
-#endif
 
-        // ---- RHS: one thread per (element, group of four slots of one direction): blocal / f3,
-        //      integration.f90:96-104,258-263.  R[d] is loaded once per Gauss point for the four slots. ----
-#if MOVFEM_RHS_PER_SLOT
-        // A/B variant: one thread per (element, slot) -- EB*MEP tasks keep every warp busy (the default below has EB*MEP/4
-        // tasks: 72 of 256 threads for the 20-node element, and ncu shows 29 % of the kernel's samples stalled at barriers).
-        // Each (slot, polarisation) sum runs over the Gauss points in the same order: bit-identical.
+        // ---- RHS: blocal / f3, integration.f90:96-104,258-263: one thread per (element, slot) -- EB*MEP tasks keep every warp
+        //      busy (one thread per group of four slots left 72 of 256 threads working on the 20-node element and 29 % of the
+        //      kernel's warp samples at barriers; measured -4 % on the kernel, profiles/r02_ab_results.md) ----
         if (A.phase_mask & 2) {
             for (int i = tid; i < nb * MEP; i += CFG::THREADS) {
                 const int cs = i / MEP, sl = i % MEP;
@@ -636,38 +570,6 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                 reinterpret_cast<double4 *>(A.be)[(e - A.e_base) * ME + cdof] = make_double4(bacc[0], bacc[1], bacc[2], bacc[3]);
             }
         }
-#else
-        if (A.phase_mask & 2) {
-            constexpr int NQ = MEP / 4;
-            for (int i = tid; i < nb * NQ; i += CFG::THREADS) {
-                const int cs = i / NQ, q4 = (i % NQ) * 4;
-                const int cd = s_sdir[q4];
-                double bacc[4][4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) bacc[k][c] = 0.0;
-                const double *R0 = s_geo + cs * GEO + GR + cd * 4, *ph = s_phi + q4;
-#pragma unroll
-                for (int g = 0; g < NGP; ++g) {
-                    const double2 p01 = *reinterpret_cast<const double2 *>(ph + g * MEP), p23 = *reinterpret_cast<const double2 *>(ph + g * MEP + 2);
-                    const double2 r01 = *reinterpret_cast<const double2 *>(R0 + g * EB * GEO), r23 = *reinterpret_cast<const double2 *>(R0 + g * EB * GEO + 2);
-                    const double phi[4] = {p01.x, p01.y, p23.x, p23.y}, R[4] = {r01.x, r01.y, r23.x, r23.y};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) bacc[k][c] = dfma(phi[k], R[c], bacc[k][c]);
-                }
-                const int64_t e = s_el[cs * 4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int cdof = s_slot[q4 + k];
-                    if (cdof >= 0)
-                        reinterpret_cast<double4 *>(A.be)[(e - A.e_base) * ME + cdof] = make_double4(bacc[k][0], bacc[k][1], bacc[k][2], bacc[k][3]);
-                }
-            }
-        }
-#endif
     }
 }
 

@@ -48,28 +48,143 @@ struct ExactArgs {
     int stretched;                 // this list goes through the GPML form of f1/f2 with h != 1 (scheme 0 layers)
 };
 
-// per (element, Gauss point) cache, the module variables of integration.f90:16-17 restated: nf_ji, wgt, mf1, Re mf2, gpml
+// per (element, Gauss point) cache, the module variables of integration.f90:16-17 restated: nf_ji, wgt, mf1, Re mf2 ...
 struct ExactGp {
-    double ji[3][3], wgt, m1[6], m2[6], h[3], hf[3];   // hf: h1*h3/h2, h1*h2/h3, h2*h3/h1 (integration.f90:171-188)
+    double ji[3][3], wgt, m1[6], m2[6];
+};
+// ... and gpml (stretched lists only): h1, h2, h3 and h1*h3/h2, h1*h2/h3, h2*h3/h1 (integration.f90:171-188)
+struct ExactH {
+    double h[3], hf[3];
 };
 
 template <int MN, int ME, int NGP>
 struct ExactCfg {
-    static constexpr int EB = 8, THREADS = 256;
+    // A group of up to EB flagged elements is worked on at a time, chosen so that the group's flagged pairs fill whole
+    // rounds of the CTA's threads (20-node bricks have 36 such pairs each: 14 elements = 504 of 512 thread slots).
+    static constexpr int EB = 14, THREADS = 256, ITEMS = 2 * THREADS;
     static constexpr int NDD = 13;                       // staged per node: z, mu^-1 (6), Re sigma (6)
-    static constexpr size_t SMEM = sizeof(ExactGp) * EB * NGP + sizeof(double) * (EB * MN * NDD + EB * 6) + sizeof(int) * (EB * 8 + 4);
+    static constexpr size_t SMEM = sizeof(ExactGp) * EB * NGP + sizeof(double) * (EB * MN * NDD + EB * 6) + sizeof(int) * (EB * 8 + 4 + 32 + THREADS);
+    static constexpr size_t SMEM_H = sizeof(ExactH) * EB * NGP;   // added for stretched lists
 };
+
+// alocal(im, jm) of one element (integration.f90:76-86): sum over the Gauss points of wgt*(f1 + i*w32*f2) in the reference's
+// operation order.  DIAG: only the 11, 22, 33 components of mu^-1 and Re sigma are non-zero anywhere in the element, so the
+// terms of f1 / f2 that carry another component are exact +-0 and are left out (the sums are unchanged).
+template <bool DIAG>
+__device__ __forceinline__ void exact_pair(const ElemTables &T, const ExactGp *__restrict__ Pg, const ExactH *__restrict__ Hg, int ngp, int im, int jm,
+                                           int di, int dj, bool gpml_form, double w32, double &are, double &aim) {
+    constexpr int zm = DIAG ? 0x2929 : 0x3f3f;
+    for (int g = 0; g < ngp; ++g) {
+        const ExactGp &P = Pg[g];
+        // mix_grad_ln v_fem.f90:478-483, grad_xi :515-518, vf_elem_curl :55-59, vf_elem_ve :41-43
+        double a1[3], a2[3], b1[3], b2[3], va[3], vb[3];
+        {
+            double dn[3], v[3];
+#pragma unroll
+            for (int mm = 0; mm < 3; ++mm) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int nn = 0; nn < 3; ++nn) sacc = sacc + P.ji[mm][nn] * T.dphi[g][im][nn];
+                dn[mm] = sacc; v[mm] = P.ji[mm][di];
+            }
+            a1[0] = dn[1] * v[2]; a2[0] = dn[2] * v[1];
+            a1[1] = dn[2] * v[0]; a2[1] = dn[0] * v[2];
+            a1[2] = dn[0] * v[1]; a2[2] = dn[1] * v[0];
+            const double ph = T.phi[g][im];
+#pragma unroll
+            for (int mm = 0; mm < 3; ++mm) va[mm] = ph * v[mm];
+        }
+        {
+            double dn[3], v[3];
+#pragma unroll
+            for (int mm = 0; mm < 3; ++mm) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int nn = 0; nn < 3; ++nn) sacc = sacc + P.ji[mm][nn] * T.dphi[g][jm][nn];
+                dn[mm] = sacc; v[mm] = P.ji[mm][dj];
+            }
+            b1[0] = dn[1] * v[2]; b2[0] = dn[2] * v[1];
+            b1[1] = dn[2] * v[0]; b2[1] = dn[0] * v[2];
+            b1[2] = dn[0] * v[1]; b2[2] = dn[1] * v[0];
+            const double ph = T.phi[g][jm];
+#pragma unroll
+            for (int mm = 0; mm < 3; ++mm) vb[mm] = ph * v[mm];
+        }
+        const double *mu = P.m1, *sg = P.m2;
+        double v1, v2;
+        // f1, integration.f90:171-207: A(p,s) = cv1 of im, B(q,t) = cv2 of jm
+#define MOVFEM_T(sign, hfac, mk, aa, bb)                                            \
+    if (zm & (1 << (mk))) { const double t_ = (((hfac) * mu[mk]) * (aa)) * (bb); r = (sign) > 0 ? r + t_ : r - t_; }
+#define MOVFEM_U(sign, mk, aa, bb)                                                  \
+    if (zm & (1 << (mk))) { const double t_ = (mu[mk] * (aa)) * (bb); r = (sign) > 0 ? r + t_ : r - t_; }
+        if (gpml_form) {
+            double h1 = 1.0, h2 = 1.0, h3 = 1.0, f13_2 = 1.0, f12_3 = 1.0, f23_1 = 1.0;   // unstretched: (1*1)/1 = 1 exactly
+            if (Hg) {
+                const ExactH &H = Hg[g];
+                h1 = H.h[0]; h2 = H.h[1]; h3 = H.h[2]; f13_2 = H.hf[0]; f12_3 = H.hf[1]; f23_1 = H.hf[2];
+            }
+            double r = 0.0;
+            MOVFEM_T(+1, f13_2, 0, a1[0], b1[0]) MOVFEM_T(-1, h1, 0, a2[0], b1[0]) MOVFEM_T(-1, h1, 0, a1[0], b2[0]) MOVFEM_T(+1, f12_3, 0, a2[0], b2[0])
+            MOVFEM_T(+1, h1, 1, a1[0], b1[1]) MOVFEM_T(-1, f12_3, 1, a2[0], b1[1]) MOVFEM_T(-1, h3, 1, a1[0], b2[1]) MOVFEM_T(+1, h2, 1, a2[0], b2[1])
+            MOVFEM_T(+1, h3, 2, a1[0], b1[2]) MOVFEM_T(-1, h2, 2, a2[0], b1[2]) MOVFEM_T(-1, f13_2, 2, a1[0], b2[2]) MOVFEM_T(+1, h1, 2, a2[0], b2[2])
+            MOVFEM_T(+1, h1, 1, a1[1], b1[0]) MOVFEM_T(-1, h3, 1, a2[1], b1[0]) MOVFEM_T(-1, f12_3, 1, a1[1], b2[0]) MOVFEM_T(+1, h2, 1, a2[1], b2[0])
+            MOVFEM_T(+1, f12_3, 3, a1[1], b1[1]) MOVFEM_T(-1, h2, 3, a2[1], b1[1]) MOVFEM_T(-1, h2, 3, a1[1], b2[1]) MOVFEM_T(+1, f23_1, 3, a2[1], b2[1])
+            MOVFEM_T(+1, h2, 4, a1[1], b1[2]) MOVFEM_T(-1, f23_1, 4, a2[1], b1[2]) MOVFEM_T(-1, h1, 4, a1[1], b2[2]) MOVFEM_T(+1, h3, 4, a2[1], b2[2])
+            MOVFEM_T(+1, h3, 2, a1[2], b1[0]) MOVFEM_T(-1, f13_2, 2, a2[2], b1[0]) MOVFEM_T(-1, h2, 2, a1[2], b2[0]) MOVFEM_T(+1, h1, 2, a2[2], b2[0])
+            MOVFEM_T(+1, h2, 4, a1[2], b1[1]) MOVFEM_T(-1, h1, 4, a2[2], b1[1]) MOVFEM_T(-1, f23_1, 4, a1[2], b2[1]) MOVFEM_T(+1, h3, 4, a2[2], b2[1])
+            MOVFEM_T(+1, f23_1, 5, a1[2], b1[2]) MOVFEM_T(-1, h3, 5, a2[2], b1[2]) MOVFEM_T(-1, h3, 5, a1[2], b2[2]) MOVFEM_T(+1, f13_2, 5, a2[2], b2[2])
+            v1 = r;
+            // f2, integration.f90:228-232: h1*h2*h3*cv2(q)*m(k)*cv1(p), nine terms summed left to right
+            const double hhh = (h1 * h2) * h3;
+            double q = 0.0;
+#define MOVFEM_M(mk, bq, ap) if (zm & (256 << (mk))) q = q + ((hhh * vb[bq]) * sg[mk]) * va[ap];
+            MOVFEM_M(0, 0, 0) MOVFEM_M(1, 1, 0) MOVFEM_M(2, 2, 0) MOVFEM_M(1, 0, 1) MOVFEM_M(3, 1, 1) MOVFEM_M(4, 2, 1)
+            MOVFEM_M(2, 0, 2) MOVFEM_M(4, 1, 2) MOVFEM_M(5, 2, 2)
+#undef MOVFEM_M
+            v2 = q;
+        } else {
+            double r = 0.0;
+            MOVFEM_U(+1, 0, a1[0], b1[0]) MOVFEM_U(-1, 0, a2[0], b1[0]) MOVFEM_U(-1, 0, a1[0], b2[0]) MOVFEM_U(+1, 0, a2[0], b2[0])
+            MOVFEM_U(+1, 1, a1[0], b1[1]) MOVFEM_U(-1, 1, a2[0], b1[1]) MOVFEM_U(-1, 1, a1[0], b2[1]) MOVFEM_U(+1, 1, a2[0], b2[1])
+            MOVFEM_U(+1, 2, a1[0], b1[2]) MOVFEM_U(-1, 2, a2[0], b1[2]) MOVFEM_U(-1, 2, a1[0], b2[2]) MOVFEM_U(+1, 2, a2[0], b2[2])
+            MOVFEM_U(+1, 1, a1[1], b1[0]) MOVFEM_U(-1, 1, a2[1], b1[0]) MOVFEM_U(-1, 1, a1[1], b2[0]) MOVFEM_U(+1, 1, a2[1], b2[0])
+            MOVFEM_U(+1, 3, a1[1], b1[1]) MOVFEM_U(-1, 3, a2[1], b1[1]) MOVFEM_U(-1, 3, a1[1], b2[1]) MOVFEM_U(+1, 3, a2[1], b2[1])
+            MOVFEM_U(+1, 4, a1[1], b1[2]) MOVFEM_U(-1, 4, a2[1], b1[2]) MOVFEM_U(-1, 4, a1[1], b2[2]) MOVFEM_U(+1, 4, a2[1], b2[2])
+            MOVFEM_U(+1, 2, a1[2], b1[0]) MOVFEM_U(-1, 2, a2[2], b1[0]) MOVFEM_U(-1, 2, a1[2], b2[0]) MOVFEM_U(+1, 2, a2[2], b2[0])
+            MOVFEM_U(+1, 4, a1[2], b1[1]) MOVFEM_U(-1, 4, a2[2], b1[1]) MOVFEM_U(-1, 4, a1[2], b2[1]) MOVFEM_U(+1, 4, a2[2], b2[1])
+            MOVFEM_U(+1, 5, a1[2], b1[2]) MOVFEM_U(-1, 5, a2[2], b1[2]) MOVFEM_U(-1, 5, a1[2], b2[2]) MOVFEM_U(+1, 5, a2[2], b2[2])
+            v1 = r;
+            // f2 Dirichlet form, integration.f90:234-236: three parenthesised rows (every product is formed: +-0 where a component
+            // is zero, the association of the reference is kept)
+            double rows[3];
+#pragma unroll
+            for (int pp = 0; pp < 3; ++pp) {
+                const int k0 = sym3(0, pp), k1 = sym3(1, pp), k2 = sym3(2, pp);
+                rows[pp] = ((vb[0] * sg[k0]) * va[pp] + (vb[1] * sg[k1]) * va[pp]) + (vb[2] * sg[k2]) * va[pp];
+            }
+            v2 = (rows[0] + rows[1]) + rows[2];
+        }
+#undef MOVFEM_T
+#undef MOVFEM_U
+        // alocal, integration.f90:84: a = a + wgt*(f1 + cmplx(0,omega)*f2), cmplx() single precision (Q2)
+        are = are + P.wgt * v1;
+        aim = aim + P.wgt * (w32 * v2);
+    }
+}
 
 template <int MN, int ME, int NGP>
 __global__ void __launch_bounds__(256, 2) exact_kernel(ExactArgs A) {
     using CFG = ExactCfg<MN, ME, NGP>;
     constexpr int EB = CFG::EB, NDD = CFG::NDD, NORD = MN == 8 ? 2 : 3;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     ExactGp *s_gp = reinterpret_cast<ExactGp *>(smem_raw);                    // [EB][NGP]
     double *s_nd = reinterpret_cast<double *>(s_gp + EB * NGP);               // [EB][MN][NDD]
     double *s_xy = s_nd + EB * MN * NDD;                                      // [EB][6]: xs[3], ys[3]
-    int *s_el = reinterpret_cast<int *>(s_xy + EB * 6);                       // [EB][8]: element, row, flags[3], npairs, prefix
-    int *s_n = s_el + EB * 8;
+    int *s_el = reinterpret_cast<int *>(s_xy + EB * 6);                       // [EB][8]: element, lane, flags[3], npairs, prefix, zero masks
+    int *s_n = s_el + EB * 8;                                                 // [4]
+    int *s_cnt = s_n + 4;                                                     // [32] flagged pairs of every lane of the batch
+    uint32_t *s_any = reinterpret_cast<uint32_t *>(s_cnt + 32);               // [THREADS] batch words of the next 256 steps of the walk
+    ExactH *s_h = reinterpret_cast<ExactH *>(s_any + CFG::THREADS);           // [EB][NGP], stretched lists only
 
     const ElemTables &T = *A.T;
     const MeshDims &m = A.m;
@@ -78,43 +193,56 @@ __global__ void __launch_bounds__(256, 2) exact_kernel(ExactArgs A) {
     const double w32 = f32r(A.omega);
     const int nbatch = (A.nlist + 31) / 32;
 
-    for (int b = blockIdx.x; b < nbatch; b += gridDim.x) {
+    // The CTA walks the batches b = blockIdx.x + k*gridDim.x.  Meshes without residue pairs (all linear-element BASELINE
+    // configs) only pay a scan: 256 steps of the walk are looked at at once, one batch word per thread.
+    for (int k0 = 0; (int64_t)blockIdx.x + (int64_t)k0 * gridDim.x < nbatch; k0 += CFG::THREADS) {
+        __syncthreads();   // s_any of the previous 256 steps no longer read
+        const int64_t bmine = (int64_t)blockIdx.x + (int64_t)(k0 + tid) * gridDim.x;
+        const uint32_t mine = bmine < nbatch ? A.batchany[(A.row0 >> 5) + bmine] : 0u;
+        s_any[tid] = mine;
+        if (!__syncthreads_or(mine != 0u)) continue;
+    for (int kk = 0; kk < CFG::THREADS; ++kk) {
+        const int64_t b64 = (int64_t)blockIdx.x + (int64_t)(k0 + kk) * gridDim.x;
+        if (b64 >= nbatch) break;
+        const int b = (int)b64;
         const int64_t brow = A.row0 + (int64_t)b * 32;
-        const uint32_t any = A.batchany[brow >> 5];
+        const uint32_t any = s_any[kk];
         if (any == 0) continue;
-        for (uint32_t rest = any; rest;) {
-            __syncthreads();   // previous group consumed
-            if (tid == 0) {
-                int n = 0;
-                uint32_t r = rest;
-                while (r && n < EB) {
-                    const int l = __ffs(r) - 1;
-                    r &= r - 1;
-                    if (b * 32 + l < A.nlist) {
-                        s_el[n * 8] = A.list[b * 32 + l];
-                        s_el[n * 8 + 1] = l;
-                        ++n;
-                    }
-                }
-                s_n[0] = n;
+        __syncthreads();   // previous batch consumed
+        if (tid < 32) {
+            int c = 0;
+            if (((any >> tid) & 1u) && b * 32 + tid < A.nlist) {
+                const uint32_t *fl = A.pairflags + (brow + tid) * A.W;
+                for (int w = 0; w < A.W; ++w) c += __popc(fl[w]);
             }
-            {   // every thread advances `rest` the same way
-                int cnt = 0;
-                while (rest && cnt < EB) { rest &= rest - 1; ++cnt; }
+            s_cnt[tid] = c;
+        }
+        if (tid == 0) s_n[2] = 0;   // next lane to look at
+        for (;;) {
+            __syncthreads();   // previous group consumed; s_cnt / s_n[2] visible
+            if (tid == 0) {
+                int n = 0, total = 0, l = s_n[2];
+                for (; l < 32 && n < EB; ++l) {
+                    const int c = s_cnt[l];
+                    if (c == 0) continue;
+                    if (n > 0 && total + c > CFG::ITEMS) break;
+                    s_el[n * 8] = A.list[b * 32 + l];
+                    s_el[n * 8 + 1] = l;
+                    s_el[n * 8 + 5] = c; s_el[n * 8 + 6] = total; s_el[n * 8 + 7] = 0;
+                    total += c;
+                    ++n;
+                }
+                s_n[2] = l; s_n[0] = n; s_n[1] = total;
             }
             __syncthreads();
             const int n = s_n[0];
-            if (n == 0) continue;
+            if (n == 0) break;
             // ---- phase 0: stage the node data of the group's elements; flags; pair counts ----
             if (tid < n) {
                 const int e = s_el[tid * 8];
                 int f[3] = {0, 0, 0};
                 if (A.stretched) effective_pml(m, A.pml, e, f);
                 s_el[tid * 8 + 2] = f[0]; s_el[tid * 8 + 3] = f[1]; s_el[tid * 8 + 4] = f[2];
-                const uint32_t *fl = A.pairflags + (brow + s_el[tid * 8 + 1]) * A.W;
-                int c = 0;
-                for (int w = 0; w < A.W; ++w) c += __popc(fl[w]);
-                s_el[tid * 8 + 5] = c;
             }
             for (int i = tid; i < n * MN; i += CFG::THREADS) {
                 const int s = i / MN, l = i % MN;
@@ -133,11 +261,6 @@ __global__ void __launch_bounds__(256, 2) exact_kernel(ExactArgs A) {
                 }
             }
             __syncthreads();
-            if (tid == 0) {
-                int acc = 0;
-                for (int s = 0; s < n; ++s) { s_el[s * 8 + 6] = acc; acc += s_el[s * 8 + 5]; }
-                s_n[1] = acc;
-            }
             // ---- phase 1: one thread per (Gauss point, element): int_elem_params, integration.f90:60-74,108-137 ----
             for (int i = tid; i < n * NGP; i += CFG::THREADS) {
                 const int g = i / n, s = i % n;
@@ -176,8 +299,10 @@ __global__ void __launch_bounds__(256, 2) exact_kernel(ExactArgs A) {
 #pragma unroll
                     for (int k = 0; k < 6; ++k) { m1[k] = m1[k] + ln * nd[l * NDD + 1 + k]; m2[k] = m2[k] + ln * nd[l * NDD + 7 + k]; }
                 }
+                int zm = 0;   // which tensor components are non-zero at some Gauss point: a zero factor makes a term of f1 / f2 an exact +-0
 #pragma unroll
-                for (int k = 0; k < 6; ++k) { P.m1[k] = m1[k]; P.m2[k] = m2[k]; }
+                for (int k = 0; k < 6; ++k) { P.m1[k] = m1[k]; P.m2[k] = m2[k]; zm |= (m1[k] != 0.0 ? 1 << k : 0) | (m2[k] != 0.0 ? 256 << k : 0); }
+                atomicOr(&s_el[s * 8 + 7], zm);
                 // gpml(i,:) = Re gpml_h (integration.f90:16,125, Q18) with the lagging flags (Q17)
                 double h1 = 1.0, h2 = 1.0, h3 = 1.0;
                 if (A.stretched) {
@@ -185,12 +310,18 @@ __global__ void __launch_bounds__(256, 2) exact_kernel(ExactArgs A) {
                     h2 = gpml_axis(A.pml, s_el[s * 8 + 3], 1, xg[1], A.omega).x;
                     h3 = gpml_axis(A.pml, s_el[s * 8 + 4], 2, xg[2], A.omega).x;
                 }
-                P.h[0] = h1; P.h[1] = h2; P.h[2] = h3;
-                P.hf[0] = (h1 * h3) / h2; P.hf[1] = (h1 * h2) / h3; P.hf[2] = (h2 * h3) / h1;
+                if (A.stretched) {
+                    ExactH &H = s_h[s * NGP + g];
+                    H.h[0] = h1; H.h[1] = h2; H.h[2] = h3;
+                    H.hf[0] = (h1 * h3) / h2; H.hf[1] = (h1 * h2) / h3; H.hf[2] = (h2 * h3) / h1;
+                }
             }
             __syncthreads();
             // ---- phase 2: one thread per flagged (element, pair): alocal, integration.f90:76-86 ----
             const int total = s_n[1];
+            int gmask = 0;
+            for (int q = 0; q < n; ++q) gmask |= s_el[q * 8 + 7];
+            const bool diag = (gmask & ~0x2929) == 0;   // bits 0-5: mu^-1 components, 8-13: Re sigma; 0x29 = {11, 22, 33}
             for (int item = tid; item < total; item += CFG::THREADS) {
                 int s = 0;
                 while (s + 1 < n && s_el[(s + 1) * 8 + 6] <= item) ++s;
@@ -214,102 +345,17 @@ __global__ void __launch_bounds__(256, 2) exact_kernel(ExactArgs A) {
                 const int im = gh >= gl ? hi : lo, jm = gh >= gl ? lo : hi;
                 const int di = T.edir[im], dj = T.edir[jm];
                 double are = 0.0, aim = 0.0;
-                for (int g = 0; g < NGP; ++g) {
-                    const ExactGp &P = s_gp[s * NGP + g];
-                    // mix_grad_ln v_fem.f90:478-483, grad_xi :515-518, vf_elem_curl :55-59, vf_elem_ve :41-43
-                    double a1[3], a2[3], b1[3], b2[3], va[3], vb[3];
-                    {
-                        double dn[3], v[3];
-#pragma unroll
-                        for (int mm = 0; mm < 3; ++mm) {
-                            double sacc = 0.0;
-#pragma unroll
-                            for (int nn = 0; nn < 3; ++nn) sacc = sacc + P.ji[mm][nn] * T.dphi[g][im][nn];
-                            dn[mm] = sacc; v[mm] = P.ji[mm][di];
-                        }
-                        a1[0] = dn[1] * v[2]; a2[0] = dn[2] * v[1];
-                        a1[1] = dn[2] * v[0]; a2[1] = dn[0] * v[2];
-                        a1[2] = dn[0] * v[1]; a2[2] = dn[1] * v[0];
-                        const double ph = T.phi[g][im];
-#pragma unroll
-                        for (int mm = 0; mm < 3; ++mm) va[mm] = ph * v[mm];
-                    }
-                    {
-                        double dn[3], v[3];
-#pragma unroll
-                        for (int mm = 0; mm < 3; ++mm) {
-                            double sacc = 0.0;
-#pragma unroll
-                            for (int nn = 0; nn < 3; ++nn) sacc = sacc + P.ji[mm][nn] * T.dphi[g][jm][nn];
-                            dn[mm] = sacc; v[mm] = P.ji[mm][dj];
-                        }
-                        b1[0] = dn[1] * v[2]; b2[0] = dn[2] * v[1];
-                        b1[1] = dn[2] * v[0]; b2[1] = dn[0] * v[2];
-                        b1[2] = dn[0] * v[1]; b2[2] = dn[1] * v[0];
-                        const double ph = T.phi[g][jm];
-#pragma unroll
-                        for (int mm = 0; mm < 3; ++mm) vb[mm] = ph * v[mm];
-                    }
-                    const double *mu = P.m1, *sg = P.m2;
-                    double v1, v2;
-                    // f1, integration.f90:171-207: A(p,s) = cv1 of im, B(q,t) = cv2 of jm; a term whose factors contain an exact
-                    // zero adds +-0 and is skipped (the sum is unchanged)
-#define MOVFEM_T(sign, hfac, mk, aa, bb)                                            \
-    if (mu[mk] != 0.0) { const double t_ = (((hfac) * mu[mk]) * (aa)) * (bb); r = (sign) > 0 ? r + t_ : r - t_; }
-#define MOVFEM_U(sign, mk, aa, bb)                                                  \
-    if (mu[mk] != 0.0) { const double t_ = (mu[mk] * (aa)) * (bb); r = (sign) > 0 ? r + t_ : r - t_; }
-                    if (gpml_form) {
-                        const double h1 = P.h[0], h2 = P.h[1], h3 = P.h[2], f13_2 = P.hf[0], f12_3 = P.hf[1], f23_1 = P.hf[2];
-                        double r = 0.0;
-                        MOVFEM_T(+1, f13_2, 0, a1[0], b1[0]) MOVFEM_T(-1, h1, 0, a2[0], b1[0]) MOVFEM_T(-1, h1, 0, a1[0], b2[0]) MOVFEM_T(+1, f12_3, 0, a2[0], b2[0])
-                        MOVFEM_T(+1, h1, 1, a1[0], b1[1]) MOVFEM_T(-1, f12_3, 1, a2[0], b1[1]) MOVFEM_T(-1, h3, 1, a1[0], b2[1]) MOVFEM_T(+1, h2, 1, a2[0], b2[1])
-                        MOVFEM_T(+1, h3, 2, a1[0], b1[2]) MOVFEM_T(-1, h2, 2, a2[0], b1[2]) MOVFEM_T(-1, f13_2, 2, a1[0], b2[2]) MOVFEM_T(+1, h1, 2, a2[0], b2[2])
-                        MOVFEM_T(+1, h1, 1, a1[1], b1[0]) MOVFEM_T(-1, h3, 1, a2[1], b1[0]) MOVFEM_T(-1, f12_3, 1, a1[1], b2[0]) MOVFEM_T(+1, h2, 1, a2[1], b2[0])
-                        MOVFEM_T(+1, f12_3, 3, a1[1], b1[1]) MOVFEM_T(-1, h2, 3, a2[1], b1[1]) MOVFEM_T(-1, h2, 3, a1[1], b2[1]) MOVFEM_T(+1, f23_1, 3, a2[1], b2[1])
-                        MOVFEM_T(+1, h2, 4, a1[1], b1[2]) MOVFEM_T(-1, f23_1, 4, a2[1], b1[2]) MOVFEM_T(-1, h1, 4, a1[1], b2[2]) MOVFEM_T(+1, h3, 4, a2[1], b2[2])
-                        MOVFEM_T(+1, h3, 2, a1[2], b1[0]) MOVFEM_T(-1, f13_2, 2, a2[2], b1[0]) MOVFEM_T(-1, h2, 2, a1[2], b2[0]) MOVFEM_T(+1, h1, 2, a2[2], b2[0])
-                        MOVFEM_T(+1, h2, 4, a1[2], b1[1]) MOVFEM_T(-1, h1, 4, a2[2], b1[1]) MOVFEM_T(-1, f23_1, 4, a1[2], b2[1]) MOVFEM_T(+1, h3, 4, a2[2], b2[1])
-                        MOVFEM_T(+1, f23_1, 5, a1[2], b1[2]) MOVFEM_T(-1, h3, 5, a2[2], b1[2]) MOVFEM_T(-1, h3, 5, a1[2], b2[2]) MOVFEM_T(+1, f13_2, 5, a2[2], b2[2])
-                        v1 = r;
-                        // f2, integration.f90:228-232: h1*h2*h3*cv2(q)*m(k)*cv1(p), nine terms summed left to right
-                        const double hhh = (h1 * h2) * h3;
-                        double q = 0.0;
-#define MOVFEM_M(mk, bq, ap) if (sg[mk] != 0.0) q = q + ((hhh * vb[bq]) * sg[mk]) * va[ap];
-                        MOVFEM_M(0, 0, 0) MOVFEM_M(1, 1, 0) MOVFEM_M(2, 2, 0) MOVFEM_M(1, 0, 1) MOVFEM_M(3, 1, 1) MOVFEM_M(4, 2, 1)
-                        MOVFEM_M(2, 0, 2) MOVFEM_M(4, 1, 2) MOVFEM_M(5, 2, 2)
-#undef MOVFEM_M
-                        v2 = q;
-                    } else {
-                        double r = 0.0;
-                        MOVFEM_U(+1, 0, a1[0], b1[0]) MOVFEM_U(-1, 0, a2[0], b1[0]) MOVFEM_U(-1, 0, a1[0], b2[0]) MOVFEM_U(+1, 0, a2[0], b2[0])
-                        MOVFEM_U(+1, 1, a1[0], b1[1]) MOVFEM_U(-1, 1, a2[0], b1[1]) MOVFEM_U(-1, 1, a1[0], b2[1]) MOVFEM_U(+1, 1, a2[0], b2[1])
-                        MOVFEM_U(+1, 2, a1[0], b1[2]) MOVFEM_U(-1, 2, a2[0], b1[2]) MOVFEM_U(-1, 2, a1[0], b2[2]) MOVFEM_U(+1, 2, a2[0], b2[2])
-                        MOVFEM_U(+1, 1, a1[1], b1[0]) MOVFEM_U(-1, 1, a2[1], b1[0]) MOVFEM_U(-1, 1, a1[1], b2[0]) MOVFEM_U(+1, 1, a2[1], b2[0])
-                        MOVFEM_U(+1, 3, a1[1], b1[1]) MOVFEM_U(-1, 3, a2[1], b1[1]) MOVFEM_U(-1, 3, a1[1], b2[1]) MOVFEM_U(+1, 3, a2[1], b2[1])
-                        MOVFEM_U(+1, 4, a1[1], b1[2]) MOVFEM_U(-1, 4, a2[1], b1[2]) MOVFEM_U(-1, 4, a1[1], b2[2]) MOVFEM_U(+1, 4, a2[1], b2[2])
-                        MOVFEM_U(+1, 2, a1[2], b1[0]) MOVFEM_U(-1, 2, a2[2], b1[0]) MOVFEM_U(-1, 2, a1[2], b2[0]) MOVFEM_U(+1, 2, a2[2], b2[0])
-                        MOVFEM_U(+1, 4, a1[2], b1[1]) MOVFEM_U(-1, 4, a2[2], b1[1]) MOVFEM_U(-1, 4, a1[2], b2[1]) MOVFEM_U(+1, 4, a2[2], b2[1])
-                        MOVFEM_U(+1, 5, a1[2], b1[2]) MOVFEM_U(-1, 5, a2[2], b1[2]) MOVFEM_U(-1, 5, a1[2], b2[2]) MOVFEM_U(+1, 5, a2[2], b2[2])
-                        v1 = r;
-                        // f2 Dirichlet form, integration.f90:234-236: three parenthesised rows
-                        double rows[3];
-#pragma unroll
-                        for (int pp = 0; pp < 3; ++pp) {
-                            const int k0 = sym3(0, pp), k1 = sym3(1, pp), k2 = sym3(2, pp);
-                            rows[pp] = ((vb[0] * sg[k0]) * va[pp] + (vb[1] * sg[k1]) * va[pp]) + (vb[2] * sg[k2]) * va[pp];
-                        }
-                        v2 = (rows[0] + rows[1]) + rows[2];
-                    }
-#undef MOVFEM_T
-#undef MOVFEM_U
-                    // alocal, integration.f90:84: a = a + wgt*(f1 + cmplx(0,omega)*f2), cmplx() single precision (Q2)
-                    are = are + P.wgt * v1;
-                    aim = aim + P.wgt * (w32 * v2);
-                }
+                const ExactGp *Pg = s_gp + s * NGP;
+                const ExactH *Hg = A.stretched ? s_h + s * NGP : nullptr;
+                // isotropic-diagonal mu^-1 and Re sigma (components 11, 22, 33 only) in the whole group: 12 of the 36 terms of f1
+                // and 3 of the 9 of f2 can be non-zero; otherwise every term is evaluated (an exact zero factor adds +-0)
+                if (diag) exact_pair<true>(T, Pg, Hg, NGP, im, jm, di, dj, gpml_form, w32, are, aim);
+                else exact_pair<false>(T, Pg, Hg, NGP, im, jm, di, dj, gpml_form, w32, are, aim);
                 const int64_t row = brow + lane;
                 A.KM[(((row >> 5) * A.NP + p) << 5) + (row & 31)] = make_double2(are * kExactScale, aim * kExactScale);
             }
         }
+    }
     }
 }
 

@@ -17,38 +17,7 @@
 
 namespace movfem {
 
-#ifndef MOVFEM_FIN_THREADS
-#define MOVFEM_FIN_THREADS 128      // entries per gather block.  Measured on config 2 (tools/ab_gather_block.sh): 64: 0.400 ms, 128: 0.334, 256: 0.342, 512: 0.361
-#endif
-constexpr int kFinThreads = MOVFEM_FIN_THREADS;
-
-// Cache-policy experiments for A/B builds (make OUT=... EXTRA=-DMOVFEM_GATHER_LD=2; defaults generate the code measured in
-// round 1).  The K/M store is read once per assembly in scattered 16-byte pieces and A is written once: neither profits
-// from an L1 line, and evict-first keeps them from displacing the contribution index in L2.
-#ifndef MOVFEM_GATHER_LD
-#define MOVFEM_GATHER_LD 0      // 0 plain load; 1 __ldcs (streaming, evict-first); 2 ld.global.nc.L1::no_allocate; 3 cp.async.cg straight into shared memory
-#endif
-#ifndef MOVFEM_GATHER_ST
-#define MOVFEM_GATHER_ST 0      // 0 plain store; 1 __stcs (streaming)
-#endif
-__device__ __forceinline__ double2 ld_km(const double2 *p) {
-#if MOVFEM_GATHER_LD == 1
-    return __ldcs(p);
-#elif MOVFEM_GATHER_LD == 2
-    double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-    return v;
-#else
-    return *p;
-#endif
-}
-__device__ __forceinline__ void st_a(double2 *p, double2 v) {
-#if MOVFEM_GATHER_ST == 1
-    __stcs(p, v);
-#else
-    *p = v;
-#endif
-}
+constexpr int kFinThreads = 128;      // entries per gather block.  Measured on config 2: 64: 0.400 ms, 128: 0.334, 256: 0.342, 512: 0.361
 
 // Contribution index, compressed once per mesh: per block of kFinThreads entries the 64-bit position of its first
 // contribution (cblk) and per entry a 16-bit offset from it (an entry has <= 4 contributions, so a block has <= 4*kFinThreads).
@@ -118,7 +87,7 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
             const double2 v = kmg[i];
             double re = v.x, im = w32 * v.y;
             if (mode == 0) { re = f32r(re); im = f32r(im); }
-            st_a(a + i, make_double2(re, im));
+            a[i] = make_double2(re, im);
             nzflag = !(re == 0.0 && im == 0.0);
         }
     } else {
@@ -132,19 +101,14 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = threadIdx.x + k * kFinThreads;
-#if MOVFEM_GATHER_LD == 3
-            if (c < n) {   // LDGSTS: global -> shared without the register round trip, L1 bypassed (.cg)
+            if (c < n) {   // LDGSTS: global -> shared without the register round trip, L1 bypassed (.cg); measured -10 % against
+                           // plain loads, __ldcs +15 %, ld.global.nc.L1::no_allocate +1 % (profiles/r02_ab_results.md)
                 const unsigned dst = (unsigned)__cvta_generic_to_shared(&vals[c]);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(KM + sidx[k]) : "memory");
             }
-#else
-            if (c < n) vals[c] = ld_km(KM + sidx[k]);
-#endif
         }
-#if MOVFEM_GATHER_LD == 3
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
         __syncthreads();
         if (i < nzu) {
             const int lo = offs[threadIdx.x];
@@ -182,7 +146,7 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
             if (cache == 1) kmg[i] = make_double2(k, mm);
             double re = k + kx, im = w32 * mm + mx;
             if (mode == 0) { re = f32r(re); im = f32r(im); }
-            st_a(a + i, make_double2(re, im));
+            a[i] = make_double2(re, im);
             nzflag = !(re == 0.0 && im == 0.0);
         }
     }
@@ -190,6 +154,12 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
     if (threadIdx.x == 0) {
         blk_nonzero[blk] = cnt;
         if (total_nonzero && cnt) atomicAdd(total_nonzero, (unsigned long long)cnt);   // integer: order-independent
+    }
+    // signature of the stripped set (which entries rem_zeros removes): lets MOVFEM_MODE_KEEP_PATTERN tell whether the caller's
+    // irn/jcn still match the delivered pattern.  Wrapping integer sums: order independent.
+    if (total_nonzero && mode == 0 && i < nzu && !nzflag) {
+        atomicAdd(total_nonzero + 1, (unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ull);
+        atomicAdd(total_nonzero + 2, ((unsigned long long)(i + 1) * 0xC2B2AE3D27D4EB4Full) ^ (unsigned long long)(i >> 7));
     }
 }
 
@@ -212,6 +182,13 @@ compact_kernel(int64_t nzu, const int64_t *__restrict__ blk_off, const int *__re
         const int64_t p = blk_off[blockIdx.x] + off;
         irn_c[p] = irn[i]; jcn_c[p] = jcn[i]; a_c[p] = v;
     }
+}
+
+// float32-exact values (tap T2, global_assembly.f90:157) as complex64 for the host link: half the bytes, widened back to
+// complex128 on the host without loss (api.cu: pipe_d2h)
+__global__ void narrow_kernel(int64_t n, const double2 *__restrict__ a, float2 *__restrict__ a32) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const double2 v = a[i]; a32[i] = make_float2((float)v.x, (float)v.y); }
 }
 
 // CSR row pointers of delivered (row-sorted, 1-based) triplets: rowptr[r] = first entry with irn >= row_lo + r + 1

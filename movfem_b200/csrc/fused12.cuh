@@ -39,12 +39,13 @@ struct Fused12Args {
     double2 *KM;                   // K/M store at this launch's first row: [batch][78][32]
     double *be;                    // [element - e_base][12][4]
     int *status;
-    const int *flags;              // flags[0]: any dmu != 0
+    const int *flags;              // flags[0]: any dmu != 0, [2]: any off-diagonal sigma component (node_kernel)
     uint32_t *pairflags;           // [row][W] at this launch's first row
     uint32_t *batchany;            // at this launch's first batch
     unsigned long long *nflag;
     int W;
     int no_l1;                     // test hook: no element-level tiny-pair flags
+    int skip_unless_changed;       // launch is a cache refresh: exit unless flags[1] (Re sigma changed)
 };
 
 struct Fused12Cfg {
@@ -57,14 +58,15 @@ struct Fused12Cfg {
                                    sizeof(int64_t) * EB + sizeof(int) * (EB * 3 + 2 * ME + 3 * MN);
 };
 
+template <bool DO_KM>
 __global__ void __launch_bounds__(256, 2) fused12_kernel(Fused12Args A) {
     using C = Fused12Cfg;
     constexpr int MN = C::MN, ME = C::ME, NGP = C::NGP, EB = C::EB, NDW = C::NDW, NREC = C::NREC, RST = C::RST, NP = C::NP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_qt = reinterpret_cast<double *>(smem_raw);              // [12][NGP][32]: Q (0-5, sym3 order), T (6-11)
-    double *s_nodes = s_qt + C::QT_D;                                 // [EB][NSTR]
-    double *s_R = s_nodes + C::NODES_D;                               // [NGP][EB][RST]
-    double *s_tab = s_R + C::R_D;                                     // [NGP][4][ME]: dphi (0-2), phi (3), slot order
+    double *s_R = s_qt + C::QT_D;                                     // [NGP][EB][RST]
+    double *s_nodes = s_R + C::R_D;                                   // [EB][NSTR]
+    double *s_tab = s_nodes + C::NODES_D;                             // [NGP][4][ME]: dphi (0-2), phi (3), slot order
     double *s_dN = s_tab + C::TAB_D;                                  // [MN][4][NGP]: dN/dxi (0-2), N (3)
     double *s_phi = s_dN + C::DN_D;                                   // [NGP][ME] phi in slot order
     unsigned long long *s_scale = reinterpret_cast<unsigned long long *>(s_phi + C::PHI_D);   // [EB][2]
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(256, 2) fused12_kernel(Fused12Args A) {
     const ElemTables &T = *A.T;
     const MeshDims &m = A.m;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (A.skip_unless_changed && A.flags[1] == 0) return;
 
     for (int i = tid; i < NGP * ME; i += C::THREADS) {
         const int g = i / ME, sl = i % ME;
@@ -121,6 +124,10 @@ __global__ void __launch_bounds__(256, 2) fused12_kernel(Fused12Args A) {
     const double psig = f32r(A.omega * kEps0);   // pset_pmodel, problem.f90:250
     const double w32 = f32r(A.omega);            // cmplx(0.d0,-omega), problem.f90:112
     const int has_dmu = A.flags[0];
+    // mu = mu0 I at every node and sigma diagonal at every node (every linear-element BASELINE mesh): the interpolation needs 7
+    // of its 24 columns and J, G, Q, T, R have closed forms in the five non-zero entries of J (x and y are tensor-product
+    // lines, so J = [[a,0,p],[0,b,q],[0,0,r]] with a = dx/2, b = dy/2 and (p,q,r) the xi-gradient of z, n_fem.f90:193 included)
+    const bool simple = !has_dmu && A.flags[2] == 0;
 
     for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
         const int first = batch * EB;
@@ -136,28 +143,85 @@ __global__ void __launch_bounds__(256, 2) fused12_kernel(Fused12Args A) {
         if (batch + (int)gridDim.x < nbatch) prepare_request(batch + gridDim.x);   // s_rbase / s_rxy: no reader until the request below
 
         // ---- phase G: thread = (Gauss point g = warp, element s = lane) ----
-        if (lane < nb) {
+        if (simple && lane < nb) {
             const int g = warp, s = lane;
             const double *nd = s_nodes + s * C::NSTR;
-            // interpolation to the Gauss point (p_intmodels problem.f90:139-142; N_l-weighted part of p_source :424-457)
+            double s0 = 0.0, s3 = 0.0, s5 = 0.0, e12 = 0.0, e15 = 0.0, e18 = 0.0, e21 = 0.0, p = 0.0, q = 0.0, r = 0.0;
+#pragma unroll
+            for (int l = 0; l < MN; ++l) {
+                const double2 *r2 = reinterpret_cast<const double2 *>(nd + l * NDW);
+                const double2 ze = r2[0], s01 = r2[4], s23 = r2[5], s45 = r2[6], i01 = r2[7], i23 = r2[8];
+                const double ln = s_dN[(l * 4 + 3) * NGP + g];
+                const double le = ln * ze.y;
+                if (DO_KM) { s0 = dfma(ln, s01.x, s0); s3 = dfma(ln, s23.y, s3); s5 = dfma(ln, s45.y, s5); }
+                e12 = dfma(le, i01.x - psig, e12); e15 = dfma(le, s01.x, e15);
+                e18 = dfma(le, i23.y - psig, e18); e21 = dfma(le, s23.y, e21);
+                p = dfma(s_dN[(l * 4 + 0) * NGP + g], ze.x, p);
+                q = dfma(s_dN[(l * 4 + 1) * NGP + g], ze.x, q);
+                r = dfma(s_dN[(l * 4 + 2) * NGP + g], ze.x, r);
+            }
+            const double a = 0.5 * (nd[NREC] - nd[2 * NDW + NREC]), b = 0.5 * (nd[NDW + NREC + 1] - nd[NREC + 1]);
+            const double det = (a * b) * r;
+            if (det == 0.0) atomicCAS(A.status, 0, -3);
+            const double w = det * T.rw[g][3];
+            const double rad = 1.0 / fabs(det);
+            const double G00 = (b * r) * rad, G11 = (a * r) * rad, G22 = (a * b) * rad, G02 = -(p * b) * rad, G12 = -(a * q) * rad;
+            if (DO_KM) {
+                double *qo = s_qt + g * 32 + s;
+                constexpr int QS = NGP * 32;
+                const double fm = (w / (det * det)) * nd[2];      // (w/det^2) * mu^-1 (the same scalar at every node)
+                const double q00 = fm * dfma(a, a, p * p), q11 = fm * dfma(b, b, q * q), q22 = fm * (r * r);
+                qo[0 * QS] = q00; qo[1 * QS] = fm * (p * q); qo[2 * QS] = fm * (p * r);
+                qo[3 * QS] = q11; qo[4 * QS] = fm * (q * r); qo[5 * QS] = q22;
+                const double S0 = w * s0, S1 = w * s3, S2 = w * s5;
+                const double t00 = S0 * (G00 * G00), t11 = S1 * (G11 * G11);
+                const double t22 = dfma(S0 * G02, G02, dfma(S1 * G12, G12, (S2 * G22) * G22));
+                qo[6 * QS] = t00; qo[7 * QS] = 0.0; qo[8 * QS] = (S0 * G00) * G02;
+                qo[9 * QS] = t11; qo[10 * QS] = (S1 * G11) * G12; qo[11 * QS] = t22;
+                atomicMax(&s_scale[s * 2], (unsigned long long)__double_as_longlong(fabs(q00) + fabs(q11) + fabs(q22)));
+                atomicMax(&s_scale[s * 2 + 1], (unsigned long long)__double_as_longlong(fabs(t00) + fabs(t11) + fabs(t22)));
+            }
+            // R[d][pol] = G[:,d] . (w src_pol): src_1 = (A1, 0, 0), src_2 = (0, A2, 0) for a diagonal sigma
+            const double a1x = w * (-e15 * w32), a1y = w * (-(e12 * w32)), a2x = w * (e21 * w32), a2y = w * (e18 * w32);
+            double *Ro = s_R + (size_t)(g * EB + s) * RST;
+            *reinterpret_cast<double2 *>(Ro + 0) = make_double2(G00 * a1x, G00 * a1y);
+            *reinterpret_cast<double2 *>(Ro + 2) = make_double2(0.0, 0.0);
+            *reinterpret_cast<double2 *>(Ro + 4) = make_double2(0.0, 0.0);
+            *reinterpret_cast<double2 *>(Ro + 6) = make_double2(G11 * a2x, G11 * a2y);
+            *reinterpret_cast<double2 *>(Ro + 8) = make_double2(G02 * a1x, G02 * a1y);
+            *reinterpret_cast<double2 *>(Ro + 10) = make_double2(G12 * a2x, G12 * a2y);
+        } else if (lane < nb) {
+            const int g = warp, s = lane;
+            const double *nd = s_nodes + s * C::NSTR;
+            // interpolation to the Gauss point (p_intmodels problem.f90:139-142; N_l-weighted part of p_source :424-457).
+            // Measured against a tensor-core (mma.sync.m8n8k4.f64) interpolation phase with a reused buffer: the extra two
+            // block barriers cost more than the eightfold re-read of the node records (4.3 vs 5.3 ms on 4 M elements).
             double mu[6] = {0, 0, 0, 0, 0, 0}, sr[6] = {0, 0, 0, 0, 0, 0};
             double c12[3] = {0, 0, 0}, c15[3] = {0, 0, 0}, c18[3] = {0, 0, 0}, c21[3] = {0, 0, 0};
             double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
             const double xs0 = nd[2 * NDW + NREC], xs1 = nd[NREC], ys0 = nd[NREC + 1], ys1 = nd[NDW + NREC + 1];
 #pragma unroll
             for (int l = 0; l < MN; ++l) {
-                const double *r = nd + l * NDW;
+                // record: z, e | mu^-1 (6) | Re sigma (6) | Im sigma (6), 16-byte aligned: 128-bit loads (conflict-free over the
+                // 32 lanes, whose records are 89 16-byte chunks apart)
+                const double2 *r2 = reinterpret_cast<const double2 *>(nd + l * NDW);
+                const double2 ze = r2[0], s01 = r2[4], s23 = r2[5], s45 = r2[6], i01 = r2[7], i23 = r2[8], i45 = r2[9];
                 const double ln = s_dN[(l * 4 + 3) * NGP + g];
-                const double el = r[1], le = ln * el;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) { mu[k] = dfma(ln, r[2 + k], mu[k]); sr[k] = dfma(ln, r[8 + k], sr[k]); }
-                // Im(dsigma) = Im(sigma) - psig on the diagonal (pdelta_model, problem.f90:329-331); e_l = f32(omega b0 z_l)
-                c12[0] = dfma(le, r[14] - psig, c12[0]); c12[1] = dfma(le, r[15], c12[1]); c12[2] = dfma(le, r[16], c12[2]);
-                c15[0] = dfma(le, r[8], c15[0]);         c15[1] = dfma(le, r[9], c15[1]);  c15[2] = dfma(le, r[10], c15[2]);
-                c18[0] = dfma(le, r[15], c18[0]);        c18[1] = dfma(le, r[17] - psig, c18[1]); c18[2] = dfma(le, r[18], c18[2]);
-                c21[0] = dfma(le, r[9], c21[0]);         c21[1] = dfma(le, r[11], c21[1]); c21[2] = dfma(le, r[12], c21[2]);
+                const double le = ln * ze.y;             // N_l * e_l,  e_l = f32(omega b0 z_l)
+                if (DO_KM) {
+                    const double2 m01 = r2[1], m23 = r2[2], m45 = r2[3];
+                    mu[0] = dfma(ln, m01.x, mu[0]); mu[1] = dfma(ln, m01.y, mu[1]); mu[2] = dfma(ln, m23.x, mu[2]);
+                    mu[3] = dfma(ln, m23.y, mu[3]); mu[4] = dfma(ln, m45.x, mu[4]); mu[5] = dfma(ln, m45.y, mu[5]);
+                    sr[0] = dfma(ln, s01.x, sr[0]); sr[1] = dfma(ln, s01.y, sr[1]); sr[2] = dfma(ln, s23.x, sr[2]);
+                    sr[3] = dfma(ln, s23.y, sr[3]); sr[4] = dfma(ln, s45.x, sr[4]); sr[5] = dfma(ln, s45.y, sr[5]);
+                }
+                // Im(dsigma) = Im(sigma) - psig on the diagonal (pdelta_model, problem.f90:329-331)
+                c12[0] = dfma(le, i01.x - psig, c12[0]); c12[1] = dfma(le, i01.y, c12[1]); c12[2] = dfma(le, i23.x, c12[2]);
+                c15[0] = dfma(le, s01.x, c15[0]);        c15[1] = dfma(le, s01.y, c15[1]); c15[2] = dfma(le, s23.x, c15[2]);
+                c18[0] = dfma(le, i01.y, c18[0]);        c18[1] = dfma(le, i23.y - psig, c18[1]); c18[2] = dfma(le, i45.x, c18[2]);
+                c21[0] = dfma(le, s01.y, c21[0]);        c21[1] = dfma(le, s23.y, c21[1]); c21[2] = dfma(le, s45.x, c21[2]);
                 // nf_jacobian, n_fem.f90:359-366: l ascending, no FMA (reference bits for J, det, w)
-                const double x = (kNodeI27[l] ? xs1 : xs0), y = (kNodeJ27[l] ? ys1 : ys0), z = r[0];
+                const double x = (kNodeI27[l] ? xs1 : xs0), y = (kNodeJ27[l] ? ys1 : ys0), z = ze.x;
 #pragma unroll
                 for (int mm = 0; mm < 3; ++mm) {
                     const double dn = s_dN[(l * 4 + mm) * NGP + g];
@@ -181,8 +245,6 @@ __global__ void __launch_bounds__(256, 2) fused12_kernel(Fused12Args A) {
             G[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * rad;
             double pc1[3] = {0, 0, 0}, pc2[3] = {0, 0, 0};
             if (has_dmu) {   // p_pcurl, problem.f90:362-374 (mu != mu0 only)
-                const int64_t id0 = s_rbase ? 0 : 0;
-                (void)id0;
                 int ie, je, ke;
                 elem_ijk(m, s_el[s], ie, je, ke);
                 const int64_t base = (int64_t)(ie - 1) * m.nyz + (int64_t)(je - 1) * m.nnz + (ke - 1);
@@ -199,7 +261,7 @@ __global__ void __launch_bounds__(256, 2) fused12_kernel(Fused12Args A) {
             double *qo = s_qt + g * 32 + s;
             constexpr int QS = NGP * 32;
             double trq = 0.0, trt = 0.0;
-            {   // Q = (w/det^2) J mu^-1 J^T
+            if (DO_KM) {   // Q = (w/det^2) J mu^-1 J^T
                 const double f = w / (det * det);
                 double Jm[3][3];
 #pragma unroll
@@ -217,7 +279,7 @@ __global__ void __launch_bounds__(256, 2) fused12_kernel(Fused12Args A) {
                         if (a == b) trq += fabs(qv);
                     }
             }
-            {   // T = G^T S G, S = w Re sigma_g (integration.f90:234-236, Q3)
+            if (DO_KM) {   // T = G^T S G, S = w Re sigma_g (integration.f90:234-236, Q3)
                 double S[6], SG[3][3];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) S[k] = w * sr[k];
@@ -236,8 +298,10 @@ __global__ void __launch_bounds__(256, 2) fused12_kernel(Fused12Args A) {
                         if (a == b) trt += fabs(tv);
                     }
             }
-            atomicMax(&s_scale[s * 2], (unsigned long long)__double_as_longlong(trq));
-            atomicMax(&s_scale[s * 2 + 1], (unsigned long long)__double_as_longlong(trt));
+            if (DO_KM) {
+                atomicMax(&s_scale[s * 2], (unsigned long long)__double_as_longlong(trq));
+                atomicMax(&s_scale[s * 2 + 1], (unsigned long long)__double_as_longlong(trt));
+            }
             {   // R[d][pol] = G[:,d] . (w src_pol);  src = (dmpf + pcrl) * cmplx32(0,-omega)  (problem.f90:112)
                 // pol 1 dmpf = (+Im ds*e, -Re ds*e), pol 2 = (-Im ds*e, +Re ds*e)
                 double a1x[3], a1y[3], a2x[3], a2y[3];
@@ -262,7 +326,7 @@ __global__ void __launch_bounds__(256, 2) fused12_kernel(Fused12Args A) {
         __syncthreads();
         if (batch + (int)gridDim.x < nbatch) request_nodes(batch + gridDim.x);   // s_nodes is dead: lands during phase C / R
 
-        if (warp < 6) {
+        if (DO_KM && warp < 6) {
             // ---- phase C: tile `warp` = direction class `warp`; lanes are elements (inner loop of contract.cuh) ----
             const int c = warp;
             const int ti = c_ct.tile_ti[c], tj = c_ct.tile_tj[c];
@@ -331,8 +395,8 @@ __global__ void __launch_bounds__(256, 2) fused12_kernel(Fused12Args A) {
             }
         } else {
             // ---- phase R: one thread per (element, group of four slots of one direction): blocal / f3,
-            //      integration.f90:96-104,258-263 ----
-            for (int i = tid - 192; i < nb * 3; i += 64) {
+            //      integration.f90:96-104,258-263 (warps 6-7 beside phase C; every warp in the RHS-only pass) ----
+            for (int i = DO_KM ? tid - 192 : tid; i < nb * 3; i += DO_KM ? 64 : 256) {
                 const int cs = i / 3, q4 = (i % 3) * 4;
                 const int cd = s_sdir[q4];
                 double bacc[4][4];

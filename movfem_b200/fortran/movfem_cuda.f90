@@ -33,7 +33,7 @@ module movfem_cuda
 
     type(c_ptr), save          :: handle = c_null_ptr
     integer(c_int64_t), save   :: movfem_nz_upper = 0     ! capacity irn/jcn/a need (<= nnze)
-    integer(c_int32_t), parameter :: MODE_T2 = 0
+    integer(c_int32_t), parameter :: MODE_T2 = 0, MODE_KEEP_PATTERN = 256      ! MOVFEM_MODE_T2, MOVFEM_MODE_KEEP_PATTERN
 
     interface
         integer(c_int) function movfem_create(desc, device, h) bind(C, name='movfem_create')
@@ -88,15 +88,21 @@ contains
         if (nl > 1) bdm_ldz(1:nl-1) = l_dz(1:nl-1)
     end subroutine movfem_cuda_set_boundary_model
 
-    ! Called from ga_init (global_assembly.f90:26) in place of ga_cgne / ga_nzindx.  Fills the module
-    ! variables the rest of the program consumes: nne, nnze (MoVFEM_3DMT.f90:72-78), gne (solution.f90:331-336).
-    subroutine movfem_cuda_init()
+    ! Called from ga_init (global_assembly.f90:26) in place of ga_cgne / ga_nzindx:
+    !     call movfem_cuda_init(sym, nne, nnze, gne)
+    ! It fills the module variables of global_assembly the rest of the program consumes -- nne, nnze (MoVFEM_3DMT.f90:72-78),
+    ! gne (solution.f90:331-336) -- which arrive as ARGUMENTS: this module must not `use global_assembly`, because
+    ! global_assembly uses this module (a circular module dependency does not compile).  Modules used here: geometry, n_fem,
+    ! v_fem, problem, boundary_conds, kind_param -- none of them uses global_assembly (tests/test_c_harness.py sorts the graph).
+    subroutine movfem_cuda_init(sym, nne, nnze, gne)
         use geometry, only: g_nx, g_ny, g_nz, g_nordx, nextd, g_nsf, g_nzl, g_xp, g_yp, g_zp, g_mu, g_ztop
         use n_fem, only: nf_mn
         use v_fem, only: vf_me
         use problem, only: ndir, pe_sch
         use boundary_conds, only: dirichlet, bd_inimod, gpml_sch, a0, b0, nn
-        use global_assembly, only: nne, nnze, gne, sym
+        logical, intent(in)               :: sym
+        integer, intent(out)              :: nne, nnze
+        integer, allocatable, intent(out) :: gne(:,:)
         type(movfem_desc) :: d
         integer(c_int) :: rc
         integer(c_int32_t) :: nne_c
@@ -123,15 +129,23 @@ contains
 
     ! Replaces  call global_vfem(irn,jcn,a,rhs)  and the find_zeros/rem_zeros block (MoVFEM_3DMT.f90:82-97).
     ! ii is the loop index of the frequency loop (MoVFEM_3DMT.f90:62); nz returns mumps_par%nz.
-    subroutine movfem_cuda_assemble(ii, irn, jcn, a, rhs, nz)
+    ! keep_pattern (optional, .true. when irn/jcn are the SAME arrays the previous call filled, i.e. their allocation was hoisted
+    ! out of the frequency loop): the static pattern is not sent again, a third of the device-to-host traffic.
+    subroutine movfem_cuda_assemble(ii, irn, jcn, a, rhs, nz, keep_pattern)
         use geometry, only: omega, g_sigma
         integer, intent(in)                          :: ii
         integer, intent(inout)                       :: irn(*), jcn(*)
         complex(kind=double), intent(inout)          :: a(*), rhs(*)
         integer, intent(out)                         :: nz
+        logical, intent(in), optional                :: keep_pattern
         integer(c_int64_t) :: nz_c
         integer(c_int) :: rc
-        rc = movfem_assemble(handle, int(ii, c_int32_t), omega, g_sigma, irn, jcn, a, rhs, nz_c, MODE_T2)
+        integer(c_int32_t) :: mode
+        mode = MODE_T2
+        if (present(keep_pattern)) then
+            if (keep_pattern) mode = MODE_T2 + MODE_KEEP_PATTERN
+        end if
+        rc = movfem_assemble(handle, int(ii, c_int32_t), omega, g_sigma, irn, jcn, a, rhs, nz_c, mode)
         if (rc /= 0) call die('movfem_assemble', rc)
         nz = int(nz_c)
     end subroutine movfem_cuda_assemble

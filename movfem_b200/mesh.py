@@ -248,6 +248,15 @@ def config(n: int, *, scale: float = 1.0, dirichlet: int | None = None) -> Model
     raise ValueError(n)
 
 
+CONFIG_NAMES = {1: "config1_shipped_linear", 2: "config2_quadratic_gpml_fang", 3: "config3_lagrange_aniso_gpml_zhou",
+                4: "config4_sweep_linear", 5: "config5_large_topography"}
+
+
+def config_name(n: int) -> str:
+    """Name of BASELINE.json configs[n-1] without building the mesh."""
+    return CONFIG_NAMES[n]
+
+
 def config5_submesh() -> Model:
     """The parity mesh of BASELINE configs[4]: 40x40x20 linear elements with the FULL topography amplitude
     (300 m on every interface, tapering to 0 at the bottom / top planes), nextd = 4, GPML Fang, f = 1 Hz."""

@@ -96,5 +96,6 @@ int main(int argc, char **argv)
         free(gne); free(irn); free(jcn); free(a); free(rhs);
         movfem_destroy(h);
     }
+    if (rc == MOVFEM_OK) printf("OK\n");
     return rc == MOVFEM_OK ? 0 : 1;
 }

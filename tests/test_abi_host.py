@@ -123,22 +123,24 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
-def test_bench_phase_roofs_uses_the_survey_figures():
-    """bench.py's per-phase roofline table (both fractions for every phase) is a pure function: check it on
-    round-1's measured phase times -- the contraction must reproduce the headline FP64 fraction."""
+def test_bench_step_roofs_uses_the_survey_figures():
+    """bench.py's roofline table (both fractions for the step and for its kernels) is a pure function: check it
+    on round-1's measured phase times of config 2 -- the contraction must reproduce that round's headline FP64 fraction."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
     b = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(b)
-    m = mesh.config(2)
-    ph = {"ms_node": 0.0436, "ms_geometry": 0.2878, "ms_contract": 0.4337, "ms_gather": 0.3344}
-    r = b.phase_roofs(m, 600220, 24676330, ph, 34.87, 6556.5)
-    assert set(r) == {"node", "geometry", "contract", "gather"}
-    assert abs(r["contract"]["tflops"] - 250776 * 48000 / 0.4337e-3 * 1e-12) < 1e-9
-    assert 0.79 < r["contract"]["frac_fp64"] < 0.80
-    assert abs(r["gather"]["gbs"] - (24676330 * 32 + 600220 * 64) / 0.3344e-3 * 1e-9) < 1e-6
-    assert r["node"]["frac_fp64"] is None and 0 < r["node"]["frac_hbm"] < 1
-    assert b.phase_roofs(m, 1, 1, {}, 34.87, 6556.5) == {}
+    ph = {"ms_node": 0.0436, "ms_geometry": 0.2878, "ms_contract": 0.4337, "ms_fused": 0.0, "ms_exact": 0.0, "ms_gather": 0.3344}
+    r = b.step_roofs(36, 48000, 24676330, ph, 1.169, 34.87, 6556.5)
+    assert abs(r["flop_kernels"]["tflops"] - 250776 * 48000 / 0.4337e-3 * 1e-12) < 1e-9
+    assert 0.79 < r["flop_kernels"]["frac_fp64"] < 0.80 and r["flop_kernels"]["kernels"] == "contract_kernel"
+    assert abs(r["gather"]["gbs"] - 24676330 * 32 / 0.3344e-3 * 1e-9) < 1e-6
+    assert abs(r["step"]["tflops"] - 250776 * 48000 / 1.169e-3 * 1e-12) < 1e-9 and 0.29 < r["step"]["frac_fp64"] < 0.30
+    assert abs(r["step"]["gbs"] - 9900 * 48000 / 1.169e-3 * 1e-9) < 1e-6
+    assert abs(sum(r["share_of_step"].values()) - (0.0436 + 0.2878 + 0.4337 + 0.3344) / 1.169) < 1e-12
+    # linear elements: the fused kernel carries the flops
+    r12 = b.step_roofs(12, 1000, 51000, {"ms_fused": 0.5, "ms_contract": 0.1, "ms_gather": 0.2}, 1.0, 30.0, 6000.0)
+    assert r12["flop_kernels"]["kernels"].startswith("fused12_kernel") and abs(r12["flop_kernels"]["ms"] - 0.6) < 1e-12
 
 
 def test_global_vfem_refuses_arrays_that_are_not_the_callers_fortran_types():

@@ -296,20 +296,48 @@ def test_error_codes_replace_stops():
 
 
 def test_keep_pattern_mode_skips_static_irn_jcn():
-    """MOVFEM_MODE_KEEP_PATTERN: irn/jcn of the previous call are left alone (same values as a full call), and a
-    first call with the flag still delivers them."""
-    m = _small(20, 0, 1)
+    """MOVFEM_MODE_KEEP_PATTERN: when the caller passes the SAME irn/jcn arrays the previous call filled and the delivered set
+    is unchanged (same nz, same signature of the stripped entries), they are not sent again; other arrays -- or a first call
+    -- get the pattern.  Also on a mesh whose zero strip removes entries (20-node elements, GPML Fang: compacted pattern)."""
+    for sch in (1, 0):
+        m = _small(20, 0, sch)
+        asm = host.Assembly(m)
+        full = asm.global_vfem(1, m.omega(1), m.sigma_for(1), mode=abi.MODE_T2)
+        nz = full[4]
+        irn, jcn = full[0].copy(), full[1].copy()
+        a = np.empty(asm.nz_upper, np.complex128); rhs = np.empty(2 * asm.nne, np.complex128)
+        r0 = asm.global_vfem(1, m.omega(1), m.sigma_for(1), mode=abi.MODE_T2 | abi.MODE_KEEP_PATTERN, irn=irn, jcn=jcn, a=a, rhs=rhs)
+        assert r0[4] == nz and np.array_equal(irn[:nz], full[0][:nz])       # other arrays than the last call's: delivered
+        irn[:] = -7; jcn[:] = -7                                            # same arrays again: left alone
+        r1 = asm.global_vfem(1, m.omega(1), m.sigma_for(1), mode=abi.MODE_T2 | abi.MODE_KEEP_PATTERN, irn=irn, jcn=jcn, a=a, rhs=rhs)
+        assert r1[4] == nz and np.all(irn == -7) and np.all(jcn == -7)
+        assert np.array_equal(a[:nz], full[2][:nz]) and np.array_equal(rhs, full[3])
+        r2 = asm.global_vfem(1, m.omega(1), m.sigma_for(1), mode=abi.MODE_T2, irn=irn, jcn=jcn, a=a, rhs=rhs)   # without the flag: always delivered
+        assert np.array_equal(irn[:nz], full[0][:nz]) and np.array_equal(jcn[:nz], full[1][:nz]) and r2[4] == nz
+        asm.close()
+
+
+def test_pageable_and_pinned_caller_arrays_deliver_the_same_bits():
+    """movfem_assemble into pageable arrays (what a Fortran allocate gives: pinned staging ring, complex64 over the link and
+    widening on the host) and into pinned arrays (direct copies) must deliver identical triplets."""
+    import torch
+    m = _small(27, 0, 0)
     asm = host.Assembly(m)
-    full = asm.global_vfem(1, m.omega(1), m.sigma_for(1), mode=abi.MODE_T2)
-    irn = np.full(asm.nz_upper, -7, np.int32); jcn = np.full(asm.nz_upper, -7, np.int32)
-    r1 = asm.global_vfem(1, m.omega(1), m.sigma_for(1), mode=abi.MODE_T2 | abi.MODE_KEEP_PATTERN, irn=irn, jcn=jcn)
-    assert r1[4] == full[4] and np.all(irn[: r1[4]] == -7) == (full[4] == asm.nz_upper)   # untouched iff nothing was stripped
-    asm2 = host.Assembly(m)
-    r2 = asm2.global_vfem(1, m.omega(1), m.sigma_for(1), mode=abi.MODE_T2 | abi.MODE_KEEP_PATTERN)
-    nz = full[4]
-    assert r2[4] == nz and np.array_equal(r2[0][:nz], full[0][:nz]) and np.array_equal(r2[1][:nz], full[1][:nz])
-    assert np.array_equal(r2[2][:nz], full[2][:nz]) and np.array_equal(r1[2][:nz], full[2][:nz])
-    asm.close(); asm2.close()
+    om, sg = m.omega(1), m.sigma_for(1)
+    page = asm.global_vfem(1, om, sg, mode=abi.MODE_T2)
+    nz = page[4]
+    pin = lambda n, dt: torch.empty(n, dtype=dt, pin_memory=True).numpy()   # noqa: E731
+    p_irn, p_jcn = pin(asm.nz_upper, torch.int32), pin(asm.nz_upper, torch.int32)
+    p_a, p_rhs = pin(2 * asm.nz_upper, torch.float64).view(np.complex128), pin(4 * asm.nne, torch.float64).view(np.complex128)
+    pinned = asm.global_vfem(1, om, sg, mode=abi.MODE_T2, irn=p_irn, jcn=p_jcn, a=p_a, rhs=p_rhs)
+    assert pinned[4] == nz
+    for k in range(3):
+        assert np.array_equal(page[k][:nz], pinned[k][:nz]), k
+    assert np.array_equal(page[3], pinned[3])
+    t1 = asm.global_vfem(1, om, sg, mode=abi.MODE_T1)                       # double values: never narrowed
+    t1p = asm.global_vfem(1, om, sg, mode=abi.MODE_T1, irn=p_irn, jcn=p_jcn, a=p_a, rhs=p_rhs)
+    assert np.array_equal(t1[2][: t1[4]], t1p[2][: t1p[4]])
+    asm.close()
 
 
 def test_device_resident_api():
