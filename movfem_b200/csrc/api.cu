@@ -375,7 +375,7 @@ int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist,
         if (DO_QT) {
             ContractArgs C;
             C.qt = h->d_qt; C.nlist = n; C.KM = h->d_KM + (size_t)(km_row0 + off) * h->NP; C.flags = h->d_flags;
-            C.skip_unless_changed = skip_unless_changed;
+            C.skip_unless_changed = skip_unless_changed; C.skip_if_simple = A.skip_if_simple;
             C.escale = getenv("MOVFEM_TEST_NO_L1") ? nullptr : h->d_escale + km_row0 + off;   // test hook: no element-level flags
             C.pairflags = h->d_pairflags + (size_t)(km_row0 + off) * h->flagW;
             C.batchany = h->d_batchany + (km_row0 + off) / 32; C.nflag = h->d_nflag; C.W = h->flagW;
@@ -396,10 +396,11 @@ int launch_fused12(movfem_handle *h, const ElemArgs &A, int skip_unless_changed)
     if (h->n_plain <= 0) return 0;
     int rc = const_table_acquire(h);
     if (rc) return rc;
+    using FC = Fused12Cfg<DO_KM>;
     auto kern = fused12_kernel<DO_KM>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fused12Cfg::SMEM));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FC::SMEM));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Fused12Cfg::THREADS, Fused12Cfg::SMEM));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FC::THREADS, FC::SMEM));
     Fused12Args F;
     F.m = A.m; F.omega = A.omega; F.T = A.T; F.nodes = A.nodes; F.xp = A.xp; F.yp = A.yp;
     F.list = h->d_list_plain; F.nlist = h->n_plain; F.e_base = h->e_base; F.KM = h->d_KM; F.be = h->d_be;
@@ -408,7 +409,7 @@ int launch_fused12(movfem_handle *h, const ElemArgs &A, int skip_unless_changed)
     F.skip_unless_changed = skip_unless_changed;
     const int nb = (h->n_plain + 31) / 32;
     if (kernel_event(h, 3, true)) return MOVFEM_E_CUDA;
-    kern<<<std::min(nb, std::max(1, per_sm) * h->num_sms), Fused12Cfg::THREADS, Fused12Cfg::SMEM, h->stream>>>(F);
+    kern<<<std::min(nb, std::max(1, per_sm) * h->num_sms), FC::THREADS, FC::SMEM, h->stream>>>(F);
     h->launches += 1;
     CK(cudaGetLastError());
     if (kernel_event(h, 3, false)) return MOVFEM_E_CUDA;
@@ -421,16 +422,20 @@ int run_elements(movfem_handle *h, ElemArgs &A, bool full) {
     const bool fused = GP::ME == 12 && !getenv("MOVFEM_NO_FUSED12");
     // unstretched elements: K_e, M_e are frequency independent -> computed on the first
     // frequency and whenever Re(sigma) changed; their RHS is rebuilt every frequency
+    // Linear elements: fused12_kernel takes the unstretched list when mu = mu0 and sigma is diagonal everywhere (it decides on
+    // the device, from node_kernel's flags) and the generic kernels are told to stand down in exactly that case.
+    A.skip_if_simple = fused ? 1 : 0;
     if (full) {
-        if (fused) { if ((rc = launch_fused12<true>(h, A, 0))) return rc; }
-        else if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 0, 0))) return rc;
+        if (fused && (rc = launch_fused12<true>(h, A, 0))) return rc;
+        if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 0, 0))) return rc;
     } else {
-        if (fused) { if ((rc = launch_fused12<false>(h, A, 0))) return rc; }
-        else if ((rc = launch_elements<GP, CP, false>(h, A, h->d_list_plain, h->n_plain, 0, 0))) return rc;
+        if (fused && (rc = launch_fused12<false>(h, A, 0))) return rc;
+        if ((rc = launch_elements<GP, CP, false>(h, A, h->d_list_plain, h->n_plain, 0, 0))) return rc;
         // refresh K/M only if the node kernel saw Re(sigma) change
-        if (fused) { if ((rc = launch_fused12<true>(h, A, 1))) return rc; }
-        else if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 0, 1))) return rc;
+        if (fused && (rc = launch_fused12<true>(h, A, 1))) return rc;
+        if ((rc = launch_elements<GP, CP, true>(h, A, h->d_list_plain, h->n_plain, 0, 1))) return rc;
     }
+    A.skip_if_simple = 0;
     // stretched (GPML, scheme 0) elements: the stored stretch is Re(h) = 1 + a0*rho^n (Q18), independent of omega, so
     // their K_e, M_e are cached like the others; only element (1,1,1) can change, when its lagging flags do (Q17), and
     // movfem_assemble_device then asks for a full pass
@@ -865,7 +870,7 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
     ElemArgs A;
     A.m = m; A.pml = h->pml; A.omega = omega; A.T = h->d_tab; A.nodes = h->d_nodes; A.xp = h->d_xp; A.yp = h->d_yp;
     A.list = nullptr; A.nlist = 0; A.e_base = h->e_base; A.qt = nullptr; A.be = h->d_be; A.escale = nullptr; A.status = h->d_status; A.flags = h->d_flags;
-    A.skip_unless_changed = 0;
+    A.skip_unless_changed = 0; A.skip_if_simple = 0;
     A.phase_mask = 3;
     if (const char *pm = getenv("MOVFEM_PHASE_MASK")) A.phase_mask = atoi(pm);   // profiling aid only
     int rc;

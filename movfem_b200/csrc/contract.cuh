@@ -55,6 +55,7 @@ struct ContractArgs {
     double2 *KM;          // K/M store at this launch's first row: [batch][NP][32 lanes]
     const int *flags;     // flags[1]: Re sigma changed (cache refresh launches)
     int skip_unless_changed;
+    int skip_if_simple;   // linear elements: exit when fused12_kernel handles the list (flags[0] == 0 and flags[2] == 0)
     // tiny-pair flags (exact.cuh): a pair whose K_e and M_e are both below kTinyRel of the element's scale is a round-off
     // residue of a mathematically zero entry; the reference's residue decides what rem_zeros strips, so it is re-evaluated
     const double2 *escale;          // [list position] (K scale, M scale) from geometry_kernel
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) contract_kernel(Contr
     constexpr int CB = CFG::CB, STAGE_D = CFG::STAGE_D, NP = CFG::NP;
     constexpr bool PML = CFG::PML;
     if (A.skip_unless_changed && A.flags[1] == 0) return;
+    if (A.skip_if_simple && A.flags[0] == 0 && A.flags[2] == 0) return;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_stage = reinterpret_cast<double *>(smem_raw);

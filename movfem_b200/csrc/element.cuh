@@ -109,6 +109,7 @@ struct ElemArgs {
     int *status;
     const int *flags;     // flags[0] any dmu, flags[1] Re sigma changed
     int skip_unless_changed;   // launch is a cache refresh: exit unless flags[1]
+    int skip_if_simple;        // linear elements: exit when fused12_kernel handles the list (flags[0] == 0 and flags[2] == 0)
     int phase_mask;            // profiling aid (MOVFEM_PHASE_MASK): bit0 B, bit1 RHS; default 3
 };
 
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
     constexpr int GR = 0;                                   // R overwrites the record's first 12 columns
     constexpr int CLO = DO_QT ? 0 : 12, CHI = DO_QT ? CFG::NCOL : 24, NCOLA = CHI - CLO;   // active columns
     if (A.skip_unless_changed && A.flags[1] == 0) return;
+    if (A.skip_if_simple && A.flags[0] == 0 && A.flags[2] == 0) return;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *s_phi = reinterpret_cast<double *>(smem_raw);             // [NGP][MEP] phi in slot order
