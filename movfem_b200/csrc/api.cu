@@ -85,6 +85,7 @@ struct movfem_handle {
     double2 *d_escale;       // [km_rows] element scales (K, M) from geometry_kernel
     uint32_t *d_pairflags;   // [km_rows][flagW] pairs to re-evaluate
     uint32_t *d_batchany;    // [km_rows/32] rows with flagged pairs
+    uint32_t *d_forcek;      // [km_rows][flagW] pairs whose K_e must be re-evaluated although their imaginary part is non-zero
     unsigned long long *d_nflag;   // [0] flagged (element, pair)s of the last cold pass, [1] entries in doubt of the last gather
     unsigned long long *h_nflag;   // pinned copy
     int flagW;
@@ -452,7 +453,7 @@ int run_elements(movfem_handle *h, ElemArgs &A, bool full) {
 void free_all(movfem_handle *h) {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_xp, h->d_yp, h->d_zp, h->d_mu, h->d_sigma, h->d_nodes, h->d_tab, h->d_share, h->d_gne, h->d_ownE,
-                    h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_cblk, h->d_off16, h->d_pure, h->d_kmg, h->d_escale, h->d_pairflags, h->d_batchany, h->d_nflag, h->d_src, h->d_KM,
+                    h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_cblk, h->d_off16, h->d_pure, h->d_kmg, h->d_escale, h->d_pairflags, h->d_batchany, h->d_forcek, h->d_nflag, h->d_src, h->d_KM,
                     h->d_be, h->d_qt, h->d_bdtab, h->d_bdlist, h->d_kmrow, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum, h->d_total, h->d_csr,
                     h->d_status, h->d_flags};
     for (void *p : ptrs)
@@ -709,6 +710,8 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     h->flagW = (h->NP + 31) / 32;
     CK(dmalloc(&h->d_escale, (size_t)h->km_rows)); CK(dmalloc(&h->d_pairflags, (size_t)h->km_rows * h->flagW));
     CK(dmalloc(&h->d_batchany, (size_t)h->km_rows / 32 + 1)); CK(dmalloc(&h->d_nflag, 2));
+    CK(dmalloc(&h->d_forcek, (size_t)h->km_rows * h->flagW));
+    CK(cudaMemset(h->d_forcek, 0, sizeof(uint32_t) * (size_t)h->km_rows * h->flagW));
     CK(cudaMemset(h->d_escale, 0, sizeof(double2) * (size_t)h->km_rows));
     CK(cudaMemset(h->d_pairflags, 0, sizeof(uint32_t) * (size_t)h->km_rows * h->flagW));
     CK(cudaMemset(h->d_batchany, 0, sizeof(uint32_t) * ((size_t)h->km_rows / 32 + 1)));
@@ -790,7 +793,7 @@ static int launch_exact(movfem_handle *h, double omega) {
     const MeshDims &m = h->m;
     ExactArgs X;
     X.m = m; X.pml = h->pml; X.omega = omega; X.T = h->d_tab; X.nodes = h->d_nodes; X.xp = h->d_xp; X.yp = h->d_yp;
-    X.batchany = h->d_batchany; X.pairflags = h->d_pairflags; X.W = h->flagW; X.NP = h->NP; X.gne = h->d_gne; X.KM = h->d_KM;
+    X.batchany = h->d_batchany; X.pairflags = h->d_pairflags; X.forcek = h->d_forcek; X.W = h->flagW; X.NP = h->NP; X.gne = h->d_gne; X.KM = h->d_KM;
     auto run = [&](auto kern, size_t smem, size_t smem_h) -> int {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + smem_h)));
         for (int pass = 0; pass < 2; ++pass) {
@@ -823,7 +826,7 @@ static int launch_gather(movfem_handle *h, double omega, int32_t mode, int cache
     if (const char *t = getenv("MOVFEM_TEST_DOUBT_ABS")) sscanf(t, "%lf,%lf", &dk, &dm);   // test hook (tests/test_gpu_parity.py)
     gather_finalize_kernel<<<h->nblk_fin, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cblk, h->d_off16, h->d_src, h->d_KM, h->d_a,
                                                               h->d_blkcnt, gmode, cache, h->d_pure, h->d_kmg, h->d_flags, nullptr, h->d_total,
-                                                              h->NP, h->flagW, h->d_pairflags, h->d_batchany, h->d_nflag + 1, dk, dm);
+                                                              h->NP, h->flagW, h->d_pairflags, h->d_batchany, h->d_forcek, h->d_nflag + 1, dk, dm);
     h->launches += 1;
     CK(cudaGetLastError());
     if (mode == MOVFEM_MODE_T2) CK(cudaMemcpyAsync(h->h_count, h->d_total, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -855,6 +858,7 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
     if (full) {   // a cold pass re-derives the tiny-pair flags
         if (h->flags_dirty) {
             CK(cudaMemsetAsync(h->d_pairflags, 0, sizeof(uint32_t) * (size_t)h->km_rows * h->flagW, st));
+            CK(cudaMemsetAsync(h->d_forcek, 0, sizeof(uint32_t) * (size_t)h->km_rows * h->flagW, st));
             CK(cudaMemsetAsync(h->d_batchany, 0, sizeof(uint32_t) * (size_t)(h->km_rows / 32 + 1), st));
             h->flags_dirty = false;
         }
@@ -1275,8 +1279,8 @@ int movfem_debug_element(movfem_handle *h, int32_t ide, double *Ke, double *Me, 
                     cudaMemcpyDeviceToHost));
     for (int p = 0; p < h->NP; ++p) {
         double kx = km[p].x, mx = km[p].y;
-        if (std::fabs(kx) < kExactBelow && std::fabs(mx) < kExactBelow) {   // re-evaluated pair (exact.cuh): K_e, and w32*M_e summed the reference's way
-            kx *= kExactUnscale;
+        if (std::fabs(kx) < kLazyBelow && std::fabs(mx) < kExactBelow) {   // re-evaluated pair (exact.cuh): w32*M_e summed the reference's way,
+            kx *= std::fabs(kx) < kExactBelow ? kExactUnscale : kLazyUnscale;   // K_e likewise or the fast path's value (marked by its scale)
             mx = h->w32_last != 0.0 ? mx * kExactUnscale / h->w32_last : 0.0;
         }
         if (Ke) Ke[p] = kx;

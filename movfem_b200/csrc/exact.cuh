@@ -28,6 +28,7 @@
 namespace movfem {
 
 constexpr double kExactScale = 0x1p-600, kExactUnscale = 0x1p+600, kExactBelow = 0x1p-500, kFlagAbs = 0x1p-400;
+constexpr double kLazyScale = 0x1p-300, kLazyUnscale = 0x1p+300, kLazyBelow = 0x1p-200;   // K_e of the fast path kept beside a re-evaluated imaginary part
 constexpr double kTinyRel = 1e-9;
 
 struct ExactArgs {
@@ -42,6 +43,7 @@ struct ExactArgs {
     int64_t row0;                  // K/M row of list position 0
     const uint32_t *batchany;      // [km_rows/32]: bit l = row 32*b+l has flagged pairs
     const uint32_t *pairflags;     // [km_rows][W]: bit p = packed pair p of the row is to be re-evaluated
+    const uint32_t *forcek;        // [km_rows][W]: ... including its K_e even if its imaginary part is non-zero (set by the gather)
     int W, NP;
     const int *gne;                // gne(ne,me): [im][e]
     double2 *KM;                   // whole K/M store: [row/32][NP][32]
@@ -70,48 +72,62 @@ struct ExactCfg {
 // alocal(im, jm) of one element (integration.f90:76-86): sum over the Gauss points of wgt*(f1 + i*w32*f2) in the reference's
 // operation order.  DIAG: only the 11, 22, 33 components of mu^-1 and Re sigma are non-zero anywhere in the element, so the
 // terms of f1 / f2 that carry another component are exact +-0 and are left out (the sums are unchanged).
-template <bool DIAG>
+template <bool DIAG, bool WANT_K, bool WANT_M>
 __device__ __forceinline__ void exact_pair(const ElemTables &T, const ExactGp *__restrict__ Pg, const ExactH *__restrict__ Hg, int ngp, int im, int jm,
                                            int di, int dj, bool gpml_form, double w32, double &are, double &aim) {
     constexpr int zm = DIAG ? 0x2929 : 0x3f3f;
     for (int g = 0; g < ngp; ++g) {
         const ExactGp &P = Pg[g];
         // mix_grad_ln v_fem.f90:478-483, grad_xi :515-518, vf_elem_curl :55-59, vf_elem_ve :41-43
-        double a1[3], a2[3], b1[3], b2[3], va[3], vb[3];
+        double a1[3] = {0, 0, 0}, a2[3] = {0, 0, 0}, b1[3] = {0, 0, 0}, b2[3] = {0, 0, 0}, va[3] = {0, 0, 0}, vb[3] = {0, 0, 0};
         {
-            double dn[3], v[3];
+            double dn[3] = {0, 0, 0}, v[3];
 #pragma unroll
             for (int mm = 0; mm < 3; ++mm) {
-                double sacc = 0.0;
+                if (WANT_K) {
+                    double sacc = 0.0;
 #pragma unroll
-                for (int nn = 0; nn < 3; ++nn) sacc = sacc + P.ji[mm][nn] * T.dphi[g][im][nn];
-                dn[mm] = sacc; v[mm] = P.ji[mm][di];
+                    for (int nn = 0; nn < 3; ++nn) sacc = sacc + P.ji[mm][nn] * T.dphi[g][im][nn];
+                    dn[mm] = sacc;
+                }
+                v[mm] = P.ji[mm][di];
             }
-            a1[0] = dn[1] * v[2]; a2[0] = dn[2] * v[1];
-            a1[1] = dn[2] * v[0]; a2[1] = dn[0] * v[2];
-            a1[2] = dn[0] * v[1]; a2[2] = dn[1] * v[0];
-            const double ph = T.phi[g][im];
+            if (WANT_K) {
+                a1[0] = dn[1] * v[2]; a2[0] = dn[2] * v[1];
+                a1[1] = dn[2] * v[0]; a2[1] = dn[0] * v[2];
+                a1[2] = dn[0] * v[1]; a2[2] = dn[1] * v[0];
+            }
+            if (WANT_M) {
+                const double ph = T.phi[g][im];
 #pragma unroll
-            for (int mm = 0; mm < 3; ++mm) va[mm] = ph * v[mm];
+                for (int mm = 0; mm < 3; ++mm) va[mm] = ph * v[mm];
+            }
         }
         {
-            double dn[3], v[3];
+            double dn[3] = {0, 0, 0}, v[3];
 #pragma unroll
             for (int mm = 0; mm < 3; ++mm) {
-                double sacc = 0.0;
+                if (WANT_K) {
+                    double sacc = 0.0;
 #pragma unroll
-                for (int nn = 0; nn < 3; ++nn) sacc = sacc + P.ji[mm][nn] * T.dphi[g][jm][nn];
-                dn[mm] = sacc; v[mm] = P.ji[mm][dj];
+                    for (int nn = 0; nn < 3; ++nn) sacc = sacc + P.ji[mm][nn] * T.dphi[g][jm][nn];
+                    dn[mm] = sacc;
+                }
+                v[mm] = P.ji[mm][dj];
             }
-            b1[0] = dn[1] * v[2]; b2[0] = dn[2] * v[1];
-            b1[1] = dn[2] * v[0]; b2[1] = dn[0] * v[2];
-            b1[2] = dn[0] * v[1]; b2[2] = dn[1] * v[0];
-            const double ph = T.phi[g][jm];
+            if (WANT_K) {
+                b1[0] = dn[1] * v[2]; b2[0] = dn[2] * v[1];
+                b1[1] = dn[2] * v[0]; b2[1] = dn[0] * v[2];
+                b1[2] = dn[0] * v[1]; b2[2] = dn[1] * v[0];
+            }
+            if (WANT_M) {
+                const double ph = T.phi[g][jm];
 #pragma unroll
-            for (int mm = 0; mm < 3; ++mm) vb[mm] = ph * v[mm];
+                for (int mm = 0; mm < 3; ++mm) vb[mm] = ph * v[mm];
+            }
         }
         const double *mu = P.m1, *sg = P.m2;
-        double v1, v2;
+        double v1 = 0.0, v2 = 0.0;
         // f1, integration.f90:171-207: A(p,s) = cv1 of im, B(q,t) = cv2 of jm
 #define MOVFEM_T(sign, hfac, mk, aa, bb)                                            \
     if (zm & (1 << (mk))) { const double t_ = (((hfac) * mu[mk]) * (aa)) * (bb); r = (sign) > 0 ? r + t_ : r - t_; }
@@ -124,6 +140,7 @@ __device__ __forceinline__ void exact_pair(const ElemTables &T, const ExactGp *_
                 h1 = H.h[0]; h2 = H.h[1]; h3 = H.h[2]; f13_2 = H.hf[0]; f12_3 = H.hf[1]; f23_1 = H.hf[2];
             }
             double r = 0.0;
+            if (WANT_K) {
             MOVFEM_T(+1, f13_2, 0, a1[0], b1[0]) MOVFEM_T(-1, h1, 0, a2[0], b1[0]) MOVFEM_T(-1, h1, 0, a1[0], b2[0]) MOVFEM_T(+1, f12_3, 0, a2[0], b2[0])
             MOVFEM_T(+1, h1, 1, a1[0], b1[1]) MOVFEM_T(-1, f12_3, 1, a2[0], b1[1]) MOVFEM_T(-1, h3, 1, a1[0], b2[1]) MOVFEM_T(+1, h2, 1, a2[0], b2[1])
             MOVFEM_T(+1, h3, 2, a1[0], b1[2]) MOVFEM_T(-1, h2, 2, a2[0], b1[2]) MOVFEM_T(-1, f13_2, 2, a1[0], b2[2]) MOVFEM_T(+1, h1, 2, a2[0], b2[2])
@@ -133,17 +150,21 @@ __device__ __forceinline__ void exact_pair(const ElemTables &T, const ExactGp *_
             MOVFEM_T(+1, h3, 2, a1[2], b1[0]) MOVFEM_T(-1, f13_2, 2, a2[2], b1[0]) MOVFEM_T(-1, h2, 2, a1[2], b2[0]) MOVFEM_T(+1, h1, 2, a2[2], b2[0])
             MOVFEM_T(+1, h2, 4, a1[2], b1[1]) MOVFEM_T(-1, h1, 4, a2[2], b1[1]) MOVFEM_T(-1, f23_1, 4, a1[2], b2[1]) MOVFEM_T(+1, h3, 4, a2[2], b2[1])
             MOVFEM_T(+1, f23_1, 5, a1[2], b1[2]) MOVFEM_T(-1, h3, 5, a2[2], b1[2]) MOVFEM_T(-1, h3, 5, a1[2], b2[2]) MOVFEM_T(+1, f13_2, 5, a2[2], b2[2])
+            }
             v1 = r;
             // f2, integration.f90:228-232: h1*h2*h3*cv2(q)*m(k)*cv1(p), nine terms summed left to right
             const double hhh = (h1 * h2) * h3;
             double q = 0.0;
+            if (WANT_M) {
 #define MOVFEM_M(mk, bq, ap) if (zm & (256 << (mk))) q = q + ((hhh * vb[bq]) * sg[mk]) * va[ap];
             MOVFEM_M(0, 0, 0) MOVFEM_M(1, 1, 0) MOVFEM_M(2, 2, 0) MOVFEM_M(1, 0, 1) MOVFEM_M(3, 1, 1) MOVFEM_M(4, 2, 1)
             MOVFEM_M(2, 0, 2) MOVFEM_M(4, 1, 2) MOVFEM_M(5, 2, 2)
+            }
 #undef MOVFEM_M
             v2 = q;
         } else {
             double r = 0.0;
+            if (WANT_K) {
             MOVFEM_U(+1, 0, a1[0], b1[0]) MOVFEM_U(-1, 0, a2[0], b1[0]) MOVFEM_U(-1, 0, a1[0], b2[0]) MOVFEM_U(+1, 0, a2[0], b2[0])
             MOVFEM_U(+1, 1, a1[0], b1[1]) MOVFEM_U(-1, 1, a2[0], b1[1]) MOVFEM_U(-1, 1, a1[0], b2[1]) MOVFEM_U(+1, 1, a2[0], b2[1])
             MOVFEM_U(+1, 2, a1[0], b1[2]) MOVFEM_U(-1, 2, a2[0], b1[2]) MOVFEM_U(-1, 2, a1[0], b2[2]) MOVFEM_U(+1, 2, a2[0], b2[2])
@@ -153,22 +174,25 @@ __device__ __forceinline__ void exact_pair(const ElemTables &T, const ExactGp *_
             MOVFEM_U(+1, 2, a1[2], b1[0]) MOVFEM_U(-1, 2, a2[2], b1[0]) MOVFEM_U(-1, 2, a1[2], b2[0]) MOVFEM_U(+1, 2, a2[2], b2[0])
             MOVFEM_U(+1, 4, a1[2], b1[1]) MOVFEM_U(-1, 4, a2[2], b1[1]) MOVFEM_U(-1, 4, a1[2], b2[1]) MOVFEM_U(+1, 4, a2[2], b2[1])
             MOVFEM_U(+1, 5, a1[2], b1[2]) MOVFEM_U(-1, 5, a2[2], b1[2]) MOVFEM_U(-1, 5, a1[2], b2[2]) MOVFEM_U(+1, 5, a2[2], b2[2])
+            }
             v1 = r;
             // f2 Dirichlet form, integration.f90:234-236: three parenthesised rows (every product is formed: +-0 where a component
             // is zero, the association of the reference is kept)
-            double rows[3];
+            if (WANT_M) {
+                double rows[3];
 #pragma unroll
-            for (int pp = 0; pp < 3; ++pp) {
-                const int k0 = sym3(0, pp), k1 = sym3(1, pp), k2 = sym3(2, pp);
-                rows[pp] = ((vb[0] * sg[k0]) * va[pp] + (vb[1] * sg[k1]) * va[pp]) + (vb[2] * sg[k2]) * va[pp];
+                for (int pp = 0; pp < 3; ++pp) {
+                    const int k0 = sym3(0, pp), k1 = sym3(1, pp), k2 = sym3(2, pp);
+                    rows[pp] = ((vb[0] * sg[k0]) * va[pp] + (vb[1] * sg[k1]) * va[pp]) + (vb[2] * sg[k2]) * va[pp];
+                }
+                v2 = (rows[0] + rows[1]) + rows[2];
             }
-            v2 = (rows[0] + rows[1]) + rows[2];
         }
 #undef MOVFEM_T
 #undef MOVFEM_U
         // alocal, integration.f90:84: a = a + wgt*(f1 + cmplx(0,omega)*f2), cmplx() single precision (Q2)
-        are = are + P.wgt * v1;
-        aim = aim + P.wgt * (w32 * v2);
+        if (WANT_K) are = are + P.wgt * v1;
+        if (WANT_M) aim = aim + P.wgt * (w32 * v2);
     }
 }
 
@@ -349,10 +373,30 @@ __global__ void __launch_bounds__(256, 2) exact_kernel(ExactArgs A) {
                 const ExactH *Hg = A.stretched ? s_h + s * NGP : nullptr;
                 // isotropic-diagonal mu^-1 and Re sigma (components 11, 22, 33 only) in the whole group: 12 of the 36 terms of f1
                 // and 3 of the 9 of f2 can be non-zero; otherwise every term is evaluated (an exact zero factor adds +-0)
-                if (diag) exact_pair<true>(T, Pg, Hg, NGP, im, jm, di, dj, gpml_form, w32, are, aim);
-                else exact_pair<false>(T, Pg, Hg, NGP, im, jm, di, dj, gpml_form, w32, are, aim);
+                // The imaginary part first (f2: a quarter of the work).  If it is non-zero the entry survives whatever K_e is, so
+                // the fast path's K_e stays -- marked as NOT re-evaluated by its scaling (2^-300 instead of 2^-600) -- unless the
+                // gather found an entry whose exact imaginary parts cancel and asked for this pair's K_e (forcek).
+                if (diag) exact_pair<true, false, true>(T, Pg, Hg, NGP, im, jm, di, dj, gpml_form, w32, are, aim);
+                else exact_pair<false, false, true>(T, Pg, Hg, NGP, im, jm, di, dj, gpml_form, w32, are, aim);
                 const int64_t row = brow + lane;
-                A.KM[(((row >> 5) * A.NP + p) << 5) + (row & 31)] = make_double2(are * kExactScale, aim * kExactScale);
+                double2 *slot = A.KM + ((((row >> 5) * A.NP + p) << 5) + (row & 31));
+                const double kold = slot->x, akold = fabs(kold);
+                const bool forced = (A.forcek[(brow + lane) * A.W + (p >> 5)] >> (p & 31)) & 1u;
+                // the slot's K_e: re-evaluated at an earlier frequency (0 < |.| < 2^-500; K_e(ref) does not depend on omega: keep),
+                // the fast path's value marked lazy (2^-500 <= |.| < 2^-200) or unmarked, or an exact zero (always evaluated)
+                double kout;
+                bool evaluate = forced || aim == 0.0 || akold == 0.0;
+                if (akold != 0.0 && akold < kExactBelow) { kout = kold; evaluate = false; }
+                else if (!evaluate) {
+                    kout = akold < kLazyBelow ? kold : kold * kLazyScale;
+                    if (!(fabs(kout) >= kExactBelow && fabs(kout) < kLazyBelow)) evaluate = true;   // cannot carry the mark
+                }
+                if (evaluate) {
+                    if (diag) exact_pair<true, true, false>(T, Pg, Hg, NGP, im, jm, di, dj, gpml_form, w32, are, aim);
+                    else exact_pair<false, true, false>(T, Pg, Hg, NGP, im, jm, di, dj, gpml_form, w32, are, aim);
+                    kout = are * kExactScale;
+                }
+                *slot = make_double2(kout, aim * kExactScale);
             }
         }
     }

@@ -67,7 +67,7 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
                        int *__restrict__ blk_nonzero, int mode, int cache, const uint32_t *__restrict__ pure,
                        double2 *__restrict__ kmg, const int *__restrict__ flags, const int *__restrict__ blk_list,
                        unsigned long long *__restrict__ total_nonzero, int NP, int W, uint32_t *__restrict__ pairflags,
-                       uint32_t *__restrict__ batchany, unsigned long long *__restrict__ n_doubt,
+                       uint32_t *__restrict__ batchany, uint32_t *__restrict__ forcek, unsigned long long *__restrict__ n_doubt,
                        double doubt_abs_k, double doubt_abs_m /* test hook: doubt every entry below these sizes; < 0 = off */) {
     __shared__ double2 vals[4 * kFinThreads];
     __shared__ uint16_t offs[kFinThreads + 1];
@@ -117,28 +117,35 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
             // scaled by 2^-600); they carry K_e and the imaginary part with w32 already inside.  An entry made of such
             // contributions only is summed exactly as the reference's a(idd)=a(idd)+aij does, so its (0,0) test agrees.
             double k = 0.0, mm = 0.0, kx = 0.0, mx = 0.0, ak = 0.0, am = 0.0;
-            int ninexact = 0;
+            int ninexact = 0, nlazy = 0;
             for (int c = lo; c < hi; ++c) {
                 const double2 v = vals[c];
-                if (fabs(v.x) < 0x1p-500 && fabs(v.y) < 0x1p-500) {
-                    kx = kx + v.x * 0x1p+600;
+                const double ax = fabs(v.x);
+                if (fabs(v.y) < 0x1p-500 && ax < 0x1p-200) {          // re-evaluated slot: exact imaginary part, scaled by 2^-600
                     mx = mx + v.y * 0x1p+600;
+                    if (ax < 0x1p-500) kx = kx + v.x * 0x1p+600;      // ... and exact K_e
+                    else { kx = kx + v.x * 0x1p+300; ++nlazy; }       // ... beside the fast path's K_e (scaled by 2^-300): inexact
                 } else {
                     k = k + v.x; mm = mm + v.y;
                     ak += fabs(v.x); am += fabs(v.y);
                     ++ninexact;
                 }
             }
-            // cancellation ACROSS elements down to round-off: the entry's zero test is in doubt -> flag its contributions for
-            // re-evaluation; the host re-runs exact_kernel and this gather (none on the BASELINE meshes)
-            if (ninexact && pairflags && ((fabs(k) <= 1e-9 * ak && fabs(mm) <= 1e-9 * am) || (fabs(k) <= doubt_abs_k && fabs(mm) <= doubt_abs_m))) {
+            // The entry's zero test is in doubt when it cancels ACROSS elements down to round-off (fast-path contributions), or
+            // when its exact imaginary parts sum to zero while a K_e beside them is the fast path's: flag the contributions for
+            // (full) re-evaluation; the host re-runs exact_kernel and this gather (none on the BASELINE meshes)
+            const bool doubt_x = ninexact && ((fabs(k) <= 1e-9 * ak && fabs(mm) <= 1e-9 * am) || (fabs(k) <= doubt_abs_k && fabs(mm) <= doubt_abs_m));
+            const bool doubt_l = nlazy && !ninexact && mx == 0.0;
+            if ((doubt_x || doubt_l) && pairflags) {
                 for (int c = lo; c < hi; ++c) {
                     const double2 v = vals[c];
-                    if (fabs(v.x) < 0x1p-500 && fabs(v.y) < 0x1p-500) continue;
+                    const bool reev = fabs(v.y) < 0x1p-500 && fabs(v.x) < 0x1p-200;
+                    if (reev && fabs(v.x) < 0x1p-500) continue;        // fully re-evaluated already
                     const uint32_t sx = src[c0 + c];
                     const int64_t row = (int64_t)((sx >> 5) / (uint32_t)NP) * 32 + (sx & 31);
                     const int pr = (int)((sx >> 5) % (uint32_t)NP);
                     atomicOr(pairflags + row * W + (pr >> 5), 1u << (pr & 31));
+                    atomicOr(forcek + row * W + (pr >> 5), 1u << (pr & 31));
                     atomicOr(batchany + (row >> 5), 1u << (row & 31));
                 }
                 atomicAdd(n_doubt, 1ull);
