@@ -94,7 +94,6 @@ struct movfem_handle {
     double w32_last, omega_last;
     int cache_last;
     bool have_result;
-    uint32_t *d_pure;        // bit per entry: only unstretched elements contribute (gathered K/M cacheable across a sweep)
     double2 *d_kmg;          // the cache: gathered (K, M) per entry, allocated on the second frequency if memory allows
     int kmg_state;           // 0 not allocated, 1 allocated / to be filled, 2 valid, -1 does not fit
     uint32_t *d_src;
@@ -115,7 +114,7 @@ struct movfem_handle {
     int *d_blkcnt;
     int64_t *d_blkoff, *d_finbsum;
     int64_t *d_csr;                // row pointers of the last device result (movfem_device_csr), built on request
-    unsigned long long *d_total;   // delivered (non-zero) entries of the last T2 assembly
+    unsigned long long *d_total;   // [0] entries stripped by find_zeros in the last T2 assembly, [1..2] signature of the stripped set
     bool offsets_valid;            // d_blkoff holds the scan of the last assembly's block counts
     int nblk_fin;
     int *d_status, *d_flags;
@@ -453,7 +452,7 @@ int run_elements(movfem_handle *h, ElemArgs &A, bool full) {
 void free_all(movfem_handle *h) {
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_xp, h->d_yp, h->d_zp, h->d_mu, h->d_sigma, h->d_nodes, h->d_tab, h->d_share, h->d_gne, h->d_ownE,
-                    h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_cblk, h->d_off16, h->d_pure, h->d_kmg, h->d_escale, h->d_pairflags, h->d_batchany, h->d_forcek, h->d_nflag, h->d_src, h->d_KM,
+                    h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_cblk, h->d_off16, h->d_kmg, h->d_escale, h->d_pairflags, h->d_batchany, h->d_forcek, h->d_nflag, h->d_src, h->d_KM,
                     h->d_be, h->d_qt, h->d_bdtab, h->d_bdlist, h->d_kmrow, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum, h->d_total, h->d_csr,
                     h->d_status, h->d_flags};
     for (void *p : ptrs)
@@ -544,15 +543,6 @@ int build_pattern(movfem_handle *h) {
         CK(dmalloc(&h->d_cblk, (size_t)nblk + 1));
         CK(dmalloc(&h->d_off16, (size_t)h->nzu));
         if (nblk > 0) compress_cptr_kernel<<<nblk, kFinThreads, 0, h->stream>>>(h->nzu, h->d_cptr, h->d_cblk, h->d_off16);
-        h->launches += 1;
-        CK(cudaGetLastError());
-    }
-    {
-        const int nblk = (int)((h->nzu + kFinThreads - 1) / kFinThreads);
-        CK(dmalloc(&h->d_pure, (size_t)(h->nzu + 31) / 32));
-        if (nblk > 0)
-            // every K/M row is frequency independent (Q18), so every entry's gathered (K, M) can be cached across a sweep
-            pure_mask_kernel<<<nblk, kFinThreads, 0, h->stream>>>(h->nzu, h->d_cblk, h->d_off16, h->d_src, h->NP, h->km_rows, h->d_pure);
         h->launches += 1;
         CK(cudaGetLastError());
     }
@@ -824,8 +814,8 @@ static int launch_gather(movfem_handle *h, double omega, int32_t mode, int cache
     CK(cudaMemsetAsync(h->d_nflag + 1, 0, sizeof(unsigned long long), st));
     double dk = -1.0, dm = -1.0;
     if (const char *t = getenv("MOVFEM_TEST_DOUBT_ABS")) sscanf(t, "%lf,%lf", &dk, &dm);   // test hook (tests/test_gpu_parity.py)
-    gather_finalize_kernel<<<h->nblk_fin, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cblk, h->d_off16, h->d_src, h->d_KM, h->d_a,
-                                                              h->d_blkcnt, gmode, cache, h->d_pure, h->d_kmg, h->d_flags, nullptr, h->d_total,
+    gather_finalize_kernel<<<(h->nblk_fin + kGatherSub - 1) / kGatherSub, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cblk, h->d_off16, h->d_src, h->d_KM, h->d_a,
+                                                              h->d_blkcnt, gmode, cache, h->d_kmg, h->d_flags, h->nblk_fin, h->d_total,
                                                               h->NP, h->flagW, h->d_pairflags, h->d_batchany, h->d_forcek, h->d_nflag + 1, dk, dm);
     h->launches += 1;
     CK(cudaGetLastError());
@@ -957,7 +947,7 @@ int movfem_device_result(const movfem_handle *hc, const int32_t **irn, const int
         if (h->nflag_last > 0 || h->h_nflag[1] > 0) h->flags_dirty = true;
         if (h->mode_last == MOVFEM_MODE_T1) h->nz_last = h->nzu;
         else {
-            h->nz_last = h->h_count[0];
+            h->nz_last = h->nzu - h->h_count[0];   // h_count[0]: entries stripped by find_zeros
             if (h->nz_last != h->nzu) {   // find_zeros > 0: rem_zeros (global_assembly.f90:134-150)
                 if (!h->offsets_valid) {
                     const int nb = (h->nblk_fin + kScanTile - 1) / kScanTile;

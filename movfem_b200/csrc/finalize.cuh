@@ -17,6 +17,7 @@
 
 namespace movfem {
 
+constexpr int kGatherSub = 1;         // blocks of kFinThreads entries per gather CTA (2: twice the reads in flight per thread, measured 0-4 % slower)
 constexpr int kFinThreads = 128;      // entries per gather block.  Measured on config 2: 64: 0.400 ms, 128: 0.334, 256: 0.342, 512: 0.361
 
 // Contribution index, compressed once per mesh: per block of kFinThreads entries the 64-bit position of its first
@@ -32,56 +33,69 @@ compress_cptr_kernel(int64_t nzu, const int64_t *__restrict__ cptr, int64_t *__r
     if (i < nzu) off16[i] = (uint16_t)(cptr[i] - b0);
 }
 
-// pure[i/32] bit i%32: every contribution of entry i comes from an unstretched element (K/M row < pml_row0), i.e. the
-// gathered (K, M) of the entry is frequency independent and can be cached across a sweep
-__global__ void __launch_bounds__(kFinThreads)
-pure_mask_kernel(int64_t nzu, const int64_t *__restrict__ cblk, const uint16_t *__restrict__ off16, const uint32_t *__restrict__ src,
-                 int NP, int64_t pml_row0, uint32_t *__restrict__ pure) {
-    const int64_t i = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
-    bool p = false;
-    if (i < nzu) {
-        const int64_t c0 = cblk[blockIdx.x];
-        const int lo = off16[i];
-        const int hi = (threadIdx.x + 1 < kFinThreads && i + 1 < nzu) ? off16[i + 1] : (int)(cblk[blockIdx.x + 1] - c0);
-        p = true;
-        for (int c = lo; c < hi; ++c) {
-            const uint32_t s = src[c0 + c];
-            const int64_t row = (int64_t)((s >> 5) / (uint32_t)NP) * 32 + (s & 31);
-            if (row >= pml_row0) p = false;
-        }
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, p);
-    if ((threadIdx.x & 31) == 0 && i < nzu) pure[i >> 5] = bal;
-}
-
 // mode 0 (T2): values rounded through float32, per-block count of surviving (non-zero) entries
 // mode 1 (T1): double values, nothing stripped
+// (Measured and dropped in round 2: a persistent CTA with a three-stage software pipeline over its blocks -- indices of block
+// j+2, reads of block j+1 in flight while block j is summed -- is 4-6 % SLOWER than one block per 128 entries: 16 resident
+// blocks per SM already overlap the index -> value chains of different blocks.)
 // Phase 1: the block's <= 4*kFinThreads contributions are fetched by all threads (independent random 16-byte reads, up to four
 // in flight per thread) into shared memory; phase 2: one thread per entry sums its contributions in ascending order.
-// cache: 0 none; 1 fill kmg[i] = gathered (K, M) of every entry; 2 use it for the pure entries (a later frequency of a
-// sweep: streaming 16-byte reads instead of the gather) unless the node kernel saw Re(sigma) change (flags[1]), in which
-// case the call refills it.
+// cache: 0 none; 1 fill kmg[i] = gathered (K, M) of every entry; 2 use it (a later frequency of a sweep: streaming 16-byte
+// reads instead of the gather) unless the node kernel saw Re(sigma) change (flags[1]), in which case the call refills it.
 __global__ void __launch_bounds__(kFinThreads)
 gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk, const uint16_t *__restrict__ off16,
                        const uint32_t *__restrict__ src, const double2 *__restrict__ KM, double2 *__restrict__ a,
-                       int *__restrict__ blk_nonzero, int mode, int cache, const uint32_t *__restrict__ pure,
-                       double2 *__restrict__ kmg, const int *__restrict__ flags, const int *__restrict__ blk_list,
+                       int *__restrict__ blk_nonzero, int mode, int cache,
+                       double2 *__restrict__ kmg, const int *__restrict__ flags, int nblk,
                        unsigned long long *__restrict__ total_nonzero, int NP, int W, uint32_t *__restrict__ pairflags,
                        uint32_t *__restrict__ batchany, uint32_t *__restrict__ forcek, unsigned long long *__restrict__ n_doubt,
                        double doubt_abs_k, double doubt_abs_m /* test hook: doubt every entry below these sizes; < 0 = off */) {
-    __shared__ double2 vals[4 * kFinThreads];
-    __shared__ uint16_t offs[kFinThreads + 1];
-    const int blk = blk_list ? blk_list[blockIdx.x] : (int)blockIdx.x;   // the structured fast path leaves only some blocks here
-    const int64_t i = (int64_t)blk * kFinThreads + threadIdx.x;
-    const int64_t c0 = cblk[blk];
-    const int n = (int)(cblk[blk + 1] - c0);
+    // kGatherSub blocks of kFinThreads entries per CTA: twice the scattered reads in flight per thread at the same occupancy
+    __shared__ double2 vals[kGatherSub][4 * kFinThreads];
+    __shared__ uint16_t offs[kGatherSub][kFinThreads + 1];
     if (cache == 2 && flags[1] != 0) cache = 1;
+    int64_t c0s[kGatherSub];
+    int ns[kGatherSub];
+    if (!(cache == 2)) {
+#pragma unroll
+        for (int sb = 0; sb < kGatherSub; ++sb) {
+            const int blk = blockIdx.x * kGatherSub + sb;
+            c0s[sb] = 0; ns[sb] = 0;
+            if (blk >= nblk) continue;
+            const int64_t i = (int64_t)blk * kFinThreads + threadIdx.x;
+            c0s[sb] = cblk[blk];
+            ns[sb] = (int)(cblk[blk + 1] - c0s[sb]);
+            if (i < nzu) offs[sb][threadIdx.x] = off16[i];
+            uint32_t sidx[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = threadIdx.x + k * kFinThreads;
+                sidx[k] = c < ns[sb] ? src[c0s[sb] + c] : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = threadIdx.x + k * kFinThreads;
+                if (c < ns[sb]) {   // LDGSTS: global -> shared without the register round trip, L1 bypassed (.cg); measured -10 % against
+                                    // plain loads, __ldcs +15 %, ld.global.nc.L1::no_allocate +1 % (profiles/r02_ab_results.md)
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(&vals[sb][c]);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(KM + sidx[k]) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
+#pragma unroll
+    for (int sb = 0; sb < kGatherSub; ++sb) {
+    const int blk = blockIdx.x * kGatherSub + sb;
+    if (blk >= nblk) break;
+    const int64_t i = (int64_t)blk * kFinThreads + threadIdx.x;
+    const int64_t c0 = c0s[sb];
+    const int n = ns[sb];
     int nzflag = 0;
-    // later frequency of a sweep: a block whose entries are all pure streams them from the cache; a block with any
-    // entry that a GPML element touches runs the staged gather below (block-uniform decision)
-    bool pure_e = true;
-    if (cache == 2 && i < nzu) pure_e = (pure[i >> 5] >> (i & 31)) & 1u;
-    const bool stream = cache == 2 && __syncthreads_and(pure_e);
+    // later frequency of a sweep: every K_e, M_e is frequency independent (Q18), so every entry streams from the gathered cache
+    const bool stream = cache == 2;
     if (stream) {
         if (i < nzu) {
             const double2 v = kmg[i];
@@ -91,35 +105,16 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
             nzflag = !(re == 0.0 && im == 0.0);
         }
     } else {
-        if (i < nzu) offs[threadIdx.x] = off16[i];
-        uint32_t sidx[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = threadIdx.x + k * kFinThreads;
-            sidx[k] = c < n ? src[c0 + c] : 0u;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = threadIdx.x + k * kFinThreads;
-            if (c < n) {   // LDGSTS: global -> shared without the register round trip, L1 bypassed (.cg); measured -10 % against
-                           // plain loads, __ldcs +15 %, ld.global.nc.L1::no_allocate +1 % (profiles/r02_ab_results.md)
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(&vals[c]);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(KM + sidx[k]) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
         if (i < nzu) {
-            const int lo = offs[threadIdx.x];
-            const int hi = (threadIdx.x + 1 < kFinThreads && i + 1 < nzu) ? offs[threadIdx.x + 1] : n;
+            const int lo = offs[sb][threadIdx.x];
+            const int hi = (threadIdx.x + 1 < kFinThreads && i + 1 < nzu) ? offs[sb][threadIdx.x + 1] : n;
             // Contributions re-evaluated in the reference's operation order (exact.cuh) are recognised by magnitude (both parts
             // scaled by 2^-600); they carry K_e and the imaginary part with w32 already inside.  An entry made of such
             // contributions only is summed exactly as the reference's a(idd)=a(idd)+aij does, so its (0,0) test agrees.
             double k = 0.0, mm = 0.0, kx = 0.0, mx = 0.0, ak = 0.0, am = 0.0;
             int ninexact = 0, nlazy = 0;
             for (int c = lo; c < hi; ++c) {
-                const double2 v = vals[c];
+                const double2 v = vals[sb][c];
                 const double ax = fabs(v.x);
                 if (fabs(v.y) < 0x1p-500 && ax < 0x1p-200) {          // re-evaluated slot: exact imaginary part, scaled by 2^-600
                     mx = mx + v.y * 0x1p+600;
@@ -138,7 +133,7 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
             const bool doubt_l = nlazy && !ninexact && mx == 0.0;
             if ((doubt_x || doubt_l) && pairflags) {
                 for (int c = lo; c < hi; ++c) {
-                    const double2 v = vals[c];
+                    const double2 v = vals[sb][c];
                     const bool reev = fabs(v.y) < 0x1p-500 && fabs(v.x) < 0x1p-200;
                     if (reev && fabs(v.x) < 0x1p-500) continue;        // fully re-evaluated already
                     const uint32_t sx = src[c0 + c];
@@ -160,13 +155,18 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
     const int cnt = __syncthreads_count(nzflag);
     if (threadIdx.x == 0) {
         blk_nonzero[blk] = cnt;
-        if (total_nonzero && cnt) atomicAdd(total_nonzero, (unsigned long long)cnt);   // integer: order-independent
+        // find_zeros: the number of STRIPPED entries is accumulated (integer: order-independent), so a block without exact zeros --
+        // nearly every block -- touches no shared counter.  (Counting the survivors instead cost one same-address atomic per
+        // 128 entries: 12.8 M serialised atomics on config 5.)
+        const int valid = (int)min((int64_t)kFinThreads, nzu - (int64_t)blk * kFinThreads);
+        if (total_nonzero && mode == 0 && cnt != valid) atomicAdd(total_nonzero, (unsigned long long)(valid - cnt));
     }
     // signature of the stripped set (which entries rem_zeros removes): lets MOVFEM_MODE_KEEP_PATTERN tell whether the caller's
     // irn/jcn still match the delivered pattern.  Wrapping integer sums: order independent.
     if (total_nonzero && mode == 0 && i < nzu && !nzflag) {
         atomicAdd(total_nonzero + 1, (unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ull);
         atomicAdd(total_nonzero + 2, ((unsigned long long)(i + 1) * 0xC2B2AE3D27D4EB4Full) ^ (unsigned long long)(i >> 7));
+    }
     }
 }
 
