@@ -147,6 +147,10 @@ int movfem_device_result(const movfem_handle *h, const int32_t **irn, const int3
    into irn/jcn/a, rows local to the handle) completes it: row r holds entries rowptr[r] .. rowptr[r+1]-1, its
    column indices are jcn (1-based) and its values a.  Valid until the next assemble on the handle.           */
 int movfem_device_csr(const movfem_handle *h, const int64_t **rowptr, int32_t *nrows);
+/* A device consumer of that CSR view: y = A x (complex128 device vectors of nne entries) for the complex symmetric matrix whose
+   upper triangle is the last device result -- the residual / refinement step of a GPU sparse solver.  ms_device (optional):
+   device time of the two kernels.  Whole-mesh handles only (a slab handle returns MOVFEM_E_UNSUPPORTED).               */
+int movfem_device_spmv(const movfem_handle *h, const double *x_dev, double *y_dev, double *ms_device);
 
 /* Forget the cached K_e/M_e of the unstretched elements: the next assemble recomputes every
    element (what a single-frequency run does).  A sweep keeps them.            */

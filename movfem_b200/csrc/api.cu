@@ -1077,6 +1077,35 @@ static int deliver(movfem_handle *h, void *dst, const void *src_dev, size_t byte
     return pipe_d2h(h, dst, src_dev, bytes, 0);
 }
 
+// y = A x on the device from the CSR view of the last result (a consumer of movfem_device_csr)
+int movfem_device_spmv(const movfem_handle *hc, const double *x_dev, double *y_dev, double *ms_device) {
+    movfem_handle *h = const_cast<movfem_handle *>(hc);
+    if (!h || !x_dev || !y_dev) return MOVFEM_E_BADARG;
+    if (h->nrows != h->nne) return MOVFEM_E_UNSUPPORTED;      // a slab handle holds only its rows: the mirrored part needs the others
+    const int64_t *rowptr = nullptr;
+    int32_t nrows = 0;
+    int rc = movfem_device_csr(h, &rowptr, &nrows);
+    if (rc) return rc;
+    const int32_t *d_irn, *d_jcn;
+    const double *d_a, *d_rhs;
+    int64_t nz = 0;
+    if ((rc = movfem_device_result(h, &d_irn, &d_jcn, &d_a, &d_rhs, &nz))) return rc;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, h->stream));
+    spmv_upper_rows_kernel<<<(unsigned)(((int64_t)nrows * 32 + 255) / 256), 256, 0, h->stream>>>(nrows, rowptr, d_jcn, reinterpret_cast<const double2 *>(d_a),
+                                                                                             reinterpret_cast<const double2 *>(x_dev), reinterpret_cast<double2 *>(y_dev));
+    if (nz > 0)
+        spmv_upper_mirror_kernel<<<(unsigned)((nz + 255) / 256), 256, 0, h->stream>>>(nz, d_irn, d_jcn, reinterpret_cast<const double2 *>(d_a),
+                                                                                   reinterpret_cast<const double2 *>(x_dev), reinterpret_cast<double2 *>(y_dev));
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaGetLastError());
+    CK(cudaEventSynchronize(e1));
+    if (ms_device) { float t = 0; cudaEventElapsedTime(&t, e0, e1); *ms_device = t; }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return MOVFEM_OK;
+}
+
 int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega, const double *g_sigma, int32_t *irn, int32_t *jcn,
                     double *a, double *rhs, int64_t *nz_out, int32_t mode_flags) {
     if (!h || !g_sigma || !irn || !jcn || !a || !rhs || !nz_out) return MOVFEM_E_BADARG;

@@ -211,6 +211,32 @@ __global__ void csr_rowptr_kernel(int nrows, int row_lo, int64_t nz, const int *
     rowptr[r] = lo;
 }
 
+// A device consumer of the CSR hand-off: y = A x for the complex SYMMETRIC matrix whose upper triangle is the
+// delivered result (what a GPU sparse solver's residual check or an iterative refinement step needs).  Pass 1: one warp per row
+// over its stored entries (diagonal and right of it); pass 2: the mirrored entries, y_c += a_rc x_r, by atomics.
+__device__ __forceinline__ double2 zmul2(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__global__ void spmv_upper_rows_kernel(int nrows, const int64_t *__restrict__ rowptr, const int *__restrict__ jcn, const double2 *__restrict__ a,
+                                       const double2 *__restrict__ x, double2 *__restrict__ y) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= nrows) return;
+    double sx = 0.0, sy = 0.0;
+    for (int64_t k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) {
+        const double2 t = zmul2(a[k], x[jcn[k] - 1]);
+        sx += t.x; sy += t.y;
+    }
+    for (int o = 16; o; o >>= 1) { sx += __shfl_down_sync(0xffffffffu, sx, o); sy += __shfl_down_sync(0xffffffffu, sy, o); }
+    if (lane == 0) y[r] = make_double2(sx, sy);
+}
+__global__ void spmv_upper_mirror_kernel(int64_t nz, const int *__restrict__ irn, const int *__restrict__ jcn, const double2 *__restrict__ a,
+                                         const double2 *__restrict__ x, double2 *__restrict__ y) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nz) return;
+    const int r = irn[k] - 1, c = jcn[k] - 1;
+    if (r == c) return;
+    const double2 t = zmul2(a[k], x[r]);
+    atomicAdd(&y[c].x, t.x); atomicAdd(&y[c].y, t.y);
+}
+
 // b(gne + (d-1)*nne) += blocal(d): sum of the <= 4 sharing elements in ascending element order
 __global__ void rhs_kernel(int nrows, const int *__restrict__ rown, const double4 *__restrict__ be, double2 *__restrict__ rhs) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;   // row local to the handle's slab; rhs is [2][nrows]

@@ -29,8 +29,11 @@
 // version (all warps geometry, then all warps contraction, TMA-staged records) 4.30; the same with a tensor-core (DMMA)
 // interpolation phase and a reused buffer 5.30 (two more block barriers); warp-specialised with direct global loads 3.77;
 // + cp.async staging 3.67; + no global-load chain at the top of a batch, one reciprocal per Gauss point, no sums of
-// identically-zero source components, lower half only of diagonal tiles 3.58 (this file); four producer warps of two Gauss
-// points (10 warps, 96 registers, spills in the tile loop) 4.05.  geometry_kernel + contract_kernel: 5.59.
+// identically-zero source components, lower half only of diagonal tiles 3.58; + element ids two batches ahead and a partly
+// rolled node loop 3.36 (this file); four producer warps of two Gauss points (10 warps, 96 registers, spills in the tile
+// loop) 4.05; b_e formed by four of the consumer warps from a double-buffered R block 3.38 (no gain: the producers wait for
+// their scattered 16-byte node-field reads, 27 sectors per request, not for their own instructions -- the next step is a
+// field-major node layout so that a warp's request is 256 contiguous bytes).  geometry_kernel + contract_kernel: 5.59.
 //
 // Replaces for linear elements: MoVFEM_3DMT.f90:193-211 (element loop body), integration.f90:60-106 (int_elem_params,
 // alocal, blocal), n_fem.f90:66-102,355-395, v_fem.f90:38-60, problem.f90:70-149.
@@ -124,13 +127,18 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
         // The node fields of a batch arrive by cp.async (16 bytes per lane and chunk, L1 bypassed), issued one batch ahead by
         // the two producer warps (four nodes each): the global-memory latency of the scattered records (27 sectors per
         // request) is hidden behind the closed forms, the RHS and the consumers' contraction of the previous batch.
-        // element id and half-widths a = dx/2, b = dy/2 of the NEXT batch are fetched together with its node fields and carried in
-        // registers, so no global-memory round trip sits at the top of a batch
-        int e_nx = 0;
+        // Three-deep software pipeline of the producers' own inputs: the element id of batch k+2 is loaded while the node fields
+        // (cp.async) and the half-widths a = dx/2, b = dy/2 of batch k+1 are fetched with the id loaded one batch earlier, so no
+        // dependent global-memory round trip (list -> x/y lines and node addresses) sits inside a batch
+        int e_nx = 0, e_nx2 = 0;
         double a_nx = 0.0, b_nx = 0.0;
-        auto prefetch = [&](int batch_) {
+        auto load_id = [&](int batch_) {
             const int pos_ = batch_ * 32 + lane;
-            e_nx = pos_ < A.nlist ? A.list[pos_] : A.list[A.nlist - 1];
+            return batch_ < nbatch ? (pos_ < A.nlist ? A.list[pos_] : A.list[A.nlist - 1]) : 0;
+        };
+        auto prefetch = [&](int batch_) {      // batch_ is the batch whose id is in e_nx2
+            e_nx = e_nx2;
+            e_nx2 = load_id(batch_ + (int)gridDim.x);
             int ie_, je_, ke_;
             elem_ijk(m, e_nx, ie_, je_, ke_);
             a_nx = 0.5 * (__ldg(A.xp + ie_) - __ldg(A.xp + ie_ - 1)); b_nx = 0.5 * (__ldg(A.yp + je_) - __ldg(A.yp + je_ - 1));
@@ -148,6 +156,7 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        e_nx2 = load_id(blockIdx.x);
         if ((int)blockIdx.x < nbatch) prefetch(blockIdx.x);
         // mu = mu0 I at every node (flags[0] == 0): one scalar for the whole mesh
         const double mu0inv = DO_KM ? __ldg(reinterpret_cast<const double *>(A.nodes + ((int64_t)(A.e_base / (m.ny * m.nz)) * m.nyz)) + 2) : 0.0;
@@ -168,8 +177,8 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
             double s0[4], s3[4], s5[4], e12[4], e15[4], e18[4], e21[4], zp[4], zq[4], zr[4];
 #pragma unroll
             for (int gi = 0; gi < 4; ++gi) { s0[gi] = s3[gi] = s5[gi] = e12[gi] = e15[gi] = e18[gi] = e21[gi] = zp[gi] = zq[gi] = zr[gi] = 0.0; }
-#pragma unroll
-            for (int l = 0; l < MN; ++l) {
+#pragma unroll 2
+            for (int l = 0; l < MN; ++l) {   // (not fully unrolled: the producers' code competes with the consumers' for the instruction cache)
                 const double2 *st = s_stage + (l * 6) * 32 + lane;
                 const double2 ze = st[0], s01 = st[32], s23 = st[64], i01 = st[128], i23 = st[160];
                 const double s33 = DO_KM ? st[96].y : 0.0;

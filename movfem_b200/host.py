@@ -62,6 +62,7 @@ def lib():
         L.movfem_assemble_device.argtypes = [vp, i32, dbl, vp, i32]
         L.movfem_device_result.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
         L.movfem_device_csr.argtypes = [vp, C.POINTER(vp), C.POINTER(i32)]
+        L.movfem_device_spmv.argtypes = [vp, vp, vp, C.POINTER(dbl)]
         L.movfem_set_stream.argtypes = [vp, vp]
         L.movfem_get_stats.argtypes = [vp, C.POINTER(MovfemStats)]
         L.movfem_last_error.argtypes = [vp]
@@ -78,7 +79,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "movfem_create", "movfem_destroy", "movfem_sizes", "movfem_get_gne", "movfem_get_pattern", "movfem_assemble",
-    "movfem_assemble_device", "movfem_device_result", "movfem_device_csr", "movfem_set_stream", "movfem_get_stats", "movfem_last_error",
+    "movfem_assemble_device", "movfem_device_result", "movfem_device_csr", "movfem_device_spmv", "movfem_set_stream", "movfem_get_stats", "movfem_last_error",
     "movfem_version", "movfem_debug_element", "movfem_reset_cache", "movfem_fp64_peak", "movfem_slab_rows",
     "movfem_geo_innermodel",
 ]
@@ -213,6 +214,12 @@ class Assembly:
         rp, n = C.c_void_p(), C.c_int32()
         self._check(lib().movfem_device_csr(self._h, C.byref(rp), C.byref(n)))
         return rp.value, n.value
+
+    def device_spmv(self, x_dev_ptr: int, y_dev_ptr: int) -> float:
+        """y = A x on the device from the last device result (complex128 device vectors of nne entries); returns the device ms."""
+        ms = C.c_double(0)
+        self._check(lib().movfem_device_spmv(self._h, C.c_void_p(x_dev_ptr), C.c_void_p(y_dev_ptr), C.byref(ms)))
+        return ms.value
 
     def reset_cache(self):
         """Next call recomputes every element's K_e/M_e (cold single-frequency assembly)."""

@@ -365,6 +365,17 @@ def test_device_resident_api():
     assert int(rt.cudaMemcpy(rp.ctypes.data, p_rp, rp.nbytes, 2)) == 0 and nrows == asm.nne
     assert np.array_equal(rp, np.searchsorted(irn[:nz], np.arange(1, nrows + 2), side="left"))
     assert rp[0] == 0 and rp[-1] == nz and np.all(jcn[rp[:-1]] == np.arange(1, nrows + 1))   # every row starts at its diagonal
+    # ... and a device consumer of that view: y = A x for the complex symmetric matrix whose upper triangle was delivered
+    import scipy.sparse as sp
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(asm.nne) + 1j * rng.standard_normal(asm.nne)
+    d_x = torch.from_numpy(x.view(np.float64).copy()).cuda()
+    d_y = torch.zeros(2 * asm.nne, dtype=torch.float64, device="cuda")
+    ms = asm.device_spmv(d_x.data_ptr(), d_y.data_ptr())
+    U = sp.coo_matrix((a[:nz], (irn[:nz] - 1, jcn[:nz] - 1)), shape=(asm.nne, asm.nne)).tocsr()
+    want = U @ x + U.T @ x - U.diagonal() * x
+    got = d_y.cpu().numpy().view(np.complex128)
+    assert ms > 0 and rel_err(got, want) <= 1e-13
     asm.close()
 
 
