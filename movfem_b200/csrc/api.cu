@@ -73,6 +73,7 @@ struct movfem_handle {
     double *d_xp, *d_yp, *d_zp, *d_mu;
     double2 *d_sigma;
     NodeRec *d_nodes;
+    double *d_nsoa;          // linear elements: field-major node fields [6][npt] for fused12_kernel
     ElemTables *d_tab;
     ShareTables *d_share;
     int *d_gne, *d_ownE;
@@ -364,7 +365,7 @@ int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist,
     A.skip_unless_changed = skip_unless_changed;
     for (int64_t cb = 0; cb < nbatch_all; cb += chunk_b) {
         const int off = (int)(cb * 32), n = (int)std::min<int64_t>(nlist - off, chunk_b * 32);
-        A.list = d_list + off; A.nlist = n; A.qt = DO_QT ? h->d_qt : nullptr;
+        A.list = d_list + off; A.nlist = n; A.qt = DO_QT ? h->d_qt : nullptr; A.be_row0 = km_row0 + off;
         A.escale = DO_QT ? h->d_escale + km_row0 + off : nullptr;
         const int ngb = (n + GEO::EB - 1) / GEO::EB;
         if (kernel_event(h, 0, true)) return MOVFEM_E_CUDA;
@@ -402,7 +403,7 @@ int launch_fused12(movfem_handle *h, const ElemArgs &A, int skip_unless_changed)
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FC::THREADS, FC::SMEM));
     Fused12Args F;
-    F.m = A.m; F.omega = A.omega; F.T = A.T; F.nodes = A.nodes; F.xp = A.xp; F.yp = A.yp;
+    F.m = A.m; F.omega = A.omega; F.T = A.T; F.nodes = A.nodes; F.xp = A.xp; F.yp = A.yp; F.zp = h->d_zp; F.soa = h->d_nsoa; F.soa_stride = (size_t)A.m.npt;
     F.list = h->d_list_plain; F.nlist = h->n_plain; F.e_base = h->e_base; F.KM = h->d_KM; F.be = h->d_be;
     F.status = h->d_status; F.flags = h->d_flags; F.pairflags = h->d_pairflags; F.batchany = h->d_batchany; F.nflag = h->d_nflag; F.W = h->flagW;
     F.no_l1 = getenv("MOVFEM_TEST_NO_L1") ? 1 : 0;
@@ -451,7 +452,7 @@ int run_elements(movfem_handle *h, ElemArgs &A, bool full) {
 
 void free_all(movfem_handle *h) {
     cudaSetDevice(h->device);
-    void *ptrs[] = {h->d_xp, h->d_yp, h->d_zp, h->d_mu, h->d_sigma, h->d_nodes, h->d_tab, h->d_share, h->d_gne, h->d_ownE,
+    void *ptrs[] = {h->d_xp, h->d_yp, h->d_zp, h->d_mu, h->d_sigma, h->d_nodes, h->d_nsoa, h->d_tab, h->d_share, h->d_gne, h->d_ownE,
                     h->d_ownL, h->d_irn, h->d_jcn, h->d_irn_c, h->d_jcn_c, h->d_rown, h->d_cptr, h->d_cblk, h->d_off16, h->d_kmg, h->d_escale, h->d_pairflags, h->d_batchany, h->d_forcek, h->d_nflag, h->d_src, h->d_KM,
                     h->d_be, h->d_qt, h->d_bdtab, h->d_bdlist, h->d_kmrow, h->d_a, h->d_a_c, h->d_rhs, h->d_list_plain, h->d_list_pml, h->d_blkcnt, h->d_blkoff, h->d_finbsum, h->d_total, h->d_csr,
                     h->d_status, h->d_flags};
@@ -611,6 +612,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     CK(dmalloc(&h->d_xp, (size_t)m.nnx)); CK(dmalloc(&h->d_yp, (size_t)m.nny));
     CK(dmalloc(&h->d_zp, (size_t)m.npt)); CK(dmalloc(&h->d_mu, (size_t)6 * m.npt));
     CK(dmalloc(&h->d_sigma, (size_t)6 * m.npt)); CK(dmalloc(&h->d_nodes, (size_t)m.npt));
+    if (m.me == 12) CK(dmalloc(&h->d_nsoa, (size_t)6 * m.npt));
     CK(cudaMemcpy(h->d_xp, d->g_xp, sizeof(double) * m.nnx, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_yp, d->g_yp, sizeof(double) * m.nny, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_zp, d->g_zp, sizeof(double) * m.npt, cudaMemcpyHostToDevice));
@@ -709,7 +711,7 @@ int movfem_create(const movfem_desc *d, int device, movfem_handle **out) {
     CK(cudaMallocHost((void **)&h->h_nflag, 2 * sizeof(unsigned long long)));
     h->h_nflag[0] = h->h_nflag[1] = 0;
     h->flags_dirty = false; h->nflag_last = 0; h->have_result = false;
-    CK(dmalloc(&h->d_be, (size_t)(h->e_end - h->e_base) * m.me * 4));
+    CK(dmalloc(&h->d_be, (size_t)h->km_rows * m.me * 4));   // by K/M row, lists padded to 32 (be_index)
     {   // Q|P,T scratch: whole 32-element batches of the larger of the two lists, capped (launch_elements chunks)
         const size_t cb = sizeof(double) * (size_t)m.ngp * 32;
         const size_t need = std::max((size_t)((h->n_plain + 31) / 32) * 12 * cb, (size_t)((h->n_pml + 31) / 32) * 51 * cb);
@@ -856,7 +858,7 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
     }
     CK(cudaEventRecord(h->ev[EV_H2D], st));
     node_kernel<<<(h->node_hi - h->node_lo + 127) / 128, 128, 0, st>>>(h->node_lo, h->node_hi, omega, h->d_zp, h->d_mu, reinterpret_cast<const double2 *>(g_sigma_dev),
-                                                    h->d_nodes, h->d_status, h->d_flags, h->km_valid ? 1 : 0);
+                                                    h->d_nodes, h->d_status, h->d_flags, h->km_valid ? 1 : 0, h->d_nsoa, (size_t)m.npt);
     h->launches += 1;
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev[EV_NODE], st));
@@ -1305,7 +1307,7 @@ int movfem_debug_element(movfem_handle *h, int32_t ide, double *Ke, double *Me, 
         if (Ke) Ke[p] = kx;
         if (Me) Me[p] = mx;
     }
-    if (be) CK(cudaMemcpy(be, h->d_be + e * h->m.me * 4, sizeof(double) * h->m.me * 4, cudaMemcpyDeviceToHost));
+    if (be) CK(cudaMemcpy2D(be, 4 * sizeof(double), h->d_be + 4 * be_index(kr, h->m.me, 0), 32 * 4 * sizeof(double), 4 * sizeof(double), h->m.me, cudaMemcpyDeviceToHost));
     return MOVFEM_OK;
 }
 

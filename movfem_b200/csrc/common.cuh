@@ -38,6 +38,10 @@ struct __align__(16) NodeRec {
 static_assert(sizeof(NodeRec) == 26 * 8, "NodeRec layout");
 constexpr int kNodeDoubles = 26;
 
+// Element right-hand sides b_e are stored by K/M row (position in the launch lists, see contract.cuh), 32 rows interleaved:
+// [row / 32][local DOF][row % 32] of (pol 1 re, im, pol 2 re, im) -- a warp whose lanes are 32 consecutive rows stores 1 kB runs
+__host__ __device__ __forceinline__ size_t be_index(int64_t kr, int me, int dof) { return ((size_t)(kr >> 5) * me + dof) * 32 + (size_t)(kr & 31); }
+
 constexpr int kMaxGp = 27, kMaxMn = 27, kMaxMe = 54, kMaxMep = 56, kMaxSlots = 60;
 
 // Reference-element tables at the Gauss points (global memory, read through L1).

@@ -188,7 +188,7 @@ __global__ void dirichlet_rhs_kernel(int nlist, const int *__restrict__ list, Me
         bda0 = zadd(bda0, zmul(zscale(dne0, ex1), al));
         bda1 = zadd(bda1, zmul(zscale(dne1, ey2), al));
     }
-    double4 *bo = reinterpret_cast<double4 *>(be) + ((size_t)(e - e_base) * m.me + im);
+    double4 *bo = reinterpret_cast<double4 *>(be) + be_index(kr, m.me, im);
     double4 v = *bo;
     v.x -= bda0.x; v.y -= bda0.y; v.z -= bda1.x; v.w -= bda1.y;
     *bo = v;

@@ -38,7 +38,9 @@ namespace movfem {
 // ------------------------------------------------------------------------------------------
 __global__ void node_kernel(int n0, int npt, double omega, const double *__restrict__ zp, const double *__restrict__ mu,
                             const double2 *__restrict__ sigma, NodeRec *__restrict__ out, int *__restrict__ status,
-                            int *__restrict__ flags /* [0]: any dmu != 0, [1]: Re sigma changed, [2]: any off-diagonal sigma */, int check_re) {
+                            int *__restrict__ flags /* [0]: any dmu != 0, [1]: Re sigma changed, [2]: any off-diagonal sigma */, int check_re,
+                            double *__restrict__ soa /* linear elements: field-major copy [6][npt_all] of e, Re sigma 00 11 22, Im sigma 00 11 (fused12.cuh) */,
+                            size_t soa_stride) {
     const int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;   // [n0, npt): the node planes this handle's slab touches
     if (i >= npt) return;
     double a[6];
@@ -87,6 +89,10 @@ __global__ void node_kernel(int n0, int npt, double omega, const double *__restr
     if (changed) flags[1] = 1;
     if (s[1].x != 0.0 || s[1].y != 0.0 || s[2].x != 0.0 || s[2].y != 0.0 || s[4].x != 0.0 || s[4].y != 0.0) flags[2] = 1;
     out[i] = r;
+    if (soa) {
+        soa[i] = r.e; soa[soa_stride + i] = r.sre[0]; soa[2 * soa_stride + i] = r.sre[3]; soa[3 * soa_stride + i] = r.sre[5];
+        soa[4 * soa_stride + i] = r.sim[0]; soa[5 * soa_stride + i] = r.sim[3];
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -102,6 +108,7 @@ struct ElemArgs {
     const int *list;      // element ids (0-based) this launch handles
     int nlist;
     int e_base;           // first element stored in KM / be (slab handles keep only their slab + halo)
+    int64_t be_row0;      // K/M row of list[0] (b_e is stored by row, be_index)
     double *qt;           // scratch [nbatch32][NCMP][NGP][32]: Q|P and T per (element, Gauss point), see contract.cuh
     double *be;           // [ne][ME][4]  (re,im) x 2 polarisations
     double2 *escale;      // [list position]: (ngp * max_g tr Q|P, ngp * max_g tr T): the element's K / M magnitude, the scale the
@@ -568,8 +575,7 @@ __global__ void __launch_bounds__(CFG::THREADS, CFG::MINB) geometry_kernel(ElemA
                     bacc[0] = dfma(phi, r01.x, bacc[0]); bacc[1] = dfma(phi, r01.y, bacc[1]);
                     bacc[2] = dfma(phi, r23.x, bacc[2]); bacc[3] = dfma(phi, r23.y, bacc[3]);
                 }
-                const int64_t e = s_el[cs * 4];
-                reinterpret_cast<double4 *>(A.be)[(e - A.e_base) * ME + cdof] = make_double4(bacc[0], bacc[1], bacc[2], bacc[3]);
+                reinterpret_cast<double4 *>(A.be)[be_index(A.be_row0 + first + cs, ME, cdof)] = make_double4(bacc[0], bacc[1], bacc[2], bacc[3]);
             }
         }
     }

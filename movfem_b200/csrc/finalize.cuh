@@ -42,7 +42,7 @@ compress_cptr_kernel(int64_t nzu, const int64_t *__restrict__ cptr, int64_t *__r
 // in flight per thread) into shared memory; phase 2: one thread per entry sums its contributions in ascending order.
 // cache: 0 none; 1 fill kmg[i] = gathered (K, M) of every entry; 2 use it (a later frequency of a sweep: streaming 16-byte
 // reads instead of the gather) unless the node kernel saw Re(sigma) change (flags[1]), in which case the call refills it.
-__global__ void __launch_bounds__(kFinThreads)
+__global__ void __launch_bounds__(kFinThreads, 2048 / kFinThreads)
 gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk, const uint16_t *__restrict__ off16,
                        const uint32_t *__restrict__ src, const double2 *__restrict__ KM, double2 *__restrict__ a,
                        int *__restrict__ blk_nonzero, int mode, int cache,
@@ -51,7 +51,7 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
                        uint32_t *__restrict__ batchany, uint32_t *__restrict__ forcek, unsigned long long *__restrict__ n_doubt,
                        double doubt_abs_k, double doubt_abs_m /* test hook: doubt every entry below these sizes; < 0 = off */) {
     // kGatherSub blocks of kFinThreads entries per CTA: twice the scattered reads in flight per thread at the same occupancy
-    __shared__ double2 vals[kGatherSub][4 * kFinThreads];
+    __shared__ double2 vals[kGatherSub][4 * kFinThreads + 4];
     __shared__ uint16_t offs[kGatherSub][kFinThreads + 1];
     if (cache == 2 && flags[1] != 0) cache = 1;
     int64_t c0s[kGatherSub];
@@ -113,6 +113,25 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
             // contributions only is summed exactly as the reference's a(idd)=a(idd)+aij does, so its (0,0) test agrees.
             double k = 0.0, mm = 0.0, kx = 0.0, mx = 0.0, ak = 0.0, am = 0.0;
             int ninexact = 0, nlazy = 0;
+            // Fast path (the kernel is issue bound: 326 instructions per warp before this, profiles/r02_summary.md): the <= 4
+            // contributions are read without a loop or a branch (absent ones are +0.0: x + 0.0 leaves the running sum of
+            // a(idd)=a(idd)+aij bit-identical) and the magnitude test is done on the exponent words; the loop below runs only in
+            // a warp that holds a re-evaluated (or exactly zero) contribution
+            const int nc = hi - lo;
+            const double2 z2 = make_double2(0.0, 0.0);
+            const double2 v0 = nc > 0 ? vals[sb][lo] : z2, v1 = nc > 1 ? vals[sb][lo + 1] : z2;
+            const double2 v2 = nc > 2 ? vals[sb][lo + 2] : z2, v3 = nc > 3 ? vals[sb][lo + 3] : z2;
+            auto tagged = [](const double2 &v) {   // |v.y| < 2^-500 and |v.x| < 2^-200, on the high words
+                return ((unsigned)__double2hiint(v.y) & 0x7fffffffu) < 0x20b00000u && ((unsigned)__double2hiint(v.x) & 0x7fffffffu) < 0x33700000u;
+            };
+            const bool slow = (nc > 0 && tagged(v0)) || (nc > 1 && tagged(v1)) || (nc > 2 && tagged(v2)) || (nc > 3 && tagged(v3));
+            if (!__any_sync(__activemask(), slow)) {
+                k = (((k + v0.x) + v1.x) + v2.x) + v3.x;
+                mm = (((mm + v0.y) + v1.y) + v2.y) + v3.y;
+                ak = ((fabs(v0.x) + fabs(v1.x)) + fabs(v2.x)) + fabs(v3.x);
+                am = ((fabs(v0.y) + fabs(v1.y)) + fabs(v2.y)) + fabs(v3.y);
+                ninexact = nc;
+            } else
             for (int c = lo; c < hi; ++c) {
                 const double2 v = vals[sb][c];
                 const double ax = fabs(v.x);

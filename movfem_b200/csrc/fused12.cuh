@@ -44,19 +44,30 @@
 #include "contract.cuh"
 #include "element.cuh"
 
+#ifndef F12_UNROLL_G
+#define F12_UNROLL_G 8
+#endif
+#ifndef F12_UNROLL_L
+#define F12_UNROLL_L 8
+#endif
+
 namespace movfem {
+
+constexpr int kF12UnrollG = F12_UNROLL_G, kF12UnrollL = F12_UNROLL_L;
 
 struct Fused12Args {
     MeshDims m;
     double omega;
     const ElemTables *T;
     const NodeRec *nodes;
-    const double *xp, *yp;
+    const double *xp, *yp, *zp;
+    const double *soa;             // field-major node fields [6][soa_stride]: e, Re sigma 00 11 22, Im sigma 00 11 (node_kernel)
+    size_t soa_stride;
     const int *list;               // element ids (0-based) of this launch, K/M row order
     int nlist;
     int e_base;
     double2 *KM;                   // K/M store at this launch's first row: [batch][78][32]
-    double *be;                    // [element - e_base][12][4]
+    double *be;                    // by K/M row (be_index): [row / 32][12][row % 32][4]
     int *status;
     const int *flags;              // flags[0]: any dmu != 0, [1]: Re sigma changed, [2]: any off-diagonal sigma (node_kernel)
     uint32_t *pairflags;           // [row][W] at this launch's first row
@@ -70,41 +81,46 @@ struct Fused12Args {
 template <bool DO_KM>
 struct Fused12Cfg {
     static constexpr int MN = 8, ME = 12, NGP = 8, NP = 78;
-    static constexpr int NW = DO_KM ? 8 : 2, THREADS = NW * 32, MINB = DO_KM ? 2 : 8;
-    static constexpr size_t BLK_D = (size_t)12 * NGP * 32;                  // one [component][g][lane] block of doubles
-    static constexpr size_t TAB_D = (size_t)NGP * 4 * ME, DN_D = (size_t)MN * 4 * NGP, PHI_D = (size_t)NGP * ME;
-    static constexpr int NCH = MN * 6;                                      // staged 16-byte chunks per element: 6 per node record
-    static constexpr size_t STG_D = (size_t)NCH * 32 * 2;                   // node-field staging [chunk][lane] of double2
-    static constexpr size_t SMEM = sizeof(double) * ((DO_KM ? 3 : 1) * BLK_D + STG_D + TAB_D + DN_D + PHI_D) + sizeof(unsigned long long) * (2 * 32 * 2 + 4) +
-                                   sizeof(int) * (2 * ME + MN);
+    static constexpr int NW = 8, THREADS = NW * 32, MINB = DO_KM ? 2 : 3;
+    static constexpr size_t QT_D = (size_t)12 * NGP * 32;                   // one Q|T block [component][g][lane] of doubles
+    static constexpr size_t R_D = (size_t)8 * NGP * 32;                     // one source block: the 8 not identically zero components
+    static constexpr size_t SF_D = (size_t)7 * MN * 32;                     // staged node fields [field][node][lane]: z, e, Re sigma 00 11 22, Im sigma 00 11
+    static constexpr size_t TR_D = (size_t)2 * NGP * 32 * 2;                // [2][g][lane] (tr Q, tr T)
+    static constexpr size_t TAB_D = (size_t)NGP * 4 * ME, DN_D = (size_t)MN * 4 * NGP, PHI_D = (size_t)NGP * ME, XY_D = 4 * 32;
+    static constexpr size_t SMEM = sizeof(double) * ((DO_KM ? 2 * QT_D + TR_D : 0) + 2 * R_D + SF_D + TAB_D + DN_D + PHI_D + XY_D) +
+                                   sizeof(unsigned long long) * 8 + sizeof(int) * (2 * ME + MN + 4 * 32 + 6 * 16);
 };
-
-__device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
 template <bool DO_KM>
 __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>::MINB) fused12_kernel(Fused12Args A) {
     using C = Fused12Cfg<DO_KM>;
-    constexpr int MN = C::MN, ME = C::ME, NGP = C::NGP, NP = C::NP, NW = C::NW;
+    constexpr int MN = C::MN, ME = C::ME, NGP = C::NGP, NP = C::NP;
     constexpr int QS = NGP * 32;                                      // component stride inside a block
     if (A.skip_unless_changed && A.flags[1] == 0) return;
     if (A.flags[0] != 0 || A.flags[2] != 0) return;                   // mu != mu0 or off-diagonal sigma: the generic path runs instead
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *s_R = reinterpret_cast<double *>(smem_raw);               // [12 = d*4 + (pol, re|im)][NGP][32]
-    double *s_qt = s_R + C::BLK_D;                                    // [2][12][NGP][32]: Q (0-5, sym3 order), T (6-11)   (DO_KM)
-    double2 *s_stage = reinterpret_cast<double2 *>(s_R + (DO_KM ? 3 : 1) * C::BLK_D);   // [48 = node*6 + field][32 lanes]: (z,e), sigma re 01|23|45, im 01|23
-    double *s_tab = s_R + (DO_KM ? 3 : 1) * C::BLK_D + C::STG_D;      // [NGP][4][ME]: dphi (0-2), phi (3), slot order
+    double *s_R = reinterpret_cast<double *>(smem_raw);               // [2][8][NGP][32]: (d0,pol1) (d1,pol2) (d2,pol1) (d2,pol2), re|im each
+    double *s_qt = s_R + 2 * C::R_D;                                  // [2][12][NGP][32]: Q (0-5, sym3 order), T (6-11)   (DO_KM)
+    double *s_tr = s_qt + (DO_KM ? 2 * C::QT_D : 0);                  // [2][NGP][32][2]                                      (DO_KM)
+    double *s_sf = s_tr + (DO_KM ? C::TR_D : 0);                      // [7][MN][32]: z, e, Re sigma 00, 11, 22, Im sigma 00, 11
+    double *s_tab = s_sf + C::SF_D;                                   // [NGP][4][ME]: dphi (0-2), phi (3), slot order
     double *s_dN = s_tab + C::TAB_D;                                  // [MN][4][NGP]: dN/dxi (0-2), N (3)
     double *s_phi = s_dN + C::DN_D;                                   // [NGP][ME] phi in slot order
-    unsigned long long *s_scale = reinterpret_cast<unsigned long long *>(s_phi + C::PHI_D);   // [2][32][2]
-    uint64_t *full = reinterpret_cast<uint64_t *>(s_scale + 2 * 32 * 2), *empty = full + 2;
-    int *s_slot = reinterpret_cast<int *>(empty + 2);                 // [ME] slot -> local DOF
+    double *s_xy = s_phi + C::PHI_D;                                  // [4][32]: x0, x1, y0, y1 of the staged batch
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_xy + C::XY_D), *empty = full + 2, *staged = full + 4;
+    int *s_slot = reinterpret_cast<int *>(full + 8);                  // [ME] slot -> local DOF
     int *s_sdir = s_slot + ME;                                        // [ME] slot -> direction
     int *s_noff = s_sdir + ME;                                        // [MN] node offset from the element's base node
+    int *s_ids = s_noff + MN;                                         // [4][32] element ids of batches j & 3
+    int *s_pidx = s_ids + 4 * 32;                                     // [6 tiles][16]: packed-triangle index of pair (i, j) of the tile, -1: not stored
 
     const ElemTables &T = *A.T;
     const MeshDims &m = A.m;
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int nbatch = (A.nlist + 31) / 32;
+    const int G = (int)gridDim.x;
+    const int nb = (int)blockIdx.x < nbatch ? (nbatch - (int)blockIdx.x + G - 1) / G : 0;   // batches of this CTA: blockIdx.x + j G
 
     for (int i = tid; i < NGP * ME; i += C::THREADS) s_phi[i] = T.phi[i / ME][T.slot_dof[i % ME]];
     if (DO_KM)
@@ -112,243 +128,251 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
     for (int i = tid; i < ME; i += C::THREADS) { s_slot[i] = T.slot_dof[i]; s_sdir[i] = T.slot_dir[i]; }
     for (int i = tid; i < MN; i += C::THREADS) s_noff[i] = T.node_off[i];
     for (int i = tid; i < MN * 4 * NGP; i += C::THREADS) s_dN[i] = T.dNt[(i / NGP) * 32 + (i % NGP)];
-    if (tid == 0 && DO_KM) {
-        for (int b = 0; b < 2; ++b) { mbar_init(&full[b], 2); mbar_init(&empty[b], 6); }
+    auto id_src = [&](int j_) {                                       // list entry of lane `lane` in this CTA's j-th batch (clamped)
+        const int pos_ = ((int)blockIdx.x + j_ * G) * 32 + lane;
+        return A.list + (pos_ < A.nlist ? pos_ : A.nlist - 1);
+    };
+    if (warp == 0 && nb > 0) s_ids[lane] = *id_src(0);
+    if (DO_KM && tid < 6 * 16) {
+        const int c_ = tid >> 4, i_ = (tid >> 2) & 3, j_ = tid & 3;
+        const int si = 4 * c_ct.tile_ti[c_] + i_, sj = 4 * c_ct.tile_tj[c_] + j_, im = c_ct.slot_dof[si], jm = c_ct.slot_dof[sj];
+        const int hi = im > jm ? im : jm, lo = im > jm ? jm : im;
+        s_pidx[tid] = sj <= si ? hi * (hi + 1) / 2 + lo : -1;
+    }
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) { mbar_init(&full[b], 8); mbar_init(&empty[b], 6); }
+        mbar_init(staged, 64);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (nb == 0) return;
 
-    const int nbatch = (A.nlist + 31) / 32;
-    if (warp >= NW - 2) {
-        // ================= producers: Gauss points g0 .. g0+3, polarisation pw of the RHS =================
-        const int pw = warp - (NW - 2), g0 = 4 * pw;
-        const double psig = f32r(A.omega * kEps0);   // pset_pmodel, problem.f90:250
-        const double w32 = f32r(A.omega);            // cmplx(0.d0,-omega), problem.f90:112
-        // The node fields of a batch arrive by cp.async (16 bytes per lane and chunk, L1 bypassed), issued one batch ahead by
-        // the two producer warps (four nodes each): the global-memory latency of the scattered records (27 sectors per
-        // request) is hidden behind the closed forms, the RHS and the consumers' contraction of the previous batch.
-        // Three-deep software pipeline of the producers' own inputs: the element id of batch k+2 is loaded while the node fields
-        // (cp.async) and the half-widths a = dx/2, b = dy/2 of batch k+1 are fetched with the id loaded one batch earlier, so no
-        // dependent global-memory round trip (list -> x/y lines and node addresses) sits inside a batch
-        int e_nx = 0, e_nx2 = 0;
-        double a_nx = 0.0, b_nx = 0.0;
-        auto load_id = [&](int batch_) {
-            const int pos_ = batch_ * 32 + lane;
-            return batch_ < nbatch ? (pos_ < A.nlist ? A.list[pos_] : A.list[A.nlist - 1]) : 0;
-        };
-        auto prefetch = [&](int batch_) {      // batch_ is the batch whose id is in e_nx2
-            e_nx = e_nx2;
-            e_nx2 = load_id(batch_ + (int)gridDim.x);
-            int ie_, je_, ke_;
-            elem_ijk(m, e_nx, ie_, je_, ke_);
-            a_nx = 0.5 * (__ldg(A.xp + ie_) - __ldg(A.xp + ie_ - 1)); b_nx = 0.5 * (__ldg(A.yp + je_) - __ldg(A.yp + je_ - 1));
-            const NodeRec *base_ = A.nodes + ((int64_t)(ie_ - 1) * m.nyz + (int64_t)(je_ - 1) * m.nnz + (ke_ - 1));
+    const bool fetcher = warp >= 6;                                   // warps 6, 7: node-field copies (four nodes each) and, with DO_KM, the RHS
+    const int pw = warp - 6;
+    const double psig = f32r(A.omega * kEps0);   // pset_pmodel, problem.f90:250
+    const double w32 = f32r(A.omega);            // cmplx(0.d0,-omega), problem.f90:112
+    // mu = mu0 I at every node (flags[0] == 0): one scalar for the whole mesh
+    const double mu0inv = DO_KM ? __ldg(reinterpret_cast<const double *>(A.nodes + ((int64_t)(A.e_base / (m.ny * m.nz)) * m.nyz)) + 2) : 0.0;
+    const double wt = T.rw[warp][3];
+
+    // ---- node fields, x / y lines of batch j and the element ids of batch j+1: asynchronous copies, completion on `staged` ----
+    auto cp_async = [&](void *dst_, const void *src_, auto bytes_tag) {
+        constexpr int BYTES = decltype(bytes_tag)::value;
+        const unsigned d_ = (unsigned)__cvta_generic_to_shared(dst_);
+        if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d_), "l"(src_) : "memory");
+        else if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d_), "l"(src_) : "memory");
+        else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d_), "l"(src_) : "memory");
+    };
+    auto prefetch = [&](int j_) {
+        const int e_ = s_ids[(j_ & 3) * 32 + lane];
+        int ie_, je_, ke_;
+        elem_ijk(m, e_, ie_, je_, ke_);
+        // Field-major node arrays: the 32 lanes of a request are 32 consecutive elements of a k-column (nearly always), i.e. 32
+        // consecutive nodes -- 256 contiguous bytes per copy instead of 32 sectors of an array of records
+        const int64_t n0_ = (int64_t)(ie_ - 1) * m.nyz + (int64_t)(je_ - 1) * m.nnz + (ke_ - 1);
 #pragma unroll
-            for (int l4 = 0; l4 < 4; ++l4) {
-                const int l = 4 * pw + l4;
-                const double2 *r2 = reinterpret_cast<const double2 *>(base_ + s_noff[l]);
-                constexpr int foff[6] = {0, 4, 5, 6, 7, 8};
+        for (int l4 = 0; l4 < 4; ++l4) {
+            const int l = 4 * pw + l4;
+            const int64_t n_ = n0_ + s_noff[l];
+            cp_async(s_sf + (0 * MN + l) * 32 + lane, A.zp + n_, std::integral_constant<int, 8>{});
 #pragma unroll
-                for (int f = 0; f < 6; ++f) {
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(s_stage + (l * 6 + f) * 32 + lane);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(r2 + foff[f]) : "memory");
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        e_nx2 = load_id(blockIdx.x);
-        if ((int)blockIdx.x < nbatch) prefetch(blockIdx.x);
-        // mu = mu0 I at every node (flags[0] == 0): one scalar for the whole mesh
-        const double mu0inv = DO_KM ? __ldg(reinterpret_cast<const double *>(A.nodes + ((int64_t)(A.e_base / (m.ny * m.nz)) * m.nyz)) + 2) : 0.0;
-        double wt[4];
-#pragma unroll
-        for (int gi = 0; gi < 4; ++gi) wt[gi] = T.rw[g0 + gi][3];
-        int k = 0;
-        for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x, ++k) {
-            const int buf = k & 1;
-            const int pos = batch * 32 + lane;
-            const bool live = pos < A.nlist;
-            const int e = e_nx;
-            const double a = a_nx, b = b_nx;
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            bar_sync_producers();                          // both warps' copies have landed
-            // interpolation to this warp's four Gauss points (p_intmodels problem.f90:139-142; N_l-weighted part of p_source
-            // :424-457) and the xi-gradient of z (nf_jacobian, n_fem.f90:359-366)
-            double s0[4], s3[4], s5[4], e12[4], e15[4], e18[4], e21[4], zp[4], zq[4], zr[4];
-#pragma unroll
-            for (int gi = 0; gi < 4; ++gi) { s0[gi] = s3[gi] = s5[gi] = e12[gi] = e15[gi] = e18[gi] = e21[gi] = zp[gi] = zq[gi] = zr[gi] = 0.0; }
-#pragma unroll 2
-            for (int l = 0; l < MN; ++l) {   // (not fully unrolled: the producers' code competes with the consumers' for the instruction cache)
-                const double2 *st = s_stage + (l * 6) * 32 + lane;
-                const double2 ze = st[0], s01 = st[32], s23 = st[64], i01 = st[128], i23 = st[160];
-                const double s33 = DO_KM ? st[96].y : 0.0;
-                const double di1 = i01.x - psig, di2 = i23.y - psig;   // Im(dsigma) on the diagonal (pdelta_model, problem.f90:329-331)
-#pragma unroll
-                for (int gi = 0; gi < 4; ++gi) {
-                    const int g = g0 + gi;
-                    const double ln = s_dN[(l * 4 + 3) * NGP + g];
-                    const double le = ln * ze.y;                       // N_l e_l, e_l = f32(omega b0 z_l)
-                    if (DO_KM) { s0[gi] = dfma(ln, s01.x, s0[gi]); s3[gi] = dfma(ln, s23.y, s3[gi]); s5[gi] = dfma(ln, s33, s5[gi]); }
-                    e12[gi] = dfma(le, di1, e12[gi]); e15[gi] = dfma(le, s01.x, e15[gi]);
-                    e18[gi] = dfma(le, di2, e18[gi]); e21[gi] = dfma(le, s23.y, e21[gi]);
-                    zp[gi] = dfma(s_dN[(l * 4 + 0) * NGP + g], ze.x, zp[gi]);
-                    zq[gi] = dfma(s_dN[(l * 4 + 1) * NGP + g], ze.x, zq[gi]);
-                    zr[gi] = dfma(s_dN[(l * 4 + 2) * NGP + g], ze.x, zr[gi]);
-                }
-            }
-            bar_sync_producers();                          // the staged fields are consumed: refill for the next batch
-            if (batch + (int)gridDim.x < nbatch) prefetch(batch + gridDim.x);
-            if (DO_KM && k >= 2) mbar_wait(&empty[buf], (unsigned)(((k >> 1) - 1) & 1));   // the consumers are done with this buffer
-            if (DO_KM && pw == 0) { s_scale[(buf * 32 + lane) * 2] = 0ull; s_scale[(buf * 32 + lane) * 2 + 1] = 0ull; }
-            if (DO_KM) bar_sync_producers();                                               // scales zeroed before either warp's max
-            double trq = 0.0, trt = 0.0;
-#pragma unroll
-            for (int gi = 0; gi < 4; ++gi) {
-                const int g = g0 + gi;
-                const double p = zp[gi], q = zq[gi], r = zr[gi];
-                const double det = (a * b) * r;
-                if (det == 0.0 && live) atomicCAS(A.status, 0, -3);
-                const double w = det * wt[gi];
-                const double rad = 1.0 / fabs(det);                    // Q6: nf_ji = adj(J)/abs(det)
-                const double G00 = (b * r) * rad, G11 = (a * r) * rad, G22 = (a * b) * rad, G02 = -(p * b) * rad, G12 = -(a * q) * rad;
-                if (DO_KM) {
-                    double *qo = s_qt + (size_t)buf * C::BLK_D + g * 32 + lane;
-                    const double fm = (det < 0.0 ? -wt[gi] : wt[gi]) * rad * mu0inv;   // (w/det^2) mu^-1 = (wt/det) mu^-1: Q = fm J J^T
-                    const double q00 = fm * dfma(a, a, p * p), q11 = fm * dfma(b, b, q * q), q22 = fm * (r * r);
-                    qo[0 * QS] = q00; qo[1 * QS] = fm * (p * q); qo[2 * QS] = fm * (p * r);
-                    qo[3 * QS] = q11; qo[4 * QS] = fm * (q * r); qo[5 * QS] = q22;
-                    // T = G^T S G, S = w Re sigma_g (integration.f90:234-236, Q3), sigma diagonal
-                    const double S0 = w * s0[gi], S1 = w * s3[gi], S2 = w * s5[gi];
-                    const double t00 = S0 * (G00 * G00), t11 = S1 * (G11 * G11);
-                    const double t22 = dfma(S0 * G02, G02, dfma(S1 * G12, G12, (S2 * G22) * G22));
-                    qo[6 * QS] = t00; qo[7 * QS] = 0.0; qo[8 * QS] = (S0 * G00) * G02;
-                    qo[9 * QS] = t11; qo[10 * QS] = (S1 * G11) * G12; qo[11 * QS] = t22;
-                    trq = fmax(trq, fabs(q00) + fabs(q11) + fabs(q22));
-                    trt = fmax(trt, fabs(t00) + fabs(t11) + fabs(t22));
-                }
-                // R[d][pol] = G[:,d] . (w src_pol);  src = dmpf * cmplx32(0,-omega) (problem.f90:112); for a diagonal sigma
-                // src_1 = (A1, 0, 0), src_2 = (0, A2, 0):  pol 1 dmpf = (+Im ds*e, -Re ds*e), pol 2 = (-Im ds*e, +Re ds*e)
-                const double a1x = w * (-e15[gi] * w32), a1y = w * (-(e12[gi] * w32)), a2x = w * (e21[gi] * w32), a2y = w * (e18[gi] * w32);
-                double *Ro = s_R + g * 32 + lane;
-                Ro[0 * QS] = G00 * a1x; Ro[1 * QS] = G00 * a1y; Ro[2 * QS] = 0.0;       Ro[3 * QS] = 0.0;
-                Ro[4 * QS] = 0.0;       Ro[5 * QS] = 0.0;       Ro[6 * QS] = G11 * a2x; Ro[7 * QS] = G11 * a2y;
-                Ro[8 * QS] = G02 * a1x; Ro[9 * QS] = G02 * a1y; Ro[10 * QS] = G12 * a2x; Ro[11 * QS] = G12 * a2y;
-            }
-            if (DO_KM) {
-                // the element's K / M scale for the tiny-pair test of the epilogue: max over the Gauss points, order independent
-                atomicMax(&s_scale[(buf * 32 + lane) * 2], (unsigned long long)__double_as_longlong(trq));
-                atomicMax(&s_scale[(buf * 32 + lane) * 2 + 1], (unsigned long long)__double_as_longlong(trt));
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[buf]);    // release: this warp's Q|T and scales are visible to the consumers
-            }
-            bar_sync_producers();                          // R of all eight Gauss points is in place
-            // ---- RHS, polarisation pw: b_e(j) = sum_g phi_j(g) R[d_j][pol](g)  (blocal / f3, integration.f90:96-104,258-263) ----
-            if (live) {
-                double2 *bo = reinterpret_cast<double2 *>(A.be) + ((size_t)(e - A.e_base) * ME) * 2 + pw;
-#pragma unroll
-                for (int q4 = 0; q4 < ME; q4 += 4) {
-                    const int cd = s_sdir[q4];
-                    double br[4] = {0, 0, 0, 0}, bi[4] = {0, 0, 0, 0};
-                    // diagonal sigma: the source of polarisation 1 is along x, of polarisation 2 along y, so R[d][pol] is
-                    // identically zero for (d, pol) = (1, 1) and (0, 2) -- written as zeros above, not summed here
-                    if (cd == 2 || cd == pw) {
-                        const double *Rr = s_R + (size_t)(cd * 4 + 2 * pw) * QS + lane, *Ri = Rr + QS;
-#pragma unroll
-                        for (int g = 0; g < NGP; ++g) {
-                            const double rr = Rr[g * 32], ri = Ri[g * 32];
-                            const double2 p01 = *reinterpret_cast<const double2 *>(s_phi + g * ME + q4), p23 = *reinterpret_cast<const double2 *>(s_phi + g * ME + q4 + 2);
-                            br[0] = dfma(p01.x, rr, br[0]); bi[0] = dfma(p01.x, ri, bi[0]);
-                            br[1] = dfma(p01.y, rr, br[1]); bi[1] = dfma(p01.y, ri, bi[1]);
-                            br[2] = dfma(p23.x, rr, br[2]); bi[2] = dfma(p23.x, ri, bi[2]);
-                            br[3] = dfma(p23.y, rr, br[3]); bi[3] = dfma(p23.y, ri, bi[3]);
-                        }
-                    }
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) bo[(size_t)s_slot[q4 + kk] * 2] = make_double2(br[kk], bi[kk]);
-                }
-            }
-            bar_sync_producers();                          // R may be overwritten
+            for (int f = 0; f < 6; ++f) cp_async(s_sf + ((1 + f) * MN + l) * 32 + lane, A.soa + f * A.soa_stride + n_, std::integral_constant<int, 8>{});
         }
-        return;
-    }
+        if (pw == 0) {
+            cp_async(s_xy + lane, A.xp + ie_ - 1, std::integral_constant<int, 8>{}); cp_async(s_xy + 32 + lane, A.xp + ie_, std::integral_constant<int, 8>{});
+            cp_async(s_xy + 64 + lane, A.yp + je_ - 1, std::integral_constant<int, 8>{}); cp_async(s_xy + 96 + lane, A.yp + je_, std::integral_constant<int, 8>{});
+            if (j_ + 1 < nb) cp_async(s_ids + ((j_ + 1) & 3) * 32 + lane, id_src(j_ + 1), std::integral_constant<int, 4>{});
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(staged)) : "memory");
+    };
 
-    // ================= consumers: tile `warp` = direction class `warp` (inner loop of contract.cuh) =================
-    if (DO_KM) {
-        const int c = warp;
-        const int ti = c_ct.tile_ti[c], tj = c_ct.tile_tj[c];
-        const int dI = cls_dI(c), dJ = cls_dJ(c);
-        const int k1I = dI == 2 ? 1 : 2, k2I = dI == 0 ? 1 : 0, k1J = dJ == 2 ? 1 : 2, k2J = dJ == 0 ? 1 : 0;
-        const double tau = ((dI == 1) != (dJ == 1)) ? -1.0 : 1.0;
-        const int cq0 = c_ct.comp[0][c][0], cq1 = c_ct.comp[0][c][1], cq2 = c_ct.comp[0][c][2], cq3 = c_ct.comp[0][c][3], cq4 = c_ct.comp[0][c][4];
-        const double *Y1 = s_tab + k1I * ME + 4 * ti, *Y2 = s_tab + k2I * ME + 4 * ti, *Y3 = s_tab + 3 * ME + 4 * ti;
-        const double *X1 = s_tab + k1J * ME + 4 * tj, *X2 = s_tab + k2J * ME + 4 * tj, *X3 = s_tab + 3 * ME + 4 * tj;
-        int k = 0;
-        for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x, ++k) {
-            const int buf = k & 1;
-            mbar_wait(&full[buf], (unsigned)((k >> 1) & 1));
-            const double *S = s_qt + (size_t)buf * C::BLK_D + lane;
-            double accK[16], accM[16];
+    // ---- geometry of Gauss point `warp` of batch j: interpolation, J, det, G = J^-1, Q, T and the source R in closed form ----
+    auto geometry = [&](int j_) {
+        const int buf = j_ & 1, g = warp;
+        mbar_wait(staged, (unsigned)(j_ & 1));
+        if (j_ >= 2) mbar_wait(&empty[buf], (unsigned)(((j_ >> 1) - 1) & 1));      // the readers of this buffer (batch j-2) are done
+        const bool live = ((int)blockIdx.x + j_ * G) * 32 + lane < A.nlist;
+        const double a = 0.5 * (s_xy[32 + lane] - s_xy[lane]), b = 0.5 * (s_xy[96 + lane] - s_xy[64 + lane]);
+        // interpolation (p_intmodels problem.f90:139-142; N_l-weighted part of p_source :424-457) and the xi-gradient of z
+        // (nf_jacobian, n_fem.f90:359-366)
+        double s0 = 0.0, s3 = 0.0, s5 = 0.0, e12 = 0.0, e15 = 0.0, e18 = 0.0, e21 = 0.0, zp = 0.0, zq = 0.0, zr = 0.0;
+#pragma unroll kF12UnrollL
+        for (int l = 0; l < MN; ++l) {
+            const double2 ze = make_double2(s_sf[(0 * MN + l) * 32 + lane], s_sf[(1 * MN + l) * 32 + lane]);
+            const double r00 = s_sf[(2 * MN + l) * 32 + lane], r11 = s_sf[(3 * MN + l) * 32 + lane];
+            const double di1 = s_sf[(5 * MN + l) * 32 + lane] - psig, di2 = s_sf[(6 * MN + l) * 32 + lane] - psig;   // Im(dsigma), pdelta_model problem.f90:329-331
+            const double ln = s_dN[(l * 4 + 3) * NGP + g];
+            const double le = ln * ze.y;                               // N_l e_l, e_l = f32(omega b0 z_l)
+            if (DO_KM) { s0 = dfma(ln, r00, s0); s3 = dfma(ln, r11, s3); s5 = dfma(ln, s_sf[(4 * MN + l) * 32 + lane], s5); }
+            e12 = dfma(le, di1, e12); e15 = dfma(le, r00, e15);
+            e18 = dfma(le, di2, e18); e21 = dfma(le, r11, e21);
+            zp = dfma(s_dN[(l * 4 + 0) * NGP + g], ze.x, zp);
+            zq = dfma(s_dN[(l * 4 + 1) * NGP + g], ze.x, zq);
+            zr = dfma(s_dN[(l * 4 + 2) * NGP + g], ze.x, zr);
+        }
+        const double p = zp, q = zq, r = zr;
+        const double det = (a * b) * r;
+        if (det == 0.0 && live) atomicCAS(A.status, 0, -3);
+        const double w = det * wt;
+        const double rad = 1.0 / fabs(det);                            // Q6: nf_ji = adj(J)/abs(det)
+        const double G00 = (b * r) * rad, G11 = (a * r) * rad, G22 = (a * b) * rad, G02 = -(p * b) * rad, G12 = -(a * q) * rad;
+        if (DO_KM) {
+            double *qo = s_qt + (size_t)buf * C::QT_D + g * 32 + lane;
+            const double fm = (det < 0.0 ? -wt : wt) * rad * mu0inv;   // (w/det^2) mu^-1 = (wt/det) mu^-1: Q = fm J J^T
+            const double q00 = fm * dfma(a, a, p * p), q11 = fm * dfma(b, b, q * q), q22 = fm * (r * r);
+            qo[0 * QS] = q00; qo[1 * QS] = fm * (p * q); qo[2 * QS] = fm * (p * r);
+            qo[3 * QS] = q11; qo[4 * QS] = fm * (q * r); qo[5 * QS] = q22;
+            // T = G^T S G, S = w Re sigma_g (integration.f90:234-236, Q3), sigma diagonal
+            const double S0 = w * s0, S1 = w * s3, S2 = w * s5;
+            const double t00 = S0 * (G00 * G00), t11 = S1 * (G11 * G11);
+            const double t22 = dfma(S0 * G02, G02, dfma(S1 * G12, G12, (S2 * G22) * G22));
+            qo[6 * QS] = t00; qo[7 * QS] = 0.0; qo[8 * QS] = (S0 * G00) * G02;
+            qo[9 * QS] = t11; qo[10 * QS] = (S1 * G11) * G12; qo[11 * QS] = t22;
+            // the element's K / M scale for the tiny-pair test of the epilogue (maximum over the Gauss points, taken by the readers)
+            *reinterpret_cast<double2 *>(s_tr + ((size_t)(buf * NGP + g) * 32 + lane) * 2) =
+                make_double2(fabs(q00) + fabs(q11) + fabs(q22), fabs(t00) + fabs(t11) + fabs(t22));
+        }
+        // R[d][pol] = G[:,d] . (w src_pol);  src = dmpf * cmplx32(0,-omega) (problem.f90:112); for a diagonal sigma
+        // src_1 = (A1, 0, 0), src_2 = (0, A2, 0):  pol 1 dmpf = (+Im ds*e, -Re ds*e), pol 2 = (-Im ds*e, +Re ds*e);
+        // R[1][pol 1] and R[0][pol 2] are identically zero and not stored
+        const double a1x = w * (-e15 * w32), a1y = w * (-(e12 * w32)), a2x = w * (e21 * w32), a2y = w * (e18 * w32);
+        double *Ro = s_R + (size_t)buf * C::R_D + g * 32 + lane;
+        Ro[0 * QS] = G00 * a1x; Ro[1 * QS] = G00 * a1y; Ro[2 * QS] = G11 * a2x; Ro[3 * QS] = G11 * a2y;
+        Ro[4 * QS] = G02 * a1x; Ro[5 * QS] = G02 * a1y; Ro[6 * QS] = G12 * a2x; Ro[7 * QS] = G12 * a2y;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[buf]);                        // release: this Gauss point of the batch is in place
+    };
+
+    // ---- RHS unit (four slots q4..q4+3, polarisation pol) of batch j: b_e(j) = sum_g phi_j(g) R[d_j][pol](g)
+    //      (blocal / f3, integration.f90:96-104,258-263) ----
+    auto rhs_unit = [&](int j_, int q4, int pol) {
+        const int buf = j_ & 1;
+        if (!(((int)blockIdx.x + j_ * G) * 32 + lane < A.nlist)) return;
+        // b_e by K/M row: lanes are 32 consecutive rows, so a store covers 1 kB (the other polarisation fills the gaps)
+        double2 *bo = reinterpret_cast<double2 *>(A.be) + ((size_t)((int)blockIdx.x + j_ * G) * ME * 32 + lane) * 2 + pol;
+        const int cd = s_sdir[q4];
+        double br[4] = {0, 0, 0, 0}, bi[4] = {0, 0, 0, 0};
+        // diagonal sigma: the source of polarisation 1 is along x, of polarisation 2 along y, so R[d][pol] is identically zero
+        // for (d, pol) = (1, 1) and (0, 2): zeros are delivered, nothing is summed
+        if (cd == 2 || cd == pol) {
+            const double *Rr = s_R + (size_t)buf * C::R_D + (size_t)(cd == 2 ? 4 + 2 * pol : 2 * pol) * QS + lane, *Ri = Rr + QS;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { accK[i] = 0.0; accM[i] = 0.0; }
-            // a diagonal tile (classes xx, yy, zz) stores only its lower half: the six pairs above the diagonal are not formed
-            auto contract = [&](auto diag_tag) {
-                constexpr bool DIAG = decltype(diag_tag)::value;
-#pragma unroll 4
-                for (int g = 0; g < NGP; ++g) {
-                    const int o = g * 4 * ME;
-                    const double q00 = S[(cq0 * NGP + g) * 32], q01 = S[(cq1 * NGP + g) * 32], q10 = S[(cq2 * NGP + g) * 32],
-                                 q11 = S[(cq3 * NGP + g) * 32], tt = S[(cq4 * NGP + g) * 32];
-                    double b1[4], b2[4], bw[4], xa[4], xb[4], xc[4], ya[4], yb[4], yc[4];
-                    ld4(xa, X1 + o); ld4(xb, X2 + o); ld4(xc, X3 + o);
-                    ld4(ya, Y1 + o); ld4(yb, Y2 + o); ld4(yc, Y3 + o);
+            for (int g = 0; g < NGP; ++g) {
+                const double rr = Rr[g * 32], ri = Ri[g * 32];
+                const double2 p01 = *reinterpret_cast<const double2 *>(s_phi + g * ME + q4), p23 = *reinterpret_cast<const double2 *>(s_phi + g * ME + q4 + 2);
+                br[0] = dfma(p01.x, rr, br[0]); bi[0] = dfma(p01.x, ri, bi[0]);
+                br[1] = dfma(p01.y, rr, br[1]); bi[1] = dfma(p01.y, ri, bi[1]);
+                br[2] = dfma(p23.x, rr, br[2]); bi[2] = dfma(p23.x, ri, bi[2]);
+                br[3] = dfma(p23.y, rr, br[3]); bi[3] = dfma(p23.y, ri, bi[3]);
+            }
+        }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        b1[j] = dfma(q00, xa[j], -(q01 * xb[j]));
-                        b2[j] = dfma(q10, xa[j], -(q11 * xb[j]));
-                        bw[j] = xc[j] * tt;
-                    }
+        for (int kk = 0; kk < 4; ++kk) bo[(size_t)s_slot[q4 + kk] * 64] = make_double2(br[kk], bi[kk]);
+    };
+
+    // ---- tile `c` (direction class c) of batch j: the inner loop of contract.cuh on the Q|T the eight warps left in shared memory ----
+    const int c = warp < 6 ? warp : 0;
+    const int ti = c_ct.tile_ti[c], tj = c_ct.tile_tj[c];
+    const int dI = cls_dI(c), dJ = cls_dJ(c);
+    const int k1I = dI == 2 ? 1 : 2, k2I = dI == 0 ? 1 : 0, k1J = dJ == 2 ? 1 : 2, k2J = dJ == 0 ? 1 : 0;
+    const double tau = ((dI == 1) != (dJ == 1)) ? -1.0 : 1.0;
+    const int cq0 = c_ct.comp[0][c][0], cq1 = c_ct.comp[0][c][1], cq2 = c_ct.comp[0][c][2], cq3 = c_ct.comp[0][c][3], cq4 = c_ct.comp[0][c][4];
+    const double *Y1 = s_tab + k1I * ME + 4 * ti, *Y2 = s_tab + k2I * ME + 4 * ti, *Y3 = s_tab + 3 * ME + 4 * ti;
+    const double *X1 = s_tab + k1J * ME + 4 * tj, *X2 = s_tab + k2J * ME + 4 * tj, *X3 = s_tab + 3 * ME + 4 * tj;
+    auto tile = [&](int j_) {
+        const int buf = j_ & 1, batch = (int)blockIdx.x + j_ * G;
+        const double *S = s_qt + (size_t)buf * C::QT_D + lane;
+        double accK[16], accM[16];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const double y1 = ya[i], y2 = yb[i], y3 = yc[i];
+        for (int i = 0; i < 16; ++i) { accK[i] = 0.0; accM[i] = 0.0; }
+        // (one code path for all six tiles and a short unrolled body: the kernel is bound by instruction fetch, not by the FP64
+        // pipe -- the six pairs above the diagonal of a diagonal tile are formed and dropped)
+#pragma unroll kF12UnrollG
+        for (int g = 0; g < NGP; ++g) {
+            const int o = g * 4 * ME;
+            const double q00 = S[(cq0 * NGP + g) * 32], q01 = S[(cq1 * NGP + g) * 32], q10 = S[(cq2 * NGP + g) * 32],
+                         q11 = S[(cq3 * NGP + g) * 32], tt = S[(cq4 * NGP + g) * 32];
+            double b1[4], b2[4], bw[4], xa[4], xb[4], xc[4], ya[4], yb[4], yc[4];
+            ld4(xa, X1 + o); ld4(xb, X2 + o); ld4(xc, X3 + o);
+            ld4(ya, Y1 + o); ld4(yb, Y2 + o); ld4(yc, Y3 + o);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (DIAG && j > i) continue;
-                            accK[i * 4 + j] = dfma(y1, b1[j], dfma(-y2, b2[j], accK[i * 4 + j]));
-                            accM[i * 4 + j] = dfma(y3, bw[j], accM[i * 4 + j]);
-                        }
-                    }
+            for (int j = 0; j < 4; ++j) {
+                b1[j] = dfma(q00, xa[j], -(q01 * xb[j]));
+                b2[j] = dfma(q10, xa[j], -(q11 * xb[j]));
+                bw[j] = xc[j] * tt;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double y1 = ya[i], y2 = yb[i], y3 = yc[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    accK[i * 4 + j] = dfma(y1, b1[j], dfma(-y2, b2[j], accK[i * 4 + j]));
+                    accM[i * 4 + j] = dfma(y3, bw[j], accM[i * 4 + j]);
                 }
-            };
-            if (ti == tj) contract(std::true_type{}); else contract(std::false_type{});
-            const double thrK = A.no_l1 ? -1.0 : kTinyRelC * NGP * __longlong_as_double((long long)s_scale[(buf * 32 + lane) * 2]);
-            const double thrM = A.no_l1 ? -1.0 : kTinyRelC * NGP * __longlong_as_double((long long)s_scale[(buf * 32 + lane) * 2 + 1]);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[buf]);       // the buffer (and its scales) may be refilled
-            // write-out: packed lower triangle by LOCAL DOF index, 32 elements interleaved -> 512-byte coalesced stores
-            if (batch * 32 + lane < A.nlist) {
-                double2 *KMo = A.KM + (size_t)batch * NP * 32 + lane;
+            }
+        }
+        double trq = 0.0, trt = 0.0;
+#pragma unroll 2
+        for (int g = 0; g < NGP; ++g) {
+            const double2 t2 = *reinterpret_cast<const double2 *>(s_tr + ((size_t)(buf * NGP + g) * 32 + lane) * 2);
+            trq = fmax(trq, t2.x); trt = fmax(trt, t2.y);
+        }
+        const double thrK = A.no_l1 ? -1.0 : kTinyRelC * NGP * trq, thrM = A.no_l1 ? -1.0 : kTinyRelC * NGP * trt;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[buf]);           // the buffer (and its scales) may be refilled
+        // write-out: packed lower triangle by LOCAL DOF index, 32 elements interleaved -> 512-byte coalesced stores
+        if (batch * 32 + lane < A.nlist) {
+            double2 *KMo = A.KM + (size_t)batch * NP * 32 + lane;
+            const int *pi = s_pidx + c * 16;
+            unsigned fm = 0u;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const int p = pi[t];
+                if (p >= 0) {
+                    const double kv = accK[t] * tau, mv = accM[t];
+                    KMo[p * 32] = make_double2(kv, mv);
+                    const double ak = fabs(kv), am = fabs(mv);
+                    if ((ak <= thrK && am <= thrM) || (ak < kFlagAbsC && am < kFlagAbsC)) fm |= 1u << t;
+                }
+            }
+            if (fm) {                                       // tiny pairs (rare): flagged for exact_kernel
                 uint32_t *pfl = A.pairflags + (size_t)(batch * 32 + lane) * A.W;
-                int nfl = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int si = 4 * ti + i, im = c_ct.slot_dof[si];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int sj = 4 * tj + j, jm = c_ct.slot_dof[sj];
-                        if (sj <= si) {
-                            const int hi = im > jm ? im : jm, lo = im > jm ? jm : im;
-                            const int p = hi * (hi + 1) / 2 + lo;
-                            const double kv = accK[i * 4 + j] * tau, mv = accM[i * 4 + j];
-                            KMo[p * 32] = make_double2(kv, mv);
-                            const double ak = fabs(kv), am = fabs(mv);
-                            if ((ak <= thrK && am <= thrM) || (ak < kFlagAbsC && am < kFlagAbsC)) {
-                                atomicOr(pfl + (p >> 5), 1u << (p & 31));
-                                ++nfl;
-                            }
-                        }
-                    }
+                atomicAdd(A.nflag, (unsigned long long)__popc(fm));
+                atomicOr(A.batchany + batch, 1u << lane);
+                while (fm) {
+                    const int t = __ffs(fm) - 1;
+                    fm &= fm - 1;
+                    const int p = pi[t];
+                    atomicOr(pfl + (p >> 5), 1u << (p & 31));
                 }
-                if (nfl) { atomicOr(A.batchany + batch, 1u << lane); atomicAdd(A.nflag, (unsigned long long)nfl); }
+            }
+        }
+    };
+
+    // ================= the pipeline: geometry of batch k+1 (all warps), then the tile / RHS / copies of batch k =================
+    if (fetcher) prefetch(0);
+    geometry(0);
+    if (fetcher && nb > 1) { mbar_wait(&full[0], 0u); prefetch(1); }   // (one staging buffer: batch j+1 is copied once every warp has read batch j)
+    for (int k = 0; k < nb; ++k) {
+        if (k + 1 < nb) geometry(k + 1);
+        const unsigned par = (unsigned)((k >> 1) & 1);
+        if (!fetcher) {
+            mbar_wait(&full[k & 1], par);
+            if (DO_KM) tile(k);
+            else {
+                rhs_unit(k, 4 * (warp >> 1), warp & 1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[k & 1]);             // R of this buffer may be overwritten
+            }
+        } else {
+            if (DO_KM) {
+                mbar_wait(&full[k & 1], par);
+#pragma unroll 1
+                for (int q4 = 0; q4 < ME; q4 += 4) rhs_unit(k, q4, pw);
+            }
+            if (k + 2 < nb) {
+                mbar_wait(&full[(k + 1) & 1], (unsigned)(((k + 1) >> 1) & 1));   // every warp has read the staged fields of batch k+1
+                prefetch(k + 2);
             }
         }
     }

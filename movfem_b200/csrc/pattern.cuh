@@ -255,7 +255,7 @@ row_kernel(MeshDims m, const ShareTables *__restrict__ stp, const int *__restric
     if (lane == 0) {
         if (!FILL) { rowcnt[rl] = nuniq; rowcand[rl] = ncand; }
         else
-            for (int i = 0; i < 4; ++i) rown[(int64_t)rl * 4 + i] = s_el[w][i] < 0 ? -1 : (s_el[w][i] - e_base) * me + (s_ll[w][i] - 1);
+            for (int i = 0; i < 4; ++i) rown[(int64_t)rl * 4 + i] = s_el[w][i] < 0 ? -1 : (int)be_index(kmrow[s_el[w][i] - e_base], me, s_ll[w][i] - 1);
     }
 }
 
