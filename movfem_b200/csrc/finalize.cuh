@@ -35,14 +35,18 @@ compress_cptr_kernel(int64_t nzu, const int64_t *__restrict__ cptr, int64_t *__r
 
 // mode 0 (T2): values rounded through float32, per-block count of surviving (non-zero) entries
 // mode 1 (T1): double values, nothing stripped
-// (Measured and dropped in round 2: a persistent CTA with a three-stage software pipeline over its blocks -- indices of block
-// j+2, reads of block j+1 in flight while block j is summed -- is 4-6 % SLOWER than one block per 128 entries: 16 resident
-// blocks per SM already overlap the index -> value chains of different blocks.)
+// What does NOT bound this kernel (B200, 205 M entries of config 5 at half scale, 2.50 ms = 4.0 TB/s of algorithmic traffic;
+// profiles/r02_summary.md): the scattered 16-byte reads (reading K/M sequentially instead: -3 %), the instruction count
+// (-8.5 % instructions, issue 73 -> 66 %: +-0), the reads in flight (two blocks per CTA: -2 %, four: +27 % from the lost
+// occupancy), CTA turnover (a persistent grid-stride CTA per slot: +10 to +30 %), a three-stage software pipeline over the
+// blocks of a persistent CTA (+4 to +6 %).  DRAM 48 %, L2 48 %, issue 66 %: the index -> value -> sum chain of 16 resident
+// 128-entry blocks per SM is where it stands.
 // Phase 1: the block's <= 4*kFinThreads contributions are fetched by all threads (independent random 16-byte reads, up to four
 // in flight per thread) into shared memory; phase 2: one thread per entry sums its contributions in ascending order.
 // cache: 0 none; 1 fill kmg[i] = gathered (K, M) of every entry; 2 use it (a later frequency of a sweep: streaming 16-byte
 // reads instead of the gather) unless the node kernel saw Re(sigma) change (flags[1]), in which case the call refills it.
-__global__ void __launch_bounds__(kFinThreads, 2048 / kFinThreads)
+constexpr int kGatherMinBlocks = kGatherSub == 1 ? 2048 / kFinThreads : (kGatherSub == 2 ? 12 : 6);
+__global__ void __launch_bounds__(kFinThreads, kGatherMinBlocks)
 gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk, const uint16_t *__restrict__ off16,
                        const uint32_t *__restrict__ src, const double2 *__restrict__ KM, double2 *__restrict__ a,
                        int *__restrict__ blk_nonzero, int mode, int cache,
@@ -54,12 +58,14 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
     __shared__ double2 vals[kGatherSub][4 * kFinThreads + 4];
     __shared__ uint16_t offs[kGatherSub][kFinThreads + 1];
     if (cache == 2 && flags[1] != 0) cache = 1;
+    const int bid = blockIdx.x;
+    {
     int64_t c0s[kGatherSub];
     int ns[kGatherSub];
     if (!(cache == 2)) {
 #pragma unroll
         for (int sb = 0; sb < kGatherSub; ++sb) {
-            const int blk = blockIdx.x * kGatherSub + sb;
+            const int blk = bid * kGatherSub + sb;
             c0s[sb] = 0; ns[sb] = 0;
             if (blk >= nblk) continue;
             const int64_t i = (int64_t)blk * kFinThreads + threadIdx.x;
@@ -88,7 +94,7 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
     }
 #pragma unroll
     for (int sb = 0; sb < kGatherSub; ++sb) {
-    const int blk = blockIdx.x * kGatherSub + sb;
+    const int blk = bid * kGatherSub + sb;
     if (blk >= nblk) break;
     const int64_t i = (int64_t)blk * kFinThreads + threadIdx.x;
     const int64_t c0 = c0s[sb];
@@ -118,13 +124,19 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
             // a(idd)=a(idd)+aij bit-identical) and the magnitude test is done on the exponent words; the loop below runs only in
             // a warp that holds a re-evaluated (or exactly zero) contribution
             const int nc = hi - lo;
-            const double2 z2 = make_double2(0.0, 0.0);
-            const double2 v0 = nc > 0 ? vals[sb][lo] : z2, v1 = nc > 1 ? vals[sb][lo + 1] : z2;
-            const double2 v2 = nc > 2 ? vals[sb][lo + 2] : z2, v3 = nc > 3 ? vals[sb][lo + 3] : z2;
+            // unconditional loads (the staging array has four spare slots; a slot past the entry's last contribution holds
+            // another entry's value or stale data and is replaced by +0.0 before any arithmetic): selects, no branches
+            const double2 *vp = &vals[sb][lo];
+            double2 v0 = vp[0], v1 = vp[1], v2 = vp[2], v3 = vp[3];
             auto tagged = [](const double2 &v) {   // |v.y| < 2^-500 and |v.x| < 2^-200, on the high words
-                return ((unsigned)__double2hiint(v.y) & 0x7fffffffu) < 0x20b00000u && ((unsigned)__double2hiint(v.x) & 0x7fffffffu) < 0x33700000u;
+                return (((unsigned)__double2hiint(v.y) & 0x7fffffffu) < 0x20b00000u) & (((unsigned)__double2hiint(v.x) & 0x7fffffffu) < 0x33700000u);
             };
-            const bool slow = (nc > 0 && tagged(v0)) || (nc > 1 && tagged(v1)) || (nc > 2 && tagged(v2)) || (nc > 3 && tagged(v3));
+            const bool slow = ((nc > 0) & tagged(v0)) | ((nc > 1) & tagged(v1)) | ((nc > 2) & tagged(v2)) | ((nc > 3) & tagged(v3));
+            auto keep = [](double2 &v, bool on) {             // bitwise select (+0.0 when absent)
+                const long long mk = on ? -1ll : 0ll;
+                v.x = __longlong_as_double(__double_as_longlong(v.x) & mk); v.y = __longlong_as_double(__double_as_longlong(v.y) & mk);
+            };
+            keep(v0, nc > 0); keep(v1, nc > 1); keep(v2, nc > 2); keep(v3, nc > 3);
             if (!__any_sync(__activemask(), slow)) {
                 k = (((k + v0.x) + v1.x) + v2.x) + v3.x;
                 mm = (((mm + v0.y) + v1.y) + v2.y) + v3.y;
@@ -185,6 +197,7 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
     if (total_nonzero && mode == 0 && i < nzu && !nzflag) {
         atomicAdd(total_nonzero + 1, (unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ull);
         atomicAdd(total_nonzero + 2, ((unsigned long long)(i + 1) * 0xC2B2AE3D27D4EB4Full) ^ (unsigned long long)(i >> 7));
+    }
     }
     }
 }
