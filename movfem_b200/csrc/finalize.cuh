@@ -39,7 +39,7 @@ compress_cptr_kernel(int64_t nzu, const int64_t *__restrict__ cptr, int64_t *__r
 // profiles/r02_summary.md): the scattered 16-byte reads (reading K/M sequentially instead: -3 %), the instruction count
 // (-8.5 % instructions, issue 73 -> 66 %: +-0), the reads in flight (two blocks per CTA: -2 %, four: +27 % from the lost
 // occupancy), CTA turnover (a persistent grid-stride CTA per slot: +10 to +30 %), a three-stage software pipeline over the
-// blocks of a persistent CTA (+4 to +6 %).  DRAM 48 %, L2 48 %, issue 66 %: the index -> value -> sum chain of 16 resident
+// blocks of a persistent CTA (+4 to +6 %), L2 prefetch of the index lines of a block 2-8 k blocks ahead (+6 %).  DRAM 48 %, L2 48 %, issue 66 %: the index -> value -> sum chain of 16 resident
 // 128-entry blocks per SM is where it stands.
 // Phase 1: the block's <= 4*kFinThreads contributions are fetched by all threads (independent random 16-byte reads, up to four
 // in flight per thread) into shared memory; phase 2: one thread per entry sums its contributions in ascending order.

@@ -45,7 +45,7 @@
 #include "element.cuh"
 
 #ifndef F12_UNROLL_G
-#define F12_UNROLL_G 8
+#define F12_UNROLL_G 4
 #endif
 #ifndef F12_UNROLL_L
 #define F12_UNROLL_L 8
@@ -85,7 +85,7 @@ struct Fused12Cfg {
     static constexpr size_t QT_D = (size_t)12 * NGP * 32;                   // one Q|T block [component][g][lane] of doubles
     static constexpr size_t R_D = (size_t)8 * NGP * 32;                     // one source block: the 8 not identically zero components
     static constexpr size_t SF_D = (size_t)7 * MN * 32;                     // staged node fields [field][node][lane]: z, e, Re sigma 00 11 22, Im sigma 00 11
-    static constexpr size_t TR_D = (size_t)2 * NGP * 32 * 2;                // [2][g][lane] (tr Q, tr T)
+    static constexpr size_t TR_D = (size_t)2 * NGP * 32;                    // [2][g][lane] float2 (tr Q, tr T): a scale, rounded up
     static constexpr size_t TAB_D = (size_t)NGP * 4 * ME, DN_D = (size_t)MN * 4 * NGP, PHI_D = (size_t)NGP * ME, XY_D = 4 * 32;
     static constexpr size_t SMEM = sizeof(double) * ((DO_KM ? 2 * QT_D + TR_D : 0) + 2 * R_D + SF_D + TAB_D + DN_D + PHI_D + XY_D) +
                                    sizeof(unsigned long long) * 8 + sizeof(int) * (2 * ME + MN + 4 * 32 + 6 * 16);
@@ -102,10 +102,10 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_R = reinterpret_cast<double *>(smem_raw);               // [2][8][NGP][32]: (d0,pol1) (d1,pol2) (d2,pol1) (d2,pol2), re|im each
     double *s_qt = s_R + 2 * C::R_D;                                  // [2][12][NGP][32]: Q (0-5, sym3 order), T (6-11)   (DO_KM)
-    double *s_tr = s_qt + (DO_KM ? 2 * C::QT_D : 0);                  // [2][NGP][32][2]                                      (DO_KM)
+    double *s_tr = s_qt + (DO_KM ? 2 * C::QT_D : 0);                  // [2][NGP][32] float2                                  (DO_KM)
     double *s_sf = s_tr + (DO_KM ? C::TR_D : 0);                      // [7][MN][32]: z, e, Re sigma 00, 11, 22, Im sigma 00, 11
     double *s_tab = s_sf + C::SF_D;                                   // [NGP][4][ME]: dphi (0-2), phi (3), slot order
-    double *s_dN = s_tab + C::TAB_D;                                  // [MN][4][NGP]: dN/dxi (0-2), N (3)
+    double *s_dN = s_tab + C::TAB_D;                                  // [NGP][MN][4]: dN/dxi (0-2), N (3) -- the four weights of (g, node) in two 16-byte loads
     double *s_phi = s_dN + C::DN_D;                                   // [NGP][ME] phi in slot order
     double *s_xy = s_phi + C::PHI_D;                                  // [4][32]: x0, x1, y0, y1 of the staged batch
     uint64_t *full = reinterpret_cast<uint64_t *>(s_xy + C::XY_D), *empty = full + 2, *staged = full + 4;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
         for (int i = tid; i < (int)C::TAB_D; i += C::THREADS) s_tab[i] = g_ct_at[i];
     for (int i = tid; i < ME; i += C::THREADS) { s_slot[i] = T.slot_dof[i]; s_sdir[i] = T.slot_dir[i]; }
     for (int i = tid; i < MN; i += C::THREADS) s_noff[i] = T.node_off[i];
-    for (int i = tid; i < MN * 4 * NGP; i += C::THREADS) s_dN[i] = T.dNt[(i / NGP) * 32 + (i % NGP)];
+    for (int i = tid; i < MN * 4 * NGP; i += C::THREADS) s_dN[i] = T.dNt[(((i >> 2) % MN) * 4 + (i & 3)) * 32 + i / (4 * MN)];
     auto id_src = [&](int j_) {                                       // list entry of lane `lane` in this CTA's j-th batch (clamped)
         const int pos_ = ((int)blockIdx.x + j_ * G) * 32 + lane;
         return A.list + (pos_ < A.nlist ? pos_ : A.nlist - 1);
@@ -201,14 +201,15 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
             const double2 ze = make_double2(s_sf[(0 * MN + l) * 32 + lane], s_sf[(1 * MN + l) * 32 + lane]);
             const double r00 = s_sf[(2 * MN + l) * 32 + lane], r11 = s_sf[(3 * MN + l) * 32 + lane];
             const double di1 = s_sf[(5 * MN + l) * 32 + lane] - psig, di2 = s_sf[(6 * MN + l) * 32 + lane] - psig;   // Im(dsigma), pdelta_model problem.f90:329-331
-            const double ln = s_dN[(l * 4 + 3) * NGP + g];
+            const double2 dn01 = *reinterpret_cast<const double2 *>(s_dN + (g * MN + l) * 4), dn2n = *reinterpret_cast<const double2 *>(s_dN + (g * MN + l) * 4 + 2);
+            const double ln = dn2n.y;
             const double le = ln * ze.y;                               // N_l e_l, e_l = f32(omega b0 z_l)
             if (DO_KM) { s0 = dfma(ln, r00, s0); s3 = dfma(ln, r11, s3); s5 = dfma(ln, s_sf[(4 * MN + l) * 32 + lane], s5); }
             e12 = dfma(le, di1, e12); e15 = dfma(le, r00, e15);
             e18 = dfma(le, di2, e18); e21 = dfma(le, r11, e21);
-            zp = dfma(s_dN[(l * 4 + 0) * NGP + g], ze.x, zp);
-            zq = dfma(s_dN[(l * 4 + 1) * NGP + g], ze.x, zq);
-            zr = dfma(s_dN[(l * 4 + 2) * NGP + g], ze.x, zr);
+            zp = dfma(dn01.x, ze.x, zp);
+            zq = dfma(dn01.y, ze.x, zq);
+            zr = dfma(dn2n.x, ze.x, zr);
         }
         const double p = zp, q = zq, r = zr;
         const double det = (a * b) * r;
@@ -229,8 +230,8 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
             qo[6 * QS] = t00; qo[7 * QS] = 0.0; qo[8 * QS] = (S0 * G00) * G02;
             qo[9 * QS] = t11; qo[10 * QS] = (S1 * G11) * G12; qo[11 * QS] = t22;
             // the element's K / M scale for the tiny-pair test of the epilogue (maximum over the Gauss points, taken by the readers)
-            *reinterpret_cast<double2 *>(s_tr + ((size_t)(buf * NGP + g) * 32 + lane) * 2) =
-                make_double2(fabs(q00) + fabs(q11) + fabs(q22), fabs(t00) + fabs(t11) + fabs(t22));
+            reinterpret_cast<float2 *>(s_tr)[(buf * NGP + g) * 32 + lane] =
+                make_float2(__double2float_ru(fabs(q00) + fabs(q11) + fabs(q22)), __double2float_ru(fabs(t00) + fabs(t11) + fabs(t22)));
         }
         // R[d][pol] = G[:,d] . (w src_pol);  src = dmpf * cmplx32(0,-omega) (problem.f90:112); for a diagonal sigma
         // src_1 = (A1, 0, 0), src_2 = (0, A2, 0):  pol 1 dmpf = (+Im ds*e, -Re ds*e), pol 2 = (-Im ds*e, +Re ds*e);
@@ -285,39 +286,47 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
         double accK[16], accM[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { accK[i] = 0.0; accM[i] = 0.0; }
-        // (one code path for all six tiles and a short unrolled body: the kernel is bound by instruction fetch, not by the FP64
-        // pipe -- the six pairs above the diagonal of a diagonal tile are formed and dropped)
+        // a diagonal tile (classes xx, yy, zz): the column operands are the row operands (six broadcast loads less per Gauss
+        // point: the kernel is bound by the shared-memory pipe) and the six pairs above the diagonal are not formed
+        auto contract = [&](auto diag_tag) {
+            constexpr bool DIAG = decltype(diag_tag)::value;
 #pragma unroll kF12UnrollG
-        for (int g = 0; g < NGP; ++g) {
-            const int o = g * 4 * ME;
-            const double q00 = S[(cq0 * NGP + g) * 32], q01 = S[(cq1 * NGP + g) * 32], q10 = S[(cq2 * NGP + g) * 32],
-                         q11 = S[(cq3 * NGP + g) * 32], tt = S[(cq4 * NGP + g) * 32];
-            double b1[4], b2[4], bw[4], xa[4], xb[4], xc[4], ya[4], yb[4], yc[4];
-            ld4(xa, X1 + o); ld4(xb, X2 + o); ld4(xc, X3 + o);
-            ld4(ya, Y1 + o); ld4(yb, Y2 + o); ld4(yc, Y3 + o);
+            for (int g = 0; g < NGP; ++g) {
+                const int o = g * 4 * ME;
+                const double q00 = S[(cq0 * NGP + g) * 32], q01 = S[(cq1 * NGP + g) * 32], q10 = S[(cq2 * NGP + g) * 32],
+                             q11 = S[(cq3 * NGP + g) * 32], tt = S[(cq4 * NGP + g) * 32];
+                double b1[4], b2[4], bw[4], xa[4], xb[4], xc[4], ya[4], yb[4], yc[4];
+                ld4(ya, Y1 + o); ld4(yb, Y2 + o); ld4(yc, Y3 + o);
+                if (DIAG) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                b1[j] = dfma(q00, xa[j], -(q01 * xb[j]));
-                b2[j] = dfma(q10, xa[j], -(q11 * xb[j]));
-                bw[j] = xc[j] * tt;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double y1 = ya[i], y2 = yb[i], y3 = yc[i];
+                    for (int j = 0; j < 4; ++j) { xa[j] = ya[j]; xb[j] = yb[j]; xc[j] = yc[j]; }
+                } else { ld4(xa, X1 + o); ld4(xb, X2 + o); ld4(xc, X3 + o); }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    accK[i * 4 + j] = dfma(y1, b1[j], dfma(-y2, b2[j], accK[i * 4 + j]));
-                    accM[i * 4 + j] = dfma(y3, bw[j], accM[i * 4 + j]);
+                    b1[j] = dfma(q00, xa[j], -(q01 * xb[j]));
+                    b2[j] = dfma(q10, xa[j], -(q11 * xb[j]));
+                    bw[j] = xc[j] * tt;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double y1 = ya[i], y2 = yb[i], y3 = yc[i];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (DIAG && j > i) continue;
+                        accK[i * 4 + j] = dfma(y1, b1[j], dfma(-y2, b2[j], accK[i * 4 + j]));
+                        accM[i * 4 + j] = dfma(y3, bw[j], accM[i * 4 + j]);
+                    }
                 }
             }
-        }
-        double trq = 0.0, trt = 0.0;
-#pragma unroll 2
+        };
+        if (ti == tj) contract(std::true_type{}); else contract(std::false_type{});
+        float trq = 0.f, trt = 0.f;
+#pragma unroll
         for (int g = 0; g < NGP; ++g) {
-            const double2 t2 = *reinterpret_cast<const double2 *>(s_tr + ((size_t)(buf * NGP + g) * 32 + lane) * 2);
-            trq = fmax(trq, t2.x); trt = fmax(trt, t2.y);
+            const float2 t2 = reinterpret_cast<const float2 *>(s_tr)[(buf * NGP + g) * 32 + lane];
+            trq = fmaxf(trq, t2.x); trt = fmaxf(trt, t2.y);
         }
-        const double thrK = A.no_l1 ? -1.0 : kTinyRelC * NGP * trq, thrM = A.no_l1 ? -1.0 : kTinyRelC * NGP * trt;
+        const double thrK = A.no_l1 ? -1.0 : kTinyRelC * NGP * (double)trq, thrM = A.no_l1 ? -1.0 : kTinyRelC * NGP * (double)trt;
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[buf]);           // the buffer (and its scales) may be refilled
         // write-out: packed lower triangle by LOCAL DOF index, 32 elements interleaved -> 512-byte coalesced stores
