@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <chrono>
 #include <vector>
 
 #include "../../include/movfem_b200.h"
@@ -392,13 +393,13 @@ int launch_elements(movfem_handle *h, ElemArgs &A, const int *d_list, int nlist,
 }
 
 // the linear-element path in one kernel (fused12.cuh): geometry, contraction and element RHS of the unstretched list
-template <bool DO_KM>
-int launch_fused12(movfem_handle *h, const ElemArgs &A, int skip_unless_changed) {
+template <bool DO_KM, bool ISO>
+int launch_fused12_variant(movfem_handle *h, const ElemArgs &A, int skip_unless_changed) {
     if (h->n_plain <= 0) return 0;
     int rc = const_table_acquire(h);
     if (rc) return rc;
     using FC = Fused12Cfg<DO_KM>;
-    auto kern = fused12_kernel<DO_KM>;
+    auto kern = fused12_kernel<DO_KM, ISO>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FC::SMEM));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FC::THREADS, FC::SMEM));
@@ -415,6 +416,13 @@ int launch_fused12(movfem_handle *h, const ElemArgs &A, int skip_unless_changed)
     CK(cudaGetLastError());
     if (kernel_event(h, 3, false)) return MOVFEM_E_CUDA;
     return 0;
+}
+
+// both variants are launched; node_kernel's flags[3] (equal diagonal sigma everywhere or not) lets exactly one of them work
+template <bool DO_KM>
+int launch_fused12(movfem_handle *h, const ElemArgs &A, int skip_unless_changed) {
+    int rc = launch_fused12_variant<DO_KM, true>(h, A, skip_unless_changed);
+    return rc ? rc : launch_fused12_variant<DO_KM, false>(h, A, skip_unless_changed);
 }
 
 template <class GP, class CP, class GQ, class CQ>
@@ -1115,6 +1123,11 @@ int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega, const do
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const bool want_keep = (mode_flags & MOVFEM_MODE_KEEP_PATTERN) != 0;
+    const bool trace = getenv("MOVFEM_TRACE_E2E") != nullptr;   // host wall-clock of the call's stages on stderr
+    const auto tr0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (trace) fprintf(stderr, "[movfem e2e] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count());
+    };
     const bool pin_irn = host_is_pinned(irn), pin_jcn = host_is_pinned(jcn), pin_a = host_is_pinned(a), pin_rhs = host_is_pinned(rhs);
     CK(cudaEventRecord(h->ev[EV_START], st));
     // IRN/JCN of the structural pattern never change: when the caller wants them every call (no KEEP_PATTERN), its arrays are
@@ -1127,13 +1140,16 @@ int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega, const do
     }
     CK(cudaMemcpyAsync(h->d_sigma + (size_t)6 * h->node_lo, reinterpret_cast<const double2 *>(g_sigma) + (size_t)6 * h->node_lo,
                        sizeof(double2) * (size_t)6 * (h->node_hi - h->node_lo), cudaMemcpyHostToDevice, st));
+    lap("copies issued");
     int rc = movfem_assemble_device(h, freq_index, omega, reinterpret_cast<const double *>(h->d_sigma), mode);
     if (rc) { cudaStreamSynchronize(h->copy_stream); return rc; }
+    lap("kernels launched");
     const int32_t *d_irn, *d_jcn;
     const double *d_a, *d_rhs;
     int64_t nz = 0;
     rc = movfem_device_result(h, &d_irn, &d_jcn, &d_a, &d_rhs, &nz);
     if (rc) { cudaStreamSynchronize(h->copy_stream); return rc; }
+    lap("device result complete");
     // values: into pinned memory one asynchronous copy at the link rate; into pageable memory complex64 over the link and
     // widening by the host threads that have to touch the destination anyway (T2 values are float32-exact).  Measured on
     // config 5 (1.63 G entries): widening into PINNED memory is slower than the plain 16 B/entry copy (0.67 s vs 0.47 s)
@@ -1148,7 +1164,9 @@ int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega, const do
     // fills only its own rows, so several handles can complete one array
     for (int dd = 0; dd < 2; ++dd)
         if ((rc = deliver(h, rhs + 2 * ((size_t)dd * h->nne + h->row_lo), d_rhs + 2 * (size_t)dd * h->nrows, sizeof(double2) * (size_t)h->nrows, pin_rhs))) return rc;
+    lap("value copies issued");
     CK(cudaStreamSynchronize(h->copy_stream));
+    lap("pattern copy stream done");
     // pattern: already on its way (speculative copy, nothing stripped), still in the caller's arrays (KEEP_PATTERN and the
     // same delivered set -- same nz and same signature of the stripped entries -- in the same arrays), or sent now
     const int64_t sig0 = h->compacted ? h->h_count[1] : 0, sig1 = h->compacted ? h->h_count[2] : 0;
@@ -1163,10 +1181,14 @@ int movfem_assemble(movfem_handle *h, int32_t freq_index, double omega, const do
     if (mode == MOVFEM_MODE_T2) h->last_compacted = h->compacted;
     CK(cudaEventRecord(h->ev[EV_D2H], st));
     CK(cudaStreamSynchronize(st));
+    lap("all copies done");
     *nz_out = nz;
     auto ms = [&](int a_, int b_) { float t = 0; cudaEventElapsedTime(&t, h->ev[a_], h->ev[b_]); return (double)t; };
     h->stats.ms_h2d = ms(EV_START, EV_H2D); h->stats.ms_d2h = ms(EV_FINAL, EV_D2H);
     h->stats.ms_total = ms(EV_START, EV_D2H); h->stats.nz = nz; h->stats.launches = h->launches;
+    if (trace)
+        fprintf(stderr, "[movfem e2e] device ms: h2d %.2f node %.2f element %.2f (fused %.2f) gather %.2f finalize %.2f d2h %.2f total %.2f\n", h->stats.ms_h2d,
+                h->stats.ms_node, h->stats.ms_element, h->stats.ms_fused, h->stats.ms_gather, h->stats.ms_finalize, h->stats.ms_d2h, h->stats.ms_total);
     return MOVFEM_OK;
 }
 

@@ -38,7 +38,7 @@ namespace movfem {
 // ------------------------------------------------------------------------------------------
 __global__ void node_kernel(int n0, int npt, double omega, const double *__restrict__ zp, const double *__restrict__ mu,
                             const double2 *__restrict__ sigma, NodeRec *__restrict__ out, int *__restrict__ status,
-                            int *__restrict__ flags /* [0]: any dmu != 0, [1]: Re sigma changed, [2]: any off-diagonal sigma */, int check_re,
+                            int *__restrict__ flags /* [0]: any dmu != 0, [1]: Re sigma changed, [2]: any off-diagonal sigma, [3]: sigma_11 != sigma_22 or _33 */, int check_re,
                             double *__restrict__ soa /* linear elements: field-major copy [6][npt_all] of e, Re sigma 00 11 22, Im sigma 00 11 (fused12.cuh) */,
                             size_t soa_stride) {
     const int i = n0 + blockIdx.x * blockDim.x + threadIdx.x;   // [n0, npt): the node planes this handle's slab touches
@@ -88,6 +88,7 @@ __global__ void node_kernel(int n0, int npt, double omega, const double *__restr
     if (anyd) flags[0] = 1;
     if (changed) flags[1] = 1;
     if (s[1].x != 0.0 || s[1].y != 0.0 || s[2].x != 0.0 || s[2].y != 0.0 || s[4].x != 0.0 || s[4].y != 0.0) flags[2] = 1;
+    if (s[0].x != s[3].x || s[0].x != s[5].x || s[0].y != s[3].y) flags[3] = 1;   // the diagonal entries fused12_kernel reads differ
     out[i] = r;
     if (soa) {
         soa[i] = r.e; soa[soa_stride + i] = r.sre[0]; soa[2 * soa_stride + i] = r.sre[3]; soa[3 * soa_stride + i] = r.sre[5];

@@ -69,7 +69,7 @@ struct Fused12Args {
     double2 *KM;                   // K/M store at this launch's first row: [batch][78][32]
     double *be;                    // by K/M row (be_index): [row / 32][12][row % 32][4]
     int *status;
-    const int *flags;              // flags[0]: any dmu != 0, [1]: Re sigma changed, [2]: any off-diagonal sigma (node_kernel)
+    const int *flags;              // flags[0]: any dmu != 0, [1]: Re sigma changed, [2]: any off-diagonal sigma, [3]: unequal diagonal (node_kernel)
     uint32_t *pairflags;           // [row][W] at this launch's first row
     uint32_t *batchany;            // at this launch's first batch
     unsigned long long *nflag;
@@ -91,13 +91,17 @@ struct Fused12Cfg {
                                    sizeof(unsigned long long) * 8 + sizeof(int) * (2 * ME + MN + 4 * 32 + 6 * 16);
 };
 
-template <bool DO_KM>
+// ISO: sigma = s I at every node (flags[3] == 0; every linear-element BASELINE mesh): three of the seven node fields are copies
+// of others and are neither staged nor interpolated -- the results are bit-identical to the general variant's, which runs
+// when some node has unequal diagonal entries (api.cu launches both; the device flag picks one)
+template <bool DO_KM, bool ISO>
 __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>::MINB) fused12_kernel(Fused12Args A) {
     using C = Fused12Cfg<DO_KM>;
     constexpr int MN = C::MN, ME = C::ME, NGP = C::NGP, NP = C::NP;
     constexpr int QS = NGP * 32;                                      // component stride inside a block
     if (A.skip_unless_changed && A.flags[1] == 0) return;
     if (A.flags[0] != 0 || A.flags[2] != 0) return;                   // mu != mu0 or off-diagonal sigma: the generic path runs instead
+    if ((A.flags[3] == 0) != ISO) return;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *s_R = reinterpret_cast<double *>(smem_raw);               // [2][8][NGP][32]: (d0,pol1) (d1,pol2) (d2,pol1) (d2,pol2), re|im each
@@ -176,7 +180,8 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
             const int64_t n_ = n0_ + s_noff[l];
             cp_async(s_sf + (0 * MN + l) * 32 + lane, A.zp + n_, std::integral_constant<int, 8>{});
 #pragma unroll
-            for (int f = 0; f < 6; ++f) cp_async(s_sf + ((1 + f) * MN + l) * 32 + lane, A.soa + f * A.soa_stride + n_, std::integral_constant<int, 8>{});
+            for (int f = 0; f < 6; ++f)
+                if (!ISO || f == 0 || f == 1 || f == 4) cp_async(s_sf + ((1 + f) * MN + l) * 32 + lane, A.soa + f * A.soa_stride + n_, std::integral_constant<int, 8>{});
         }
         if (pw == 0) {
             cp_async(s_xy + lane, A.xp + ie_ - 1, std::integral_constant<int, 8>{}); cp_async(s_xy + 32 + lane, A.xp + ie_, std::integral_constant<int, 8>{});
@@ -199,18 +204,19 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
 #pragma unroll kF12UnrollL
         for (int l = 0; l < MN; ++l) {
             const double2 ze = make_double2(s_sf[(0 * MN + l) * 32 + lane], s_sf[(1 * MN + l) * 32 + lane]);
-            const double r00 = s_sf[(2 * MN + l) * 32 + lane], r11 = s_sf[(3 * MN + l) * 32 + lane];
-            const double di1 = s_sf[(5 * MN + l) * 32 + lane] - psig, di2 = s_sf[(6 * MN + l) * 32 + lane] - psig;   // Im(dsigma), pdelta_model problem.f90:329-331
+            const double r00 = s_sf[(2 * MN + l) * 32 + lane], r11 = ISO ? r00 : s_sf[(3 * MN + l) * 32 + lane];
+            const double di1 = s_sf[(5 * MN + l) * 32 + lane] - psig, di2 = ISO ? di1 : s_sf[(6 * MN + l) * 32 + lane] - psig;   // Im(dsigma), pdelta_model problem.f90:329-331
             const double2 dn01 = *reinterpret_cast<const double2 *>(s_dN + (g * MN + l) * 4), dn2n = *reinterpret_cast<const double2 *>(s_dN + (g * MN + l) * 4 + 2);
             const double ln = dn2n.y;
             const double le = ln * ze.y;                               // N_l e_l, e_l = f32(omega b0 z_l)
-            if (DO_KM) { s0 = dfma(ln, r00, s0); s3 = dfma(ln, r11, s3); s5 = dfma(ln, s_sf[(4 * MN + l) * 32 + lane], s5); }
+            if (DO_KM) { s0 = dfma(ln, r00, s0); if (!ISO) { s3 = dfma(ln, r11, s3); s5 = dfma(ln, s_sf[(4 * MN + l) * 32 + lane], s5); } }
             e12 = dfma(le, di1, e12); e15 = dfma(le, r00, e15);
-            e18 = dfma(le, di2, e18); e21 = dfma(le, r11, e21);
+            if (!ISO) { e18 = dfma(le, di2, e18); e21 = dfma(le, r11, e21); }
             zp = dfma(dn01.x, ze.x, zp);
             zq = dfma(dn01.y, ze.x, zq);
             zr = dfma(dn2n.x, ze.x, zr);
         }
+        if (ISO) { s3 = s0; s5 = s0; e18 = e12; e21 = e15; }       // the same sums of the same values
         const double p = zp, q = zq, r = zr;
         const double det = (a * b) * r;
         if (det == 0.0 && live) atomicCAS(A.status, 0, -3);

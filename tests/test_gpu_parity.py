@@ -114,6 +114,19 @@ def test_parity_anisotropic_sigma_and_mu():
     asm.close()
 
 
+def test_parity_linear_elements_unequal_diagonal_sigma():
+    """Linear elements, mu = mu0, DIAGONAL sigma with unequal entries: the general variant of fused12_kernel (the isotropic
+    one stands down on node_kernel's flag); the unmodified model runs the isotropic variant on frequency 1."""
+    m = _small(8, 0, 1)
+    m.sigma_re[:, 3] *= 1.5
+    m.sigma_re[:, 5] *= 0.25
+    asm, o = host.Assembly(m), Oracle(m)
+    _check(compare_assembly(asm, o, m, ifreq=1))
+    assert asm.stats()["ms_fused"] > 0.0
+    _check(compare_assembly(asm, o, m, ifreq=2))
+    asm.close()
+
+
 @pytest.mark.parametrize("name", ["small_mn8_gpml_zhou", "small_mn8_dirichlet", "small_mn20_gpml_fang", "small_mn27_gpml_zhou"])
 def test_golden_fixtures(name):
     sys.path.insert(0, os.path.join(HERE, "golden"))
