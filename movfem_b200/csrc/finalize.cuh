@@ -18,7 +18,10 @@
 namespace movfem {
 
 constexpr int kGatherSub = 1;         // blocks of kFinThreads entries per gather CTA (2: twice the reads in flight per thread, measured 0-4 % slower)
-constexpr int kFinThreads = 128;      // entries per gather block.  Measured on config 2: 64: 0.400 ms, 128: 0.334, 256: 0.342, 512: 0.361
+#ifndef FIN_THREADS
+#define FIN_THREADS 128
+#endif
+constexpr int kFinThreads = FIN_THREADS;      // entries per gather block.  Measured on config 2: 64: 0.400 ms, 128: 0.334, 256: 0.342, 512: 0.361
 
 // Contribution index, compressed once per mesh: per block of kFinThreads entries the 64-bit position of its first
 // contribution (cblk) and per entry a 16-bit offset from it (an entry has <= 4 contributions, so a block has <= 4*kFinThreads).
@@ -39,8 +42,10 @@ compress_cptr_kernel(int64_t nzu, const int64_t *__restrict__ cptr, int64_t *__r
 // profiles/r02_summary.md): the scattered 16-byte reads (reading K/M sequentially instead: -3 %), the instruction count
 // (-8.5 % instructions, issue 73 -> 66 %: +-0), the reads in flight (two blocks per CTA: -2 %, four: +27 % from the lost
 // occupancy), CTA turnover (a persistent grid-stride CTA per slot: +10 to +30 %), a three-stage software pipeline over the
-// blocks of a persistent CTA (+4 to +6 %), L2 prefetch of the index lines of a block 2-8 k blocks ahead (+6 %).  DRAM 48 %, L2 48 %, issue 66 %: the index -> value -> sum chain of 16 resident
-// 128-entry blocks per SM is where it stands.
+// blocks of a persistent CTA (+4 to +6 %), 256 entries per block (+-0; 512: +9 %), L2 prefetch of the index lines of a block 2-8 k blocks ahead (+6 %).  DRAM 48 %, L2 48 %, issue 66 %: the index -> value -> sum chain of 16 resident
+// 128-entry blocks per SM is where it stands: without the sum (first contribution only) 2.17 ms, without the K/M reads 1.17 ms,
+// of which 0.85 ms is the launch rate of 1.6 M 128-thread CTAs (tools/micro/stream_bench.cu: a dependent base -> index -> value
+// -> store chain of this shape streams 5.1 TB/s, a plain copy 6.9 TB/s).
 // Phase 1: the block's <= 4*kFinThreads contributions are fetched by all threads (independent random 16-byte reads, up to four
 // in flight per thread) into shared memory; phase 2: one thread per entry sums its contributions in ascending order.
 // cache: 0 none; 1 fill kmg[i] = gathered (K, M) of every entry; 2 use it (a later frequency of a sweep: streaming 16-byte
