@@ -411,7 +411,9 @@ int launch_fused12_variant(movfem_handle *h, const ElemArgs &A, int skip_unless_
     F.skip_unless_changed = skip_unless_changed;
     const int nb = (h->n_plain + 31) / 32;
     if (kernel_event(h, 3, true)) return MOVFEM_E_CUDA;
-    kern<<<std::min(nb, std::max(1, per_sm) * h->num_sms), FC::THREADS, FC::SMEM, h->stream>>>(F);
+    int grid = std::min(nb, std::max(1, per_sm) * h->num_sms);
+    if (const char *g = getenv("MOVFEM_TEST_FUSED_GRID")) grid = std::max(1, std::min(grid, atoi(g)));   // test hook: many batches per CTA on small meshes
+    kern<<<grid, FC::THREADS, FC::SMEM, h->stream>>>(F);
     h->launches += 1;
     CK(cudaGetLastError());
     if (kernel_event(h, 3, false)) return MOVFEM_E_CUDA;

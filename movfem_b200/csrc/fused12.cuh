@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
         s_pidx[tid] = sj <= si ? hi * (hi + 1) / 2 + lo : -1;
     }
     if (tid == 0) {
-        for (int b = 0; b < 2; ++b) { mbar_init(&full[b], 8); mbar_init(&empty[b], 6); }
+        // every thread arrives for itself (release of its own stores / loads): 8 x 32 writers of a batch, 6 x 32 readers
+        for (int b = 0; b < 2; ++b) { mbar_init(&full[b], 8 * 32); mbar_init(&empty[b], 6 * 32); }
         mbar_init(staged, 64);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -246,8 +247,7 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
         double *Ro = s_R + (size_t)buf * C::R_D + g * 32 + lane;
         Ro[0 * QS] = G00 * a1x; Ro[1 * QS] = G00 * a1y; Ro[2 * QS] = G11 * a2x; Ro[3 * QS] = G11 * a2y;
         Ro[4 * QS] = G02 * a1x; Ro[5 * QS] = G02 * a1y; Ro[6 * QS] = G12 * a2x; Ro[7 * QS] = G12 * a2y;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[buf]);                        // release: this Gauss point of the batch is in place
+        mbar_arrive(&full[buf]);                                       // release: this thread's share of the batch is in place
     };
 
     // ---- RHS unit (four slots q4..q4+3, polarisation pol) of batch j: b_e(j) = sum_g phi_j(g) R[d_j][pol](g)
@@ -333,8 +333,7 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
             trq = fmaxf(trq, t2.x); trt = fmaxf(trt, t2.y);
         }
         const double thrK = A.no_l1 ? -1.0 : kTinyRelC * NGP * (double)trq, thrM = A.no_l1 ? -1.0 : kTinyRelC * NGP * (double)trt;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[buf]);           // the buffer (and its scales) may be refilled
+        mbar_arrive(&empty[buf]);                           // the buffer (and its scales) may be refilled
         // write-out: packed lower triangle by LOCAL DOF index, 32 elements interleaved -> 512-byte coalesced stores
         if (batch * 32 + lane < A.nlist) {
             double2 *KMo = A.KM + (size_t)batch * NP * 32 + lane;
@@ -376,8 +375,7 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
             if (DO_KM) tile(k);
             else {
                 rhs_unit(k, 4 * (warp >> 1), warp & 1);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[k & 1]);             // R of this buffer may be overwritten
+                mbar_arrive(&empty[k & 1]);                            // R of this buffer may be overwritten
             }
         } else {
             if (DO_KM) {

@@ -114,6 +114,18 @@ def test_parity_anisotropic_sigma_and_mu():
     asm.close()
 
 
+def test_fused12_pipeline_many_batches_per_cta(monkeypatch):
+    """fused12_kernel with two CTAs for the whole mesh (test hook): every CTA walks several 32-element batches, i.e. the
+    double-buffered mbarrier pipeline (staged / full / empty) wraps around -- on BASELINE-size meshes only config 5 does."""
+    monkeypatch.setenv("MOVFEM_TEST_FUSED_GRID", "2")
+    m = mesh.build_model("fused_pipeline", 14, 9, 8, 1000., 1100., 900., 2, 2, 1, dirichlet=0, gpml_sch=1, freqs=(0.5, 3.0),
+                         sigma_fn=mesh._layered((1500., 1500., 500., 1500.)), topo_amp=50.0)
+    asm, o = host.Assembly(m), Oracle(m)
+    _check(compare_assembly(asm, o, m, ifreq=1))
+    _check(compare_assembly(asm, o, m, ifreq=2))
+    asm.close()
+
+
 def test_parity_linear_elements_unequal_diagonal_sigma():
     """Linear elements, mu = mu0, DIAGONAL sigma with unequal entries: the general variant of fused12_kernel (the isotropic
     one stands down on node_kernel's flag); the unmodified model runs the isotropic variant on frequency 1."""

@@ -14,6 +14,18 @@ for mn, dirichlet, sch, inimod in ((8, 0, 1, 1), (20, 0, 0, 1), (27, 1, 1, 3), (
         r = asm.global_vfem(f, m.omega(f), m.sigma_for(f))
     print(mn, dirichlet, sch, inimod, r[4], float(np.abs(r[2][: r[4]]).max()))
     asm.close()
+# linear elements, many batches per CTA of fused12_kernel (MOVFEM_TEST_FUSED_GRID=2): its mbarrier pipeline; both sigma variants
+os.environ["MOVFEM_TEST_FUSED_GRID"] = "2"
+for aniso in (False, True):
+    m = mesh.build_model("san_fused", 14, 9, 8, 1000., 1100., 900., 2, 2, 1, dirichlet=0, gpml_sch=1, freqs=(0.5, 3.0),
+                         sigma_fn=mesh._layered((1500., 1500., 500., 1500.)), topo_amp=50.0)
+    if aniso: m.sigma_re[:, 3] *= 1.5
+    asm = host.Assembly(m)
+    for f in (1, 2, 2):
+        r = asm.global_vfem(f, m.omega(f), m.sigma_for(f))
+    print("fused12 pipeline", aniso, m.ne, r[4], float(np.abs(r[2][: r[4]]).max()))
+    asm.close()
+del os.environ["MOVFEM_TEST_FUSED_GRID"]
 # geomodel -> grid nodes (movfem_geo_innermodel)
 for name in sorted(mrv.GEO_CASES):
     m, n_air, inp = mrv.geo_case(name)
