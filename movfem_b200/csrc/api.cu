@@ -826,6 +826,13 @@ static int launch_gather(movfem_handle *h, double omega, int32_t mode, int cache
     CK(cudaMemsetAsync(h->d_nflag + 1, 0, sizeof(unsigned long long), st));
     double dk = -1.0, dm = -1.0;
     if (const char *t = getenv("MOVFEM_TEST_DOUBT_ABS")) sscanf(t, "%lf,%lf", &dk, &dm);   // test hook (tests/test_gpu_parity.py)
+    if (cache == 2) {
+        const int per = kStreamThreads * kStreamPer;
+        stream_finalize_kernel<<<(unsigned)((h->nzu + per - 1) / per), kStreamThreads, 0, st>>>(h->nzu, f32r(omega), h->d_kmg, h->d_a, h->d_blkcnt, gmode, h->d_flags,
+                                                                                              h->nblk_fin, h->d_total);
+        h->launches += 1;
+        CK(cudaGetLastError());
+    }
     gather_finalize_kernel<<<(h->nblk_fin + kGatherSub - 1) / kGatherSub, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cblk, h->d_off16, h->d_src, h->d_KM, h->d_a,
                                                               h->d_blkcnt, gmode, cache, h->d_kmg, h->d_flags, h->nblk_fin, h->d_total,
                                                               h->NP, h->flagW, h->d_pairflags, h->d_batchany, h->d_forcek, h->d_nflag + 1, dk, dm);

@@ -48,8 +48,8 @@ compress_cptr_kernel(int64_t nzu, const int64_t *__restrict__ cptr, int64_t *__r
 // -> store chain of this shape streams 5.1 TB/s, a plain copy 6.9 TB/s).
 // Phase 1: the block's <= 4*kFinThreads contributions are fetched by all threads (independent random 16-byte reads, up to four
 // in flight per thread) into shared memory; phase 2: one thread per entry sums its contributions in ascending order.
-// cache: 0 none; 1 fill kmg[i] = gathered (K, M) of every entry; 2 use it (a later frequency of a sweep: streaming 16-byte
-// reads instead of the gather) unless the node kernel saw Re(sigma) change (flags[1]), in which case the call refills it.
+// cache: 0 none; 1 fill kmg[i] = gathered (K, M) of every entry; 2: stream_finalize_kernel (below) has delivered the entries from
+// that cache -- nothing to do -- unless the node kernel saw Re(sigma) change (flags[1]), in which case this call refills it.
 constexpr int kGatherMinBlocks = kGatherSub == 1 ? 2048 / kFinThreads : (kGatherSub == 2 ? 12 : 6);
 __global__ void __launch_bounds__(kFinThreads, kGatherMinBlocks)
 gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk, const uint16_t *__restrict__ off16,
@@ -62,12 +62,15 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
     // kGatherSub blocks of kFinThreads entries per CTA: twice the scattered reads in flight per thread at the same occupancy
     __shared__ double2 vals[kGatherSub][4 * kFinThreads + 4];
     __shared__ uint16_t offs[kGatherSub][kFinThreads + 1];
-    if (cache == 2 && flags[1] != 0) cache = 1;
+    if (cache == 2) {                       // a later frequency of a sweep: stream_finalize_kernel does the work unless Re(sigma) changed
+        if (flags[1] == 0) return;
+        cache = 1;
+    }
     const int bid = blockIdx.x;
     {
     int64_t c0s[kGatherSub];
     int ns[kGatherSub];
-    if (!(cache == 2)) {
+    {
 #pragma unroll
         for (int sb = 0; sb < kGatherSub; ++sb) {
             const int blk = bid * kGatherSub + sb;
@@ -105,17 +108,7 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
     const int64_t c0 = c0s[sb];
     const int n = ns[sb];
     int nzflag = 0;
-    // later frequency of a sweep: every K_e, M_e is frequency independent (Q18), so every entry streams from the gathered cache
-    const bool stream = cache == 2;
-    if (stream) {
-        if (i < nzu) {
-            const double2 v = kmg[i];
-            double re = v.x, im = w32 * v.y;
-            if (mode == 0) { re = f32r(re); im = f32r(im); }
-            a[i] = make_double2(re, im);
-            nzflag = !(re == 0.0 && im == 0.0);
-        }
-    } else {
+    {
         if (i < nzu) {
             const int lo = offs[sb][threadIdx.x];
             const int hi = (threadIdx.x + 1 < kFinThreads && i + 1 < nzu) ? offs[sb][threadIdx.x + 1] : n;
@@ -204,6 +197,52 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
         atomicAdd(total_nonzero + 2, ((unsigned long long)(i + 1) * 0xC2B2AE3D27D4EB4Full) ^ (unsigned long long)(i >> 7));
     }
     }
+    }
+}
+
+// A later frequency of a sweep (cache == 2): every K_e, M_e is frequency independent (Q18), so every entry streams from the
+// gathered cache kmg.  Four entries per thread, loads first: a CTA per 128 entries with one 16-byte load per thread is bound by
+// the CTA launch rate (tools/micro/stream_bench.cu: 3.9 TB/s; 6.9 TB/s from 512-thread CTAs).  Returns at once when the node
+// kernel saw Re(sigma) change: gather_finalize_kernel, launched behind it, then refills the cache.
+constexpr int kStreamThreads = 256, kStreamPer = 4;
+__global__ void __launch_bounds__(kStreamThreads)
+stream_finalize_kernel(int64_t nzu, double w32, const double2 *__restrict__ kmg, double2 *__restrict__ a, int *__restrict__ blk_nonzero,
+                       int mode, const int *__restrict__ flags, int nblk, unsigned long long *__restrict__ total_nonzero) {
+    static_assert(kFinThreads == 128 && kStreamThreads == 2 * kFinThreads, "block bookkeeping below");
+    if (flags[1] != 0) return;
+    __shared__ int cnt[2 * kStreamPer];
+    if (threadIdx.x < 2 * kStreamPer) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * (kStreamThreads * kStreamPer);
+    double2 v[kStreamPer];
+#pragma unroll
+    for (int e = 0; e < kStreamPer; ++e) {
+        const int64_t i = base + e * kStreamThreads + threadIdx.x;
+        v[e] = i < nzu ? kmg[i] : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int e = 0; e < kStreamPer; ++e) {
+        const int64_t i = base + e * kStreamThreads + threadIdx.x;
+        double re = v[e].x, im = w32 * v[e].y;
+        if (mode == 0) { re = f32r(re); im = f32r(im); }
+        const bool live = i < nzu, nz = live && !(re == 0.0 && im == 0.0);
+        if (live) a[i] = make_double2(re, im);
+        const unsigned bal = __ballot_sync(0xffffffffu, nz);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&cnt[2 * e + (threadIdx.x >> 7)], __popc(bal));
+        if (total_nonzero && mode == 0 && live && !nz) {      // signature of the stripped set, as in gather_finalize_kernel
+            atomicAdd(total_nonzero + 1, (unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ull);
+            atomicAdd(total_nonzero + 2, ((unsigned long long)(i + 1) * 0xC2B2AE3D27D4EB4Full) ^ (unsigned long long)(i >> 7));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * kStreamPer) {
+        const int blk = blockIdx.x * (2 * kStreamPer) + threadIdx.x;
+        if (blk < nblk) {
+            const int c = cnt[threadIdx.x];
+            blk_nonzero[blk] = c;
+            const int valid = (int)min((int64_t)kFinThreads, nzu - (int64_t)blk * kFinThreads);
+            if (total_nonzero && mode == 0 && c != valid) atomicAdd(total_nonzero, (unsigned long long)(valid - c));
+        }
     }
 }
 

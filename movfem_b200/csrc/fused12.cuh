@@ -1,39 +1,44 @@
-// movfem_b200/csrc/fused12.cuh -- the 8-node / 12-DOF (linear) element path in ONE warp-specialised kernel.
+// movfem_b200/csrc/fused12.cuh -- the 8-node / 12-DOF (linear) element path in ONE kernel.
 //
 // BASELINE configs 1, 4 and 5 are linear-element meshes (5: 32 M elements).  There the two-kernel element path of
 // element.cuh + contract.cuh is bound by its own HBM round trips and block barriers, not by arithmetic: per element
 // 768 B of Q|T scratch are written by geometry_kernel and re-read by contract_kernel next to 1 248 B of K_e/M_e --
-// against 10 944 algorithmic flops -- and ncu shows 30 % of the warp samples at barriers or waiting for the
-// staged node records.  This kernel keeps the per-Gauss-point tensors on chip and has NO block-wide barrier in its loop:
+// against 10 944 algorithmic flops.  This kernel keeps the per-Gauss-point tensors on chip and has no
+// block-wide barrier in its loop:
 //
-//   batch = 32 consecutive elements of the unstretched list (LANES ARE ELEMENTS everywhere), CTA = 8 warps
-//   producers (warps 6, 7; four Gauss points each): the node fields of a batch arrive by cp.async (16 bytes per lane and
-//       chunk), issued one batch ahead; interpolation to the Gauss points, then J,
-//       det, G = J^-1, Q = (w/det^2) J mu^-1 J^T, T = G^T S G and the source R in CLOSED FORM: x and y are tensor-product
+//   batch = 32 consecutive elements of the unstretched list (LANES ARE ELEMENTS everywhere), CTA = 8 warps, 2 CTAs per SM.
+//   Per batch every warp does two things, the second one batch behind the first:
+//   (1) geometry of ONE Gauss point (warp w = Gauss point w) of batch k+1: interpolation of the staged node fields, then J,
+//       det, G = J^-1, Q = (w/det^2) J mu^-1 J^T, T = G^T S G and the source R in CLOSED FORM -- x and y are tensor-product
 //       lines, so J = [[a,0,p],[0,b,q],[0,0,r]] with a = dx/2, b = dy/2 and (p,q,r) the xi-gradient of z (the n_fem.f90:193
-//       typo is in the table).  Q|T go to one of two shared-memory buffers [component][g][lane], signalled by an mbarrier;
-//       R stays in a third block from which the same two warps form b_e = sum_g phi_j R[d_j] (integration.f90:96-104), one
-//       polarisation each
-//   consumers (warps 0-5): one 4x4 tile of the lower triangle each (the 12 DOFs are three direction-uniform groups of four,
-//       so the six tiles are the six direction classes), operands warp-uniform broadcast loads -- the inner loop of
-//       contract.cuh -- from the buffer the producers filled while the previous batch was contracted; K_e, M_e leave as
-//       512-byte coalesced stores, with the tiny-pair test of exact.cuh in the epilogue
+//       typo is in the table).  Q|T and R go to one of two shared-memory buffers [component][g][lane]; every thread
+//       arrives on the buffer's `full` mbarrier
+//   (2) of batch k -- warps 0-5: one 4x4 tile of the lower triangle each (the 12 DOFs are three direction-uniform groups of
+//       four, so the six tiles are the six direction classes; operands are warp-uniform broadcast loads: the inner loop of
+//       contract.cuh), K_e, M_e leave as 512-byte coalesced stores with the tiny-pair test of exact.cuh in the epilogue,
+//       then the threads arrive on `empty`; warps 6, 7: b_e = sum_g phi_j R[d_j] (integration.f90:96-104), one
+//       polarisation each, stored by K/M row (be_index: 1 kB runs), then the asynchronous copies (cp.async, completion
+//       on the `staged` mbarrier) of the node fields of batch k+2 from the FIELD-MAJOR node arrays node_kernel writes
+//       next to its records: the 32 lanes of a copy are 32 consecutive nodes of a k-column, 256 contiguous bytes
 //
 // The closed forms hold when mu = mu0 I and sigma is diagonal at every node (node_kernel reports both; every
 // linear-element BASELINE mesh): otherwise the kernel returns at once and the generic two-kernel path does the work
 // (api.cu launches both; exactly one of them runs).  They agree with the reference's arithmetic to rounding (<= 1e-15);
 // the entries whose last bits matter are re-evaluated in the reference's own operation order by exact_kernel.
-// The RHS-only pass of a cached frequency (DO_KM = false) is the same code with the two producer warps only.
+// The RHS-only pass of a cached frequency (DO_KM = false) is the same geometry with the six RHS units on warps 0-5.
 //
-// Measured on the way (B200, 4 M elements of config 5 at half scale, ms of this kernel; profiles/r02_summary.md): block-phased
-// version (all warps geometry, then all warps contraction, TMA-staged records) 4.30; the same with a tensor-core (DMMA)
-// interpolation phase and a reused buffer 5.30 (two more block barriers); warp-specialised with direct global loads 3.77;
-// + cp.async staging 3.67; + no global-load chain at the top of a batch, one reciprocal per Gauss point, no sums of
-// identically-zero source components, lower half only of diagonal tiles 3.58; + element ids two batches ahead and a partly
-// rolled node loop 3.36 (this file); four producer warps of two Gauss points (10 warps, 96 registers, spills in the tile
-// loop) 4.05; b_e formed by four of the consumer warps from a double-buffered R block 3.38 (no gain: the producers wait for
-// their scattered 16-byte node-field reads, 27 sectors per request, not for their own instructions -- the next step is a
-// field-major node layout so that a warp's request is 256 contiguous bytes).  geometry_kernel + contract_kernel: 5.59.
+// How it got here (B200, 4.2 M elements of config 5 at half scale, ms of this kernel; profiles/r02_summary.md).  Warp
+// specialised, two producer warps (four Gauss points each) feeding six tile warps: 3.37 -- ncu: instruction-cache hit rate
+// 82 %, the GPC-level instruction cache at 95 % of its request rate (62 kB of straight-line SASS executed once per batch),
+// tile warps waiting for the producers half of the time; producer alone 2.44, tile warps alone 1.75.  One Gauss point per
+// warp, one code path for the tiles, compact epilogue (this structure): 3.18 -- instruction cache 99.7 %, now the
+// shared-memory / LSU data pipe at 81-86 % of its wavefront rate is the limit, so what followed removes wavefronts:
+// field-major node arrays instead of 208-byte records (32 sectors -> 2-3 per copy) and b_e by K/M row (32 -> 8 wavefronts
+// per store): 2.38; diagonal tiles reuse their row operands, Gauss-point weights as two 16-byte loads, float scales: 2.25;
+// isotropic-sigma variant (four staged fields instead of seven): 2.04 = 22.5 TFLOP/s algorithmic, 0.64 of the measured
+// FP64 peak.  geometry_kernel + contract_kernel on the same elements: 5.59.  Tried and dropped: DMMA interpolation phase
+// (block barriers: 5.30), four producer warps (register spills: 4.05), asynchronous id / line prefetch in the producers
+// (3.47), producers on one SM sub-partition (3.50), rolled Gauss-point / node loops (2 x unrolled: 3.53).
 //
 // Replaces for linear elements: MoVFEM_3DMT.f90:193-211 (element loop body), integration.f90:60-106 (int_elem_params,
 // alocal, blocal), n_fem.f90:66-102,355-395, v_fem.f90:38-60, problem.f90:70-149.

@@ -40,7 +40,7 @@ def main(rep, workload):
         k["top_stalls_per_issue"] = {n: round(v, 2) for v, n in st}
         kernels.append(k)
         name = next((n for n in NAMES if n in k["kernel"]), None)
-        if name:
+        if name and k.get("duration_us", 0.0) >= 20.0:   # (a variant that stood down on a device flag returns within microseconds: not a launch of the kernel's work)
             tot[name] = tot.get(name, 0.0) + k.get("dram_read", 0.0) + k.get("dram_write", 0.0)
             cnt[name] = cnt.get(name, 0) + 1
     print(json.dumps({"source": rep, "workload": workload, "note": "one cold assembly; ncu replays each launch (cold cache, serialised): compare shares, not absolutes",
