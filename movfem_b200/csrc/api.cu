@@ -833,9 +833,15 @@ static int launch_gather(movfem_handle *h, double omega, int32_t mode, int cache
         h->launches += 1;
         CK(cudaGetLastError());
     }
-    gather_finalize_kernel<<<(h->nblk_fin + kGatherSub - 1) / kGatherSub, kFinThreads, 0, st>>>(h->nzu, f32r(omega), h->d_cblk, h->d_off16, h->d_src, h->d_KM, h->d_a,
-                                                              h->d_blkcnt, gmode, cache, h->d_kmg, h->d_flags, h->nblk_fin, h->d_total,
-                                                              h->NP, h->flagW, h->d_pairflags, h->d_batchany, h->d_forcek, h->d_nflag + 1, dk, dm);
+    const int ngroups = (h->nblk_fin + kGatherSub - 1) / kGatherSub;
+    if (cache == 2)   // only a refill after a change of Re(sigma) has work here: a grid the size of the machine, not of the matrix
+        gather_finalize_kernel<true><<<std::min(ngroups, h->num_sms * kGatherMinBlocks), kFinThreads, 0, st>>>(
+            h->nzu, f32r(omega), h->d_cblk, h->d_off16, h->d_src, h->d_KM, h->d_a, h->d_blkcnt, gmode, cache, h->d_kmg, h->d_flags, h->nblk_fin, h->d_total,
+            h->NP, h->flagW, h->d_pairflags, h->d_batchany, h->d_forcek, h->d_nflag + 1, dk, dm);
+    else
+        gather_finalize_kernel<false><<<ngroups, kFinThreads, 0, st>>>(
+            h->nzu, f32r(omega), h->d_cblk, h->d_off16, h->d_src, h->d_KM, h->d_a, h->d_blkcnt, gmode, cache, h->d_kmg, h->d_flags, h->nblk_fin, h->d_total,
+            h->NP, h->flagW, h->d_pairflags, h->d_batchany, h->d_forcek, h->d_nflag + 1, dk, dm);
     h->launches += 1;
     CK(cudaGetLastError());
     if (mode == MOVFEM_MODE_T2) CK(cudaMemcpyAsync(h->h_count, h->d_total, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));

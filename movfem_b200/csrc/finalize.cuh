@@ -51,6 +51,9 @@ compress_cptr_kernel(int64_t nzu, const int64_t *__restrict__ cptr, int64_t *__r
 // cache: 0 none; 1 fill kmg[i] = gathered (K, M) of every entry; 2: stream_finalize_kernel (below) has delivered the entries from
 // that cache -- nothing to do -- unless the node kernel saw Re(sigma) change (flags[1]), in which case this call refills it.
 constexpr int kGatherMinBlocks = kGatherSub == 1 ? 2048 / kFinThreads : (kGatherSub == 2 ? 12 : 6);
+// LOOP: grid-stride over the blocks (the refill launch behind stream_finalize_kernel: a small grid whose CTAs return at once
+// when there is nothing to refill -- 10-30 % slower than one CTA per block when it does work, see above)
+template <bool LOOP>
 __global__ void __launch_bounds__(kFinThreads, kGatherMinBlocks)
 gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk, const uint16_t *__restrict__ off16,
                        const uint32_t *__restrict__ src, const double2 *__restrict__ KM, double2 *__restrict__ a,
@@ -66,8 +69,8 @@ gather_finalize_kernel(int64_t nzu, double w32, const int64_t *__restrict__ cblk
         if (flags[1] == 0) return;
         cache = 1;
     }
-    const int bid = blockIdx.x;
-    {
+    const int ngroups = (nblk + kGatherSub - 1) / kGatherSub;
+    for (int bid = blockIdx.x; bid < ngroups; bid += LOOP ? (int)gridDim.x : ngroups) {
     int64_t c0s[kGatherSub];
     int ns[kGatherSub];
     {
