@@ -38,7 +38,8 @@
 // isotropic-sigma variant (four staged fields instead of seven): 2.04 = 22.5 TFLOP/s algorithmic, 0.64 of the measured
 // FP64 peak.  geometry_kernel + contract_kernel on the same elements: 5.59.  Tried and dropped: DMMA interpolation phase
 // (block barriers: 5.30), four producer warps (register spills: 4.05), asynchronous id / line prefetch in the producers
-// (3.47), producers on one SM sub-partition (3.50), rolled Gauss-point / node loops (2 x unrolled: 3.53).
+// (3.47), producers on one SM sub-partition (3.50), rolled Gauss-point / node loops (2 x unrolled: 3.53), two Gauss points x 16
+// elements per warp in the geometry (half the distinct addresses per field load, same wavefronts: 2.07 against 2.05).
 //
 // Replaces for linear elements: MoVFEM_3DMT.f90:193-211 (element loop body), integration.f90:60-106 (int_elem_params,
 // alocal, blocal), n_fem.f90:66-102,355-395, v_fem.f90:38-60, problem.f90:70-149.
