@@ -118,6 +118,7 @@ struct movfem_handle {
     int64_t *d_csr;                // row pointers of the last device result (movfem_device_csr), built on request
     unsigned long long *d_total;   // [0] entries stripped by find_zeros in the last T2 assembly, [1..2] signature of the stripped set
     bool offsets_valid;            // d_blkoff holds the scan of the last assembly's block counts
+    int64_t comp_nz, comp_sig[2];  // delivered count and signature of the stripped set d_blkoff / d_irn_c / d_jcn_c were made for (-1: none)
     int nblk_fin;
     int *d_status, *d_flags;
     // pinned host scratch
@@ -806,7 +807,7 @@ static int launch_exact(movfem_handle *h, double omega) {
             if (X.nlist <= 0) continue;
             const int nb = (X.nlist + 31) / 32;
             if (kernel_event(h, 2, true)) return MOVFEM_E_CUDA;
-            kern<<<std::min(nb, 2 * h->num_sms), 256, smem + (pass ? smem_h : 0), h->stream>>>(X);
+            kern<<<std::min(nb, EXACT_MINB * h->num_sms), 256, smem + (pass ? smem_h : 0), h->stream>>>(X);
             h->launches += 1;
             CK(cudaGetLastError());
             if (kernel_event(h, 2, false)) return MOVFEM_E_CUDA;
@@ -974,20 +975,24 @@ int movfem_device_result(const movfem_handle *hc, const int32_t **irn, const int
         else {
             h->nz_last = h->nzu - h->h_count[0];   // h_count[0]: entries stripped by find_zeros
             if (h->nz_last != h->nzu) {   // find_zeros > 0: rem_zeros (global_assembly.f90:134-150)
-                if (!h->offsets_valid) {
+                // the same entries stripped as in the last compaction (same count, same order-independent signature from the
+                // gather): the block offsets and the compacted IRN/JCN are still right, only the values are compacted again
+                const bool same_set = h->d_a_c && h->comp_nz == h->nz_last && h->comp_sig[0] == h->h_count[1] && h->comp_sig[1] == h->h_count[2];
+                if (!h->offsets_valid && !same_set) {
                     const int nb = (h->nblk_fin + kScanTile - 1) / kScanTile;
                     scan_block_sums<<<nb, kScanThreads, 0, h->stream>>>(h->d_blkcnt, h->nblk_fin, h->d_finbsum);
                     scan_block_offsets<<<1, 1024, 0, h->stream>>>(h->d_finbsum, nb);
                     scan_finish<<<nb, kScanThreads, 0, h->stream>>>(h->d_blkcnt, h->nblk_fin, h->d_finbsum, h->d_blkoff);
                     h->launches += 3;
                     CK(cudaGetLastError());
-                    h->offsets_valid = true;
                 }
+                h->offsets_valid = true;
                 if (!h->d_a_c) {
                     CK(dmalloc(&h->d_a_c, (size_t)h->nzu)); CK(dmalloc(&h->d_irn_c, (size_t)h->nzu)); CK(dmalloc(&h->d_jcn_c, (size_t)h->nzu));
                 }
                 compact_kernel<<<h->nblk_fin, kFinThreads, 0, h->stream>>>(h->nzu, h->d_blkoff, h->d_irn, h->d_jcn, h->d_a, h->d_irn_c,
-                                                                          h->d_jcn_c, h->d_a_c);
+                                                                          h->d_jcn_c, h->d_a_c, same_set ? 0 : 1);
+                h->comp_nz = h->nz_last; h->comp_sig[0] = h->h_count[1]; h->comp_sig[1] = h->h_count[2];
                 h->launches += 1;
                 CK(cudaGetLastError());
                 CK(cudaStreamSynchronize(h->stream));

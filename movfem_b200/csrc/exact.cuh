@@ -59,11 +59,16 @@ struct ExactH {
     double h[3], hf[3];
 };
 
+#ifndef EXACT_EB
+#define EXACT_EB 7       // measured on config 2 (1.85 M flagged pairs), ms of both launches: EB 14 / 512 items / 2 CTAs per SM 1.078,
+#define EXACT_ITEMS 256  // 10 / 512 / 3: 1.081, 9 / 512 / 3: 1.027, 7 / 256 / 3: 0.937, 7 / 256 / 4 (64 registers, 152 B of spills): 0.894 --
+#define EXACT_MINB 4     // the non-FMA reference-order chains want warps in flight more than they want registers
+#endif
 template <int MN, int ME, int NGP>
 struct ExactCfg {
     // A group of up to EB flagged elements is worked on at a time, chosen so that the group's flagged pairs fill whole
-    // rounds of the CTA's threads (20-node bricks have 36 such pairs each: 14 elements = 504 of 512 thread slots).
-    static constexpr int EB = 14, THREADS = 256, ITEMS = 2 * THREADS;
+    // rounds of the CTA's threads (20-node bricks have 36 such pairs each: 7 elements = 252 of 256 thread slots).
+    static constexpr int EB = EXACT_EB, THREADS = 256, ITEMS = EXACT_ITEMS, MINB = EXACT_MINB;
     static constexpr int NDD = 13;                       // staged per node: z, mu^-1 (6), Re sigma (6)
     static constexpr size_t SMEM = sizeof(ExactGp) * EB * NGP + sizeof(double) * (EB * MN * NDD + EB * 6) + sizeof(int) * (EB * 8 + 4 + 32 + THREADS);
     static constexpr size_t SMEM_H = sizeof(ExactH) * EB * NGP;   // added for stretched lists
@@ -197,7 +202,7 @@ __device__ __forceinline__ void exact_pair(const ElemTables &T, const ExactGp *_
 }
 
 template <int MN, int ME, int NGP>
-__global__ void __launch_bounds__(256, 2) exact_kernel(ExactArgs A) {
+__global__ void __launch_bounds__(256, EXACT_MINB) exact_kernel(ExactArgs A) {
     using CFG = ExactCfg<MN, ME, NGP>;
     constexpr int EB = CFG::EB, NDD = CFG::NDD, NORD = MN == 8 ? 2 : 3;
     extern __shared__ __align__(128) unsigned char smem_raw[];

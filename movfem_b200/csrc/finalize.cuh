@@ -252,7 +252,8 @@ stream_finalize_kernel(int64_t nzu, double w32, const double2 *__restrict__ kmg,
 // order-preserving compaction of the entries whose value is not exactly (0,0)
 __global__ void __launch_bounds__(kFinThreads)
 compact_kernel(int64_t nzu, const int64_t *__restrict__ blk_off, const int *__restrict__ irn, const int *__restrict__ jcn,
-               const double2 *__restrict__ a, int *__restrict__ irn_c, int *__restrict__ jcn_c, double2 *__restrict__ a_c) {
+               const double2 *__restrict__ a, int *__restrict__ irn_c, int *__restrict__ jcn_c, double2 *__restrict__ a_c,
+               int copy_pattern /* 0: irn_c / jcn_c already hold this stripped set (same signature as the last compaction) */) {
     __shared__ int wsum[kFinThreads / 32];
     const int64_t i = (int64_t)blockIdx.x * kFinThreads + threadIdx.x;
     double2 v = make_double2(0.0, 0.0);
@@ -266,7 +267,8 @@ compact_kernel(int64_t nzu, const int64_t *__restrict__ blk_off, const int *__re
     for (int k = 0; k < w; ++k) off += wsum[k];
     if (keep) {
         const int64_t p = blk_off[blockIdx.x] + off;
-        irn_c[p] = irn[i]; jcn_c[p] = jcn[i]; a_c[p] = v;
+        if (copy_pattern) { irn_c[p] = irn[i]; jcn_c[p] = jcn[i]; }
+        a_c[p] = v;
     }
 }
 
