@@ -35,6 +35,9 @@ namespace movfem {
 
 // ------------------------------------------------------------------------------------------
 // node kernel: problem.f90:257-358 per grid node instead of per (element, node)
+// (Measured and dropped: writing only the frequency-dependent half of a record -- f32(omega b0 z), sigma -- after the first
+// assembly of a handle, the rest depending on g_zp and g_mu only: the partial-sector stores into the 208-byte records make the
+// kernel 1.8 x SLOWER, 0.134 against 0.073 ms on config 4, although it moves 35 % fewer bytes.)
 // ------------------------------------------------------------------------------------------
 __global__ void node_kernel(int n0, int npt, double omega, const double *__restrict__ zp, const double *__restrict__ mu,
                             const double2 *__restrict__ sigma, NodeRec *__restrict__ out, int *__restrict__ status,
