@@ -14,6 +14,10 @@
  *
  * The Fortran-side binding (ISO_C_BINDING) is in movfem_b200/fortran/movfem_cuda.f90 and
  * described in INTEGRATION.md.
+ *
+ * Threading: a handle is used by one host thread at a time.  Handles of DIFFERENT element types (8 / 20 / 27 nodes) on the
+ * same device share one __constant__ operand table: assemble them from one host thread (the switch drains the device first),
+ * not concurrently from several.  Handles of the same element type, and handles on different devices, are independent.
  */
 #ifndef MOVFEM_B200_H
 #define MOVFEM_B200_H

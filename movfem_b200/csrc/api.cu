@@ -15,6 +15,7 @@
 #include <cstring>
 #include <new>
 #include <chrono>
+#include <mutex>
 #include <vector>
 
 #include "../../include/movfem_b200.h"
@@ -281,6 +282,8 @@ void init_pml(const movfem_desc &d, const MeshDims &m, PmlParams &p) {
 // c_ct holds the tables of ONE element type per device.  A process normally assembles one element type; when handles
 // of different types alternate, the switch waits for the device to drain before the symbol is overwritten.
 int g_ct_owner[64];   // element type (me) resident in c_ct, per device; 0 = none
+std::mutex g_ct_mutex;  // serialises the switch; the launches that follow rely on the documented rule of include/movfem_b200.h:
+                        // handles of DIFFERENT element types on one device are not driven from several host threads at once
 
 void build_contract_tables(const MeshDims &m, const ElemTables &T, ContractTables &C) {
     std::memset(&C, 0, sizeof(C));
@@ -322,6 +325,7 @@ void build_contract_tables(const MeshDims &m, const ElemTables &T, ContractTable
 
 int const_table_acquire(movfem_handle *h) {
     if (h->device >= 64) return MOVFEM_E_BADARG;
+    std::lock_guard<std::mutex> lock(g_ct_mutex);
     if (g_ct_owner[h->device] == h->m.me) return 0;
     CK(cudaDeviceSynchronize());   // no kernel of another element type may still be reading c_ct
     CK(cudaMemcpyToSymbol(c_ct, &h->ct, sizeof(ContractTables)));
