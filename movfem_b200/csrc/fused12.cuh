@@ -39,7 +39,10 @@
 // FP64 peak.  geometry_kernel + contract_kernel on the same elements: 5.59.  Tried and dropped: DMMA interpolation phase
 // (block barriers: 5.30), four producer warps (register spills: 4.05), asynchronous id / line prefetch in the producers
 // (3.47), producers on one SM sub-partition (3.50), rolled Gauss-point / node loops (2 x unrolled: 3.53), two Gauss points x 16
-// elements per warp in the geometry (half the distinct addresses per field load, same wavefronts: 2.07 against 2.05).
+// elements per warp in the geometry (half the distinct addresses per field load, same wavefronts: 2.07 against 2.05), the
+// interpolation as mma.m8n8k4.f64 (A = N or dN/dxi from a fragment table, B = node fields of 8 elements, all rows 33 doubles apart so
+// that fragment loads and stores are conflict free; partner warps keep one accumulator column each): a third of the geometry's
+// shared-memory loads, LSU 79 %, parity green -- and 2.21 against 2.05 (long-scoreboard stalls double behind the DMMA chains).
 //
 // Replaces for linear elements: MoVFEM_3DMT.f90:193-211 (element loop body), integration.f90:60-106 (int_elem_params,
 // alocal, blocal), n_fem.f90:66-102,355-395, v_fem.f90:38-60, problem.f90:70-149.
