@@ -9,7 +9,7 @@ SECONDS=0
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$? wall=${SECONDS}s"
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err; echo "reference arm rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --headline-only --no-cpu-baseline > gpurun_out/${tag}_bench_under_ncu.log 2>&1; echo "ncu launch list rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"fused12_kernel<1, 1>|fused12_kernelILb1ELb1|gather_finalize|node_kernel|rhs_kernel" -s 4 -c 6 -o gpurun_out/${tag}_full_config5 -f python tools/run_one.py 5 None 2 > gpurun_out/${tag}_full_config5.log 2>&1; echo "ncu config5 rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"fused12|gather_finalize|node_kernel|rhs_kernel" -s 5 -c 6 -o gpurun_out/${tag}_full_config5 -f python tools/run_one.py 5 None 2 > gpurun_out/${tag}_full_config5.log 2>&1; echo "ncu config5 rc=$?"
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"geometry|contract|exact|gather_finalize|compact" -s 8 -c 8 -o gpurun_out/${tag}_full_config2 -f python tools/run_one.py 2 None 2 > gpurun_out/${tag}_full_config2.log 2>&1; echo "ncu config2 rc=$?"
 python - <<PY
 import json
