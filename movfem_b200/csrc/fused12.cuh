@@ -16,8 +16,8 @@
 //   (2) of batch k -- warps 0-5: one 4x4 tile of the lower triangle each (the 12 DOFs are three direction-uniform groups of
 //       four, so the six tiles are the six direction classes; operands are warp-uniform broadcast loads: the inner loop of
 //       contract.cuh), K_e, M_e leave as 512-byte coalesced stores with the tiny-pair test of exact.cuh in the epilogue,
-//       then the threads arrive on `empty`; warps 6, 7: b_e = sum_g phi_j R[d_j] (integration.f90:96-104), one
-//       polarisation each, stored by K/M row (be_index: 1 kB runs), then the asynchronous copies (cp.async, completion
+//       then the threads arrive on `empty`; warps 6, 7: b_e = sum_g phi_j R[d_j] (integration.f90:96-104), the x and y slot
+//       groups on one warp, the z group on the other, stored by K/M row (be_index: 1 kB runs of 32-byte stores), then the asynchronous copies (cp.async, completion
 //       on the `staged` mbarrier) of the node fields of batch k+2 from the FIELD-MAJOR node arrays node_kernel writes
 //       next to its records: the 32 lanes of a copy are 32 consecutive nodes of a k-column, 256 contiguous bytes
 //
@@ -35,8 +35,8 @@
 // shared-memory / LSU data pipe at 81-86 % of its wavefront rate is the limit, so what followed removes wavefronts:
 // field-major node arrays instead of 208-byte records (32 sectors -> 2-3 per copy) and b_e by K/M row (32 -> 8 wavefronts
 // per store): 2.38; diagonal tiles reuse their row operands, Gauss-point weights as two 16-byte loads, float scales: 2.25;
-// isotropic-sigma variant (four staged fields instead of seven): 2.04 = 22.5 TFLOP/s algorithmic, 0.64 of the measured
-// FP64 peak.  geometry_kernel + contract_kernel on the same elements: 5.59.  Tried and dropped: DMMA interpolation phase
+// isotropic-sigma variant (four staged fields instead of seven): 2.05; b_e of both polarisations in one 32-byte store per slot
+// (st.global.v4.f64: 8 wavefronts per kB instead of 16): 2.03 = 22.6 TFLOP/s algorithmic, 0.65 of the measured FP64 peak.  geometry_kernel + contract_kernel on the same elements: 5.59.  Tried and dropped: DMMA interpolation phase
 // (block barriers: 5.30), four producer warps (register spills: 4.05), asynchronous id / line prefetch in the producers
 // (3.47), producers on one SM sub-partition (3.50), rolled Gauss-point / node loops (2 x unrolled: 3.53), two Gauss points x 16
 // elements per warp in the geometry (half the distinct addresses per field load, same wavefronts: 2.07 against 2.05), the
@@ -261,13 +261,9 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
 
     // ---- RHS unit (four slots q4..q4+3, polarisation pol) of batch j: b_e(j) = sum_g phi_j(g) R[d_j][pol](g)
     //      (blocal / f3, integration.f90:96-104,258-263) ----
-    auto rhs_unit = [&](int j_, int q4, int pol) {
-        const int buf = j_ & 1;
-        if (!(((int)blockIdx.x + j_ * G) * 32 + lane < A.nlist)) return;
-        // b_e by K/M row: lanes are 32 consecutive rows, so a store covers 1 kB (the other polarisation fills the gaps)
-        double2 *bo = reinterpret_cast<double2 *>(A.be) + ((size_t)((int)blockIdx.x + j_ * G) * ME * 32 + lane) * 2 + pol;
-        const int cd = s_sdir[q4];
-        double br[4] = {0, 0, 0, 0}, bi[4] = {0, 0, 0, 0};
+    auto rhs_sums = [&](int buf, int q4, int cd, int pol, double (&br)[4], double (&bi)[4]) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) { br[kk] = 0.0; bi[kk] = 0.0; }
         // diagonal sigma: the source of polarisation 1 is along x, of polarisation 2 along y, so R[d][pol] is identically zero
         // for (d, pol) = (1, 1) and (0, 2): zeros are delivered, nothing is summed
         if (cd == 2 || cd == pol) {
@@ -282,8 +278,30 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
                 br[3] = dfma(p23.y, rr, br[3]); bi[3] = dfma(p23.y, ri, bi[3]);
             }
         }
+    };
+    // one polarisation of four slots (the RHS-only pass: six such units on six warps), 16-byte stores
+    auto rhs_unit = [&](int j_, int q4, int pol) {
+        if (!(((int)blockIdx.x + j_ * G) * 32 + lane < A.nlist)) return;
+        // b_e by K/M row: lanes are 32 consecutive rows, so a store covers 1 kB (the other polarisation fills the gaps)
+        double2 *bo = reinterpret_cast<double2 *>(A.be) + ((size_t)((int)blockIdx.x + j_ * G) * ME * 32 + lane) * 2 + pol;
+        double br[4], bi[4];
+        rhs_sums(j_ & 1, q4, s_sdir[q4], pol, br, bi);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) bo[(size_t)s_slot[q4 + kk] * 64] = make_double2(br[kk], bi[kk]);
+    };
+    // both polarisations of four slots, one 32-byte store per slot (st.global.v4.f64): a warp's store is 1 kB without gaps --
+    // 8 wavefronts for 32 bytes per lane instead of 2 x 8 for 2 x 16
+    auto rhs_group = [&](int j_, int q4) {
+        if (!(((int)blockIdx.x + j_ * G) * 32 + lane < A.nlist)) return;
+        double *bo = A.be + ((size_t)((int)blockIdx.x + j_ * G) * ME * 32 + lane) * 4;
+        const int cd = s_sdir[q4];
+        double br0[4], bi0[4], br1[4], bi1[4];
+        rhs_sums(j_ & 1, q4, cd, 0, br0, bi0);
+        rhs_sums(j_ & 1, q4, cd, 1, br1, bi1);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(bo + (size_t)s_slot[q4 + kk] * 128), "d"(br0[kk]), "d"(bi0[kk]), "d"(br1[kk]),
+                         "d"(bi1[kk]) : "memory");
     };
 
     // ---- tile `c` (direction class c) of batch j: the inner loop of contract.cuh on the Q|T the eight warps left in shared memory ----
@@ -389,8 +407,10 @@ __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>:
         } else {
             if (DO_KM) {
                 mbar_wait(&full[k & 1], par);
+                // warp 6: the x and y slot groups (one non-zero polarisation each), warp 7: the z group (both)
 #pragma unroll 1
-                for (int q4 = 0; q4 < ME; q4 += 4) rhs_unit(k, q4, pw);
+                for (int q4 = 0; q4 < ME; q4 += 4)
+                    if ((s_sdir[q4] == 2) == (pw == 1)) rhs_group(k, q4);
             }
             if (k + 2 < nb) {
                 mbar_wait(&full[(k + 1) & 1], (unsigned)(((k + 1) >> 1) & 1));   // every warp has read the staged fields of batch k+1
