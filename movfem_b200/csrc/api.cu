@@ -877,10 +877,10 @@ int movfem_assemble_device(movfem_handle *h, int32_t freq_index, double omega, c
     CK(cudaMemsetAsync(h->d_flags, 0, 4 * sizeof(int), st));
     if (full) {   // a cold pass re-derives the tiny-pair flags
         if (h->flags_dirty) {
-            const int64_t nbw = h->km_rows / 32 + 1;
-            clear_flags_kernel<<<(unsigned)((nbw + 255) / 256), 256, 0, st>>>(nbw, h->flagW, h->d_batchany, h->d_pairflags, h->d_forcek);
+            clear_flags_kernel<<<(unsigned)((h->km_rows + 511) / 512), 512, 0, st>>>(h->km_rows, h->flagW, h->d_batchany, h->d_pairflags, h->d_forcek);
             h->launches += 1;
             CK(cudaGetLastError());
+            CK(cudaMemsetAsync(h->d_batchany, 0, sizeof(uint32_t) * (size_t)(h->km_rows / 32 + 1), st));
             h->flags_dirty = false;
         }
         CK(cudaMemsetAsync(h->d_nflag, 0, 2 * sizeof(unsigned long long), st));

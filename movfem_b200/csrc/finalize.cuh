@@ -251,17 +251,12 @@ stream_finalize_kernel(int64_t nzu, double w32, const double2 *__restrict__ kmg,
 
 // Clears the pair flags of a cold pass: only the rows batchany marks carry bits (every writer of pairflags / forcek also sets
 // the row's bit there), so the bitmaps -- 772 MB on config 5 -- are not memset but walked through their 4 MB summary
-__global__ void clear_flags_kernel(int64_t nbatch, int W, uint32_t *__restrict__ batchany, uint32_t *__restrict__ pairflags, uint32_t *__restrict__ forcek) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nbatch) return;
-    uint32_t any = batchany[b];
-    if (!any) return;
-    batchany[b] = 0u;
-    while (any) {
-        const int l = __ffs(any) - 1;
-        any &= any - 1;
-        for (int w = 0; w < W; ++w) { pairflags[(b * 32 + l) * W + w] = 0u; forcek[(b * 32 + l) * W + w] = 0u; }
-    }
+__global__ void clear_flags_kernel(int64_t nrows /* km_rows */, int W, const uint32_t *__restrict__ batchany, uint32_t *__restrict__ pairflags,
+                                   uint32_t *__restrict__ forcek) {
+    // one thread per row: a warp tests one summary word; a marked row clears its W words of both bitmaps
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows || !((batchany[row >> 5] >> (row & 31)) & 1u)) return;
+    for (int w = 0; w < W; ++w) { pairflags[row * W + w] = 0u; forcek[row * W + w] = 0u; }
 }
 
 // order-preserving compaction of the entries whose value is not exactly (0,0)
