@@ -52,7 +52,9 @@ using Con36p = ContractCfg<36, 36, 27, true, 12, 2>;
 using Con54  = ContractCfg<54, 60, 27, false, 15, 4>;
 using Con54p = ContractCfg<54, 60, 27, true, 15, 2>;
 
-constexpr size_t kScratchCap = (size_t)2048 << 20;  // Q|P,T scratch: larger lists are processed in chunks (measured on the GPML layers of config 5 at half scale, ms of the element phase: 32 MB 4.52, 128 MB 3.01, 512 MB 2.61, 2 GB 2.53)
+constexpr size_t kScratchCap = (size_t)4096 << 20;  // Q|P,T scratch: larger lists are processed in chunks.  Measured: GPML layers of config 5 at half
+                                                    // scale, ms of the element phase: 32 MB 4.52, 128 MB 3.01, 512 MB 2.61, 2 GB 2.53; full config 5, ms per
+                                                    // step: 512 MB 46.2, 2 GB 45.4, 4 GB 45.05, 8 GB 45.0
 
 enum { EV_START, EV_H2D, EV_NODE, EV_ELEM, EV_GATHER, EV_FINAL, EV_D2H, EV_COUNT };
 
