@@ -135,6 +135,11 @@ def step_roofs(me, ne, nz, phases, ms_step, fp64_peak, hbm_peak, traffic=None):
     return out
 
 
+def dominant_roofline(ms_flop_kernels, ms_gather):
+    """Which of the two roofline objects the top-level `roofline` key repeats: the kernels with the larger share of the step."""
+    return "roofline_hbm" if (ms_gather or 0.0) >= (ms_flop_kernels or 0.0) else "roofline_fp64"
+
+
 def pinned(n, dt):
     import torch
     return torch.empty(n, dtype=dt, pin_memory=True)
@@ -475,8 +480,8 @@ def run_graft(args):
                                                    "48.6 B per entry + the element right-hand sides) over the same device time"}
                                           if moved and ph.get("ms_gather") else None),
                                 "note": "algorithmic bytes: SURVEY 8d's 32 B per delivered entry (read K 8 + M 8, write A 16)"}
-        dom = "roofline_hbm" if (ph.get("ms_gather") or 0.0) >= (flopk.get("ms") or 0.0) else "roofline_fp64"
-        line["roofline"] = dict(line[dom], dominant_of={"fp64_kernels_ms": flopk.get("ms"), "gather_ms": ph.get("ms_gather")}, whole=roofs)
+        line["roofline"] = dict(line[dominant_roofline(flopk.get("ms"), ph.get("ms_gather"))],
+                                dominant_of={"fp64_kernels_ms": flopk.get("ms"), "gather_ms": ph.get("ms_gather")}, whole=roofs)
         if per_config:
             line["per_config"] = per_config
         if sweep:

@@ -141,6 +141,9 @@ def test_bench_step_roofs_uses_the_survey_figures():
     # linear elements: the fused kernel carries the flops
     r12 = b.step_roofs(12, 1000, 51000, {"ms_fused": 0.5, "ms_contract": 0.1, "ms_gather": 0.2}, 1.0, 30.0, 6000.0)
     assert r12["flop_kernels"]["kernels"].startswith("fused12_kernel") and abs(r12["flop_kernels"]["ms"] - 0.6) < 1e-12
+    # the top-level `roofline` repeats the object of the kernels with the larger share of the step
+    assert b.dominant_roofline(17.7, 22.6) == "roofline_hbm" and b.dominant_roofline(0.44, 0.33) == "roofline_fp64"
+    assert b.dominant_roofline(None, 1.0) == "roofline_hbm" and b.dominant_roofline(1.0, None) == "roofline_fp64"
 
 
 def test_global_vfem_refuses_arrays_that_are_not_the_callers_fortran_types():
