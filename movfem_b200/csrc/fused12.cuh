@@ -17,9 +17,10 @@
 //       four, so the six tiles are the six direction classes; operands are warp-uniform broadcast loads: the inner loop of
 //       contract.cuh), K_e, M_e leave as 512-byte coalesced stores with the tiny-pair test of exact.cuh in the epilogue,
 //       then the threads arrive on `empty`; warps 6, 7: b_e = sum_g phi_j R[d_j] (integration.f90:96-104), the x and y slot
-//       groups on one warp, the z group on the other, stored by K/M row (be_index: 1 kB runs of 32-byte stores), then the asynchronous copies (cp.async, completion
-//       on the `staged` mbarrier) of the node fields of batch k+2 from the FIELD-MAJOR node arrays node_kernel writes
-//       next to its records: the 32 lanes of a copy are 32 consecutive nodes of a k-column, 256 contiguous bytes
+//       groups on one warp, the z group on the other, stored by K/M row (be_index: 1 kB runs of 32-byte stores), then the
+//       asynchronous copies (cp.async, completion on the `staged` mbarrier) of the node fields of batch k+2 from the
+//       FIELD-MAJOR node arrays node_kernel writes next to its records: the 32 lanes of a copy are 32 consecutive nodes of a
+//       k-column, 256 contiguous bytes
 //
 // The closed forms hold when mu = mu0 I and sigma is diagonal at every node (node_kernel reports both; every
 // linear-element BASELINE mesh): otherwise the kernel returns at once and the generic two-kernel path does the work
@@ -36,8 +37,9 @@
 // field-major node arrays instead of 208-byte records (32 sectors -> 2-3 per copy) and b_e by K/M row (32 -> 8 wavefronts
 // per store): 2.38; diagonal tiles reuse their row operands, Gauss-point weights as two 16-byte loads, float scales: 2.25;
 // isotropic-sigma variant (four staged fields instead of seven): 2.05; b_e of both polarisations in one 32-byte store per slot
-// (st.global.v4.f64: 8 wavefronts per kB instead of 16): 2.03 = 22.6 TFLOP/s algorithmic, 0.65 of the measured FP64 peak.  geometry_kernel + contract_kernel on the same elements: 5.59.  Tried and dropped: DMMA interpolation phase
-// (block barriers: 5.30), four producer warps (register spills: 4.05), asynchronous id / line prefetch in the producers
+// (st.global.v4.f64: 8 wavefronts per kB instead of 16): 2.03 = 22.6 TFLOP/s algorithmic, 0.65 of the measured FP64 peak.
+// geometry_kernel + contract_kernel on the same elements: 5.59.  Tried and dropped: DMMA interpolation phase in a block-phased
+// version (block barriers: 5.30), four producer warps (register spills: 4.05), asynchronous id / line prefetch in the producers
 // (3.47), producers on one SM sub-partition (3.50), rolled Gauss-point / node loops (2 x unrolled: 3.53), two Gauss points x 16
 // elements per warp in the geometry (half the distinct addresses per field load, same wavefronts: 2.07 against 2.05), the
 // interpolation as mma.m8n8k4.f64 (A = N or dN/dxi from a fragment table, B = node fields of 8 elements, all rows 33 doubles apart so
