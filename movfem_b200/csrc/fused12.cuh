@@ -102,9 +102,10 @@ struct Fused12Cfg {
                                    sizeof(unsigned long long) * 8 + sizeof(int) * (2 * ME + MN + 4 * 32 + 6 * 16);
 };
 
-// ISO: sigma = s I at every node (flags[3] == 0; every linear-element BASELINE mesh): three of the seven node fields are copies
+// ISO: sigma = s I at every node (flags[3] == 0; every linear-element BASELINE mesh on its first frequency): three of the seven node fields are copies
 // of others and are neither staged nor interpolated -- the results are bit-identical to the general variant's, which runs
-// when some node has unequal diagonal entries (api.cu launches both; the device flag picks one)
+// when some node has unequal diagonal entries (api.cu launches both; the device flag picks one -- both bodies in ONE kernel behind
+// a branch on the flag: 2.48 against 2.03 ms, spills and twice the code in one image)
 template <bool DO_KM, bool ISO>
 __global__ void __launch_bounds__(Fused12Cfg<DO_KM>::THREADS, Fused12Cfg<DO_KM>::MINB) fused12_kernel(Fused12Args A) {
     using C = Fused12Cfg<DO_KM>;
