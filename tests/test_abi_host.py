@@ -166,3 +166,30 @@ def test_global_vfem_refuses_arrays_that_are_not_the_callers_fortran_types():
     with pytest.raises(host.MovfemError) as ei:
         asm.global_vfem(1, 1.0, sg[:-1], **good)
     assert ei.value.code == abi.MOVFEM_E_BADARG
+
+
+def test_sass_of_the_library_uses_the_sm100_paths_the_design_names():
+    """Static check on the built library (cuobjdump -sass, no GPU): the hardware paths DESIGN.md claims are in the code that
+    ships -- TMA bulk copies + mbarriers in the generic element kernels, the FP64 tensor-core path in the interpolation phase of
+    geometry_kernel, cp.async + mbarriers and no local-memory spills in the linear-element kernel, cp.async in the gather."""
+    import shutil, subprocess, sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_opmix.py")], capture_output=True, text=True, timeout=300).stdout
+    cols, rows = None, {}
+    for line in out.splitlines():
+        cells = [c.strip() for c in line.strip().strip("|").split("|")]
+        if cells and cells[0] == "kernel":
+            cols = cells
+        elif cols and len(cells) == len(cols) and cells[0].startswith("`"):
+            rows[cells[0].strip("`")] = {c: int(v) if v else 0 for c, v in zip(cols[1:], cells[1:])}
+    def pick(sub):
+        hit = [v for k, v in rows.items() if sub in k]
+        assert hit, (sub, sorted(rows))
+        return hit
+    for r in pick("contract_kernel"):
+        assert r["UBLKCP"] > 0 and r["SYNCS"] > 0 and r["DFMA"] > 100 and r["STL"] <= 2, r      # (the GPML variant spills one register)
+    assert any(r["DMMA"] > 0 and r["UBLKCP"] > 0 for r in pick("geometry_kernel"))
+    fused = pick("fused12_kernel<true, true>")[0]
+    assert fused["LDGSTS"] > 0 and fused["SYNCS"] > 0 and fused["DFMA"] > 500 and fused["STL"] == 0 and fused["LDL"] == 0, fused
+    assert all(r["LDGSTS"] > 0 for r in pick("gather_finalize_kernel"))
