@@ -803,7 +803,7 @@ static int launch_exact(movfem_handle *h, double omega) {
     ExactArgs X;
     X.m = m; X.pml = h->pml; X.omega = omega; X.T = h->d_tab; X.nodes = h->d_nodes; X.xp = h->d_xp; X.yp = h->d_yp;
     X.batchany = h->d_batchany; X.pairflags = h->d_pairflags; X.forcek = h->d_forcek; X.W = h->flagW; X.NP = h->NP; X.gne = h->d_gne; X.KM = h->d_KM;
-    auto run = [&](auto kern, size_t smem, size_t smem_h) -> int {
+    auto run = [&](auto kern, size_t smem, size_t smem_h, int minb) -> int {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + smem_h)));
         for (int pass = 0; pass < 2; ++pass) {
             X.list = pass ? h->d_list_pml : h->d_list_plain;
@@ -813,16 +813,16 @@ static int launch_exact(movfem_handle *h, double omega) {
             if (X.nlist <= 0) continue;
             const int nb = (X.nlist + 31) / 32;
             if (kernel_event(h, 2, true)) return MOVFEM_E_CUDA;
-            kern<<<std::min(nb, EXACT_MINB * h->num_sms), 256, smem + (pass ? smem_h : 0), h->stream>>>(X);
+            kern<<<std::min(nb, minb * h->num_sms), 256, smem + (pass ? smem_h : 0), h->stream>>>(X);
             h->launches += 1;
             CK(cudaGetLastError());
             if (kernel_event(h, 2, false)) return MOVFEM_E_CUDA;
         }
         return 0;
     };
-    if (m.me == 12) return run(exact_kernel<8, 12, 8>, ExactCfg<8, 12, 8>::SMEM, ExactCfg<8, 12, 8>::SMEM_H);
-    if (m.me == 36) return run(exact_kernel<20, 36, 27>, ExactCfg<20, 36, 27>::SMEM, ExactCfg<20, 36, 27>::SMEM_H);
-    return run(exact_kernel<27, 54, 27>, ExactCfg<27, 54, 27>::SMEM, ExactCfg<27, 54, 27>::SMEM_H);
+    if (m.me == 12) return run(exact_kernel<8, 12, 8>, ExactCfg<8, 12, 8>::SMEM, ExactCfg<8, 12, 8>::SMEM_H, ExactCfg<8, 12, 8>::MINB);
+    if (m.me == 36) return run(exact_kernel<20, 36, 27>, ExactCfg<20, 36, 27>::SMEM, ExactCfg<20, 36, 27>::SMEM_H, ExactCfg<20, 36, 27>::MINB);
+    return run(exact_kernel<27, 54, 27>, ExactCfg<27, 54, 27>::SMEM, ExactCfg<27, 54, 27>::SMEM_H, ExactCfg<27, 54, 27>::MINB);
 }
 
 // gather + RHS + the counters' way back to the host

@@ -68,7 +68,8 @@ template <int MN, int ME, int NGP>
 struct ExactCfg {
     // A group of up to EB flagged elements is worked on at a time, chosen so that the group's flagged pairs fill whole
     // rounds of the CTA's threads (20-node bricks have 36 such pairs each: 7 elements = 252 of 256 thread slots).
-    static constexpr int EB = EXACT_EB, THREADS = 256, ITEMS = EXACT_ITEMS, MINB = EXACT_MINB;
+    // (the 27-node element keeps the larger groups: its flagged pairs sit in few elements -- config 3: 0.085 ms against 0.099)
+    static constexpr int EB = ME == 54 ? 14 : EXACT_EB, THREADS = 256, ITEMS = ME == 54 ? 512 : EXACT_ITEMS, MINB = ME == 54 ? 2 : EXACT_MINB;
     static constexpr int NDD = 13;                       // staged per node: z, mu^-1 (6), Re sigma (6)
     static constexpr size_t SMEM = sizeof(ExactGp) * EB * NGP + sizeof(double) * (EB * MN * NDD + EB * 6) + sizeof(int) * (EB * 8 + 4 + 32 + THREADS);
     static constexpr size_t SMEM_H = sizeof(ExactH) * EB * NGP;   // added for stretched lists
@@ -202,7 +203,7 @@ __device__ __forceinline__ void exact_pair(const ElemTables &T, const ExactGp *_
 }
 
 template <int MN, int ME, int NGP>
-__global__ void __launch_bounds__(256, EXACT_MINB) exact_kernel(ExactArgs A) {
+__global__ void __launch_bounds__(256, (ExactCfg<MN, ME, NGP>::MINB)) exact_kernel(ExactArgs A) {
     using CFG = ExactCfg<MN, ME, NGP>;
     constexpr int EB = CFG::EB, NDD = CFG::NDD, NORD = MN == 8 ? 2 : 3;
     extern __shared__ __align__(128) unsigned char smem_raw[];
